@@ -1,0 +1,155 @@
+"""Seeded synthetic atmospheres of the BASELINE.json shapes.
+
+Everything is float64, C-order, wavelength on the fastest axis - the layout the
+reference passes to its flux solvers (picaso/justdoit.py:275-283, :337-342, :392-396).
+Used by tests/, bench.py and tests/golden/make_golden.py; pure numpy.
+"""
+import numpy as np
+
+__all__ = ["geometry_1d", "reflected_inputs", "thermal_inputs", "transit_inputs",
+           "adversarial_reflected"]
+
+# Abramowitz & Stegun 25.8 half-sphere Gauss points used by the reference for
+# 1-D geometry (picaso/disco.py:67-87).
+_GAUSS = {
+    5: ([0.0985350858, 0.3045357266, 0.5620251898, 0.8019865821, 0.9601901429],
+        [0.0157479145, 0.0739088701, 0.1463869871, 0.1671746381, 0.0967815902]),
+    6: ([0.0730543287, 0.2307661380, 0.4413284812, 0.6630153097, 0.8519214003, 0.9706835728],
+        [0.0087383018, 0.0439551656, 0.0986611509, 0.1407925538, 0.1355424972, 0.0723103307]),
+    7: ([0.0562625605, 0.1802406917, 0.3526247171, 0.5471536263, 0.7342101772, 0.8853209468,
+         0.9775206136],
+        [0.0052143622, 0.0274083567, 0.0663846965, 0.1071250657, 0.1273908973, 0.1105092582,
+         0.0559673634]),
+    8: ([0.0446339553, 0.1443662570, 0.2868247571, 0.4548133152, 0.6280678354, 0.7856915206,
+         0.9086763921, 0.9822200849],
+        [0.0032951914, 0.0178429027, 0.0454393195, 0.0791995995, 0.1060473594, 0.1125057995,
+         0.0911190236, 0.0445508044]),
+}
+
+
+def geometry_1d(ngauss=5, phase=0.0):
+    """gangle, gweight, tangle, tweight, ubar0[ng,1], ubar1[ng,1], cos_theta.
+
+    Same numbers as disco.get_angles_1d + disco.compute_disco (disco.py:36-50, :67-87).
+    """
+    g, w = _GAUSS[ngauss]
+    gangle = np.array(g)
+    gweight = np.array(w)
+    tangle = np.array([0.0])
+    tweight = np.array([1.0])
+    cos_theta = np.cos(phase)
+    lon = np.arcsin((gangle - (cos_theta - 1.0) / (cos_theta + 1.0)) / (2.0 / (cos_theta + 1.0)))
+    if phase > np.pi:
+        lon = -lon
+    f = np.sin(np.arccos(tangle))
+    ubar0 = np.outer(np.cos(lon - phase), f)
+    ubar1 = np.outer(np.cos(lon), f)
+    return gangle, gweight, tangle, tweight, ubar0, ubar1, float(cos_theta)
+
+
+def _layer_fields(rng, L, W):
+    lgrid = np.arange(L)[:, None] / max(L - 1, 1)
+    dtau_og = 10.0 ** (-4.0 + 5.0 * lgrid + 0.5 * rng.standard_normal((L, W)))
+    base = rng.uniform(0.1, 0.9, size=(1, W))
+    w0_og = np.clip(base + 0.3 * (lgrid - 0.5) + 0.1 * rng.standard_normal((L, W)), 0.02, 0.98)
+    cosb_og = rng.uniform(0.0, 0.85, size=(L, W))
+    return dtau_og, w0_og, cosb_og
+
+
+def reflected_inputs(L=60, W=300, seed=1001, stream=2, delta_eddington=True, ngauss=5, phase=0.0):
+    """Inputs of get_reflected_1d / get_reflected_SH (fluxes.py:1010-1015, :2675-2679)."""
+    rng = np.random.default_rng(seed)
+    dtau_og, w0_og, cosb_og = _layer_fields(rng, L, W)
+    ftau_cld = rng.uniform(0.05, 0.95, size=(L, W))
+    ftau_ray = 1.0 - ftau_cld
+    gcos2 = 0.5 * ftau_ray
+    if delta_eddington:
+        # optics.py:412-420
+        f = cosb_og ** stream
+        w0 = w0_og * (1.0 - f) / (1.0 - w0_og * f)
+        cosb = (cosb_og - f) / (1.0 - f)
+        dtau = dtau_og * (1.0 - w0_og * f)
+    else:
+        f = np.zeros_like(cosb_og)
+        w0, cosb, dtau = w0_og.copy(), cosb_og.copy(), dtau_og.copy()
+    tau = np.vstack([np.zeros((1, W)), np.cumsum(dtau, axis=0)])
+    tau_og = np.vstack([np.zeros((1, W)), np.cumsum(dtau_og, axis=0)])
+    gangle, gweight, tangle, tweight, ubar0, ubar1, cos_theta = geometry_1d(ngauss, phase)
+    return dict(
+        nlevel=L + 1, nwno=W, wno=np.linspace(1e4 / 1.0, 1e4 / 0.3, W),
+        numg=ngauss, numt=1,
+        dtau=dtau, tau=tau, w0=w0, cosb=cosb, gcos2=gcos2, ftau_cld=ftau_cld, ftau_ray=ftau_ray,
+        dtau_og=dtau_og, tau_og=tau_og, w0_og=w0_og, cosb_og=cosb_og, f_deltaM=f,
+        surf_reflect=np.zeros(W), ubar0=ubar0, ubar1=ubar1, cos_theta=cos_theta,
+        F0PI=np.ones(W), gweight=gweight, tweight=tweight,
+        frac_a=1.0, frac_b=-1.0, frac_c=2.0, constant_back=-0.5, constant_forward=1.0,
+    )
+
+
+def adversarial_reflected(L=12, seed=7):
+    """Edge regimes of SURVEY.md section 8d run for parity only: one wavelength column each."""
+    rng = np.random.default_rng(seed)
+    cols = []
+    for w0v in (1e-6, 0.5, 0.999999):
+        for dt in (1e-10, 1e-3, 1.0, 50.0):
+            for g in (0.0, 0.5, 0.95):
+                cols.append((w0v, dt, g))
+    W = len(cols)
+    d = reflected_inputs(L=L, W=W, seed=seed, delta_eddington=False)
+    for i, (w0v, dt, g) in enumerate(cols):
+        d["w0"][:, i] = w0v
+        d["w0_og"][:, i] = w0v
+        d["dtau"][:, i] = dt * (1.0 + 0.01 * rng.standard_normal(L))
+        d["dtau_og"][:, i] = d["dtau"][:, i]
+        d["cosb"][:, i] = g
+        d["cosb_og"][:, i] = g
+    d["tau"] = np.vstack([np.zeros((1, W)), np.cumsum(d["dtau"], axis=0)])
+    d["tau_og"] = d["tau"].copy()
+    d["surf_reflect"] = np.full(W, 0.3)
+    return d
+
+
+def thermal_inputs(L=90, W=10000, seed=1002, ngauss=5, wno_range=(300.0, 10000.0),
+                   t_range=(400.0, 2000.0)):
+    """Inputs of get_thermal_1d (fluxes.py:1683-1684)."""
+    rng = np.random.default_rng(seed)
+    dtau, w0, cosb = _layer_fields(rng, L, W)
+    tlevel = np.linspace(t_range[0], t_range[1], L + 1)
+    plevel = np.logspace(-6, 2, L + 1) * 1e6
+    wno = np.linspace(wno_range[0], wno_range[1], W)
+    gangle, gweight, tangle, tweight, ubar0, ubar1, cos_theta = geometry_1d(ngauss, 0.0)
+    return dict(nlevel=L + 1, nwno=W, wno=wno, numg=ngauss, numt=1, tlevel=tlevel, dtau=dtau,
+                w0=w0, cosb=cosb, plevel=plevel, ubar1=ubar1, surf_reflect=np.zeros(W),
+                hard_surface=0, dwno=np.gradient(wno) if W > 1 else np.ones(1),
+                gweight=gweight, tweight=tweight)
+
+
+def transit_inputs(L=80, W=50000, seed=1004):
+    """Inputs of get_transit_1d (fluxes.py:2582-2583): isothermal hydrostatic H2/He envelope."""
+    rng = np.random.default_rng(seed)
+    k_b = 1.380649e-16
+    amu = 1.66053906660e-24
+    rjup = 7.1492e9
+    mjup = 1.898e30
+    G = 6.674e-8
+    V = L + 1
+    plevel = np.logspace(-6, 2, V) * 1e6                 # dyn/cm2, top -> bottom
+    tlevel = np.full(V, 1000.0)
+    mmw = np.full(L, 2.3)
+    radius, mass = 1.2 * rjup, 1.0 * mjup
+    # integrate upward from the bottom level at r=radius
+    z = np.zeros(V)
+    z[-1] = radius
+    for i in range(V - 2, -1, -1):
+        g = G * mass / z[i + 1] ** 2
+        H = k_b * tlevel[i] / (mmw[min(i, L - 1)] * amu * g)
+        z[i] = z[i + 1] + H * np.log(plevel[i + 1] / plevel[i])
+    dz = np.zeros(V)
+    dz[1:-1] = 0.5 * (z[:-2] - z[2:])
+    dz[0] = dz[1]
+    dz[-1] = dz[-2]
+    gravity = G * mass / radius ** 2
+    colden = (plevel[1:] - plevel[:-1]) / gravity
+    dtau, _, _ = _layer_fields(rng, L, W)
+    return dict(z=z, dz=dz, nlevel=V, nwno=W, rstar=6.957e10, mmw=mmw, k_b=k_b, amu=amu,
+                player=plevel, tlayer=tlevel, colden=colden, DTAU=dtau)

@@ -1,0 +1,108 @@
+"""Seeded parity cases shared by make_golden.py (reference run, build container only),
+the oracle tests (CPU) and the GPU parity tests.  Inputs are regenerated from seeds by
+picaso_b200.synth; only reference OUTPUTS are stored in the .npz fixtures."""
+import itertools
+
+import numpy as np
+
+from picaso_b200 import synth
+
+
+def reflected_cases():
+    cases = {}
+    # every single_phase x multi_phase x toon_coefficients combination, small
+    for sp, mp, tc in itertools.product((0, 1, 2, 3), (0, 1), (0, 1)):
+        cases[f"refl_combo_sp{sp}_mp{mp}_tc{tc}"] = dict(
+            build=dict(L=20, W=48, seed=100 + 8 * sp + 4 * mp + tc, phase=0.6),
+            kw=dict(single_phase=sp, multi_phase=mp, toon_coefficients=tc, get_lvl_flux=0))
+    # BASELINE config 1: 60 layers x 300 waves x 5 gauss angles, OTHG, no Raman
+    cases["refl_cfg1"] = dict(build=dict(L=60, W=300, seed=1001),
+                              kw=dict(single_phase=1, multi_phase=0, toon_coefficients=0,
+                                      get_lvl_flux=0))
+    cases["refl_cfg1_tthg_ray"] = dict(build=dict(L=60, W=300, seed=1001),
+                                       kw=dict(single_phase=3, multi_phase=0, toon_coefficients=0,
+                                               get_lvl_flux=0))
+    # level fluxes (climate path), reflective surface, non-zero b_top
+    cases["refl_lvl"] = dict(build=dict(L=24, W=40, seed=77, phase=0.3),
+                             kw=dict(single_phase=3, multi_phase=0, toon_coefficients=0,
+                                     get_lvl_flux=1),
+                             surf_reflect=0.4)
+    cases["refl_lvl_edd"] = dict(build=dict(L=16, W=33, seed=78, delta_eddington=False),
+                                 kw=dict(single_phase=1, multi_phase=1, toon_coefficients=1,
+                                         get_lvl_flux=1),
+                                 surf_reflect=0.1)
+    cases["refl_adversarial"] = dict(adversarial=True,
+                                     kw=dict(single_phase=3, multi_phase=0, toon_coefficients=0,
+                                             get_lvl_flux=0))
+    cases["refl_ragged"] = dict(build=dict(L=7, W=37, seed=5, ngauss=7, phase=2.0),
+                                kw=dict(single_phase=0, multi_phase=0, toon_coefficients=0,
+                                        get_lvl_flux=0), surf_reflect=0.25)
+    cases["refl_one_wave_one_layer"] = dict(build=dict(L=1, W=1, seed=6, ngauss=5),
+                                            kw=dict(single_phase=3, multi_phase=0,
+                                                    toon_coefficients=0, get_lvl_flux=1))
+    return cases
+
+
+def build_reflected(case):
+    if case.get("adversarial"):
+        d = synth.adversarial_reflected()
+    else:
+        d = synth.reflected_inputs(**case["build"])
+    if "surf_reflect" in case:
+        d["surf_reflect"] = np.full(d["nwno"], case["surf_reflect"])
+    return d
+
+
+def reflected_args(d, kw):
+    """positional argument list of get_reflected_1d (fluxes.py:1010-1015)."""
+    return (d["nlevel"], d["wno"], d["nwno"], d["numg"], d["numt"], d["dtau"], d["tau"], d["w0"],
+            d["cosb"], d["gcos2"], d["ftau_cld"], d["ftau_ray"], d["dtau_og"], d["tau_og"],
+            d["w0_og"], d["cosb_og"], d["surf_reflect"], d["ubar0"], d["ubar1"], d["cos_theta"],
+            d["F0PI"], kw["single_phase"], kw["multi_phase"], d["frac_a"], d["frac_b"],
+            d["frac_c"], d["constant_back"], d["constant_forward"], 1, kw["get_lvl_flux"],
+            kw["toon_coefficients"], 0.0)
+
+
+def thermal_cases():
+    cases = {}
+    for ct, hs in itertools.product((0, 1), (0, 1)):
+        cases[f"therm_ct{ct}_hs{hs}"] = dict(build=dict(L=30, W=64, seed=200 + 2 * ct + hs),
+                                             calc_type=ct, hard_surface=hs, surf_reflect=0.2 * hs)
+    # BASELINE config 2 shape at reduced wave count
+    cases["therm_cfg2_small"] = dict(build=dict(L=90, W=200, seed=1002), calc_type=0,
+                                     hard_surface=0, surf_reflect=0.0)
+    cases["therm_ragged"] = dict(build=dict(L=5, W=35, seed=9, ngauss=8), calc_type=0,
+                                 hard_surface=0, surf_reflect=0.0)
+    cases["therm_cold"] = dict(build=dict(L=12, W=40, seed=10, t_range=(60.0, 300.0),
+                                          wno_range=(50.0, 30000.0)), calc_type=0,
+                               hard_surface=0, surf_reflect=0.0)
+    return cases
+
+
+def build_thermal(case):
+    d = synth.thermal_inputs(**case["build"])
+    d["hard_surface"] = case["hard_surface"]
+    d["surf_reflect"] = np.full(d["nwno"], case["surf_reflect"])
+    d["calc_type"] = case["calc_type"]
+    return d
+
+
+def thermal_args(d):
+    """positional argument list of get_thermal_1d (fluxes.py:1683-1684)."""
+    return (d["nlevel"], d["wno"], d["nwno"], d["numg"], d["numt"], d["tlevel"], d["dtau"],
+            d["w0"], d["cosb"], d["plevel"], d["ubar1"], d["surf_reflect"], d["hard_surface"],
+            d["dwno"], d["calc_type"])
+
+
+def transit_cases():
+    return {
+        "transit_cfg4_small": dict(L=80, W=256, seed=1004),
+        "transit_ragged": dict(L=9, W=19, seed=12),
+        "transit_two_level": dict(L=1, W=5, seed=13),
+    }
+
+
+def transit_args(d):
+    """positional argument list of get_transit_1d (fluxes.py:2582-2583)."""
+    return (d["z"], d["dz"], d["nlevel"], d["nwno"], d["rstar"], d["mmw"], d["k_b"], d["amu"],
+            d["player"], d["tlayer"], d["colden"], d["DTAU"])

@@ -1,0 +1,55 @@
+"""CPU: the C oracle (oracle/) against golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+import cases as C
+import oracle
+from picaso_b200 import synth
+from util import assert_close, assert_level_close, golden
+
+RTOL = 1e-10  # oracle keeps the reference's operation order; observed ~1e-13
+
+
+@pytest.mark.parametrize("name", sorted(C.reflected_cases()))
+def test_reflected(name):
+    g = golden("reflected")
+    case = C.reflected_cases()[name]
+    d = C.build_reflected(case)
+    xint, lv = oracle.get_reflected_1d(*C.reflected_args(d, case["kw"]))
+    assert_close(xint, g[name + "/xint"], RTOL, name + " xint")
+    alb = oracle.compress_disco(d["nwno"], d["cos_theta"], xint, d["gweight"], d["tweight"],
+                                d["F0PI"])
+    assert_close(alb, g[name + "/albedo"], RTOL, name + " albedo")
+    if case["kw"]["get_lvl_flux"]:
+        for k, a in zip(("fm", "fp", "fmm", "fpm"), lv):
+            assert_level_close(a, g[name + "/" + k], what=name + " " + k)
+
+
+@pytest.mark.parametrize("name", sorted(C.thermal_cases()))
+def test_thermal(name):
+    g = golden("thermal")
+    d = C.build_thermal(C.thermal_cases()[name])
+    ftop, lv = oracle.get_thermal_1d(*C.thermal_args(d))
+    assert_close(ftop, g[name + "/ftop"], RTOL, name + " ftop")
+    th = oracle.compress_thermal(d["nwno"], ftop, d["gweight"], d["tweight"])
+    assert_close(th, g[name + "/thermal"], RTOL, name + " thermal")
+    if name + "/fm" in g.files:
+        for k, a in zip(("fm", "fp", "fmm", "fpm"), lv):
+            assert_level_close(a, g[name + "/" + k], what=name + " " + k)
+
+
+@pytest.mark.parametrize("name", sorted(C.transit_cases()))
+def test_transit(name):
+    g = golden("transit")
+    d = synth.transit_inputs(**C.transit_cases()[name])
+    F = oracle.get_transit_1d(*C.transit_args(d))
+    assert_close(F, g[name + "/F"], 1e-12, name)
+
+
+def test_threads_do_not_change_results():
+    d = synth.reflected_inputs(L=10, W=101, seed=3)
+    kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
+    a, _ = oracle.get_reflected_1d(*C.reflected_args(d, kw), nthreads=1)
+    b, _ = oracle.get_reflected_1d(*C.reflected_args(d, kw), nthreads=4)
+    assert np.array_equal(a, b)

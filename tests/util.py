@@ -1,0 +1,41 @@
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def max_rel(a, b, floor=1e-300):
+    """max |a-b| / max(|b|, floor); NaNs must coincide."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    na, nb = np.isnan(a), np.isnan(b)
+    assert np.array_equal(na, nb), "NaN pattern differs"
+    if a.size == 0:
+        return 0.0
+    ok = ~na
+    if not ok.any():
+        return 0.0
+    return float(np.max(np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), floor)))
+
+
+def assert_close(a, b, rtol, what=""):
+    e = max_rel(a, b)
+    assert e <= rtol, f"{what}: max rel err {e:.3e} > {rtol:.1e}"
+
+
+def assert_level_close(a, b, rtol=1e-6, col_atol=1e-9, what=""):
+    """Mixed criterion for level-flux arrays [...,nlevel,nwno]:
+    |d| <= rtol*|ref| + col_atol * max over the level axis of |ref|.  Deep entries that
+    decayed to ~1e-11 of the column maximum carry pure rounding-order noise."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape
+    colmax = np.max(np.abs(b), axis=-2, keepdims=True)
+    bad = np.abs(a - b) > rtol * np.abs(b) + col_atol * colmax
+    assert not bad.any(), f"{what}: {int(bad.sum())} level-flux entries outside tolerance"
