@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200-native PICASO hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json metric): reflected-light Toon89 spectrum, 60 layers x 10 000
+wavelengths x 5 Gauss angles, TTHG_ray single scattering, N=2 multiple scattering,
+delta-Eddington on (so the *_og arrays are distinct), fused disk integration.
+One step = one such spectrum per GPU (get_reflected_1d + compress_disco): a single kernel
+launch on device-resident inputs.  Steps rotate over NSETS distinct input sets whose total
+size exceeds the 126 MB L2, so every step streams its inputs from HBM.
+Multi-GPU: weak scaling - each rank owns its own 10 000-wavelength slab (wavelengths are
+independent); the per-rank albedo vectors are all-gathered (NCCL) inside the timed step.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+L, W, NG = 60, 10000, 5
+NSETS = 4
+KW = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
+LAYER_KEYS = ("dtau", "w0", "cosb", "gcos2", "ftau_cld", "ftau_ray", "dtau_og", "w0_og", "cosb_og")
+LEVEL_KEYS = ("tau", "tau_og")
+WAVE_KEYS = ("surf_reflect", "F0PI")
+# algorithmic bytes per wave-point (SURVEY.md section 8d / BASELINE.md section 4):
+# 9 layer arrays + 2 level arrays + F0PI + surf_reflect read once, G intensities written
+ALG_BYTES_PER_WAVE = (9 * L + 2 * (L + 1) + 2) * 8 + NG * 8
+METRIC = "wave-points/sec (60-layer x 10k-wave reflected Toon spectrum)"
+UNIT = "wave-points/s"
+WORKLOAD = "reflected_toon_1d L=60 W=10000 G=5 TTHG_ray N=2 delta-eddington (BASELINE headline)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.sm_max = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+        self.active = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, nm in names.items():
+                        if mask & bit:
+                            self.reasons.add(nm)
+                except Exception:
+                    pass
+            time.sleep(0.0005)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_sets(rank):
+    from picaso_b200 import synth
+    return [synth.reflected_inputs(L=L, W=W, seed=1000 + 97 * rank + i) for i in range(NSETS)]
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the CPU port of the reference algorithm (oracle/) on all host cores."""
+    if rank != 0:
+        return
+    import cases as C
+    import oracle
+    nthreads = os.cpu_count() or 1
+    d = make_sets(0)[0]
+    a = C.reflected_args(d, KW)
+    for _ in range(max(args.warmup, 1)):
+        x, _ = oracle.get_reflected_1d(*a, nthreads=nthreads)
+        oracle.compress_disco(W, d["cos_theta"], x, d["gweight"], d["tweight"], d["F0PI"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        x, _ = oracle.get_reflected_1d(*a, nthreads=nthreads)
+        oracle.compress_disco(W, d["cos_theta"], x, d["gweight"], d["tweight"], d["F0PI"])
+    dt = time.perf_counter() - t0
+    val = W * args.steps / dt
+    sample = "%d full spectra (60x10000x5) per run, C port of the reference algorithm, OpenMP over wavelengths" % args.steps
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "spectra_per_sec": args.steps / dt,
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 40)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import ctypes
+    import cases as C
+    import picaso_b200 as pb
+    from picaso_b200 import _lib
+    from picaso_b200._lib import PB_DEVICE, ReflectedArgs
+
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pb.Context(local_rank)
+    if world > 1:
+        # run our kernels on the stream NCCL's collectives are enqueued on: no host sync needed
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    warm = max(args.warmup, 3)
+
+    sets = make_sets(rank)
+    G = NG
+    dev_sets = []
+    for d in sets:
+        dd = {k: ctx.to_device(d[k]) for k in LAYER_KEYS + LEVEL_KEYS + WAVE_KEYS}
+        dev_sets.append(dd)
+    d0 = sets[0]
+    u0 = np.ascontiguousarray(d0["ubar0"]).reshape(-1)
+    u1 = np.ascontiguousarray(d0["ubar1"]).reshape(-1)
+    gw = np.ascontiguousarray(d0["gweight"])
+    tw = np.ascontiguousarray(d0["tweight"])
+    d_xint = ctx.dev_alloc(G * W * 8)
+    if world > 1:
+        alb_all = torch.empty((world, W), dtype=torch.float64, device="cuda")
+        alb_mine = torch.empty((W,), dtype=torch.float64, device="cuda")
+        d_alb = alb_mine.data_ptr()
+    else:
+        d_alb = ctx.dev_alloc(W * 8)
+
+    def make_args(dd):
+        a = ReflectedArgs()
+        a.nlayer, a.nwno, a.numg, a.numt, a.nbatch, a.ld = L, W, NG, 1, 1, W
+        for k in LAYER_KEYS + LEVEL_KEYS + WAVE_KEYS:
+            setattr(a, k, dd[k])
+        a.b_top = None
+        a.ubar0, a.ubar1, a.gweight, a.tweight = _lib.addr(u0), _lib.addr(u1), _lib.addr(gw), _lib.addr(tw)
+        a.cos_theta = d0["cos_theta"]
+        a.single_phase, a.multi_phase, a.toon_coefficients = KW["single_phase"], KW["multi_phase"], KW["toon_coefficients"]
+        a.frac_a, a.frac_b, a.frac_c = d0["frac_a"], d0["frac_b"], d0["frac_c"]
+        a.constant_back, a.constant_forward = d0["constant_back"], d0["constant_forward"]
+        a.get_toa_intensity, a.get_lvl_flux = 1, 0
+        a.xint_at_top, a.albedo = d_xint, d_alb
+        return a
+
+    cargs = [make_args(dd) for dd in dev_sets]
+    fn = ctx.lib.pb_reflected_toon_1d
+
+    def step(i):
+        ctx.check(fn(ctx.h, ctypes.byref(cargs[i % NSETS]), PB_DEVICE))
+        if world > 1:
+            dist.all_gather_into_tensor(alb_all, alb_mine)
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- parity gate on this very configuration (cheap: one set, oracle on host threads) ----
+    import oracle
+    step(0)
+    ctx.sync()
+    got = ctx.from_device(d_alb, (W,)) if world == 1 else alb_mine.cpu().numpy()
+    ox, _ = oracle.get_reflected_1d(*C.reflected_args(sets[0], KW), nthreads=os.cpu_count() or 1)
+    want = oracle.compress_disco(W, d0["cos_theta"], ox, gw, tw, sets[0]["F0PI"])
+    parity = float(np.max(np.abs(got - want) / np.abs(want)))
+    if not parity < 1e-6:
+        raise SystemExit("parity gate failed: albedo max rel err %.3e" % parity)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- warm-up: W steps, then keep going until clocks had ~0.3 s to ramp ----
+    for i in range(warm):
+        step(i)
+    ctx.sync()
+    t_end = time.perf_counter() + 0.3
+    i = warm
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            step(i)
+            i += 1
+        ctx.sync()
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ----
+    barrier()
+    l0 = ctx.launch_count()
+    sampler.active = True
+    ctx.timer_start()
+    for i in range(args.steps):
+        step(i)
+    ms = ctx.timer_stop()
+    sampler.active = False
+    launches = ctx.launch_count() - l0
+    barrier()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * W * args.steps / (ms * 1e-3)
+
+    # ---- end to end: public API, pinned host inputs, H2D + kernel + D2H per step ----
+    ke = args.e2e_steps or min(args.steps, 40)
+    pinned_sets = []
+    for d in sets:
+        pd = dict(d)
+        for k in LAYER_KEYS + LEVEL_KEYS + WAVE_KEYS:
+            buf = ctx.pinned_empty(d[k].shape)
+            buf[...] = d[k]
+            pd[k] = buf
+        pinned_sets.append(pd)
+    if world > 1:
+        ctx.set_stream(None)
+
+    def e2e_step(i):
+        d = pinned_sets[i % NSETS]
+        return pb.get_reflected_1d(*C.reflected_args(d, KW), ctx=ctx, gweight=gw, tweight=tw,
+                                   return_albedo=True)
+
+    for i in range(3):
+        xint_h, _, alb_h = e2e_step(i)
+    barrier()
+    sampler.active = True
+    t0 = time.perf_counter()
+    for i in range(ke):
+        xint_h, _, alb_h = e2e_step(i)
+    e2e_dt = time.perf_counter() - t0
+    sampler.active = False
+    sampler.stop_flag = True
+    if world > 1:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_val = world * W * ke / e2e_dt
+    h2d = sum(sets[0][k].nbytes for k in LAYER_KEYS + LEVEL_KEYS + WAVE_KEYS) + W * 8  # + b_top
+    d2h = (G + 1) * W * 8
+
+    peak, peak_src = peaks()
+    alg_bytes = ALG_BYTES_PER_WAVE * W
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("refl_toa_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "spectra_per_sec": world * args.steps / (ms * 1e-3),
+        "config": {"workload": WORKLOAD, "waves_per_gpu": W, "layers": L, "angles": G,
+                   "l2_policy": "inputs larger than L2: %d input sets x %.1f MB rotated" % (NSETS, alg_bytes / 1e6),
+                   "collective": "ncclAllGather of the per-rank albedo [W] inside the step" if world > 1 else "none",
+                   "parity_albedo_max_rel_err": parity},
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": ke, "ms_per_step": 1e3 * e2e_dt / ke,
+                "api": "picaso_b200.get_reflected_1d(..., return_albedo=True), pinned host inputs"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": "refl_toa_kernel",
+                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                     "note": "fp64-pipe-bound kernel (~50 flop/B); see DESIGN.md and profiles/"},
+        "clocks": sampler.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nthreads = os.cpu_count() or 1
+        a = C.reflected_args(sets[0], KW)
+        oracle.get_reflected_1d(*a, nthreads=nthreads)
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            x, _ = oracle.get_reflected_1d(*a, nthreads=nthreads)
+            oracle.compress_disco(W, d0["cos_theta"], x, gw, tw, sets[0]["F0PI"])
+            n += 1
+            el = time.perf_counter() - t0
+            if el > 10.0 or n >= 200:
+                break
+        t1 = time.perf_counter()
+        oracle.get_reflected_1d(*a, nthreads=1)
+        one = time.perf_counter() - t1
+        out["cpu_baseline"] = {"value": W * n / el, "unit": UNIT, "cores": nthreads, "kind": "port",
+                               "sample": "%d full 60x10000x5 spectra in %.1f s; C port of the reference algorithm (oracle/), OpenMP over wavelengths" % (n, el),
+                               "single_thread_value": W / one, "host_cpus": os.cpu_count()}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

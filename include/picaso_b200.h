@@ -1,0 +1,152 @@
+/*
+ * picaso_b200.h - C ABI of the B200-native PICASO radiative-transfer hot path.
+ *
+ * The reference (natashabatalha/picaso, commit 0369089) has no FFI: its seam is
+ * Python name binding in picaso/justdoit.py:2,8,9 (`from .fluxes import
+ * get_reflected_1d, get_thermal_1d, get_transit_1d, ...`, `from .disco import
+ * compress_disco, compress_thermal`).  Each entry point below replaces one of those
+ * numba functions; picaso_b200/fluxes.py and picaso_b200/disco.py bind them with
+ * ctypes behind the reference's exact Python signatures.
+ *
+ * Conventions
+ *  - every array is float64, wavelength on the fastest axis.  A "layer array" is
+ *    [nlayer][nwno], a "level array" [nlevel][nwno] (nlevel = nlayer + 1); `ld` is
+ *    the element distance between consecutive layers/levels (>= nwno), the same for
+ *    all layer and level inputs of one call.
+ *  - batched calls (nbatch > 1) take [nbatch] stacked atmospheres: layer arrays are
+ *    [nbatch][nlayer][ld], level arrays [nbatch][nlevel][ld], per-wave vectors
+ *    [nbatch][nwno], outputs [nbatch][...].  Geometry is shared by the batch.
+ *  - `memspace` says where ALL array pointers of the call live: PB_HOST (the library
+ *    stages them through the context's device buffers: H2D, kernels, D2H, and returns
+ *    when the outputs are valid) or PB_DEVICE (pointers from pb_dev_alloc; kernels are
+ *    enqueued on the context stream and the call returns without synchronising).
+ *  - small geometry vectors (ubar0, ubar1, gweight, tweight, tlevel, plevel, z, ...)
+ *    are ALWAYS host pointers.
+ *  - every function returns PB_OK (0) or an error code; pb_last_error() has the text.
+ *    Numerical NaN/inf propagate exactly as in the reference (no extra clamping).
+ *  - there is no CPU fallback: without a CUDA device pb_create fails.
+ */
+#ifndef PICASO_B200_H
+#define PICASO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_ctx pb_ctx;
+
+enum pb_status {
+    PB_OK = 0,
+    PB_ERR_CUDA = 1,    /* CUDA runtime failure (text in pb_last_error) */
+    PB_ERR_ARG = 2,     /* invalid argument */
+    PB_ERR_NOMEM = 3,   /* device / pinned allocation failed */
+    PB_ERR_UNSUPPORTED = 4
+};
+
+enum pb_memspace { PB_HOST = 0, PB_DEVICE = 1 };
+
+/* ---- context, memory, timing ------------------------------------------------------ */
+int pb_version(void);
+int pb_device_count(int *count);
+int pb_create(int device, pb_ctx **out);
+void pb_destroy(pb_ctx *ctx);
+const char *pb_last_error(const pb_ctx *ctx); /* ctx may be NULL: last pb_create error */
+int pb_device_name(pb_ctx *ctx, char *buf, size_t buflen);
+int pb_sm_count(pb_ctx *ctx, int *count);
+
+int pb_dev_alloc(pb_ctx *ctx, size_t bytes, void **out);
+int pb_dev_free(pb_ctx *ctx, void *ptr);
+int pb_host_alloc(pb_ctx *ctx, size_t bytes, void **out); /* page-locked host memory */
+int pb_host_free(pb_ctx *ctx, void *ptr);
+int pb_memcpy_h2d(pb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async */
+int pb_memcpy_d2h(pb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async */
+int pb_memset(pb_ctx *ctx, void *dst_dev, int value, size_t bytes);                /* async */
+int pb_sync(pb_ctx *ctx);
+/* run every later kernel/copy of this context on a caller-owned cudaStream_t (e.g. the
+ * stream a collective library uses) so that ordering needs no host synchronisation;
+ * NULL restores the context's own stream */
+int pb_set_stream(pb_ctx *ctx, void *cuda_stream);
+
+/* CUDA-event stopwatch on the context stream (the stream every kernel is launched on) */
+int pb_timer_start(pb_ctx *ctx);
+int pb_timer_stop(pb_ctx *ctx, float *elapsed_ms); /* records, synchronises, returns ms */
+/* kernels launched by this context since creation */
+uint64_t pb_launch_count(const pb_ctx *ctx);
+
+/* ---- reflected light, Toon89 two-stream ------------------------------------------- */
+/* replaces get_reflected_1d, picaso/fluxes.py:1010-1413 (incl. setup_tri_diag :89-183,
+ * tri_diag_solve :289-323) and, when `albedo` is given, compress_disco, disco.py:118-149 */
+typedef struct pb_reflected_args {
+    int nlayer, nwno, numg, numt, nbatch;
+    int64_t ld;
+    /* layer arrays */
+    const double *dtau, *w0, *cosb, *gcos2, *ftau_cld, *ftau_ray, *dtau_og, *w0_og, *cosb_og;
+    /* level arrays */
+    const double *tau, *tau_og;
+    /* per-wave vectors [nwno]; NULL = 0 (surf_reflect, b_top) or 1 (F0PI) */
+    const double *surf_reflect, *F0PI, *b_top;
+    /* geometry, host: ubar0/ubar1 [numg*numt], gweight [numg], tweight [numt] */
+    const double *ubar0, *ubar1, *gweight, *tweight;
+    double cos_theta;
+    int single_phase;      /* 0 cahoy, 1 OTHG, 2 TTHG, 3 TTHG_ray  (justdoit.py:5512-5658) */
+    int multi_phase;       /* 0 N=2, 1 N=1 */
+    int toon_coefficients; /* 0 quadrature, 1 eddington */
+    double frac_a, frac_b, frac_c, constant_back, constant_forward;
+    int get_toa_intensity, get_lvl_flux;
+    /* outputs (NULL = not wanted) */
+    double *xint_at_top;                                        /* [numg*numt][nwno] */
+    double *albedo;                                             /* [nwno], fused compress_disco */
+    double *flux_minus, *flux_plus, *flux_minus_mdpt, *flux_plus_mdpt; /* [numg*numt][nlevel][nwno] */
+} pb_reflected_args;
+
+int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *args, int memspace);
+
+/* ---- thermal emission, Toon89 two-stream + source function ------------------------- */
+/* replaces get_thermal_1d, fluxes.py:1683-1912 (blackbody :1661, blackbody_integrated
+ * :1609) and, when `thermal` is given, compress_thermal, disco.py:152-180 */
+typedef struct pb_thermal_args {
+    int nlayer, nwno, numg, numt, nbatch;
+    int64_t ld;
+    const double *dtau, *w0, *cosb;        /* layer arrays */
+    const double *wno, *dwno;              /* [nwno] (shared by the batch); dwno may be NULL if calc_type==0 */
+    const double *surf_reflect;            /* [nwno] or NULL */
+    const double *tlevel, *plevel;         /* host, [nbatch][nlevel] */
+    const double *ubar1, *gweight, *tweight; /* host */
+    int hard_surface, calc_type;
+    double *flux_at_top;                   /* [numg*numt][nwno] or NULL */
+    double *thermal;                       /* [nwno] fused compress_thermal, or NULL */
+    double *flux_minus, *flux_plus, *flux_minus_mdpt, *flux_plus_mdpt; /* [numg*numt][nlevel][nwno] or NULL */
+} pb_thermal_args;
+
+int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *args, int memspace);
+
+/* ---- transmission ------------------------------------------------------------------ */
+/* replaces get_transit_1d, fluxes.py:2582-2663 */
+typedef struct pb_transit_args {
+    int nlevel, nwno, nbatch;
+    int64_t ld;
+    const double *DTAU;                          /* layer array */
+    const double *z, *dz, *player, *tlayer;      /* host [nbatch][nlevel] */
+    const double *mmw, *colden;                  /* host [nbatch][nlevel-1] */
+    double rstar, k_b, amu;
+    double *F;                                   /* [nbatch][nwno] */
+} pb_transit_args;
+
+int pb_transit_1d(pb_ctx *ctx, const pb_transit_args *args, int memspace);
+
+/* ---- disk integration ---------------------------------------------------------------- */
+/* replaces compress_disco, disco.py:118-149: xint [ng*nt][nwno] -> albedo [nwno] */
+int pb_compress_disco(pb_ctx *ctx, int nwno, double cos_theta, const double *xint_at_top,
+                      const double *gweight, int ng, const double *tweight, int nt,
+                      const double *F0PI, double *albedo, int memspace);
+/* replaces compress_thermal, disco.py:152-180: flux [ng*nt][n] -> out [n] */
+int pb_compress_thermal(pb_ctx *ctx, int64_t n, const double *flux_at_top, const double *gweight,
+                        int ng, const double *tweight, int nt, double *out, int memspace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICASO_B200_H */

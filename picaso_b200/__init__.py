@@ -1,0 +1,36 @@
+"""picaso_b200 - B200-native (sm_100a CUDA behind a C ABI) implementation of PICASO's
+per-wavelength radiative-transfer hot path: Toon89 reflected / thermal solvers, transit
+chord integration and disk integration, behind the reference's Python signatures.
+
+    import picaso_b200
+    picaso_b200.patch(picaso.justdoit)     # drop-in behind jdi.inputs().spectrum()
+
+No PyTorch, no CPU fallback: importing is cheap, the first call creates the CUDA context
+and raises if the library or a device is missing.
+"""
+from ._lib import PicasoB200Error, Context, default_context, load_library  # noqa: F401
+from .fluxes import get_reflected_1d, get_thermal_1d, get_transit_1d  # noqa: F401
+from .disco import compress_disco, compress_thermal, get_angles_1d, get_angles_3d, compute_disco  # noqa: F401
+
+__version__ = "0.1.0"
+
+_PATCHED = ("get_reflected_1d", "get_thermal_1d", "get_transit_1d", "compress_disco",
+            "compress_thermal")
+
+
+def patch(module):
+    """Rebind the hot-path names of a loaded `picaso.justdoit` module (justdoit.py:2,9) to
+    the CUDA implementations.  Returns a dict of the replaced originals for `unpatch`."""
+    import sys
+    me = sys.modules[__name__]
+    old = {}
+    for name in _PATCHED:
+        if hasattr(module, name):
+            old[name] = getattr(module, name)
+            setattr(module, name, getattr(me, name))
+    return old
+
+
+def unpatch(module, old):
+    for name, fn in old.items():
+        setattr(module, name, fn)

@@ -1,0 +1,219 @@
+"""ctypes binding of libpicaso_b200.so (declared in include/picaso_b200.h).
+
+There is deliberately no CPU fallback: if the library is missing or no CUDA device is
+present, every entry point raises.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libpicaso_b200.so")
+
+PB_HOST, PB_DEVICE = 0, 1
+_dp = ctypes.POINTER(ctypes.c_double)
+c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+
+
+class PicasoB200Error(RuntimeError):
+    pass
+
+
+class ReflectedArgs(ctypes.Structure):
+    _fields_ = (
+        [(n, c_int) for n in ("nlayer", "nwno", "numg", "numt", "nbatch")] + [("ld", c_i64)] +
+        [(n, c_vp) for n in ("dtau", "w0", "cosb", "gcos2", "ftau_cld", "ftau_ray", "dtau_og",
+                             "w0_og", "cosb_og", "tau", "tau_og", "surf_reflect", "F0PI", "b_top",
+                             "ubar0", "ubar1", "gweight", "tweight")] +
+        [("cos_theta", c_dbl), ("single_phase", c_int), ("multi_phase", c_int),
+         ("toon_coefficients", c_int)] +
+        [(n, c_dbl) for n in ("frac_a", "frac_b", "frac_c", "constant_back", "constant_forward")] +
+        [("get_toa_intensity", c_int), ("get_lvl_flux", c_int)] +
+        [(n, c_vp) for n in ("xint_at_top", "albedo", "flux_minus", "flux_plus", "flux_minus_mdpt",
+                             "flux_plus_mdpt")])
+
+
+class ThermalArgs(ctypes.Structure):
+    _fields_ = (
+        [(n, c_int) for n in ("nlayer", "nwno", "numg", "numt", "nbatch")] + [("ld", c_i64)] +
+        [(n, c_vp) for n in ("dtau", "w0", "cosb", "wno", "dwno", "surf_reflect", "tlevel",
+                             "plevel", "ubar1", "gweight", "tweight")] +
+        [("hard_surface", c_int), ("calc_type", c_int)] +
+        [(n, c_vp) for n in ("flux_at_top", "thermal", "flux_minus", "flux_plus",
+                             "flux_minus_mdpt", "flux_plus_mdpt")])
+
+
+class TransitArgs(ctypes.Structure):
+    _fields_ = (
+        [(n, c_int) for n in ("nlevel", "nwno", "nbatch")] + [("ld", c_i64)] +
+        [(n, c_vp) for n in ("DTAU", "z", "dz", "player", "tlayer", "mmw", "colden")] +
+        [("rstar", c_dbl), ("k_b", c_dbl), ("amu", c_dbl), ("F", c_vp)])
+
+
+# every symbol include/picaso_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "pb_version": (c_int, []),
+    "pb_device_count": (c_int, [ctypes.POINTER(c_int)]),
+    "pb_create": (c_int, [c_int, ctypes.POINTER(c_vp)]),
+    "pb_destroy": (None, [c_vp]),
+    "pb_last_error": (ctypes.c_char_p, [c_vp]),
+    "pb_device_name": (c_int, [c_vp, ctypes.c_char_p, ctypes.c_size_t]),
+    "pb_sm_count": (c_int, [c_vp, ctypes.POINTER(c_int)]),
+    "pb_dev_alloc": (c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
+    "pb_dev_free": (c_int, [c_vp, c_vp]),
+    "pb_host_alloc": (c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
+    "pb_host_free": (c_int, [c_vp, c_vp]),
+    "pb_memcpy_h2d": (c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t]),
+    "pb_memcpy_d2h": (c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t]),
+    "pb_memset": (c_int, [c_vp, c_vp, c_int, ctypes.c_size_t]),
+    "pb_sync": (c_int, [c_vp]),
+    "pb_set_stream": (c_int, [c_vp, c_vp]),
+    "pb_timer_start": (c_int, [c_vp]),
+    "pb_timer_stop": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float)]),
+    "pb_launch_count": (ctypes.c_uint64, [c_vp]),
+    "pb_reflected_toon_1d": (c_int, [c_vp, ctypes.POINTER(ReflectedArgs), c_int]),
+    "pb_thermal_toon_1d": (c_int, [c_vp, ctypes.POINTER(ThermalArgs), c_int]),
+    "pb_transit_1d": (c_int, [c_vp, ctypes.POINTER(TransitArgs), c_int]),
+    "pb_compress_disco": (c_int, [c_vp, c_int, c_dbl, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp,
+                                  c_int]),
+    "pb_compress_thermal": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen the in-tree library and declare all prototypes; raises if it is not built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise PicasoB200Error(
+                    "libpicaso_b200.so is not built (%s missing). Run `python -m picaso_b200.build`; "
+                    "there is no CPU fallback." % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+class Context:
+    """One CUDA context/stream/staging arena per process and device (lazy: created on the
+    first call, i.e. after any fork/spawn of joblib or MPI workers)."""
+
+    def __init__(self, device=None):
+        self.lib = load_library()
+        if device is None:
+            device = int(os.environ.get("PICASO_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            n = c_int(0)
+            self.lib.pb_device_count(ctypes.byref(n))
+            if n.value > 0:
+                device %= n.value
+        h = c_vp()
+        rc = self.lib.pb_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise PicasoB200Error("pb_create(device=%d) failed: %s" %
+                                  (device, self.lib.pb_last_error(None).decode()))
+        self.h = h
+        self.device = device
+        self._pid = os.getpid()
+
+    def check(self, rc):
+        if rc != 0:
+            raise PicasoB200Error(self.lib.pb_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self._pid == os.getpid():
+            self.lib.pb_destroy(self.h)
+        self.h = None
+
+    # ---- helpers used by bench/tests ----
+    def device_name(self):
+        buf = ctypes.create_string_buffer(256)
+        self.check(self.lib.pb_device_name(self.h, buf, 256))
+        return buf.value.decode()
+
+    def sm_count(self):
+        n = c_int(0)
+        self.check(self.lib.pb_sm_count(self.h, ctypes.byref(n)))
+        return n.value
+
+    def sync(self):
+        self.check(self.lib.pb_sync(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(self.lib.pb_set_stream(self.h, cuda_stream_ptr))
+
+    def timer_start(self):
+        self.check(self.lib.pb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float(0)
+        self.check(self.lib.pb_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.lib.pb_launch_count(self.h))
+
+    def dev_alloc(self, nbytes):
+        p = c_vp()
+        self.check(self.lib.pb_dev_alloc(self.h, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def dev_free(self, ptr):
+        self.check(self.lib.pb_dev_free(self.h, ptr))
+
+    def to_device(self, arr):
+        """copy a numpy float64 array to a fresh device buffer; returns the device address."""
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        d = self.dev_alloc(a.nbytes)
+        self.check(self.lib.pb_memcpy_h2d(self.h, d, a.ctypes.data, a.nbytes))
+        self.sync()
+        return d
+
+    def from_device(self, ptr, shape):
+        out = np.empty(shape, dtype=np.float64)
+        self.check(self.lib.pb_memcpy_d2h(self.h, out.ctypes.data, ptr, out.nbytes))
+        self.sync()
+        return out
+
+    def pinned_empty(self, shape):
+        """numpy float64 array backed by page-locked host memory (fast async H2D/D2H)."""
+        n = int(np.prod(shape)) * 8
+        p = c_vp()
+        self.check(self.lib.pb_host_alloc(self.h, max(n, 8), ctypes.byref(p)))
+        buf = (ctypes.c_char * max(n, 8)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.float64, count=int(np.prod(shape))).reshape(shape)
+        _PINNED[arr.ctypes.data] = (self, p.value)
+        return arr
+
+    def pinned_free(self, arr):
+        ent = _PINNED.pop(arr.ctypes.data, None)
+        if ent is not None:
+            self.check(self.lib.pb_host_free(self.h, ent[1]))
+
+
+_PINNED = {}
+_default = None
+
+
+def default_context():
+    global _default
+    if _default is None or _default._pid != os.getpid():
+        _default = Context()
+    return _default
+
+
+def addr(a):
+    """address of a numpy array (or pass through an int device pointer / None)."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    return a.ctypes.data

@@ -1,0 +1,289 @@
+// pb_api.cu - context, memory, timing and staging entry points of libpicaso_b200.so.
+#include "pb_common.cuh"
+
+static char g_create_err[512] = "";
+
+int pb_fail(pb_ctx *ctx, int code, const char *fmt, ...)
+{
+    char *dst = ctx ? ctx->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" {
+
+int pb_version(void) { return 100; }
+
+int pb_device_count(int *count)
+{
+    if (!count) return PB_ERR_ARG;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return pb_fail(nullptr, PB_ERR_CUDA, "cudaGetDeviceCount -> %s", cudaGetErrorString(e));
+    }
+    return PB_OK;
+}
+
+int pb_create(int device, pb_ctx **out)
+{
+    if (!out) return PB_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return pb_fail(nullptr, PB_ERR_CUDA,
+                       "no CUDA device available (%s); picaso_b200 has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n)
+        return pb_fail(nullptr, PB_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    pb_ctx *ctx = new pb_ctx();
+    ctx->device = device;
+#define CREATE_CUDA(call)                                                                    \
+    do {                                                                                     \
+        cudaError_t e2 = (call);                                                             \
+        if (e2 != cudaSuccess) {                                                             \
+            pb_fail(nullptr, PB_ERR_CUDA, "pb_create: %s -> %s", #call, cudaGetErrorString(e2)); \
+            delete ctx;                                                                      \
+            return PB_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+    CREATE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreate(&ctx->ev_start));
+    CREATE_CUDA(cudaEventCreate(&ctx->ev_stop));
+    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+#undef CREATE_CUDA
+    *out = ctx;
+    return PB_OK;
+}
+
+void pb_destroy(pb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->ev_start);
+    cudaEventDestroy(ctx->ev_stop);
+    cudaEventDestroy(ctx->ev_copy);
+    cudaStreamDestroy(ctx->own_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char *pb_last_error(const pb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+int pb_device_name(pb_ctx *ctx, char *buf, size_t buflen)
+{
+    if (!ctx || !buf || !buflen) return PB_ERR_ARG;
+    cudaDeviceProp prop;
+    PB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    snprintf(buf, buflen, "%s (sm_%d%d, %d SMs)", prop.name, prop.major, prop.minor,
+             prop.multiProcessorCount);
+    return PB_OK;
+}
+
+int pb_sm_count(pb_ctx *ctx, int *count)
+{
+    if (!ctx || !count) return PB_ERR_ARG;
+    *count = ctx->sm_count;
+    return PB_OK;
+}
+
+int pb_dev_alloc(pb_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess)
+        return pb_fail(ctx, PB_ERR_NOMEM, "cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+    return PB_OK;
+}
+
+int pb_dev_free(pb_ctx *ctx, void *ptr)
+{
+    if (!ctx) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(ctx, cudaFree(ptr));
+    return PB_OK;
+}
+
+int pb_host_alloc(pb_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess)
+        return pb_fail(ctx, PB_ERR_NOMEM, "cudaHostAlloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+    return PB_OK;
+}
+
+int pb_host_free(pb_ctx *ctx, void *ptr)
+{
+    if (!ctx) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(ctx, cudaFreeHost(ptr));
+    return PB_OK;
+}
+
+int pb_memcpy_h2d(pb_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return PB_OK;
+}
+
+int pb_memcpy_d2h(pb_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return PB_OK;
+}
+
+int pb_memset(pb_ctx *ctx, void *dst, int value, size_t bytes)
+{
+    if (!ctx) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
+    return PB_OK;
+}
+
+int pb_sync(pb_ctx *ctx)
+{
+    if (!ctx) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_set_stream(pb_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return PB_OK;
+}
+
+int pb_timer_start(pb_ctx *ctx)
+{
+    if (!ctx) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    return PB_OK;
+}
+
+int pb_timer_stop(pb_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    PB_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
+    PB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+    return PB_OK;
+}
+
+uint64_t pb_launch_count(const pb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+} // extern "C"
+
+// ---- arena / staging -----------------------------------------------------------------
+
+void pb_arena_reset(pb_ctx *ctx)
+{
+    ctx->arena_off = 0;
+    ctx->pinned_off = 0;
+}
+
+int pb_arena_reserve(pb_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->arena_cap) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->arena) PB_CUDA(ctx, cudaFree(ctx->arena));
+    ctx->arena = nullptr;
+    ctx->arena_cap = 0;
+    size_t cap = pb_align(bytes + bytes / 8, 1 << 20);
+    cudaError_t e = cudaMalloc((void **)&ctx->arena, cap);
+    if (e != cudaSuccess)
+        return pb_fail(ctx, PB_ERR_NOMEM, "staging arena cudaMalloc(%zu) -> %s", cap,
+                       cudaGetErrorString(e));
+    ctx->arena_cap = cap;
+    return PB_OK;
+}
+
+int pb_arena_alloc(pb_ctx *ctx, size_t bytes, void **out)
+{
+    size_t off = pb_align(ctx->arena_off);
+    if (off + bytes > ctx->arena_cap)
+        return pb_fail(ctx, PB_ERR_NOMEM, "staging arena overflow: need %zu, cap %zu (reserve bug)",
+                       off + bytes, ctx->arena_cap);
+    *out = ctx->arena + off;
+    ctx->arena_off = off + bytes;
+    return PB_OK;
+}
+
+int pb_pinned_reserve(pb_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->pinned_cap) return PB_OK;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->pinned) PB_CUDA(ctx, cudaFreeHost(ctx->pinned));
+    ctx->pinned = nullptr;
+    ctx->pinned_cap = 0;
+    size_t cap = pb_align(bytes * 2, 1 << 16);
+    cudaError_t e = cudaHostAlloc((void **)&ctx->pinned, cap, cudaHostAllocDefault);
+    if (e != cudaSuccess)
+        return pb_fail(ctx, PB_ERR_NOMEM, "pinned bounce cudaHostAlloc(%zu) -> %s", cap,
+                       cudaGetErrorString(e));
+    ctx->pinned_cap = cap;
+    return PB_OK;
+}
+
+int pb_upload_small(pb_ctx *ctx, const double *host, size_t n, const double **dev_out)
+{
+    void *d = nullptr;
+    size_t bytes = n * sizeof(double);
+    PB_TRY(pb_arena_alloc(ctx, bytes, &d));
+    size_t off = pb_align(ctx->pinned_off, 64);
+    if (off + bytes > ctx->pinned_cap)
+        return pb_fail(ctx, PB_ERR_NOMEM, "pinned bounce overflow (reserve bug)");
+    memcpy(ctx->pinned + off, host, bytes);
+    ctx->pinned_off = off + bytes;
+    PB_CUDA(ctx, cudaMemcpyAsync(d, ctx->pinned + off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev_out = (const double *)d;
+    return PB_OK;
+}
+
+int pb_stage_in(pb_ctx *ctx, const double *src, int memspace, int64_t rows, int64_t width,
+                int64_t ld, const double **dev_out, int64_t *ld_out)
+{
+    if (!src) {
+        *dev_out = nullptr;
+        if (ld_out) *ld_out = width;
+        return PB_OK;
+    }
+    if (memspace == PB_DEVICE) {
+        *dev_out = src;
+        if (ld_out) *ld_out = ld;
+        return PB_OK;
+    }
+    void *d = nullptr;
+    PB_TRY(pb_arena_alloc(ctx, (size_t)rows * width * sizeof(double), &d));
+    if (ld == width || rows == 1) {
+        PB_CUDA(ctx, cudaMemcpyAsync(d, src, (size_t)rows * width * sizeof(double),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        PB_CUDA(ctx, cudaMemcpy2DAsync(d, width * sizeof(double), src, ld * sizeof(double),
+                                       width * sizeof(double), rows, cudaMemcpyHostToDevice,
+                                       ctx->stream));
+    }
+    *dev_out = (const double *)d;
+    if (ld_out) *ld_out = width;
+    return PB_OK;
+}

@@ -1,0 +1,71 @@
+// pb_common.cuh - context object, error plumbing and staging helpers shared by the
+// kernels of libpicaso_b200.so.  Host-side runtime only; no kernel lives here.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/picaso_b200.h"
+
+#define PB_PI 3.14159265358979323846
+
+struct pb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;   // every kernel of this context is launched here
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy = nullptr;
+    uint64_t launches = 0;
+    char err[512] = {0};
+    // grow-only device arena used to stage PB_HOST calls and small geometry vectors
+    char *arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
+    // grow-only pinned bounce buffer for small host vectors (geometry) so that their
+    // H2D copies are truly asynchronous
+    char *pinned = nullptr;
+    size_t pinned_cap = 0, pinned_off = 0;
+};
+
+int pb_fail(pb_ctx *ctx, int code, const char *fmt, ...);
+
+#define PB_CUDA(ctx, call)                                                                  \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return pb_fail((ctx), PB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, \
+                           cudaGetErrorString(e__));                                        \
+    } while (0)
+
+#define PB_CHECK_LAUNCH(ctx)                       \
+    do {                                           \
+        (ctx)->launches++;                         \
+        PB_CUDA((ctx), cudaGetLastError());        \
+    } while (0)
+
+#define PB_TRY(expr)                   \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != PB_OK) return rc__; \
+    } while (0)
+
+// Arena: reset at the start of every API call, bump-allocated, 256-B aligned.  Growing
+// synchronises the stream first (earlier kernels may still use the old block).
+int pb_arena_reserve(pb_ctx *ctx, size_t bytes);
+void pb_arena_reset(pb_ctx *ctx);
+int pb_arena_alloc(pb_ctx *ctx, size_t bytes, void **out);
+// copy a small host vector into the arena through the pinned bounce buffer
+int pb_upload_small(pb_ctx *ctx, const double *host, size_t n, const double **dev_out);
+// reserve pinned bounce space (call before the first pb_upload_small of an API call)
+int pb_pinned_reserve(pb_ctx *ctx, size_t bytes);
+
+// 2-D staged copies of [rows][ld] -> dense [rows][width] device blocks
+int pb_stage_in(pb_ctx *ctx, const double *src, int memspace, int64_t rows, int64_t width,
+                int64_t ld, const double **dev_out, int64_t *ld_out);
+
+static inline size_t pb_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }

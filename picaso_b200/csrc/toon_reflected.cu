@@ -1,0 +1,554 @@
+// toon_reflected.cu - reflected-light Toon89 two-stream solver for sm_100a.
+//
+// Replaces picaso/fluxes.py:1010-1413 (get_reflected_1d) together with
+// setup_tri_diag (:89-183), tri_diag_solve (:289-323) and, optionally fused,
+// disco.compress_disco (disco.py:118-149).
+//
+// B200 design (not a translation of the reference):
+//  * wavelength is the fastest axis of every input, so lane == wavelength gives fully
+//    coalesced 256-B fp64 row segments per warp; threadIdx.y == viewing angle.
+//  * TOA intensity ("single-sweep adjoint"): the reference builds the 2L x 2L
+//    tridiagonal, solves it, un-mixes Y+/-, then runs a bottom-up source-function
+//    recurrence.  Here one bottom-up sweep does all of it in registers: while the
+//    Thomas elimination walks the rows from the surface upwards (same direction as
+//    tri_diag_solve) the still-unknown solution entries are carried symbolically -
+//    the intensity at the top of the processed stack is kept as an affine function
+//    Rp + Pp * X[2l] of the next unknown, folded with the elimination relations
+//    X[n] = DS[n] - AS[n] X[n-1] as each row is eliminated.  Row 0 closes the chain.
+//    Nothing of size O(L) is stored per thread, no A/B/C/D/X arrays touch HBM, and
+//    each input element is read exactly once per angle (L1-shared across the angle
+//    warps of a CTA).
+//  * level fluxes (get_lvl_flux=1, the climate path) need every X[n]: a second kernel
+//    stores the elimination coefficients in the caller's four output arrays (they are
+//    exactly 4 doubles per level) and overwrites them with fluxes on the way down.
+#include "pb_common.cuh"
+
+namespace {
+
+struct ReflParams {
+    int L, W, G, nt;
+    int64_t ld, bs_layer, bs_level, bs_wave;
+    const double *dtau, *w0, *cosb, *gcos2, *fcld, *fray, *dtau_og, *w0_og, *cosb_og, *tau, *tau_og;
+    const double *surf, *f0pi, *btop;
+    const double *ubar0, *ubar1, *gweight, *tweight;
+    double cos_theta, frac_a, frac_b, frac_c, cback, cfwd;
+    int sp, mp, tc;
+    double *xint, *albedo;
+    double *fm, *fp, *fmm, *fpm;
+    int fuse_albedo;
+};
+
+constexpr int kWavesPerCta = 32;
+
+__device__ __forceinline__ double hg_down(double g, double ct)
+{
+    // fluxes.py:1310 - HG in the frame of the downward propagating beam (+ sign)
+    double t = 1.0 + g * g + 2.0 * g * ct;
+    return (1.0 - g * g) / sqrt(t * t * t);
+}
+
+// single-scattering phase function, fluxes.py:1303-1353
+__device__ __forceinline__ double p_single(const ReflParams &p, double g_og, double gcos2,
+                                           double fcld, double fray)
+{
+    if (p.sp == 1) return hg_down(g_og, p.cos_theta);
+    double gf = p.cfwd * g_og;
+    double gb = p.cback * g_og;
+    double f = p.frac_a + p.frac_b * pow(gb, p.frac_c);
+    double tt = f * hg_down(gf, p.cos_theta) + (1.0 - f) * hg_down(gb, p.cos_theta);
+    if (p.sp == 0) return tt + gcos2;
+    if (p.sp == 2) return tt;
+    return fcld * tt + fray * (0.75 * (1.0 + p.cos_theta * p.cos_theta));
+}
+
+// Angle-independent two-stream coefficients of one (layer, wavelength): fluxes.py:1132-1141
+__device__ __forceinline__ void toon_g(int tc, double om, double g, double &g1, double &g2)
+{
+    const double sq3 = 1.7320508075688772;
+    if (tc == 1) {
+        g1 = (7.0 - om * (4.0 + 3.0 * g)) / 4.0;
+        g2 = -(1.0 - om * (4.0 - 3.0 * g)) / 4.0;
+    } else {
+        g1 = (sq3 * 0.5) * (2.0 - om * (1.0 + g));
+        g2 = (sq3 * om * 0.5) * (1.0 - g);
+    }
+}
+
+__device__ __forceinline__ double toon_g3(int tc, double g, double u0)
+{
+    const double sq3 = 1.7320508075688772;
+    return tc == 1 ? (2.0 - 3.0 * g * u0) / 4.0 : 0.5 * (1.0 - sq3 * g * u0);
+}
+
+// ---------------------------------------------------------------------------------------
+// TOA intensity: one thread per (wavelength, angle), one bottom-up sweep.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) refl_toa_kernel(ReflParams p)
+{
+    extern __shared__ double s_int[];  // [blockDim.y][32] when fuse_albedo
+    const int lane = threadIdx.x;
+    const int w = blockIdx.x * kWavesPerCta + lane;
+    const int a = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    const bool active = (w < p.W) && (a < p.G);
+    double result = 0.0;
+    if (active) {
+        const int L = p.L;
+        const int64_t ld = p.ld;
+        const int64_t ol = (int64_t)b * p.bs_layer + w;  // layer-array offset of (l=0, w)
+        const int64_t ov = (int64_t)b * p.bs_level + w;  // level-array offset
+        const int64_t ow = (int64_t)b * p.bs_wave + w;
+        const double u0 = p.ubar0[a], u1 = p.ubar1[a];
+        const double f0 = p.f0pi ? p.f0pi[ow] : 1.0;
+        const double r = p.surf ? p.surf[ow] : 0.0;
+        const double btop = p.btop ? p.btop[ow] : 0.0;
+        const double inv_u0 = 1.0 / u0;
+        const double c2pi = 0.5 / PB_PI;
+        const double s01 = (u0 + u1) / (u0 * u1);
+        const double wgt = u0 / (u0 + u1);
+        const double ubar2 = 0.767;
+        const double t2c = (3.0 * ubar2 * ubar2 * u1 * u1 - 1.0) / 2.0;
+
+        double AS = 0.0, DS = 0.0, Pp = 0.0, Rp = 0.0;
+        double gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
+        double xd = exp(-p.tau[ov + (int64_t)L * ld] / u0);  // exp(-tau[L]/u0)
+        const double b_surface = 0.0 + r * u0 * f0 * xd;
+
+        for (int l = L - 1; l >= 0; --l) {
+            const int64_t il = ol + (int64_t)l * ld;
+            const double om = p.w0[il];
+            const double fc = p.fcld[il];
+            const double g = fc * p.cosb[il];
+            const double dt = p.dtau[il];
+            const double gc2 = p.gcos2[il];
+            double g1, g2;
+            toon_g(p.tc, om, g, g1, g2);
+            const double lam = sqrt(g1 * g1 - g2 * g2);
+            const double gam = (g1 - lam) / g2;
+            const double g3 = toon_g3(p.tc, g, u0);
+            const double g4 = 1.0 - g3;
+            const double den = lam * lam - 1.0 / (u0 * u0);
+            const double am = f0 * om * (g4 * (g1 + inv_u0) + g2 * g3) / den;
+            const double ap = f0 * om * (g3 * (g1 - inv_u0) + g2 * g4) / den;
+            const double xu = exp(-p.tau[ov + (int64_t)l * ld] / u0);
+            const double cmu = am * xu, cpu = ap * xu, cmd = am * xd, cpd = ap * xd;
+            const double E = fmin(lam * dt, 35.0);  // slice_gt(exptrm, 35), fluxes.py:1174
+            const double EP = exp(E), EM = 1.0 / EP;
+            const double e1 = EP + gam * EM, e2 = EP - gam * EM;
+            const double e3 = gam * EP + EM, e4 = gam * EP - EM;
+
+            // multiple-scattering Legendre weights, fluxes.py:1275-1287
+            double mpl, mmi;
+            if (p.mp == 0) {
+                const double t2 = gc2 * t2c;
+                mpl = 1.0 + 1.5 * g * u1 + t2;
+                mmi = 1.0 - 1.5 * g * u1 + t2;
+            } else {
+                mpl = 1.0 + 1.5 * g * u1;
+                mmi = 1.0 - 1.5 * g * u1;
+            }
+            // source-function coefficients of Y+ / Y- and the X-independent part
+            // (fluxes.py:1290-1296, :1395-1407); exp(+-E - dt/u1) = EP|EM * exp(-dt/u1)
+            const double xa = exp(-dt / u1);
+            const double lu = lam * u1;
+            const double cG = (mpl + gam * mmi) * om * c2pi * ((EP * xa - 1.0) / (lu - 1.0));
+            const double cH = (gam * mpl + mmi) * om * c2pi * ((1.0 - EM * xa) / (lu + 1.0));
+            const double At = (mpl * cpu + mmi * cmu) * om * c2pi;
+            const int64_t ilo = il;  // same offsets for the *_og arrays
+            const double ps = p_single(p, p.cosb_og[ilo], gc2, fc, p.fray[il]);
+            const double K = (p.w0_og[ilo] * f0 / (4.0 * PB_PI)) * ps *
+                                 exp(-p.tau_og[ov + (int64_t)l * ld] / u0) *
+                                 (1.0 - exp(-p.dtau_og[ilo] * s01)) * wgt +
+                             At * (1.0 - exp(-dt * s01)) * wgt;
+            double P, Q, R;
+            if (l == L - 1) {
+                // last row 2L-1, fluxes.py:178-181, and I_L = flux_zero/pi, :1266-1270
+                const double a_ = e1 - r * e3, b_ = e2 - r * e4;
+                const double d_ = b_surface - cpd + r * cmd;
+                AS = a_ / b_;
+                DS = d_ / b_;
+                P = xa * (e1 / PB_PI) + (cG + cH);
+                Q = xa * (e2 / PB_PI) + (cG - cH);
+                R = xa * (cpd / PB_PI) + K;
+            } else {
+                // interface rows between layer l and l+1: even row 2l+2 (fluxes.py:171-175)
+                double a_ = 2.0 * (1.0 - gam * gam);
+                double b_ = (e1 - e3) * (gam_n + 1.0);
+                double c_ = (e1 + e3) * (gam_n - 1.0);
+                double d_ = e3 * (cpu_n - cpd) + e1 * (cmd - cmu_n);
+                double x = 1.0 / (b_ - c_ * AS);
+                double ASe = a_ * x, DSe = (d_ - c_ * DS) * x;
+                // I_{l+1} = Rp + Pp X[2l+2],  X[2l+2] = DSe - ASe X[2l+1]
+                const double alpha = Rp + Pp * DSe;
+                const double beta = -Pp * ASe;
+                // odd row 2l+1 (fluxes.py:161-165)
+                a_ = (e1 + e3) * (gam_n - 1.0);
+                b_ = (e2 + e4) * (gam_n - 1.0);
+                c_ = 2.0 * (1.0 - gam_n * gam_n);
+                d_ = (gam_n - 1.0) * (cpu_n - cpd) + (1.0 - gam_n) * (cmd - cmu_n);
+                x = 1.0 / (b_ - c_ * ASe);
+                AS = a_ * x;
+                DS = (d_ - c_ * DSe) * x;
+                P = cG + cH;
+                Q = xa * beta + (cG - cH);
+                R = xa * alpha + K;
+            }
+            // eliminate X[2l+1] = DS - AS X[2l]:  I_l = Rp + Pp X[2l]
+            Pp = P - Q * AS;
+            Rp = R + Q * DS;
+            gam_n = gam;
+            cpu_n = cpu;
+            cmu_n = cmu;
+            xd = xu;
+        }
+        // row 0 (fluxes.py:155-158): X[0] = DS[0]
+        {
+            const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = btop - cmu_n;
+            const double x = 1.0 / (b_ - c_ * AS);
+            const double X0 = (d_ - c_ * DS) * x;
+            result = Rp + Pp * X0;
+        }
+        if (p.xint) p.xint[((int64_t)b * p.G + a) * p.W + w] = result;
+    }
+    if (p.fuse_albedo) {
+        // compress_disco (disco.py:138-149): sequential sum over (ig, it) in index order
+        s_int[threadIdx.y * kWavesPerCta + lane] = result;
+        __syncthreads();
+        if (threadIdx.y == 0 && w < p.W) {
+            double acc = 0.0;
+            for (int aa = 0; aa < p.G; ++aa) {
+                const int ig = aa / p.nt, it = aa - ig * p.nt;
+                acc = acc + s_int[aa * kWavesPerCta + lane] * p.gweight[ig] * p.tweight[it];
+            }
+            const double sym = (p.nt == 1) ? 2.0 * PB_PI : 1.0;
+            const double f0 = p.f0pi ? p.f0pi[(int64_t)b * p.bs_wave + w] : 1.0;
+            p.albedo[(int64_t)b * p.W + w] = sym * 0.5 * acc / f0 * (p.cos_theta + 1.0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Level + midpoint fluxes (get_lvl_flux=1, fluxes.py:1219-1257).  Pass 1 eliminates
+// bottom-up and parks (AS, DS) of rows 2l / 2l+1 in the four output arrays at level l;
+// pass 2 substitutes top-down and overwrites them with the fluxes.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) refl_levels_kernel(ReflParams p)
+{
+    const int lane = threadIdx.x;
+    const int w = blockIdx.x * kWavesPerCta + lane;
+    const int a = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    if (w >= p.W || a >= p.G) return;
+    const int L = p.L, V = p.L + 1;
+    const int64_t ld = p.ld;
+    const int64_t ol = (int64_t)b * p.bs_layer + w;
+    const int64_t ov = (int64_t)b * p.bs_level + w;
+    const int64_t ow = (int64_t)b * p.bs_wave + w;
+    const int64_t oo = (((int64_t)b * p.G + a) * V) * p.W + w;  // output offset of level 0
+    const double u0 = p.ubar0[a];
+    const double f0 = p.f0pi ? p.f0pi[ow] : 1.0;
+    const double r = p.surf ? p.surf[ow] : 0.0;
+    const double btop = p.btop ? p.btop[ow] : 0.0;
+    const double inv_u0 = 1.0 / u0;
+
+    double AS = 0.0, DS = 0.0, gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
+    double xd = exp(-p.tau[ov + (int64_t)L * ld] / u0);
+    const double b_surface = 0.0 + r * u0 * f0 * xd;
+    for (int l = L - 1; l >= 0; --l) {
+        const int64_t il = ol + (int64_t)l * ld;
+        const double om = p.w0[il];
+        const double g = p.fcld[il] * p.cosb[il];
+        const double dt = p.dtau[il];
+        double g1, g2;
+        toon_g(p.tc, om, g, g1, g2);
+        const double lam = sqrt(g1 * g1 - g2 * g2);
+        const double gam = (g1 - lam) / g2;
+        const double g3 = toon_g3(p.tc, g, u0), g4 = 1.0 - g3;
+        const double den = lam * lam - 1.0 / (u0 * u0);
+        const double am = f0 * om * (g4 * (g1 + inv_u0) + g2 * g3) / den;
+        const double ap = f0 * om * (g3 * (g1 - inv_u0) + g2 * g4) / den;
+        const double xu = exp(-p.tau[ov + (int64_t)l * ld] / u0);
+        const double cmu = am * xu, cpu = ap * xu, cmd = am * xd, cpd = ap * xd;
+        const double E = fmin(lam * dt, 35.0);
+        const double EP = exp(E), EM = 1.0 / EP;
+        const double e1 = EP + gam * EM, e2 = EP - gam * EM;
+        const double e3 = gam * EP + EM, e4 = gam * EP - EM;
+        double ASe = 0.0, DSe = 0.0;
+        if (l == L - 1) {
+            const double a_ = e1 - r * e3, b_ = e2 - r * e4;
+            const double d_ = b_surface - cpd + r * cmd;
+            AS = a_ / b_;
+            DS = d_ / b_;
+        } else {
+            double a_ = 2.0 * (1.0 - gam * gam);
+            double b_ = (e1 - e3) * (gam_n + 1.0);
+            double c_ = (e1 + e3) * (gam_n - 1.0);
+            double d_ = e3 * (cpu_n - cpd) + e1 * (cmd - cmu_n);
+            double x = 1.0 / (b_ - c_ * AS);
+            ASe = a_ * x;
+            DSe = (d_ - c_ * DS) * x;
+            // row 2l+2 belongs to layer l+1: park at level l+1
+            const int64_t o1 = oo + (int64_t)(l + 1) * p.W;
+            p.fm[o1] = ASe;
+            p.fp[o1] = DSe;
+            a_ = (e1 + e3) * (gam_n - 1.0);
+            b_ = (e2 + e4) * (gam_n - 1.0);
+            c_ = 2.0 * (1.0 - gam_n * gam_n);
+            d_ = (gam_n - 1.0) * (cpu_n - cpd) + (1.0 - gam_n) * (cmd - cmu_n);
+            x = 1.0 / (b_ - c_ * ASe);
+            AS = a_ * x;
+            DS = (d_ - c_ * DSe) * x;
+        }
+        // row 2l+1 belongs to layer l
+        const int64_t o0 = oo + (int64_t)l * p.W;
+        p.fmm[o0] = AS;
+        p.fpm[o0] = DS;
+        gam_n = gam;
+        cpu_n = cpu;
+        cmu_n = cmu;
+        xd = xu;
+    }
+    {
+        const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = btop - cmu_n;
+        const double x = 1.0 / (b_ - c_ * AS);
+        p.fm[oo] = 0.0;  // AS[0] = a[0] * x with a[0] = 0
+        p.fp[oo] = (d_ - c_ * DS) * x;
+    }
+    // pass 2: top-down substitution X[n] = DS[n] - AS[n] X[n-1] and the flux formulas
+    double Xprev = 0.0;
+    double fm_last = 0.0, fp_last = 0.0;
+    for (int l = 0; l < L; ++l) {
+        const int64_t il = ol + (int64_t)l * ld;
+        const int64_t o0 = oo + (int64_t)l * p.W;
+        const double X0 = p.fp[o0] - p.fm[o0] * Xprev;
+        const double X1 = p.fpm[o0] - p.fmm[o0] * X0;
+        Xprev = X1;
+        const double pos = X0 + X1, neg = X0 - X1;
+        const double om = p.w0[il];
+        const double g = p.fcld[il] * p.cosb[il];
+        const double dt = p.dtau[il];
+        double g1, g2;
+        toon_g(p.tc, om, g, g1, g2);
+        const double lam = sqrt(g1 * g1 - g2 * g2);
+        const double gam = (g1 - lam) / g2;
+        const double g3 = toon_g3(p.tc, g, u0), g4 = 1.0 - g3;
+        const double den = lam * lam - 1.0 / (u0 * u0);
+        const double am = f0 * om * (g4 * (g1 + inv_u0) + g2 * g3) / den;
+        const double ap = f0 * om * (g3 * (g1 - inv_u0) + g2 * g4) / den;
+        const double tl = p.tau[ov + (int64_t)l * ld];
+        const double xu = exp(-tl / u0);
+        const double E = fmin(lam * dt, 35.0);
+        // level l, fluxes.py:1227-1236
+        double fm = pos * gam + neg + am * xu;
+        const double fp = pos + gam * neg + ap * xu;
+        fm = fm + u0 * f0 * xu;
+        // midpoint, fluxes.py:1239-1251
+        const double EPm = exp(0.5 * E), EMm = 1.0 / EPm;
+        const double taumid = tl + 0.5 * dt;
+        const double xm = exp(-taumid / u0);
+        double fmm = gam * pos * EPm + neg * EMm + am * xm;
+        const double fpm = pos * EPm + gam * neg * EMm + ap * xm;
+        fmm = fmm + u0 * f0 * xm;
+        if (l == L - 1) {
+            // bottom level, fluxes.py:1230-1233
+            const double EP = exp(E), EM = 1.0 / EP;
+            const double xdn = exp(-p.tau[ov + (int64_t)L * ld] / u0);
+            fm_last = gam * pos * EP + neg * EM + am * xdn + u0 * f0 * xdn;
+            fp_last = pos * EP + gam * neg * EM + ap * xdn;
+        }
+        p.fm[o0] = fm;
+        p.fp[o0] = fp;
+        p.fmm[o0] = fmm;
+        p.fpm[o0] = fpm;
+    }
+    const int64_t oL = oo + (int64_t)L * p.W;
+    p.fm[oL] = fm_last;
+    p.fp[oL] = fp_last;
+    p.fmm[oL] = 0.0;  // the reference leaves the last midpoint row at zero
+    p.fpm[oL] = 0.0;
+}
+
+__global__ void compress_disco_kernel(int W, int G, int nt, double cos_theta, const double *xint,
+                                      const double *gweight, const double *tweight,
+                                      const double *f0pi, int64_t bs_wave, double *albedo)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (w >= W) return;
+    double acc = 0.0;
+    for (int a = 0; a < G; ++a) {
+        const int ig = a / nt, it = a - ig * nt;
+        acc = acc + xint[((int64_t)b * G + a) * W + w] * gweight[ig] * tweight[it];
+    }
+    const double sym = (nt == 1) ? 2.0 * PB_PI : 1.0;
+    const double f0 = f0pi ? f0pi[(int64_t)b * bs_wave + w] : 1.0;
+    albedo[(int64_t)b * W + w] = sym * 0.5 * acc / f0 * (cos_theta + 1.0);
+}
+
+} // namespace
+
+extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int memspace)
+{
+    if (!ctx || !a) return PB_ERR_ARG;
+    const int L = a->nlayer, W = a->nwno, G = a->numg * a->numt;
+    const int B = a->nbatch > 0 ? a->nbatch : 1;
+    if (L < 1 || W < 0 || G < 1) return pb_fail(ctx, PB_ERR_ARG, "reflected: bad sizes L=%d W=%d G=%d", L, W, G);
+    if (W == 0) return PB_OK;
+    if (a->ld < W) return pb_fail(ctx, PB_ERR_ARG, "reflected: ld (%lld) < nwno (%d)", (long long)a->ld, W);
+    if (!a->dtau || !a->tau || !a->w0 || !a->cosb || !a->gcos2 || !a->ftau_cld || !a->ftau_ray ||
+        !a->dtau_og || !a->tau_og || !a->w0_og || !a->cosb_og || !a->ubar0 || !a->ubar1)
+        return pb_fail(ctx, PB_ERR_ARG, "reflected: NULL input array");
+    if (a->albedo && (!a->gweight || !a->tweight))
+        return pb_fail(ctx, PB_ERR_ARG, "reflected: albedo requested without gweight/tweight");
+    if (a->single_phase < 0 || a->single_phase > 3 || a->multi_phase < 0 || a->multi_phase > 1 ||
+        a->toon_coefficients < 0 || a->toon_coefficients > 1)
+        return pb_fail(ctx, PB_ERR_ARG, "reflected: unsupported enum (single_phase=%d multi_phase=%d toon=%d)",
+                       a->single_phase, a->multi_phase, a->toon_coefficients);
+    const bool want_lvl = a->get_lvl_flux != 0;
+    if (want_lvl && (!a->flux_minus || !a->flux_plus || !a->flux_minus_mdpt || !a->flux_plus_mdpt))
+        return pb_fail(ctx, PB_ERR_ARG, "reflected: get_lvl_flux without the four level arrays");
+    const bool want_toa = a->get_toa_intensity != 0 && (a->xint_at_top || a->albedo);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    const int V = L + 1;
+    const bool host = memspace == PB_HOST;
+    const size_t nW = (size_t)W * sizeof(double);
+    // ---- reserve staging space ----
+    size_t need = 8 * 256 + 4 * pb_align((size_t)G * sizeof(double));
+    const bool fuse = want_toa && a->albedo && G <= 8;
+    const bool need_xint_scratch = want_toa && a->albedo && !fuse && (host || !a->xint_at_top);
+    if (host) {
+        need += 9 * pb_align((size_t)B * L * nW) + 2 * pb_align((size_t)B * V * nW) + 3 * pb_align(B * nW);
+        if (want_toa) need += pb_align((size_t)B * G * nW) + pb_align(B * nW);
+        if (want_lvl) need += 4 * pb_align((size_t)B * G * V * nW);
+    } else if (need_xint_scratch) {
+        need += pb_align((size_t)B * G * nW);
+    }
+    pb_arena_reset(ctx);
+    PB_TRY(pb_arena_reserve(ctx, need));
+    PB_TRY(pb_pinned_reserve(ctx, 4 * ((size_t)G + 16) * sizeof(double)));
+
+    ReflParams p;
+    memset(&p, 0, sizeof(p));
+    p.L = L; p.W = W; p.G = G; p.nt = a->numt;
+    int64_t ld = a->ld;
+    const int64_t rowsL = (int64_t)B * L, rowsV = (int64_t)B * V;
+    // og arrays may alias the corrected ones when delta-Eddington is off (optics.py:429-431)
+    auto stage_layer = [&](const double *src, const double **dst) -> int {
+        int64_t ldo;
+        return pb_stage_in(ctx, src, memspace, rowsL, W, a->ld, dst, &ldo);
+    };
+    PB_TRY(stage_layer(a->dtau, &p.dtau));
+    PB_TRY(stage_layer(a->w0, &p.w0));
+    PB_TRY(stage_layer(a->cosb, &p.cosb));
+    PB_TRY(stage_layer(a->gcos2, &p.gcos2));
+    PB_TRY(stage_layer(a->ftau_cld, &p.fcld));
+    PB_TRY(stage_layer(a->ftau_ray, &p.fray));
+    if (a->dtau_og == a->dtau) p.dtau_og = p.dtau; else PB_TRY(stage_layer(a->dtau_og, &p.dtau_og));
+    if (a->w0_og == a->w0) p.w0_og = p.w0; else PB_TRY(stage_layer(a->w0_og, &p.w0_og));
+    if (a->cosb_og == a->cosb) p.cosb_og = p.cosb; else PB_TRY(stage_layer(a->cosb_og, &p.cosb_og));
+    {
+        int64_t ldo;
+        PB_TRY(pb_stage_in(ctx, a->tau, memspace, rowsV, W, a->ld, &p.tau, &ldo));
+        if (a->tau_og == a->tau) p.tau_og = p.tau;
+        else PB_TRY(pb_stage_in(ctx, a->tau_og, memspace, rowsV, W, a->ld, &p.tau_og, &ldo));
+        PB_TRY(pb_stage_in(ctx, a->surf_reflect, memspace, B, W, W, &p.surf, &ldo));
+        PB_TRY(pb_stage_in(ctx, a->F0PI, memspace, B, W, W, &p.f0pi, &ldo));
+        PB_TRY(pb_stage_in(ctx, a->b_top, memspace, B, W, W, &p.btop, &ldo));
+    }
+    if (host) ld = W;
+    p.ld = ld;
+    p.bs_layer = (int64_t)L * ld; p.bs_level = (int64_t)V * ld; p.bs_wave = W;
+    PB_TRY(pb_upload_small(ctx, a->ubar0, G, &p.ubar0));
+    PB_TRY(pb_upload_small(ctx, a->ubar1, G, &p.ubar1));
+    if (a->gweight) PB_TRY(pb_upload_small(ctx, a->gweight, a->numg, &p.gweight));
+    if (a->tweight) PB_TRY(pb_upload_small(ctx, a->tweight, a->numt, &p.tweight));
+    p.cos_theta = a->cos_theta; p.frac_a = a->frac_a; p.frac_b = a->frac_b; p.frac_c = a->frac_c;
+    p.cback = a->constant_back; p.cfwd = a->constant_forward;
+    p.sp = a->single_phase; p.mp = a->multi_phase; p.tc = a->toon_coefficients;
+
+    // ---- outputs ----
+    double *d_xint = nullptr, *d_alb = nullptr, *d_lv[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *h_lv[4] = {a->flux_minus, a->flux_plus, a->flux_minus_mdpt, a->flux_plus_mdpt};
+    if (want_toa) {
+        if (host) {
+            if (a->xint_at_top || !fuse) PB_TRY(pb_arena_alloc(ctx, (size_t)B * G * nW, (void **)&d_xint));
+            if (a->albedo) PB_TRY(pb_arena_alloc(ctx, B * nW, (void **)&d_alb));
+        } else {
+            d_xint = a->xint_at_top;
+            if (!d_xint && need_xint_scratch) PB_TRY(pb_arena_alloc(ctx, (size_t)B * G * nW, (void **)&d_xint));
+            d_alb = a->albedo;
+        }
+    }
+    if (want_lvl)
+        for (int k = 0; k < 4; ++k) {
+            if (host) PB_TRY(pb_arena_alloc(ctx, (size_t)B * G * V * nW, (void **)&d_lv[k]));
+            else d_lv[k] = h_lv[k];
+        }
+
+    const int ay = G < 8 ? G : 8;
+    dim3 block(kWavesPerCta, ay, 1);
+    dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
+    if (want_toa) {
+        p.xint = d_xint; p.albedo = d_alb; p.fuse_albedo = fuse ? 1 : 0;
+        size_t smem = fuse ? (size_t)ay * kWavesPerCta * sizeof(double) : 0;
+        refl_toa_kernel<<<grid, block, smem, ctx->stream>>>(p);
+        PB_CHECK_LAUNCH(ctx);
+        if (a->albedo && !fuse) {
+            dim3 g2((W + 127) / 128, B);
+            compress_disco_kernel<<<g2, 128, 0, ctx->stream>>>(W, G, a->numt, a->cos_theta, d_xint,
+                                                               p.gweight, p.tweight, p.f0pi, p.bs_wave, d_alb);
+            PB_CHECK_LAUNCH(ctx);
+        }
+    } else if (a->xint_at_top && memspace == PB_DEVICE) {
+        PB_CUDA(ctx, cudaMemsetAsync(a->xint_at_top, 0, (size_t)B * G * nW, ctx->stream));
+    }
+    if (want_lvl) {
+        p.fm = d_lv[0]; p.fp = d_lv[1]; p.fmm = d_lv[2]; p.fpm = d_lv[3];
+        refl_levels_kernel<<<grid, block, 0, ctx->stream>>>(p);
+        PB_CHECK_LAUNCH(ctx);
+    }
+    if (host) {
+        if (want_toa && a->xint_at_top)
+            PB_CUDA(ctx, cudaMemcpyAsync(a->xint_at_top, d_xint, (size_t)B * G * nW, cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_toa && a->albedo)
+            PB_CUDA(ctx, cudaMemcpyAsync(a->albedo, d_alb, B * nW, cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_lvl)
+            for (int k = 0; k < 4; ++k)
+                PB_CUDA(ctx, cudaMemcpyAsync(h_lv[k], d_lv[k], (size_t)B * G * V * nW, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!want_toa && a->xint_at_top) memset(a->xint_at_top, 0, (size_t)B * G * nW);
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_compress_disco(pb_ctx *ctx, int nwno, double cos_theta, const double *xint,
+                                 const double *gweight, int ng, const double *tweight, int nt,
+                                 const double *F0PI, double *albedo, int memspace)
+{
+    if (!ctx || !xint || !gweight || !tweight || !albedo || ng < 1 || nt < 1 || nwno < 0)
+        return pb_fail(ctx, PB_ERR_ARG, "compress_disco: bad arguments");
+    if (nwno == 0) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int G = ng * nt, W = nwno;
+    const size_t nW = (size_t)W * sizeof(double);
+    pb_arena_reset(ctx);
+    PB_TRY(pb_arena_reserve(ctx, 8 * 256 + 2 * pb_align((size_t)G * 8) + pb_align((size_t)G * nW) + 2 * pb_align(nW)));
+    PB_TRY(pb_pinned_reserve(ctx, 2 * ((size_t)G + 16) * sizeof(double)));
+    const double *d_x, *d_f0, *d_gw, *d_tw;
+    int64_t ldo;
+    PB_TRY(pb_stage_in(ctx, xint, memspace, G, W, W, &d_x, &ldo));
+    PB_TRY(pb_stage_in(ctx, F0PI, memspace, 1, W, W, &d_f0, &ldo));
+    PB_TRY(pb_upload_small(ctx, gweight, ng, &d_gw));
+    PB_TRY(pb_upload_small(ctx, tweight, nt, &d_tw));
+    double *d_alb = albedo;
+    if (memspace == PB_HOST) PB_TRY(pb_arena_alloc(ctx, nW, (void **)&d_alb));
+    dim3 grid((W + 127) / 128, 1);
+    compress_disco_kernel<<<grid, 128, 0, ctx->stream>>>(W, G, nt, cos_theta, d_x, d_gw, d_tw, d_f0, W, d_alb);
+    PB_CHECK_LAUNCH(ctx);
+    if (memspace == PB_HOST) {
+        PB_CUDA(ctx, cudaMemcpyAsync(albedo, d_alb, nW, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return PB_OK;
+}

@@ -1,0 +1,505 @@
+// toon_thermal.cu - thermal-emission Toon89 two-stream + source-function solver, sm_100a.
+//
+// Replaces picaso/fluxes.py:1683-1912 (get_thermal_1d; blackbody :1661-1680,
+// blackbody_integrated :1609-1658) and, optionally fused, disco.compress_thermal
+// (disco.py:152-180).
+//
+// Same single-sweep idea as toon_reflected.cu: the TOA output flux_plus_mdpt[0] is
+// the end of an upward recurrence whose per-layer source terms are linear in the
+// tridiagonal solution, so one bottom-up sweep (Thomas elimination in the direction
+// of tri_diag_solve + symbolic carry of the upward flux) yields it in registers.
+// The Planck function is evaluated in the kernel from tlevel (no [nlevel, nwno]
+// blackbody matrix is ever materialised).
+#include "pb_common.cuh"
+
+namespace {
+
+struct ThermParams {
+    int L, W, G, nt;
+    int64_t ld, bs_layer, bs_wave;
+    const double *dtau, *w0, *cosb;
+    const double *wno, *dwno, *surf;
+    const double *tlevel, *plevel;  // [B][V] device
+    const double *ubar1, *gweight, *tweight;
+    int hard_surface, calc_type;
+    double *ftop, *thermal;
+    double *fm, *fp, *fmm, *fpm;
+    int fuse;
+};
+
+constexpr int kWavesPerCta = 32;
+constexpr double kMu1 = 0.5;  // fluxes.py:1748
+
+struct Planck {
+    double c1w, c2w;      // calc_type 0: B = c1w / (exp(c2w / T) - 1)
+    double wn, dw;        // calc_type 1
+    int type;
+    __device__ __forceinline__ void init(int calc_type, double wno, double dwno)
+    {
+        const double h = 6.62607004e-27, c = 2.99792458e+10, k = 1.38064852e-16;
+        type = calc_type;
+        if (calc_type == 0) {
+            // blackbody(t, 1/wno), fluxes.py:1676-1680
+            const double wl = 1.0 / wno;
+            c1w = (2.0 * h * c * c) / pow(wl, 5.0);
+            c2w = (h * c) / (wl * k);
+        } else {
+            wn = wno;
+            dw = dwno;
+        }
+    }
+    __device__ __forceinline__ double operator()(double t) const
+    {
+        if (type == 0) return c1w * (1.0 / (exp(c2w / t) - 1.0));
+        // blackbody_integrated, fluxes.py:1632-1656, nbb = 1
+        const double h = 6.62607004e-27, c = 2.99792458e+10, k = 1.38064852e-16;
+        const double c1 = 2 * h * c * c, c2 = h * c / k;
+        double s = 0.0;
+#pragma unroll
+        for (int kk = -1; kk <= 1; ++kk) {
+            const double wv = wn + kk * dw / 2.0;
+            s += c1 * (wv * wv * wv) / (exp(c2 * wv / t) - 1.0);
+        }
+        return s / 3.0;
+    }
+};
+
+// per-layer two-stream quantities, fluxes.py:1756-1789
+struct TLayer {
+    double b0, b1, lam, gam, q, cpu, cmu, cpd, cmd, E, EP, EM, e1, e2, e3, e4;
+};
+
+__device__ __forceinline__ void thermal_layer(double dt, double om, double g, double Btop,
+                                              double Bbot, TLayer &t)
+{
+    t.b0 = Btop;
+    t.b1 = (Bbot - Btop) / dt;
+    const double g1 = 2.0 - om * (1 + g), g2 = om * (1 - g);
+    t.lam = sqrt(g1 * g1 - g2 * g2);
+    t.gam = (g1 - t.lam) / g2;
+    t.q = 1.0 / (g1 + g2);
+    const double tp = 2 * PB_PI * kMu1;
+    t.cpu = tp * (t.b0 + t.b1 * t.q);
+    t.cmu = tp * (t.b0 - t.b1 * t.q);
+    t.cpd = tp * (t.b0 + t.b1 * dt + t.b1 * t.q);
+    t.cmd = tp * (t.b0 + t.b1 * dt - t.b1 * t.q);
+    t.E = fmin(t.lam * dt, 35.0);
+    t.EP = exp(t.E);
+    t.EM = 1.0 / t.EP;
+    t.e1 = t.EP + t.gam * t.EM;
+    t.e2 = t.EP - t.gam * t.EM;
+    t.e3 = t.gam * t.EP + t.EM;
+    t.e4 = t.gam * t.EP - t.EM;
+}
+
+// ---------------------------------------------------------------------------------------
+// TOA flux: one thread per (wavelength, angle)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
+{
+    extern __shared__ double s_f[];
+    const int lane = threadIdx.x;
+    const int w = blockIdx.x * kWavesPerCta + lane;
+    const int a = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    const bool active = (w < p.W) && (a < p.G);
+    double result = 0.0;
+    if (active) {
+        const int L = p.L, V = p.L + 1;
+        const int64_t ld = p.ld;
+        const int64_t ol = (int64_t)b * p.bs_layer + w;
+        const double *tl = p.tlevel + (int64_t)b * V;
+        const double *pl = p.plevel + (int64_t)b * V;
+        const double u = p.ubar1[a];
+        const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + w] : 0.0;
+        Planck planck;
+        planck.init(p.calc_type, p.wno[w], p.dwno ? p.dwno[w] : 0.0);
+
+        double AS = 0.0, DS = 0.0, Pp = 0.0, Rp = 0.0;
+        double gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
+        double Bbot = planck(tl[L]);
+        const double BL = Bbot;
+        for (int l = L - 1; l >= 0; --l) {
+            const int64_t il = ol + (int64_t)l * ld;
+            const double dt = p.dtau[il];
+            const double Btop = planck(tl[l]);
+            TLayer t;
+            thermal_layer(dt, p.w0[il], p.cosb[il], Btop, Bbot, t);
+            // Table 3 of Toon89 (fluxes.py:1842-1849): G = (1/mu1 - lam) Y+, H = gam (lam + 1/mu1) Y-
+            const double al1 = 2 * PB_PI * (t.b0 + t.b1 * (t.q - kMu1));
+            const double al2 = 2 * PB_PI * t.b1;
+            const double lu = t.lam * u;
+            const double kG = (1 / kMu1 - t.lam) / (lu - 1.0);
+            const double kH = t.gam * (t.lam + 1 / kMu1) / (lu + 1.0);
+            double x, cG, cH, K;
+            if (l > 0) {
+                // flux_plus recurrence, fluxes.py:1897-1901
+                x = exp(-dt / u);
+                cG = kG * (t.EP * x - 1.0);
+                cH = kH * (1.0 - t.EM * x);
+                K = al1 * (1. - x) + al2 * (u - (dt + u) * x);
+            } else {
+                // flux_plus_mdpt[0], fluxes.py:1903-1910
+                x = exp(-0.5 * dt / u);
+                const double EPh = exp(0.5 * t.E), EMh = 1 / EPh;
+                cG = kG * (t.EP * x - EPh);
+                cH = -kH * (t.EM * x - EMh);
+                K = al1 * (1. - x) + al2 * (u + 0.5 * dt - (dt + u) * x);
+            }
+            double alpha, beta;
+            if (l == L - 1) {
+                // surface boundary, fluxes.py:1802-1806, :1869-1873, last row :178-181
+                const double b_surface = p.hard_surface ? (1.0 - r) * BL * PB_PI
+                                                        : (BL + t.b1 * kMu1) * PB_PI;
+                const double a_ = t.e1 - r * t.e3, b_ = t.e2 - r * t.e4;
+                const double d_ = b_surface - t.cpd + r * t.cmd;
+                AS = a_ / b_;
+                DS = d_ / b_;
+                alpha = p.hard_surface ? (1.0 - r) * BL * 2 * PB_PI : (BL + t.b1 * u) * 2 * PB_PI;
+                beta = 0.0;
+            } else {
+                double a_ = 2.0 * (1.0 - t.gam * t.gam);
+                double b_ = (t.e1 - t.e3) * (gam_n + 1.0);
+                double c_ = (t.e1 + t.e3) * (gam_n - 1.0);
+                double d_ = t.e3 * (cpu_n - t.cpd) + t.e1 * (t.cmd - cmu_n);
+                double xi = 1.0 / (b_ - c_ * AS);
+                const double ASe = a_ * xi, DSe = (d_ - c_ * DS) * xi;
+                alpha = Rp + Pp * DSe;
+                beta = -Pp * ASe;
+                a_ = (t.e1 + t.e3) * (gam_n - 1.0);
+                b_ = (t.e2 + t.e4) * (gam_n - 1.0);
+                c_ = 2.0 * (1.0 - gam_n * gam_n);
+                d_ = (gam_n - 1.0) * (cpu_n - t.cpd) + (1.0 - gam_n) * (t.cmd - cmu_n);
+                xi = 1.0 / (b_ - c_ * ASe);
+                AS = a_ * xi;
+                DS = (d_ - c_ * DSe) * xi;
+            }
+            // F+_l = x (alpha + beta X[2l+1]) + cG (X0 + X1) + cH (X0 - X1) + K
+            const double P = cG + cH;
+            const double Q = x * beta + (cG - cH);
+            const double R = x * alpha + K;
+            Pp = P - Q * AS;
+            Rp = R + Q * DS;
+            gam_n = t.gam;
+            cpu_n = t.cpu;
+            cmu_n = t.cmu;
+            Bbot = Btop;
+        }
+        {
+            // top boundary: fake isothermal overburden, fluxes.py:1797-1800; row 0 :155-158
+            const double tau_top = p.dtau[ol] * pl[0] / (pl[1] - pl[0]);
+            const double b_top = (1.0 - exp(-tau_top / kMu1)) * Bbot * PB_PI;
+            const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = b_top - cmu_n;
+            const double xi = 1.0 / (b_ - c_ * AS);
+            const double X0 = (d_ - c_ * DS) * xi;
+            result = Rp + Pp * X0;
+        }
+        if (p.ftop) p.ftop[((int64_t)b * p.G + a) * p.W + w] = result;
+    }
+    if (p.fuse) {
+        s_f[threadIdx.y * kWavesPerCta + lane] = result;
+        __syncthreads();
+        if (threadIdx.y == 0 && w < p.W) {
+            double acc = 0.0;
+            for (int aa = 0; aa < p.G; ++aa) {
+                const int ig = aa / p.nt, it = aa - ig * p.nt;
+                acc = acc + s_f[aa * kWavesPerCta + lane] * p.gweight[ig] * p.tweight[it];
+            }
+            const double sym = (p.nt == 1) ? 1.0 : 1 / (2 * PB_PI);
+            p.thermal[(int64_t)b * p.W + w] = acc * sym;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// All four level arrays (fluxes.py:1864-1907).  Three sweeps per thread, with the
+// caller's output arrays doubling as O(L) scratch:
+//   1. bottom-up elimination, (AS,DS) of rows 2l | 2l+1 parked in (fm,fp) | (fmm,fpm)
+//   2. top-down substitution -> Y+/-; downward recurrences written to fm/fmm;
+//      Y+/- parked in fp/fpm
+//   3. bottom-up: upward recurrences overwrite fp/fpm
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) therm_levels_kernel(ThermParams p)
+{
+    const int lane = threadIdx.x;
+    const int w = blockIdx.x * kWavesPerCta + lane;
+    const int a = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    if (w >= p.W || a >= p.G) return;
+    const int L = p.L, V = p.L + 1;
+    const int64_t ld = p.ld;
+    const int64_t ol = (int64_t)b * p.bs_layer + w;
+    const int64_t oo = (((int64_t)b * p.G + a) * V) * p.W + w;
+    const double *tl = p.tlevel + (int64_t)b * V;
+    const double *pl = p.plevel + (int64_t)b * V;
+    const double u = p.ubar1[a];
+    const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + w] : 0.0;
+    Planck planck;
+    planck.init(p.calc_type, p.wno[w], p.dwno ? p.dwno[w] : 0.0);
+
+    // ---- sweep 1 ----
+    double AS = 0.0, DS = 0.0, gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
+    double Bbot = planck(tl[L]);
+    const double BL = Bbot;
+    double b1_last = 0.0;
+    for (int l = L - 1; l >= 0; --l) {
+        const int64_t il = ol + (int64_t)l * ld;
+        const double Btop = planck(tl[l]);
+        TLayer t;
+        thermal_layer(p.dtau[il], p.w0[il], p.cosb[il], Btop, Bbot, t);
+        if (l == L - 1) {
+            b1_last = t.b1;
+            const double b_surface = p.hard_surface ? (1.0 - r) * BL * PB_PI
+                                                    : (BL + t.b1 * kMu1) * PB_PI;
+            const double a_ = t.e1 - r * t.e3, b_ = t.e2 - r * t.e4;
+            const double d_ = b_surface - t.cpd + r * t.cmd;
+            AS = a_ / b_;
+            DS = d_ / b_;
+        } else {
+            double a_ = 2.0 * (1.0 - t.gam * t.gam);
+            double b_ = (t.e1 - t.e3) * (gam_n + 1.0);
+            double c_ = (t.e1 + t.e3) * (gam_n - 1.0);
+            double d_ = t.e3 * (cpu_n - t.cpd) + t.e1 * (t.cmd - cmu_n);
+            double xi = 1.0 / (b_ - c_ * AS);
+            const double ASe = a_ * xi, DSe = (d_ - c_ * DS) * xi;
+            const int64_t o1 = oo + (int64_t)(l + 1) * p.W;
+            p.fm[o1] = ASe;
+            p.fp[o1] = DSe;
+            a_ = (t.e1 + t.e3) * (gam_n - 1.0);
+            b_ = (t.e2 + t.e4) * (gam_n - 1.0);
+            c_ = 2.0 * (1.0 - gam_n * gam_n);
+            d_ = (gam_n - 1.0) * (cpu_n - t.cpd) + (1.0 - gam_n) * (t.cmd - cmu_n);
+            xi = 1.0 / (b_ - c_ * ASe);
+            AS = a_ * xi;
+            DS = (d_ - c_ * DSe) * xi;
+        }
+        const int64_t o0 = oo + (int64_t)l * p.W;
+        p.fmm[o0] = AS;
+        p.fpm[o0] = DS;
+        gam_n = t.gam;
+        cpu_n = t.cpu;
+        cmu_n = t.cmu;
+        Bbot = Btop;
+    }
+    const double B0 = Bbot;
+    const double tau_top = p.dtau[ol] * pl[0] / (pl[1] - pl[0]);
+    {
+        const double b_top = (1.0 - exp(-tau_top / kMu1)) * B0 * PB_PI;
+        const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = b_top - cmu_n;
+        const double xi = 1.0 / (b_ - c_ * AS);
+        p.fm[oo] = 0.0;
+        p.fp[oo] = (d_ - c_ * DS) * xi;
+    }
+    // ---- sweep 2: top-down ----
+    double Xprev = 0.0;
+    double fminus = (1 - exp(-tau_top / u)) * B0 * 2 * PB_PI;  // fluxes.py:1875
+    double Btop = B0;
+    for (int l = 0; l < L; ++l) {
+        const int64_t il = ol + (int64_t)l * ld;
+        const int64_t o0 = oo + (int64_t)l * p.W;
+        const double X0 = p.fp[o0] - p.fm[o0] * Xprev;
+        const double X1 = p.fpm[o0] - p.fmm[o0] * X0;
+        Xprev = X1;
+        const double pos = X0 + X1, neg = X0 - X1;
+        const double dt = p.dtau[il];
+        const double Bb = planck(tl[l + 1]);
+        TLayer t;
+        thermal_layer(dt, p.w0[il], p.cosb[il], Btop, Bb, t);
+        const double J = t.gam * (t.lam + 1 / kMu1) * pos;
+        const double K = (1 / kMu1 - t.lam) * neg;
+        const double si1 = 2 * PB_PI * (t.b0 - t.b1 * (t.q - kMu1));
+        const double si2 = 2 * PB_PI * t.b1;
+        const double xa = exp(-dt / u), xh = exp(-0.5 * dt / u);
+        const double EPh = exp(0.5 * t.E), EMh = 1 / EPh;
+        const double lu = t.lam * u;
+        // fluxes.py:1883-1893
+        const double fnext = fminus * xa + (J / (lu + 1.0)) * (t.EP - xa) +
+                             (K / (lu - 1.0)) * (xa - t.EM) + si1 * (1. - xa) +
+                             si2 * (u * xa + dt - u);
+        const double fmid = fminus * xh + (J / (lu + 1.0)) * (EPh - xh) +
+                            (K / (-lu + 1.0)) * (EMh - xh) + si1 * (1. - xh) +
+                            si2 * (u * xh + 0.5 * dt - u);
+        p.fm[o0] = fminus;
+        p.fmm[o0] = fmid;
+        p.fp[o0] = pos;   // parked for sweep 3
+        p.fpm[o0] = neg;
+        fminus = fnext;
+        Btop = Bb;
+    }
+    const int64_t oL = oo + (int64_t)L * p.W;
+    p.fm[oL] = fminus;
+    p.fmm[oL] = 0.0;
+    // ---- sweep 3: bottom-up ----
+    double fplus = p.hard_surface ? (1.0 - r) * BL * 2 * PB_PI : (BL + b1_last * u) * 2 * PB_PI;
+    p.fp[oL] = fplus;
+    p.fpm[oL] = 0.0;
+    Bbot = BL;
+    for (int l = L - 1; l >= 0; --l) {
+        const int64_t il = ol + (int64_t)l * ld;
+        const int64_t o0 = oo + (int64_t)l * p.W;
+        const double pos = p.fp[o0], neg = p.fpm[o0];
+        const double dt = p.dtau[il];
+        const double Bt = planck(tl[l]);
+        TLayer t;
+        thermal_layer(dt, p.w0[il], p.cosb[il], Bt, Bbot, t);
+        const double Gt = (1 / kMu1 - t.lam) * pos;
+        const double Ht = t.gam * (t.lam + 1 / kMu1) * neg;
+        const double al1 = 2 * PB_PI * (t.b0 + t.b1 * (t.q - kMu1));
+        const double al2 = 2 * PB_PI * t.b1;
+        const double xa = exp(-dt / u), xh = exp(-0.5 * dt / u);
+        const double EPh = exp(0.5 * t.E), EMh = 1 / EPh;
+        const double lu = t.lam * u;
+        // fluxes.py:1897-1907
+        const double fmid = fplus * xh + (Gt / (lu - 1.0)) * (t.EP * xh - EPh) -
+                            (Ht / (lu + 1.0)) * (t.EM * xh - EMh) + al1 * (1. - xh) +
+                            al2 * (u + 0.5 * dt - (dt + u) * xh);
+        fplus = fplus * xa + (Gt / (lu - 1.0)) * (t.EP * xa - 1.0) +
+                (Ht / (lu + 1.0)) * (1.0 - t.EM * xa) + al1 * (1. - xa) +
+                al2 * (u - (dt + u) * xa);
+        p.fp[o0] = fplus;
+        p.fpm[o0] = fmid;
+        Bbot = Bt;
+    }
+    if (p.ftop) p.ftop[((int64_t)b * p.G + a) * p.W + w] = p.fpm[oo];
+}
+
+__global__ void compress_thermal_kernel(int64_t n, int G, int nt, const double *flux,
+                                        const double *gweight, const double *tweight, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= n) return;
+    double acc = 0.0;
+    for (int a = 0; a < G; ++a) {
+        const int ig = a / nt, it = a - ig * nt;
+        acc = acc + flux[((int64_t)b * G + a) * n + i] * gweight[ig] * tweight[it];
+    }
+    const double sym = (nt == 1) ? 1.0 : 1 / (2 * PB_PI);
+    out[(int64_t)b * n + i] = acc * sym;
+}
+
+} // namespace
+
+extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int memspace)
+{
+    if (!ctx || !a) return PB_ERR_ARG;
+    const int L = a->nlayer, W = a->nwno, G = a->numg * a->numt;
+    const int B = a->nbatch > 0 ? a->nbatch : 1;
+    const int V = L + 1;
+    if (L < 1 || W < 0 || G < 1) return pb_fail(ctx, PB_ERR_ARG, "thermal: bad sizes L=%d W=%d G=%d", L, W, G);
+    if (W == 0) return PB_OK;
+    if (a->ld < W) return pb_fail(ctx, PB_ERR_ARG, "thermal: ld < nwno");
+    if (!a->dtau || !a->w0 || !a->cosb || !a->wno || !a->tlevel || !a->plevel || !a->ubar1)
+        return pb_fail(ctx, PB_ERR_ARG, "thermal: NULL input array");
+    if (a->calc_type != 0 && a->calc_type != 1) return pb_fail(ctx, PB_ERR_ARG, "thermal: calc_type must be 0 or 1");
+    if (a->calc_type == 1 && !a->dwno) return pb_fail(ctx, PB_ERR_ARG, "thermal: calc_type=1 needs dwno");
+    if (a->thermal && (!a->gweight || !a->tweight)) return pb_fail(ctx, PB_ERR_ARG, "thermal: thermal output needs gweight/tweight");
+    const bool want_lvl = a->flux_minus || a->flux_plus || a->flux_minus_mdpt || a->flux_plus_mdpt;
+    if (want_lvl && (!a->flux_minus || !a->flux_plus || !a->flux_minus_mdpt || !a->flux_plus_mdpt))
+        return pb_fail(ctx, PB_ERR_ARG, "thermal: level fluxes need all four arrays");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool host = memspace == PB_HOST;
+    const size_t nW = (size_t)W * sizeof(double);
+    const bool fuse = a->thermal && !want_lvl && G <= 8;
+    const bool need_ftop = a->flux_at_top || (a->thermal && !fuse);
+
+    size_t need = 16 * 256 + 2 * pb_align((size_t)B * V * 8) + 3 * pb_align((size_t)G * 8);
+    if (host) {
+        need += 3 * pb_align((size_t)B * L * nW) + 2 * pb_align(nW) + pb_align(B * nW);
+        need += pb_align((size_t)B * G * nW) + pb_align(B * nW);
+        if (want_lvl) need += 4 * pb_align((size_t)B * G * V * nW);
+    } else {
+        need += pb_align((size_t)B * G * nW);
+    }
+    pb_arena_reset(ctx);
+    PB_TRY(pb_arena_reserve(ctx, need));
+    PB_TRY(pb_pinned_reserve(ctx, (2 * (size_t)B * V + 3 * (size_t)G + 64) * sizeof(double)));
+
+    ThermParams p;
+    memset(&p, 0, sizeof(p));
+    p.L = L; p.W = W; p.G = G; p.nt = a->numt;
+    int64_t ldo;
+    PB_TRY(pb_stage_in(ctx, a->dtau, memspace, (int64_t)B * L, W, a->ld, &p.dtau, &ldo));
+    PB_TRY(pb_stage_in(ctx, a->w0, memspace, (int64_t)B * L, W, a->ld, &p.w0, &ldo));
+    PB_TRY(pb_stage_in(ctx, a->cosb, memspace, (int64_t)B * L, W, a->ld, &p.cosb, &ldo));
+    PB_TRY(pb_stage_in(ctx, a->wno, memspace, 1, W, W, &p.wno, &ldo));
+    PB_TRY(pb_stage_in(ctx, a->dwno, memspace, 1, W, W, &p.dwno, &ldo));
+    PB_TRY(pb_stage_in(ctx, a->surf_reflect, memspace, B, W, W, &p.surf, &ldo));
+    p.ld = host ? W : a->ld;
+    p.bs_layer = (int64_t)L * p.ld; p.bs_wave = W;
+    PB_TRY(pb_upload_small(ctx, a->tlevel, (size_t)B * V, &p.tlevel));
+    PB_TRY(pb_upload_small(ctx, a->plevel, (size_t)B * V, &p.plevel));
+    PB_TRY(pb_upload_small(ctx, a->ubar1, G, &p.ubar1));
+    if (a->gweight) PB_TRY(pb_upload_small(ctx, a->gweight, a->numg, &p.gweight));
+    if (a->tweight) PB_TRY(pb_upload_small(ctx, a->tweight, a->numt, &p.tweight));
+    p.hard_surface = a->hard_surface; p.calc_type = a->calc_type;
+
+    double *d_ftop = nullptr, *d_th = nullptr, *d_lv[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *h_lv[4] = {a->flux_minus, a->flux_plus, a->flux_minus_mdpt, a->flux_plus_mdpt};
+    if (host) {
+        if (need_ftop) PB_TRY(pb_arena_alloc(ctx, (size_t)B * G * nW, (void **)&d_ftop));
+        if (a->thermal) PB_TRY(pb_arena_alloc(ctx, B * nW, (void **)&d_th));
+        if (want_lvl) for (int k = 0; k < 4; ++k) PB_TRY(pb_arena_alloc(ctx, (size_t)B * G * V * nW, (void **)&d_lv[k]));
+    } else {
+        d_ftop = a->flux_at_top;
+        if (!d_ftop && need_ftop) PB_TRY(pb_arena_alloc(ctx, (size_t)B * G * nW, (void **)&d_ftop));
+        d_th = a->thermal;
+        for (int k = 0; k < 4; ++k) d_lv[k] = h_lv[k];
+    }
+    const int ay = G < 8 ? G : 8;
+    dim3 block(kWavesPerCta, ay, 1);
+    dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
+    p.ftop = d_ftop; p.thermal = d_th;
+    if (want_lvl) {
+        p.fm = d_lv[0]; p.fp = d_lv[1]; p.fmm = d_lv[2]; p.fpm = d_lv[3];
+        therm_levels_kernel<<<grid, block, 0, ctx->stream>>>(p);
+        PB_CHECK_LAUNCH(ctx);
+    } else {
+        p.fuse = fuse ? 1 : 0;
+        size_t smem = fuse ? (size_t)ay * kWavesPerCta * sizeof(double) : 0;
+        therm_toa_kernel<<<grid, block, smem, ctx->stream>>>(p);
+        PB_CHECK_LAUNCH(ctx);
+    }
+    if (a->thermal && !(fuse && !want_lvl)) {
+        dim3 g2((W + 127) / 128, B);
+        compress_thermal_kernel<<<g2, 128, 0, ctx->stream>>>(W, G, a->numt, d_ftop, p.gweight, p.tweight, d_th);
+        PB_CHECK_LAUNCH(ctx);
+    }
+    if (host) {
+        if (a->flux_at_top) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_at_top, d_ftop, (size_t)B * G * nW, cudaMemcpyDeviceToHost, ctx->stream));
+        if (a->thermal) PB_CUDA(ctx, cudaMemcpyAsync(a->thermal, d_th, B * nW, cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_lvl) for (int k = 0; k < 4; ++k)
+            PB_CUDA(ctx, cudaMemcpyAsync(h_lv[k], d_lv[k], (size_t)B * G * V * nW, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_compress_thermal(pb_ctx *ctx, int64_t n, const double *flux, const double *gweight,
+                                   int ng, const double *tweight, int nt, double *out, int memspace)
+{
+    if (!ctx || !flux || !gweight || !tweight || !out || ng < 1 || nt < 1 || n < 0)
+        return pb_fail(ctx, PB_ERR_ARG, "compress_thermal: bad arguments");
+    if (n == 0) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int G = ng * nt;
+    const size_t nb = (size_t)n * sizeof(double);
+    pb_arena_reset(ctx);
+    PB_TRY(pb_arena_reserve(ctx, 8 * 256 + 2 * pb_align((size_t)G * 8) + pb_align((size_t)G * nb) + pb_align(nb)));
+    PB_TRY(pb_pinned_reserve(ctx, 2 * ((size_t)G + 16) * sizeof(double)));
+    const double *d_x, *d_gw, *d_tw;
+    int64_t ldo;
+    PB_TRY(pb_stage_in(ctx, flux, memspace, G, n, n, &d_x, &ldo));
+    PB_TRY(pb_upload_small(ctx, gweight, ng, &d_gw));
+    PB_TRY(pb_upload_small(ctx, tweight, nt, &d_tw));
+    double *d_out = out;
+    if (memspace == PB_HOST) PB_TRY(pb_arena_alloc(ctx, nb, (void **)&d_out));
+    dim3 grid((unsigned)((n + 127) / 128), 1);
+    compress_thermal_kernel<<<grid, 128, 0, ctx->stream>>>(n, G, nt, d_x, d_gw, d_tw, d_out);
+    PB_CHECK_LAUNCH(ctx);
+    if (memspace == PB_HOST) {
+        PB_CUDA(ctx, cudaMemcpyAsync(out, d_out, nb, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return PB_OK;
+}

@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads and exports every symbol include/picaso_b200.h declares;
+without a GPU the product path fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import picaso_b200
+from picaso_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load_library()
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "picaso_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(lib):
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+        assert n in _lib.SYMBOLS, "no ctypes prototype for " + n
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_version(lib):
+    assert lib.pb_version() >= 100
+
+
+def test_struct_sizes_match_header():
+    # 5 ints + pad, i64, 18 pointers, double, 3 ints (+pad), 5 doubles, 2 ints, 6 pointers
+    assert ctypes.sizeof(_lib.ReflectedArgs) == 24 + 8 + 18 * 8 + 8 + 16 + 40 + 8 + 48
+    assert ctypes.sizeof(_lib.ThermalArgs) == 24 + 8 + 11 * 8 + 8 + 6 * 8
+    assert ctypes.sizeof(_lib.TransitArgs) == 16 + 8 + 7 * 8 + 24 + 8
+
+
+def test_no_cpu_fallback(lib):
+    n = ctypes.c_int(-1)
+    lib.pb_device_count(ctypes.byref(n))
+    if n.value > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(picaso_b200.PicasoB200Error):
+        _lib.Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "picaso_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and \
+                    "picaso_oracle" not in src, f

@@ -1,0 +1,145 @@
+"""GPU: the CUDA path (through the C ABI, host buffers) against the CPU oracle and the
+reference golden vectors.  Tolerance for all TOA / albedo / thermal / transit outputs:
+fp64 rtol 1e-6 (BASELINE.json north_star); observed errors are ~1e-11."""
+import numpy as np
+import pytest
+
+import cases as C
+import oracle
+import picaso_b200 as pb
+from picaso_b200 import synth
+from util import assert_close, assert_level_close, golden
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+@pytest.mark.parametrize("name", sorted(C.reflected_cases()))
+def test_reflected_vs_golden_and_oracle(name):
+    g = golden("reflected")
+    case = C.reflected_cases()[name]
+    d = C.build_reflected(case)
+    args = C.reflected_args(d, case["kw"])
+    xint, lv, alb = pb.get_reflected_1d(*args, gweight=d["gweight"], tweight=d["tweight"],
+                                        return_albedo=True)
+    assert_close(xint, g[name + "/xint"], RTOL, name + " xint vs reference")
+    assert_close(alb, g[name + "/albedo"], RTOL, name + " fused albedo vs reference")
+    ox, olv = oracle.get_reflected_1d(*args)
+    assert_close(xint, ox, RTOL, name + " xint vs oracle")
+    alb2 = pb.compress_disco(d["nwno"], d["cos_theta"], xint, d["gweight"], d["tweight"], d["F0PI"])
+    assert_close(alb2, g[name + "/albedo"], RTOL, name + " compress_disco")
+    if case["kw"]["get_lvl_flux"]:
+        for k, a, o in zip(("fm", "fp", "fmm", "fpm"), lv, olv):
+            assert_level_close(a, g[name + "/" + k], what=name + " " + k + " vs reference")
+            assert_level_close(a, o, what=name + " " + k + " vs oracle")
+    else:
+        assert all(not a.any() for a in lv)
+
+
+@pytest.mark.parametrize("name", sorted(C.thermal_cases()))
+def test_thermal_vs_golden_and_oracle(name):
+    g = golden("thermal")
+    d = C.build_thermal(C.thermal_cases()[name])
+    args = C.thermal_args(d)
+    ftop, lv = pb.get_thermal_1d(*args)
+    assert_close(ftop, g[name + "/ftop"], RTOL, name + " ftop vs reference")
+    f2, none, th = pb.get_thermal_1d(*args, level_fluxes=False, gweight=d["gweight"],
+                                     tweight=d["tweight"], return_thermal=True)
+    assert none is None
+    assert_close(f2, g[name + "/ftop"], RTOL, name + " single-sweep ftop vs reference")
+    assert_close(th, g[name + "/thermal"], RTOL, name + " fused thermal vs reference")
+    th2 = pb.compress_thermal(d["nwno"], ftop, d["gweight"], d["tweight"])
+    assert_close(th2, g[name + "/thermal"], RTOL, name + " compress_thermal")
+    oftop, olv = oracle.get_thermal_1d(*args)
+    assert_close(ftop, oftop, RTOL, name + " vs oracle")
+    for k, a, o in zip(("fm", "fp", "fmm", "fpm"), lv, olv):
+        assert_level_close(a, o, what=name + " " + k + " vs oracle")
+        if name + "/" + k in g.files:
+            assert_level_close(a, g[name + "/" + k], what=name + " " + k + " vs reference")
+    lvc = pb.compress_thermal(d["nwno"], lv[1], d["gweight"], d["tweight"])
+    assert lvc.shape == (d["nlevel"], d["nwno"])
+    assert_level_close(lvc, oracle.compress_thermal(d["nwno"], olv[1], d["gweight"], d["tweight"]),
+                       what="compress_thermal 4-D")
+
+
+@pytest.mark.parametrize("name", sorted(C.transit_cases()))
+def test_transit_vs_golden_and_oracle(name):
+    g = golden("transit")
+    d = synth.transit_inputs(**C.transit_cases()[name])
+    F = pb.get_transit_1d(*C.transit_args(d))
+    assert_close(F, g[name + "/F"], RTOL, name + " vs reference")
+    assert_close(F, oracle.get_transit_1d(*C.transit_args(d)), RTOL, name + " vs oracle")
+
+
+def test_empty_wave_axis():
+    d = synth.reflected_inputs(L=5, W=0, seed=1)
+    kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
+    xint, lv = pb.get_reflected_1d(*C.reflected_args(d, kw))
+    assert xint.shape == (5, 1, 0)
+
+
+def test_strided_ck_slice():
+    """X[:, :, ig] views of [L, W, K] arrays (ngauss>1 path of picaso(), justdoit.py:256-283)."""
+    d = synth.reflected_inputs(L=9, W=41, seed=21)
+    kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
+    ref, _ = oracle.get_reflected_1d(*C.reflected_args(d, kw))
+    d2 = dict(d)
+    for k in ("dtau", "tau", "w0", "cosb", "gcos2", "ftau_cld", "ftau_ray", "dtau_og", "tau_og",
+              "w0_og", "cosb_og"):
+        big = np.random.default_rng(0).random(d[k].shape + (3,))
+        big[:, :, 1] = d[k]
+        d2[k] = big[:, :, 1]
+    got, _ = pb.get_reflected_1d(*C.reflected_args(d2, kw))
+    assert_close(got, ref, RTOL, "strided")
+
+
+def test_row_padded_leading_dimension():
+    d = synth.thermal_inputs(L=11, W=50, seed=4)
+    ref, _ = oracle.get_thermal_1d(*C.thermal_args(dict(d, calc_type=0)))
+    d2 = dict(d, calc_type=0)
+    for k in ("dtau", "w0", "cosb"):
+        big = np.zeros((11, 64))
+        big[:, :50] = d[k]
+        d2[k] = big[:, :50]
+    got, _ = pb.get_thermal_1d(*C.thermal_args(d2), level_fluxes=False)
+    assert_close(got, ref, RTOL, "padded ld")
+
+
+def test_many_angles_3d_geometry():
+    """ng x nt = 6 x 4 > 8 angles: un-fused disk integration path."""
+    gangle, gweight, tangle, tweight = pb.get_angles_3d(6, 4)
+    ubar0, ubar1, cos_theta, lat, lon = pb.compute_disco(6, 4, gangle, tangle, 0.4)
+    d = synth.reflected_inputs(L=8, W=70, seed=31)
+    d.update(numg=6, numt=4, ubar0=ubar0, ubar1=ubar1, cos_theta=float(cos_theta), gweight=gweight,
+             tweight=tweight)
+    kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
+    args = C.reflected_args(d, kw)
+    xint, _, alb = pb.get_reflected_1d(*args, gweight=gweight, tweight=tweight, return_albedo=True)
+    ox, _ = oracle.get_reflected_1d(*args)
+    assert_close(xint, ox, RTOL, "3d xint")
+    assert_close(alb, oracle.compress_disco(70, float(cos_theta), ox, gweight, tweight, d["F0PI"]),
+                 RTOL, "3d albedo")
+
+
+def test_full_size_properties():
+    """BASELINE headline size (60 x 10000 x 5): oracle comparison on a wavelength sample plus
+    size-independent properties - linearity in F0PI and invariance to wavelength permutation."""
+    d = synth.reflected_inputs(L=60, W=10000, seed=1000)
+    kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
+    xint, _, alb = pb.get_reflected_1d(*C.reflected_args(d, kw), gweight=d["gweight"],
+                                       tweight=d["tweight"], return_albedo=True)
+    assert np.isfinite(xint).all()
+    ox, _ = oracle.get_reflected_1d(*C.reflected_args(d, kw), nthreads=8)
+    assert_close(xint, ox, RTOL, "headline xint")
+    d2 = dict(d, F0PI=d["F0PI"] * 3.0)
+    x3, _, alb3 = pb.get_reflected_1d(*C.reflected_args(d2, kw), gweight=d["gweight"],
+                                      tweight=d["tweight"], return_albedo=True)
+    assert_close(x3, 3.0 * xint, 1e-12, "linearity in F0PI")
+    assert_close(alb3, alb, 1e-12, "albedo independent of F0PI")
+    perm = np.random.default_rng(0).permutation(d["nwno"])
+    dp = dict(d)
+    for k, v in d.items():
+        if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[-1] == d["nwno"]:
+            dp[k] = np.ascontiguousarray(v[..., perm])
+    xp, _ = pb.get_reflected_1d(*C.reflected_args(dp, kw))
+    assert np.array_equal(xp, xint[..., perm]), "wavelengths are not independent"
