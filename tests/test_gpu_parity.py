@@ -8,7 +8,7 @@ import cases as C
 import oracle
 import picaso_b200 as pb
 from picaso_b200 import synth
-from util import assert_close, assert_level_close, golden
+from util import assert_close, assert_level_close, assert_level_close_yardstick, golden
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-6
@@ -29,9 +29,10 @@ def test_reflected_vs_golden_and_oracle(name):
     alb2 = pb.compress_disco(d["nwno"], d["cos_theta"], xint, d["gweight"], d["tweight"], d["F0PI"])
     assert_close(alb2, g[name + "/albedo"], RTOL, name + " compress_disco")
     if case["kw"]["get_lvl_flux"]:
-        for k, a, o in zip(("fm", "fp", "fmm", "fpm"), lv, olv):
-            assert_level_close(a, g[name + "/" + k], what=name + " " + k + " vs reference")
-            assert_level_close(a, o, what=name + " " + k + " vs oracle")
+        _, qlv = oracle.get_reflected_1d(*args, quad=True, nthreads=8)
+        for k, a, o, q in zip(("fm", "fp", "fmm", "fpm"), lv, olv, qlv):
+            assert_level_close_yardstick(a, g[name + "/" + k], q, what=name + " " + k + " vs reference")
+            assert_level_close_yardstick(a, o, q, what=name + " " + k + " vs oracle")
     else:
         assert all(not a.any() for a in lv)
 
@@ -52,10 +53,12 @@ def test_thermal_vs_golden_and_oracle(name):
     assert_close(th2, g[name + "/thermal"], RTOL, name + " compress_thermal")
     oftop, olv = oracle.get_thermal_1d(*args)
     assert_close(ftop, oftop, RTOL, name + " vs oracle")
-    for k, a, o in zip(("fm", "fp", "fmm", "fpm"), lv, olv):
-        assert_level_close(a, o, what=name + " " + k + " vs oracle")
+    qftop, qlv = oracle.get_thermal_1d(*args, quad=True, nthreads=8)
+    assert_close(ftop, qftop, RTOL, name + " vs binary128 yardstick")
+    for k, a, o, q in zip(("fm", "fp", "fmm", "fpm"), lv, olv, qlv):
+        assert_level_close_yardstick(a, o, q, what=name + " " + k + " vs oracle/yardstick")
         if name + "/" + k in g.files:
-            assert_level_close(a, g[name + "/" + k], what=name + " " + k + " vs reference")
+            assert_level_close_yardstick(a, g[name + "/" + k], q, what=name + " " + k + " vs reference")
     lvc = pb.compress_thermal(d["nwno"], lv[1], d["gweight"], d["tweight"])
     assert lvc.shape == (d["nlevel"], d["nwno"])
     assert_level_close(lvc, oracle.compress_thermal(d["nwno"], olv[1], d["gweight"], d["tweight"]),

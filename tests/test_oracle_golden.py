@@ -53,3 +53,21 @@ def test_threads_do_not_change_results():
     a, _ = oracle.get_reflected_1d(*C.reflected_args(d, kw), nthreads=1)
     b, _ = oracle.get_reflected_1d(*C.reflected_args(d, kw), nthreads=4)
     assert np.array_equal(a, b)
+
+
+def test_toa_outputs_are_well_conditioned_against_binary128():
+    """TOA intensity / flux / transit depth of the fp64 oracle agree with the binary128
+    evaluation of the same formulas to ~1e-9: rtol 1e-6 parity is meaningful for them."""
+    d = synth.reflected_inputs(L=40, W=24, seed=17)
+    kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
+    a, _ = oracle.get_reflected_1d(*C.reflected_args(d, kw))
+    q, _ = oracle.get_reflected_1d(*C.reflected_args(d, kw), quad=True)
+    assert_close(a, q, 1e-8, "reflected TOA fp64 vs binary128")
+    t = C.build_thermal(dict(build=dict(L=40, W=24, seed=18), calc_type=0, hard_surface=0,
+                             surf_reflect=0.0))
+    a, _ = oracle.get_thermal_1d(*C.thermal_args(t), level_fluxes=False)
+    q, _ = oracle.get_thermal_1d(*C.thermal_args(t), level_fluxes=False, quad=True)
+    assert_close(a, q, 1e-8, "thermal TOA fp64 vs binary128")
+    tr = synth.transit_inputs(L=30, W=16, seed=19)
+    assert_close(oracle.get_transit_1d(*C.transit_args(tr)),
+                 oracle.get_transit_1d(*C.transit_args(tr), quad=True), 1e-12, "transit")

@@ -39,3 +39,23 @@ def assert_level_close(a, b, rtol=1e-6, col_atol=1e-9, what=""):
     colmax = np.max(np.abs(b), axis=-2, keepdims=True)
     bad = np.abs(a - b) > rtol * np.abs(b) + col_atol * colmax
     assert not bad.any(), f"{what}: {int(bad.sum())} level-flux entries outside tolerance"
+
+
+def assert_level_close_yardstick(a, ref64, exact, rtol=1e-6, col_atol=1e-9, slack=8.0, what=""):
+    """Level-flux criterion where the reference ALGORITHM is itself ill-conditioned in fp64.
+
+    In optically thick layers the reference un-mixes Y+ = X[2l] + X[2l+1] by cancellation
+    and multiplies it by exp(min(lam*dtau, 35)), so its own fp64 output carries errors up
+    to ~1e-3 against exact arithmetic (measured with the binary128 build of the oracle on
+    deep flux_minus entries).  No independent fp64 implementation can match such entries
+    to 1e-6.  `exact` is the binary128 evaluation of the reference formulas on the same
+    inputs, `ref64` their fp64 evaluation (the oracle).  An entry passes if it meets the
+    usual mixed tolerance against `exact`, or if its error is within `slack` x the largest
+    error the fp64 reference itself makes anywhere in that column (angle, wavelength)."""
+    a, ref64, exact = (np.asarray(x, dtype=np.float64) for x in (a, ref64, exact))
+    assert a.shape == exact.shape == ref64.shape
+    colmax = np.max(np.abs(exact), axis=-2, keepdims=True)
+    ref_noise = np.max(np.abs(ref64 - exact), axis=-2, keepdims=True)
+    tol = rtol * np.abs(exact) + col_atol * colmax + slack * ref_noise
+    bad = np.abs(a - exact) > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} level-flux entries outside tolerance"
