@@ -92,7 +92,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(nm)
                 except Exception:
                     pass
-            time.sleep(0.0005)
+            time.sleep(0.01)  # 100 Hz: NVML queries take driver locks, keep them sparse
 
     def summary(self):
         if not self.ok or not self.samples:
@@ -235,7 +235,8 @@ def main():
     for i in range(warm):
         step(i)
     ctx.sync()
-    t_end = time.perf_counter() + 0.3
+    sampler.active = True  # the ramp runs the same kernel back to back: samples are under load
+    t_end = time.perf_counter() + 0.5
     i = warm
     while time.perf_counter() < t_end:
         for _ in range(20):
@@ -283,9 +284,14 @@ def main():
     barrier()
     sampler.active = True
     t0 = time.perf_counter()
+    per = []
     for i in range(ke):
+        t1 = time.perf_counter()
         xint_h, _, alb_h = e2e_step(i)
+        per.append(time.perf_counter() - t1)
     e2e_dt = time.perf_counter() - t0
+    if os.environ.get("PB_BENCH_DEBUG"):
+        sys.stderr.write("e2e per-step ms: " + " ".join("%.2f" % (1e3 * x) for x in per) + "\n")
     sampler.active = False
     sampler.stop_flag = True
     if world > 1:

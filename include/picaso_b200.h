@@ -146,6 +146,10 @@ int pb_compress_disco(pb_ctx *ctx, int nwno, double cos_theta, const double *xin
 int pb_compress_thermal(pb_ctx *ctx, int64_t n, const double *flux_at_top, const double *gweight,
                         int ng, const double *tweight, int nt, double *out, int memspace);
 
+/* ---- self test ------------------------------------------------------------------------- */
+/* evaluates the kernels' branch-free exp() and 1/x on x[n] (host pointers); test hook */
+int pb_selftest_math(pb_ctx *ctx, const double *x, int n, double *exp_out, double *rcp_out);
+
 #ifdef __cplusplus
 }
 #endif

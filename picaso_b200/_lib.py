@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libpicaso_b200.so")
+LIB_PATH = os.environ.get("PICASO_B200_LIB") or os.path.join(_HERE, "_build", "libpicaso_b200.so")
 
 PB_HOST, PB_DEVICE = 0, 1
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -79,6 +79,7 @@ SYMBOLS = {
     "pb_compress_disco": (c_int, [c_vp, c_int, c_dbl, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp,
                                   c_int]),
     "pb_compress_thermal": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int]),
+    "pb_selftest_math": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
 }
 
 _lib = None

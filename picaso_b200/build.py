@@ -40,18 +40,21 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), lib=None):
+    """defines/lib: build an A/B variant (extra -D flags) into another file name."""
+    if lib is None and not force and not _stale():
         return LIB
+    lib = lib or LIB
+    tag = os.path.basename(lib)[:-3]
     os.makedirs(OUT, exist_ok=True)
     cc = nvcc()
     objs = []
 
     def compile_one(src):
-        obj = os.path.join(OUT, src[:-3] + ".o")
-        cmd = [cc, *ARCH, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(OUT, tag + "." + src[:-3] + ".o")
+        cmd = [cc, *ARCH, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        with open(os.path.join(OUT, src[:-3] + ".ptxas.log"), "w") as f:
+        with open(os.path.join(OUT, tag + "." + src[:-3] + ".ptxas.log"), "w") as f:
             f.write(r.stderr)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, r.stderr))
@@ -61,11 +64,11 @@ def build(force=False, verbose=False):
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [cc, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static"]
+    cmd = [cc, *ARCH, "-shared", "-o", lib, *objs, "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -22,6 +22,7 @@
 //    stores the elimination coefficients in the caller's four output arrays (they are
 //    exactly 4 doubles per level) and overwrites them with fluxes on the way down.
 #include "pb_common.cuh"
+#include "pb_math.cuh"
 
 namespace {
 
@@ -54,7 +55,9 @@ __device__ __forceinline__ double p_single(const ReflParams &p, double g_og, dou
     if (p.sp == 1) return hg_down(g_og, p.cos_theta);
     double gf = p.cfwd * g_og;
     double gb = p.cback * g_og;
-    double f = p.frac_a + p.frac_b * pow(gb, p.frac_c);
+    // g_back**frac_c: the config.json default frac_c = 2 needs no pow()
+    const double gbc = (p.frac_c == 2.0) ? gb * gb : pow(gb, p.frac_c);
+    double f = p.frac_a + p.frac_b * gbc;
     double tt = f * hg_down(gf, p.cos_theta) + (1.0 - f) * hg_down(gb, p.cos_theta);
     if (p.sp == 0) return tt + gcos2;
     if (p.sp == 2) return tt;
@@ -81,66 +84,142 @@ __device__ __forceinline__ double toon_g3(int tc, double g, double u0)
 }
 
 // ---------------------------------------------------------------------------------------
-// TOA intensity: one thread per (wavelength, angle), one bottom-up sweep.
+// TOA intensity.  CTA = 32 wavelengths (lane) x NW angle-warps (threadIdx.y).
+//
+// Layers are walked bottom-up in chunks of NW.  For every chunk each warp first acts as a
+// PRODUCER for one layer of the next chunk: it loads the 11 input rows of that layer
+// (coalesced 256-B segments, each element read from HBM exactly once per CTA) and
+// computes everything that does not depend on the viewing angle - g1, g2, lambda, Gamma,
+// exp(+-lambda dtau), the single-scattering phase function (the only pow/sqrt-heavy part)
+// - into a double-buffered shared-memory tile.  Then every warp acts as the CONSUMER of
+// the current chunk for its own angle: per layer it evaluates the angle-dependent Toon
+// coefficients and advances the single-sweep elimination/adjoint recurrence held in
+// registers.  One __syncthreads per chunk.
 // ---------------------------------------------------------------------------------------
+enum { Q_G = 0, Q_OM, Q_G1, Q_G2, Q_LAM, Q_GAM, Q_EP, Q_EM, Q_DT, Q_TAU, Q_GC2, Q_S0, Q_TAUO, Q_DTO, NQ };
+
+struct ReflInputs {  // raw inputs of one (layer, wavelength)
+    double om, fc, cb, dt, gc2, fr, dto, omo, cbo, tau, tauo;
+};
+
+__device__ __forceinline__ void refl_load(const ReflParams &p, int64_t il, int64_t iv, ReflInputs &x)
+{
+    x.om = __ldg(p.w0 + il);
+    x.fc = __ldg(p.fcld + il);
+    x.cb = __ldg(p.cosb + il);
+    x.dt = __ldg(p.dtau + il);
+    x.gc2 = __ldg(p.gcos2 + il);
+    x.fr = __ldg(p.fray + il);
+    x.dto = __ldg(p.dtau_og + il);
+    x.omo = __ldg(p.w0_og + il);
+    x.cbo = __ldg(p.cosb_og + il);
+    x.tau = __ldg(p.tau + iv);
+    x.tauo = __ldg(p.tau_og + iv);
+}
+
+__device__ __forceinline__ void refl_produce(const ReflParams &p, const ReflInputs &x, double f0,
+                                             double *q /* [NQ][32] column of this lane */)
+{
+    const double g = x.fc * x.cb;
+    double g1, g2;
+    toon_g(p.tc, x.om, g, g1, g2);
+    const double lam = sqrt(g1 * g1 - g2 * g2);
+    const double gam = (g1 - lam) * pbm::krcp(g2);
+    const double E = fmin(lam * x.dt, 35.0);  // slice_gt(exptrm, 35), fluxes.py:1174
+    const double EP = pbm::kexp(E);
+    const double ps = p_single(p, x.cbo, x.gc2, x.fc, x.fr);
+    q[Q_G * 32] = g;
+    q[Q_OM * 32] = x.om;
+    q[Q_G1 * 32] = g1;
+    q[Q_G2 * 32] = g2;
+    q[Q_LAM * 32] = lam;
+    q[Q_GAM * 32] = gam;
+    q[Q_EP * 32] = EP;
+    q[Q_EM * 32] = pbm::krcp(EP);
+    q[Q_DT * 32] = x.dt;
+    q[Q_TAU * 32] = x.tau;
+    q[Q_GC2 * 32] = x.gc2;
+    q[Q_S0 * 32] = (x.omo * f0 / (4.0 * PB_PI)) * ps;
+    q[Q_TAUO * 32] = x.tauo;
+    q[Q_DTO * 32] = x.dto;
+}
+
+template <int MP /*multi_phase*/>
 __global__ void __launch_bounds__(256) refl_toa_kernel(ReflParams p)
 {
-    extern __shared__ double s_int[];  // [blockDim.y][32] when fuse_albedo
-    const int lane = threadIdx.x;
+    extern __shared__ double smem[];  // [2][NW][NQ][32]
+    const int lane = threadIdx.x, wy = threadIdx.y, NW = blockDim.y;
     const int w = blockIdx.x * kWavesPerCta + lane;
-    const int a = blockIdx.y * blockDim.y + threadIdx.y;
+    const int wc = w < p.W ? w : p.W - 1;  // clamp: every lane takes part in the tile protocol
+    const int a = blockIdx.y * NW + wy;
+    const int ac = a < p.G ? a : p.G - 1;
     const int b = blockIdx.z;
-    const bool active = (w < p.W) && (a < p.G);
-    double result = 0.0;
-    if (active) {
-        const int L = p.L;
-        const int64_t ld = p.ld;
-        const int64_t ol = (int64_t)b * p.bs_layer + w;  // layer-array offset of (l=0, w)
-        const int64_t ov = (int64_t)b * p.bs_level + w;  // level-array offset
-        const int64_t ow = (int64_t)b * p.bs_wave + w;
-        const double u0 = p.ubar0[a], u1 = p.ubar1[a];
-        const double f0 = p.f0pi ? p.f0pi[ow] : 1.0;
-        const double r = p.surf ? p.surf[ow] : 0.0;
-        const double btop = p.btop ? p.btop[ow] : 0.0;
-        const double inv_u0 = 1.0 / u0;
-        const double c2pi = 0.5 / PB_PI;
-        const double s01 = (u0 + u1) / (u0 * u1);
-        const double wgt = u0 / (u0 + u1);
-        const double ubar2 = 0.767;
-        const double t2c = (3.0 * ubar2 * ubar2 * u1 * u1 - 1.0) / 2.0;
+    const int L = p.L;
+    const int64_t ld = p.ld;
+    const int64_t ol = (int64_t)b * p.bs_layer + wc;
+    const int64_t ov = (int64_t)b * p.bs_level + wc;
+    const int64_t ow = (int64_t)b * p.bs_wave + wc;
+    const double u0 = p.ubar0[ac], u1 = p.ubar1[ac];
+    const double f0 = p.f0pi ? p.f0pi[ow] : 1.0;
+    const double r = p.surf ? p.surf[ow] : 0.0;
+    const double btop = p.btop ? p.btop[ow] : 0.0;
+    const double inv_u0 = 1.0 / u0;
+    const double inv_u1 = 1.0 / u1;
+    const double c2pi = 0.5 / PB_PI;
+    const double s01 = (u0 + u1) / (u0 * u1);
+    const double wgt = u0 / (u0 + u1);
+    const double ubar2 = 0.767;  // fluxes.py:1280
+    const double t2c = (3.0 * ubar2 * ubar2 * u1 * u1 - 1.0) / 2.0;
+    const bool same_mu = (u0 == u1);
+    const bool og_alias = (p.dtau_og == p.dtau) && (p.tau_og == p.tau);
+    const int nchunks = (L + NW - 1) / NW;
+    const int tile = NW * NQ * 32;
 
-        double AS = 0.0, DS = 0.0, Pp = 0.0, Rp = 0.0;
-        double gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
-        double xd = exp(-p.tau[ov + (int64_t)L * ld] / u0);  // exp(-tau[L]/u0)
-        const double b_surface = 0.0 + r * u0 * f0 * xd;
+    double AS = 0.0, DS = 0.0, Pp = 0.0, Rp = 0.0;
+    double gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
+    double xd = pbm::kexp(-__ldg(p.tau + ov + (int64_t)L * ld) * inv_u0);  // exp(-tau[L]/u0)
+    const double b_surface = 0.0 + r * u0 * f0 * xd;
 
-        for (int l = L - 1; l >= 0; --l) {
-            const int64_t il = ol + (int64_t)l * ld;
-            const double om = p.w0[il];
-            const double fc = p.fcld[il];
-            const double g = fc * p.cosb[il];
-            const double dt = p.dtau[il];
-            const double gc2 = p.gcos2[il];
-            double g1, g2;
-            toon_g(p.tc, om, g, g1, g2);
-            const double lam = sqrt(g1 * g1 - g2 * g2);
-            const double gam = (g1 - lam) / g2;
+    // prologue: produce chunk 0
+    {
+        const int l = L - 1 - wy;
+        if (l >= 0) {
+            ReflInputs x;
+            refl_load(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, x);
+            refl_produce(p, x, f0, smem + wy * NQ * 32 + lane);
+        }
+    }
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        // issue the loads of the next chunk before the arithmetic of this one
+        ReflInputs nx;
+        const int ln = L - 1 - ((c + 1) * NW + wy);
+        const bool have_next = (c + 1 < nchunks) && (ln >= 0);
+        if (have_next) refl_load(p, ol + (int64_t)ln * ld, ov + (int64_t)ln * ld, nx);
+
+        const double *buf = smem + (c & 1) * tile + lane;
+        const int lbase = L - 1 - c * NW;
+        const int nk = lbase + 1 < NW ? lbase + 1 : NW;
+        for (int k = 0; k < nk; ++k) {
+            const int l = lbase - k;
+            const double *q = buf + k * NQ * 32;
+            const double g = q[Q_G * 32], om = q[Q_OM * 32], g1 = q[Q_G1 * 32], g2 = q[Q_G2 * 32];
+            const double lam = q[Q_LAM * 32], gam = q[Q_GAM * 32], EP = q[Q_EP * 32], EM = q[Q_EM * 32];
+            const double dt = q[Q_DT * 32];
             const double g3 = toon_g3(p.tc, g, u0);
             const double g4 = 1.0 - g3;
-            const double den = lam * lam - 1.0 / (u0 * u0);
-            const double am = f0 * om * (g4 * (g1 + inv_u0) + g2 * g3) / den;
-            const double ap = f0 * om * (g3 * (g1 - inv_u0) + g2 * g4) / den;
-            const double xu = exp(-p.tau[ov + (int64_t)l * ld] / u0);
+            const double inv_den = pbm::krcp(lam * lam - inv_u0 * inv_u0);
+            const double fw = f0 * om;
+            const double am = fw * (g4 * (g1 + inv_u0) + g2 * g3) * inv_den;
+            const double ap = fw * (g3 * (g1 - inv_u0) + g2 * g4) * inv_den;
+            const double xu = pbm::kexp(-q[Q_TAU * 32] * inv_u0);
             const double cmu = am * xu, cpu = ap * xu, cmd = am * xd, cpd = ap * xd;
-            const double E = fmin(lam * dt, 35.0);  // slice_gt(exptrm, 35), fluxes.py:1174
-            const double EP = exp(E), EM = 1.0 / EP;
             const double e1 = EP + gam * EM, e2 = EP - gam * EM;
             const double e3 = gam * EP + EM, e4 = gam * EP - EM;
-
             // multiple-scattering Legendre weights, fluxes.py:1275-1287
             double mpl, mmi;
-            if (p.mp == 0) {
-                const double t2 = gc2 * t2c;
+            if (MP == 0) {
+                const double t2 = q[Q_GC2 * 32] * t2c;
                 mpl = 1.0 + 1.5 * g * u1 + t2;
                 mmi = 1.0 - 1.5 * g * u1 + t2;
             } else {
@@ -149,45 +228,52 @@ __global__ void __launch_bounds__(256) refl_toa_kernel(ReflParams p)
             }
             // source-function coefficients of Y+ / Y- and the X-independent part
             // (fluxes.py:1290-1296, :1395-1407); exp(+-E - dt/u1) = EP|EM * exp(-dt/u1)
-            const double xa = exp(-dt / u1);
+            const double xa = pbm::kexp(-dt * inv_u1);
             const double lu = lam * u1;
-            const double cG = (mpl + gam * mmi) * om * c2pi * ((EP * xa - 1.0) / (lu - 1.0));
-            const double cH = (gam * mpl + mmi) * om * c2pi * ((1.0 - EM * xa) / (lu + 1.0));
-            const double At = (mpl * cpu + mmi * cmu) * om * c2pi;
-            const int64_t ilo = il;  // same offsets for the *_og arrays
-            const double ps = p_single(p, p.cosb_og[ilo], gc2, fc, p.fray[il]);
-            const double K = (p.w0_og[ilo] * f0 / (4.0 * PB_PI)) * ps *
-                                 exp(-p.tau_og[ov + (int64_t)l * ld] / u0) *
-                                 (1.0 - exp(-p.dtau_og[ilo] * s01)) * wgt +
-                             At * (1.0 - exp(-dt * s01)) * wgt;
+            const double inv_l = pbm::krcp(lu * lu - 1.0);  // 1/(lu-1) = (lu+1) inv_l
+            const double omc = om * c2pi;
+            const double cG = (mpl + gam * mmi) * omc * ((EP * xa - 1.0) * ((lu + 1.0) * inv_l));
+            const double cH = (gam * mpl + mmi) * omc * ((1.0 - EM * xa) * ((lu - 1.0) * inv_l));
+            const double At = (mpl * cpu + mmi * cmu) * omc;
+            const double xs = same_mu ? xa * xa : pbm::kexp(-dt * s01);
+            double xo, xso;
+            if (og_alias) {
+                xo = xu;
+                xso = xs;
+            } else {
+                xo = pbm::kexp(-q[Q_TAUO * 32] * inv_u0);
+                xso = pbm::kexp(-q[Q_DTO * 32] * s01);
+            }
+            const double K = q[Q_S0 * 32] * xo * (1.0 - xso) * wgt + At * (1.0 - xs) * wgt;
             double P, Q, R;
             if (l == L - 1) {
                 // last row 2L-1, fluxes.py:178-181, and I_L = flux_zero/pi, :1266-1270
                 const double a_ = e1 - r * e3, b_ = e2 - r * e4;
                 const double d_ = b_surface - cpd + r * cmd;
-                AS = a_ / b_;
-                DS = d_ / b_;
+                const double ib = pbm::krcp(b_);
+                AS = a_ * ib;
+                DS = d_ * ib;
                 P = xa * (e1 / PB_PI) + (cG + cH);
                 Q = xa * (e2 / PB_PI) + (cG - cH);
                 R = xa * (cpd / PB_PI) + K;
             } else {
                 // interface rows between layer l and l+1: even row 2l+2 (fluxes.py:171-175)
+                const double gm1 = gam_n - 1.0;
+                const double e13 = (e1 + e3) * gm1;
                 double a_ = 2.0 * (1.0 - gam * gam);
                 double b_ = (e1 - e3) * (gam_n + 1.0);
-                double c_ = (e1 + e3) * (gam_n - 1.0);
                 double d_ = e3 * (cpu_n - cpd) + e1 * (cmd - cmu_n);
-                double x = 1.0 / (b_ - c_ * AS);
-                double ASe = a_ * x, DSe = (d_ - c_ * DS) * x;
+                double x = pbm::krcp(b_ - e13 * AS);
+                const double ASe = a_ * x, DSe = (d_ - e13 * DS) * x;
                 // I_{l+1} = Rp + Pp X[2l+2],  X[2l+2] = DSe - ASe X[2l+1]
                 const double alpha = Rp + Pp * DSe;
                 const double beta = -Pp * ASe;
                 // odd row 2l+1 (fluxes.py:161-165)
-                a_ = (e1 + e3) * (gam_n - 1.0);
-                b_ = (e2 + e4) * (gam_n - 1.0);
-                c_ = 2.0 * (1.0 - gam_n * gam_n);
-                d_ = (gam_n - 1.0) * (cpu_n - cpd) + (1.0 - gam_n) * (cmd - cmu_n);
-                x = 1.0 / (b_ - c_ * ASe);
-                AS = a_ * x;
+                b_ = (e2 + e4) * gm1;
+                const double c_ = 2.0 * (1.0 - gam_n * gam_n);
+                d_ = gm1 * (cpu_n - cpd) - gm1 * (cmd - cmu_n);
+                x = pbm::krcp(b_ - c_ * ASe);
+                AS = e13 * x;
                 DS = (d_ - c_ * DSe) * x;
                 P = cG + cH;
                 Q = xa * beta + (cG - cH);
@@ -201,27 +287,30 @@ __global__ void __launch_bounds__(256) refl_toa_kernel(ReflParams p)
             cmu_n = cmu;
             xd = xu;
         }
-        // row 0 (fluxes.py:155-158): X[0] = DS[0]
-        {
-            const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = btop - cmu_n;
-            const double x = 1.0 / (b_ - c_ * AS);
-            const double X0 = (d_ - c_ * DS) * x;
-            result = Rp + Pp * X0;
-        }
-        if (p.xint) p.xint[((int64_t)b * p.G + a) * p.W + w] = result;
+        if (have_next) refl_produce(p, nx, f0, smem + ((c + 1) & 1) * tile + wy * NQ * 32 + lane);
+        __syncthreads();
     }
+    double result;
+    {
+        // row 0 (fluxes.py:155-158): X[0] = DS[0]
+        const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = btop - cmu_n;
+        const double x = pbm::krcp(b_ - c_ * AS);
+        const double X0 = (d_ - c_ * DS) * x;
+        result = Rp + Pp * X0;
+    }
+    const bool active = (w < p.W) && (a < p.G);
+    if (active && p.xint) p.xint[((int64_t)b * p.G + a) * p.W + w] = result;
     if (p.fuse_albedo) {
         // compress_disco (disco.py:138-149): sequential sum over (ig, it) in index order
-        s_int[threadIdx.y * kWavesPerCta + lane] = result;
+        smem[wy * kWavesPerCta + lane] = result;
         __syncthreads();
-        if (threadIdx.y == 0 && w < p.W) {
+        if (wy == 0 && w < p.W) {
             double acc = 0.0;
             for (int aa = 0; aa < p.G; ++aa) {
                 const int ig = aa / p.nt, it = aa - ig * p.nt;
-                acc = acc + s_int[aa * kWavesPerCta + lane] * p.gweight[ig] * p.tweight[it];
+                acc = acc + smem[aa * kWavesPerCta + lane] * p.gweight[ig] * p.tweight[it];
             }
             const double sym = (p.nt == 1) ? 2.0 * PB_PI : 1.0;
-            const double f0 = p.f0pi ? p.f0pi[(int64_t)b * p.bs_wave + w] : 1.0;
             p.albedo[(int64_t)b * p.W + w] = sym * 0.5 * acc / f0 * (p.cos_theta + 1.0);
         }
     }
@@ -491,8 +580,13 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
     dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
     if (want_toa) {
         p.xint = d_xint; p.albedo = d_alb; p.fuse_albedo = fuse ? 1 : 0;
-        size_t smem = fuse ? (size_t)ay * kWavesPerCta * sizeof(double) : 0;
-        refl_toa_kernel<<<grid, block, smem, ctx->stream>>>(p);
+        const size_t smem = (size_t)2 * ay * NQ * 32 * sizeof(double);
+        if (smem > 48 * 1024) {
+            PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        if (p.mp == 0) refl_toa_kernel<0><<<grid, block, smem, ctx->stream>>>(p);
+        else refl_toa_kernel<1><<<grid, block, smem, ctx->stream>>>(p);
         PB_CHECK_LAUNCH(ctx);
         if (a->albedo && !fuse) {
             dim3 g2((W + 127) / 128, B);

@@ -13,6 +13,9 @@ from ._lib import PB_HOST, ReflectedArgs, ThermalArgs, TransitArgs, addr
 __all__ = ["get_reflected_1d", "get_thermal_1d", "get_transit_1d"]
 
 
+_ZERO = np.zeros(())
+
+
 def _f64(a):
     """float64 view with unit wavelength stride; copies only when it has to (e.g. the
     X[:, :, ig] slices picaso() passes when ngauss > 1, justdoit.py:275-283)."""
@@ -103,8 +106,10 @@ def get_reflected_1d(nlevel, wno, nwno, numg, numt, dtau, tau, w0, cosb, gcos2, 
     if nwno > 0:
         ctx.check(ctx.lib.pb_reflected_toon_1d(ctx.h, ctypes.byref(a), PB_HOST))
     if lv is None:
-        # the reference always returns four zero arrays (fluxes.py:1113-1121)
-        lv = [np.zeros((numg, numt, nlevel, nwno)) for _ in range(4)]
+        # the reference always returns four zero arrays (fluxes.py:1113-1121); hand back
+        # read-only zero-stride views of the same shape instead of touching ~100 MB per call
+        z = np.broadcast_to(_ZERO, (numg, numt, nlevel, nwno))
+        lv = [z, z, z, z]
     if return_albedo:
         return xint, tuple(lv), alb
     return xint, tuple(lv)
