@@ -167,7 +167,10 @@ def main():
     ctx = pb.Context(local_rank)
     if world > 1:
         # run our kernels on the stream NCCL's collectives are enqueued on: no host sync needed
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        # (a dedicated non-default stream: handle 0 would mean "the context's own stream")
+        side = torch.cuda.Stream()
+        torch.cuda.set_stream(side)
+        ctx.set_stream(side.cuda_stream)
     warm = max(args.warmup, 3)
 
     sets = make_sets(rank)
@@ -236,9 +239,9 @@ def main():
         step(i)
     ctx.sync()
     sampler.active = True  # the ramp runs the same kernel back to back: samples are under load
-    t_end = time.perf_counter() + 0.5
+    # fixed step count (not wall-clock) so that every rank issues the same collectives
     i = warm
-    while time.perf_counter() < t_end:
+    for _ in range(150):
         for _ in range(20):
             step(i)
             i += 1
