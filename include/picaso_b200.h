@@ -104,6 +104,35 @@ typedef struct pb_reflected_args {
 
 int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *args, int memspace);
 
+/* ---- reflected light, spherical harmonics (P1 "SH2" / P3 "SH4") ---------------------- */
+/* replaces get_reflected_SH, picaso/fluxes.py:2675-2976 (setup_2_stream_fluxes :3189,
+ * setup_4_stream_fluxes :3336, solve_4_stream_banded :3610 = scipy/LAPACK dgbsv, legP :3639)
+ * and, when `albedo` is given, compress_disco.  flx must be 0 (the reference's flx=1 branch
+ * is only used for diagnostics).  The reference scales its f_deltaM argument in place, once
+ * per angle, when a TTHG form is active; results reproduce that, the
+ * input array is NOT modified, and the final scaled array is written to `f_deltaM_out` if
+ * that is non-NULL. */
+typedef struct pb_sh_args {
+    int nlayer, nwno, numg, numt, nbatch;
+    int64_t ld;
+    const double *dtau, *w0, *ftau_cld, *ftau_ray, *f_deltaM, *dtau_og, *w0_og, *cosb_og; /* layer */
+    const double *tau, *tau_og;                                                          /* level */
+    const double *surf_reflect, *F0PI, *b_top;                                           /* [nwno] or NULL */
+    const double *ubar0, *ubar1, *gweight, *tweight;                                     /* host */
+    double cos_theta;
+    int w_single_form, w_multi_form, psingle_form;             /* 0 TTHG, 1 OTHG */
+    int w_single_rayleigh, w_multi_rayleigh, psingle_rayleigh; /* 0 off, 1 on */
+    double frac_a, frac_b, frac_c, constant_back, constant_forward;
+    int stream;      /* 2 or 4 */
+    int flx;         /* must be 0 */
+    int single_form; /* 0 explicit, 1 legendre */
+    double *xint_at_top;  /* [numg*numt][nwno] or NULL */
+    double *albedo;       /* [nwno] or NULL */
+    double *f_deltaM_out; /* [nlayer][nwno] or NULL */
+} pb_sh_args;
+
+int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *args, int memspace);
+
 /* ---- thermal emission, Toon89 two-stream + source function ------------------------- */
 /* replaces get_thermal_1d, fluxes.py:1683-1912 (blackbody :1661, blackbody_integrated
  * :1609) and, when `thermal` is given, compress_thermal, disco.py:152-180 */

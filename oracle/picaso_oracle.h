@@ -66,6 +66,21 @@ void orc_compress_disco(int nwno, double cos_theta, const double *xint_at_top,
 void orc_compress_thermal(int n, const double *flux_at_top, const double *gweight, int ng,
                           const double *tweight, int nt, double *flux);
 
+/* follows fluxes.py:2675-2976 (get_reflected_SH; setup_2_stream_fluxes :3189,
+ * setup_4_stream_fluxes :3336, solve_4_stream_banded :3610 -> LAPACK dgbsv restated).
+ * stream in {2,4}; flx=0 only.  f_deltaM [nlayer][nwno] is MODIFIED exactly like the
+ * reference modifies its argument. */
+void orc_get_reflected_SH(
+    int nlevel, int nwno, int numg, int numt,
+    const double *dtau, const double *tau, const double *w0, const double *cosb,
+    const double *ftau_cld, const double *ftau_ray, double *f_deltaM,
+    const double *dtau_og, const double *tau_og, const double *w0_og, const double *cosb_og,
+    const double *surf_reflect, const double *ubar0, const double *ubar1, double cos_theta,
+    const double *F0PI, int w_single_form, int w_multi_form, int psingle_form,
+    int w_single_rayleigh, int w_multi_rayleigh, int psingle_rayleigh,
+    double frac_a, double frac_b, double frac_c, double constant_back, double constant_forward,
+    int stream, const double *b_top, int single_form, double *xint_at_top, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

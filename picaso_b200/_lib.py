@@ -35,6 +35,20 @@ class ReflectedArgs(ctypes.Structure):
                              "flux_plus_mdpt")])
 
 
+class ShArgs(ctypes.Structure):
+    _fields_ = (
+        [(n, c_int) for n in ("nlayer", "nwno", "numg", "numt", "nbatch")] + [("ld", c_i64)] +
+        [(n, c_vp) for n in ("dtau", "w0", "ftau_cld", "ftau_ray", "f_deltaM", "dtau_og", "w0_og",
+                             "cosb_og", "tau", "tau_og", "surf_reflect", "F0PI", "b_top", "ubar0",
+                             "ubar1", "gweight", "tweight")] +
+        [("cos_theta", c_dbl)] +
+        [(n, c_int) for n in ("w_single_form", "w_multi_form", "psingle_form", "w_single_rayleigh",
+                              "w_multi_rayleigh", "psingle_rayleigh")] +
+        [(n, c_dbl) for n in ("frac_a", "frac_b", "frac_c", "constant_back", "constant_forward")] +
+        [("stream", c_int), ("flx", c_int), ("single_form", c_int)] +
+        [(n, c_vp) for n in ("xint_at_top", "albedo", "f_deltaM_out")])
+
+
 class ThermalArgs(ctypes.Structure):
     _fields_ = (
         [(n, c_int) for n in ("nlayer", "nwno", "numg", "numt", "nbatch")] + [("ld", c_i64)] +
@@ -74,6 +88,7 @@ SYMBOLS = {
     "pb_timer_stop": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float)]),
     "pb_launch_count": (ctypes.c_uint64, [c_vp]),
     "pb_reflected_toon_1d": (c_int, [c_vp, ctypes.POINTER(ReflectedArgs), c_int]),
+    "pb_reflected_sh": (c_int, [c_vp, ctypes.POINTER(ShArgs), c_int]),
     "pb_thermal_toon_1d": (c_int, [c_vp, ctypes.POINTER(ThermalArgs), c_int]),
     "pb_transit_1d": (c_int, [c_vp, ctypes.POINTER(TransitArgs), c_int]),
     "pb_compress_disco": (c_int, [c_vp, c_int, c_dbl, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp,

@@ -11,6 +11,7 @@
 // The Planck function is evaluated in the kernel from tlevel (no [nlevel, nwno]
 // blackbody matrix is ever materialised).
 #include "pb_common.cuh"
+#include "pb_math.cuh"
 
 namespace {
 
@@ -93,85 +94,151 @@ __device__ __forceinline__ void thermal_layer(double dt, double om, double g, do
 }
 
 // ---------------------------------------------------------------------------------------
-// TOA flux: one thread per (wavelength, angle)
+// TOA flux.  CTA = 32 wavelengths (lane) x NW angle-warps, same chunked producer/consumer
+// scheme as refl_toa_kernel: the Planck function of every level is evaluated once per CTA
+// into shared memory, then layers are walked bottom-up in chunks of NW; each warp produces
+// the angle-independent two-stream quantities of one layer of the next chunk (sqrt, 4
+// reciprocals, exp) and consumes the current chunk for its own angle (1 exp, 3
+// reciprocals per layer).
 // ---------------------------------------------------------------------------------------
+enum { T_LAM = 0, T_GAM, T_EP, T_EM, T_CPU, T_CMU, T_CPD, T_CMD, T_DT, T_AL1, T_AL2, T_E, T_B1, TNQ };
+
+__device__ __forceinline__ void therm_produce(double dt, double om, double g, double Btop, double Bbot,
+                                              double *q /* [TNQ][32] column of this lane */)
+{
+    // fluxes.py:1756-1789, :1846-1847
+    const double b0 = Btop;
+    const double b1 = (Bbot - Btop) * pbm::krcp(dt);
+    const double g1 = 2.0 - om * (1 + g), g2 = om * (1 - g);
+    const double lam = sqrt(g1 * g1 - g2 * g2);
+    const double gam = (g1 - lam) * pbm::krcp(g2);
+    const double qq = pbm::krcp(g1 + g2);
+    const double tp = 2 * PB_PI * kMu1;
+    const double E = fmin(lam * dt, 35.0);
+    const double EP = pbm::kexp(E);
+    q[T_LAM * 32] = lam;
+    q[T_GAM * 32] = gam;
+    q[T_EP * 32] = EP;
+    q[T_EM * 32] = pbm::krcp(EP);
+    q[T_CPU * 32] = tp * (b0 + b1 * qq);
+    q[T_CMU * 32] = tp * (b0 - b1 * qq);
+    q[T_CPD * 32] = tp * (b0 + b1 * dt + b1 * qq);
+    q[T_CMD * 32] = tp * (b0 + b1 * dt - b1 * qq);
+    q[T_DT * 32] = dt;
+    q[T_AL1 * 32] = 2 * PB_PI * (b0 + b1 * (qq - kMu1));
+    q[T_AL2 * 32] = 2 * PB_PI * b1;
+    q[T_E * 32] = E;
+    q[T_B1 * 32] = b1;
+}
+
 __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
 {
-    extern __shared__ double s_f[];
-    const int lane = threadIdx.x;
+    extern __shared__ double smem[];  // [V][32] Planck | [2][NW][TNQ][32] tiles
+    const int lane = threadIdx.x, wy = threadIdx.y, NW = blockDim.y;
     const int w = blockIdx.x * kWavesPerCta + lane;
-    const int a = blockIdx.y * blockDim.y + threadIdx.y;
+    const int wc = w < p.W ? w : p.W - 1;
+    const int a = blockIdx.y * NW + wy;
+    const int ac = a < p.G ? a : p.G - 1;
     const int b = blockIdx.z;
-    const bool active = (w < p.W) && (a < p.G);
-    double result = 0.0;
-    if (active) {
-        const int L = p.L, V = p.L + 1;
-        const int64_t ld = p.ld;
-        const int64_t ol = (int64_t)b * p.bs_layer + w;
-        const double *tl = p.tlevel + (int64_t)b * V;
-        const double *pl = p.plevel + (int64_t)b * V;
-        const double u = p.ubar1[a];
-        const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + w] : 0.0;
-        Planck planck;
-        planck.init(p.calc_type, p.wno[w], p.dwno ? p.dwno[w] : 0.0);
+    const int L = p.L, V = p.L + 1;
+    const int64_t ld = p.ld;
+    const int64_t ol = (int64_t)b * p.bs_layer + wc;
+    const double *tl = p.tlevel + (int64_t)b * V;
+    const double *pl = p.plevel + (int64_t)b * V;
+    const double u = p.ubar1[ac];
+    const double inv_u = 1.0 / u;
+    const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + wc] : 0.0;
+    double *sB = smem;
+    double *tiles = smem + (size_t)V * 32;
+    const int tile = NW * TNQ * 32;
+    const int nchunks = (L + NW - 1) / NW;
 
-        double AS = 0.0, DS = 0.0, Pp = 0.0, Rp = 0.0;
-        double gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
-        double Bbot = planck(tl[L]);
-        const double BL = Bbot;
-        for (int l = L - 1; l >= 0; --l) {
+    {
+        Planck planck;
+        planck.init(p.calc_type, p.wno[wc], p.dwno ? p.dwno[wc] : 0.0);
+        for (int v = wy; v < V; v += NW) sB[v * 32 + lane] = planck(tl[v]);
+    }
+    __syncthreads();
+    const double BL = sB[L * 32 + lane], B0 = sB[lane];
+    {
+        const int l = L - 1 - wy;
+        if (l >= 0) {
             const int64_t il = ol + (int64_t)l * ld;
-            const double dt = p.dtau[il];
-            const double Btop = planck(tl[l]);
-            TLayer t;
-            thermal_layer(dt, p.w0[il], p.cosb[il], Btop, Bbot, t);
+            therm_produce(__ldg(p.dtau + il), __ldg(p.w0 + il), __ldg(p.cosb + il), sB[l * 32 + lane],
+                          sB[(l + 1) * 32 + lane], tiles + wy * TNQ * 32 + lane);
+        }
+    }
+    __syncthreads();
+    double AS = 0.0, DS = 0.0, Pp = 0.0, Rp = 0.0;
+    double gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int ln = L - 1 - ((c + 1) * NW + wy);
+        const bool have_next = (c + 1 < nchunks) && (ln >= 0);
+        double ndt = 0.0, nom = 0.0, ncb = 0.0;
+        if (have_next) {
+            const int64_t il = ol + (int64_t)ln * ld;
+            ndt = __ldg(p.dtau + il);
+            nom = __ldg(p.w0 + il);
+            ncb = __ldg(p.cosb + il);
+        }
+        const double *buf = tiles + (c & 1) * tile + lane;
+        const int lbase = L - 1 - c * NW;
+        const int nk = lbase + 1 < NW ? lbase + 1 : NW;
+        for (int k = 0; k < nk; ++k) {
+            const int l = lbase - k;
+            const double *q = buf + k * TNQ * 32;
+            const double lam = q[T_LAM * 32], gam = q[T_GAM * 32], EP = q[T_EP * 32], EM = q[T_EM * 32];
+            const double cpu = q[T_CPU * 32], cmu = q[T_CMU * 32], cpd = q[T_CPD * 32], cmd = q[T_CMD * 32];
+            const double dt = q[T_DT * 32], al1 = q[T_AL1 * 32], al2 = q[T_AL2 * 32];
+            const double e1 = EP + gam * EM, e2 = EP - gam * EM;
+            const double e3 = gam * EP + EM, e4 = gam * EP - EM;
             // Table 3 of Toon89 (fluxes.py:1842-1849): G = (1/mu1 - lam) Y+, H = gam (lam + 1/mu1) Y-
-            const double al1 = 2 * PB_PI * (t.b0 + t.b1 * (t.q - kMu1));
-            const double al2 = 2 * PB_PI * t.b1;
-            const double lu = t.lam * u;
-            const double kG = (1 / kMu1 - t.lam) / (lu - 1.0);
-            const double kH = t.gam * (t.lam + 1 / kMu1) / (lu + 1.0);
+            const double lu = lam * u;
+            const double inv_l = pbm::krcp(lu * lu - 1.0);
+            const double kG = (1 / kMu1 - lam) * ((lu + 1.0) * inv_l);
+            const double kH = gam * (lam + 1 / kMu1) * ((lu - 1.0) * inv_l);
             double x, cG, cH, K;
             if (l > 0) {
                 // flux_plus recurrence, fluxes.py:1897-1901
-                x = exp(-dt / u);
-                cG = kG * (t.EP * x - 1.0);
-                cH = kH * (1.0 - t.EM * x);
+                x = pbm::kexp(-dt * inv_u);
+                cG = kG * (EP * x - 1.0);
+                cH = kH * (1.0 - EM * x);
                 K = al1 * (1. - x) + al2 * (u - (dt + u) * x);
             } else {
                 // flux_plus_mdpt[0], fluxes.py:1903-1910
-                x = exp(-0.5 * dt / u);
-                const double EPh = exp(0.5 * t.E), EMh = 1 / EPh;
-                cG = kG * (t.EP * x - EPh);
-                cH = -kH * (t.EM * x - EMh);
+                x = pbm::kexp(-0.5 * dt * inv_u);
+                const double EPh = pbm::kexp(0.5 * q[T_E * 32]), EMh = pbm::krcp(EPh);
+                cG = kG * (EP * x - EPh);
+                cH = -kH * (EM * x - EMh);
                 K = al1 * (1. - x) + al2 * (u + 0.5 * dt - (dt + u) * x);
             }
             double alpha, beta;
             if (l == L - 1) {
                 // surface boundary, fluxes.py:1802-1806, :1869-1873, last row :178-181
-                const double b_surface = p.hard_surface ? (1.0 - r) * BL * PB_PI
-                                                        : (BL + t.b1 * kMu1) * PB_PI;
-                const double a_ = t.e1 - r * t.e3, b_ = t.e2 - r * t.e4;
-                const double d_ = b_surface - t.cpd + r * t.cmd;
-                AS = a_ / b_;
-                DS = d_ / b_;
-                alpha = p.hard_surface ? (1.0 - r) * BL * 2 * PB_PI : (BL + t.b1 * u) * 2 * PB_PI;
+                const double b1 = q[T_B1 * 32];
+                const double b_surface = p.hard_surface ? (1.0 - r) * BL * PB_PI : (BL + b1 * kMu1) * PB_PI;
+                const double a_ = e1 - r * e3, b_ = e2 - r * e4;
+                const double d_ = b_surface - cpd + r * cmd;
+                const double ib = pbm::krcp(b_);
+                AS = a_ * ib;
+                DS = d_ * ib;
+                alpha = p.hard_surface ? (1.0 - r) * BL * 2 * PB_PI : (BL + b1 * u) * 2 * PB_PI;
                 beta = 0.0;
             } else {
-                double a_ = 2.0 * (1.0 - t.gam * t.gam);
-                double b_ = (t.e1 - t.e3) * (gam_n + 1.0);
-                double c_ = (t.e1 + t.e3) * (gam_n - 1.0);
-                double d_ = t.e3 * (cpu_n - t.cpd) + t.e1 * (t.cmd - cmu_n);
-                double xi = 1.0 / (b_ - c_ * AS);
-                const double ASe = a_ * xi, DSe = (d_ - c_ * DS) * xi;
+                const double gm1 = gam_n - 1.0;
+                const double e13 = (e1 + e3) * gm1;
+                double a_ = 2.0 * (1.0 - gam * gam);
+                double b_ = (e1 - e3) * (gam_n + 1.0);
+                double d_ = e3 * (cpu_n - cpd) + e1 * (cmd - cmu_n);
+                double xi = pbm::krcp(b_ - e13 * AS);
+                const double ASe = a_ * xi, DSe = (d_ - e13 * DS) * xi;
                 alpha = Rp + Pp * DSe;
                 beta = -Pp * ASe;
-                a_ = (t.e1 + t.e3) * (gam_n - 1.0);
-                b_ = (t.e2 + t.e4) * (gam_n - 1.0);
-                c_ = 2.0 * (1.0 - gam_n * gam_n);
-                d_ = (gam_n - 1.0) * (cpu_n - t.cpd) + (1.0 - gam_n) * (t.cmd - cmu_n);
-                xi = 1.0 / (b_ - c_ * ASe);
-                AS = a_ * xi;
+                b_ = (e2 + e4) * gm1;
+                const double c_ = 2.0 * (1.0 - gam_n * gam_n);
+                d_ = gm1 * (cpu_n - cpd) - gm1 * (cmd - cmu_n);
+                xi = pbm::krcp(b_ - c_ * ASe);
+                AS = e13 * xi;
                 DS = (d_ - c_ * DSe) * xi;
             }
             // F+_l = x (alpha + beta X[2l+1]) + cG (X0 + X1) + cH (X0 - X1) + K
@@ -180,26 +247,32 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
             const double R = x * alpha + K;
             Pp = P - Q * AS;
             Rp = R + Q * DS;
-            gam_n = t.gam;
-            cpu_n = t.cpu;
-            cmu_n = t.cmu;
-            Bbot = Btop;
+            gam_n = gam;
+            cpu_n = cpu;
+            cmu_n = cmu;
         }
-        {
-            // top boundary: fake isothermal overburden, fluxes.py:1797-1800; row 0 :155-158
-            const double tau_top = p.dtau[ol] * pl[0] / (pl[1] - pl[0]);
-            const double b_top = (1.0 - exp(-tau_top / kMu1)) * Bbot * PB_PI;
-            const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = b_top - cmu_n;
-            const double xi = 1.0 / (b_ - c_ * AS);
-            const double X0 = (d_ - c_ * DS) * xi;
-            result = Rp + Pp * X0;
-        }
-        if (p.ftop) p.ftop[((int64_t)b * p.G + a) * p.W + w] = result;
-    }
-    if (p.fuse) {
-        s_f[threadIdx.y * kWavesPerCta + lane] = result;
+        if (have_next)
+            therm_produce(ndt, nom, ncb, sB[ln * 32 + lane], sB[(ln + 1) * 32 + lane],
+                          tiles + ((c + 1) & 1) * tile + wy * TNQ * 32 + lane);
         __syncthreads();
-        if (threadIdx.y == 0 && w < p.W) {
+    }
+    double result;
+    {
+        // top boundary: fake isothermal overburden, fluxes.py:1797-1800; row 0 :155-158
+        const double tau_top = __ldg(p.dtau + ol) * pl[0] / (pl[1] - pl[0]);
+        const double b_top = (1.0 - exp(-tau_top / kMu1)) * B0 * PB_PI;
+        const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = b_top - cmu_n;
+        const double xi = pbm::krcp(b_ - c_ * AS);
+        const double X0 = (d_ - c_ * DS) * xi;
+        result = Rp + Pp * X0;
+    }
+    const bool active = (w < p.W) && (a < p.G);
+    if (active && p.ftop) p.ftop[((int64_t)b * p.G + a) * p.W + w] = result;
+    if (p.fuse) {
+        double *s_f = tiles;
+        s_f[wy * kWavesPerCta + lane] = result;
+        __syncthreads();
+        if (wy == 0 && w < p.W) {
             double acc = 0.0;
             for (int aa = 0; aa < p.G; ++aa) {
                 const int ig = aa / p.nt, it = aa - ig * p.nt;
@@ -456,7 +529,10 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
         PB_CHECK_LAUNCH(ctx);
     } else {
         p.fuse = fuse ? 1 : 0;
-        size_t smem = fuse ? (size_t)ay * kWavesPerCta * sizeof(double) : 0;
+        const size_t smem = ((size_t)V * 32 + (size_t)2 * ay * TNQ * 32) * sizeof(double);
+        if (smem > 200 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "thermal: nlevel=%d exceeds the shared-memory Planck tile", V);
+        if (smem > 48 * 1024)
+            PB_CUDA(ctx, cudaFuncSetAttribute(therm_toa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         therm_toa_kernel<<<grid, block, smem, ctx->stream>>>(p);
         PB_CHECK_LAUNCH(ctx);
     }

@@ -8,9 +8,9 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import PB_HOST, ReflectedArgs, ThermalArgs, TransitArgs, addr
+from ._lib import PB_HOST, ReflectedArgs, ShArgs, ThermalArgs, TransitArgs, addr
 
-__all__ = ["get_reflected_1d", "get_thermal_1d", "get_transit_1d"]
+__all__ = ["get_reflected_1d", "get_reflected_SH", "get_thermal_1d", "get_transit_1d"]
 
 
 _ZERO = np.zeros(())
@@ -113,6 +113,69 @@ def get_reflected_1d(nlevel, wno, nwno, numg, numt, dtau, tau, w0, cosb, gcos2, 
     if return_albedo:
         return xint, tuple(lv), alb
     return xint, tuple(lv)
+
+
+def get_reflected_SH(nlevel, nwno, numg, numt, dtau, tau, w0, cosb, ftau_cld, ftau_ray, f_deltaM,
+                     dtau_og, tau_og, w0_og, cosb_og, surf_reflect, ubar0, ubar1, cos_theta, F0PI,
+                     w_single_form, w_multi_form, psingle_form, w_single_rayleigh, w_multi_rayleigh,
+                     psingle_rayleigh, frac_a, frac_b, frac_c, constant_back, constant_forward, stream,
+                     b_top=0, flx=0, single_form=0, *, ctx=None, gweight=None, tweight=None,
+                     return_albedo=False, inplace_f_deltaM=True):
+    """CUDA replacement of fluxes.get_reflected_SH (picaso/fluxes.py:2675-2976), stream 2 or 4.
+
+    Returns ``(xint_at_top[numg,numt,nwno], flux)`` where ``flux`` is the reference's
+    all-zero ``[numg,numt,stream*nlevel,nwno]`` array (flx=0; a read-only zero view).
+    ``inplace_f_deltaM=True`` reproduces the reference's side effect on a writeable float64
+    ``f_deltaM`` argument (it is scaled once per angle when a TTHG form is active,
+    fluxes.py:2823-2824).  ``cosb`` is accepted and ignored, as in the reference.
+    """
+    if flx != 0:
+        raise NotImplementedError("get_reflected_SH(flx=1): layer fluxes are not implemented")
+    ctx = ctx or _lib.default_context()
+    nlayer = nlevel - 1
+    same = (dtau_og is dtau, w0_og is w0, tau_og is tau)
+    lay, ld = _layer_set([dtau, w0, ftau_cld, ftau_ray, f_deltaM, dtau_og, w0_og, cosb_og], nlayer, nwno)
+    lev, ldv = _layer_set([tau, tau_og], nlevel, nwno)
+    if ldv != ld:
+        lay = [np.ascontiguousarray(a) for a in lay]
+        lev = [np.ascontiguousarray(a) for a in lev]
+        ld = nwno
+    if same[0]: lay[5] = lay[0]
+    if same[1]: lay[6] = lay[1]
+    if same[2]: lev[1] = lev[0]
+    sr, f0, bt = _wvec(surf_reflect, nwno), _wvec(F0PI, nwno), _wvec(b_top, nwno)
+    u0 = np.ascontiguousarray(ubar0, dtype=np.float64).reshape(-1)
+    u1 = np.ascontiguousarray(ubar1, dtype=np.float64).reshape(-1)
+    xint = np.zeros((numg, numt, nwno))
+    alb = np.zeros(nwno) if return_albedo else None
+    drift = inplace_f_deltaM and (w_single_form == 0 or w_multi_form == 0) and \
+        isinstance(f_deltaM, np.ndarray) and f_deltaM.flags.writeable
+    fd_out = np.zeros((nlayer, nwno)) if drift else None
+    gw = tw = None
+    if return_albedo:
+        gw = np.ascontiguousarray(gweight, dtype=np.float64)
+        tw = np.ascontiguousarray(tweight, dtype=np.float64)
+    a = ShArgs()
+    a.nlayer, a.nwno, a.numg, a.numt, a.nbatch, a.ld = nlayer, nwno, numg, numt, 1, ld
+    (a.dtau, a.w0, a.ftau_cld, a.ftau_ray, a.f_deltaM, a.dtau_og, a.w0_og, a.cosb_og) = [addr(x) for x in lay]
+    a.tau, a.tau_og = addr(lev[0]), addr(lev[1])
+    a.surf_reflect, a.F0PI, a.b_top = addr(sr), addr(f0), addr(bt)
+    a.ubar0, a.ubar1, a.gweight, a.tweight = addr(u0), addr(u1), addr(gw), addr(tw)
+    a.cos_theta = float(cos_theta)
+    a.w_single_form, a.w_multi_form, a.psingle_form = int(w_single_form), int(w_multi_form), int(psingle_form)
+    a.w_single_rayleigh, a.w_multi_rayleigh, a.psingle_rayleigh = int(w_single_rayleigh), int(w_multi_rayleigh), int(psingle_rayleigh)
+    a.frac_a, a.frac_b, a.frac_c = float(frac_a), float(frac_b), float(frac_c)
+    a.constant_back, a.constant_forward = float(constant_back), float(constant_forward)
+    a.stream, a.flx, a.single_form = int(stream), 0, int(single_form)
+    a.xint_at_top, a.albedo, a.f_deltaM_out = addr(xint), addr(alb), addr(fd_out)
+    if nwno > 0:
+        ctx.check(ctx.lib.pb_reflected_sh(ctx.h, ctypes.byref(a), PB_HOST))
+        if drift:
+            f_deltaM[...] = fd_out
+    flux = np.broadcast_to(_ZERO, (numg, numt, stream * nlevel, nwno))
+    if return_albedo:
+        return xint, flux, alb
+    return xint, flux
 
 
 def get_thermal_1d(nlevel, wno, nwno, numg, numt, tlevel, dtau, w0, cosb, plevel, ubar1,

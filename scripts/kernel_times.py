@@ -1,0 +1,179 @@
+"""Device-resident kernel timings for the BASELINE.json configurations (run on the GPU box).
+
+    python scripts/kernel_times.py [--reps 50] [--only refl,thermal,transit,batch]
+
+Inputs are uploaded once; each timed launch rotates over enough distinct input sets to
+exceed the 126 MB L2.  Prints one JSON line per configuration with the achieved fraction
+of the measured HBM roofline (algorithmic bytes).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import picaso_b200 as pb  # noqa: E402
+from picaso_b200 import _lib, synth  # noqa: E402
+from picaso_b200._lib import PB_DEVICE, ReflectedArgs, ThermalArgs, TransitArgs  # noqa: E402
+
+L2_BYTES = 126e6
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timeit(ctx, launch, nsets, reps):
+    for i in range(3):
+        launch(i % nsets)
+    ctx.sync()
+    ctx.timer_start()
+    for i in range(reps):
+        launch(i % nsets)
+    return ctx.timer_stop() / reps
+
+
+def report(name, ms, alg_bytes, units, unit_name, extra=None):
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    out = {"config": name, "ms_per_launch": ms, "alg_bytes": alg_bytes, "GB/s": gbs,
+           "hbm_frac": gbs / hbm_peak(), unit_name + "/s": units / (ms * 1e-3)}
+    out.update(extra or {})
+    print(json.dumps(out), flush=True)
+
+
+def bench_reflected(ctx, L, W, G, reps, sp=3, batch=1, tag=""):
+    per_set = (9 * L + 2 * (L + 1) + 2) * 8 * W * batch
+    nsets = max(1, int(np.ceil(2 * L2_BYTES / per_set)))
+    nsets = min(nsets, 6)
+    lay = ("dtau", "w0", "cosb", "gcos2", "ftau_cld", "ftau_ray", "dtau_og", "w0_og", "cosb_og")
+    lev = ("tau", "tau_og")
+    wav = ("surf_reflect", "F0PI")
+    args, keep = [], []
+    d_x = ctx.dev_alloc(batch * G * W * 8)
+    d_a = ctx.dev_alloc(batch * W * 8)
+    for s in range(nsets):
+        ds = [synth.reflected_inputs(L=L, W=W, seed=50 + s * batch + b, ngauss=G) for b in range(batch)]
+        a = ReflectedArgs()
+        a.nlayer, a.nwno, a.numg, a.numt, a.nbatch, a.ld = L, W, G, 1, batch, W
+        for k in lay + lev + wav:
+            setattr(a, k, ctx.to_device(np.stack([d[k] for d in ds])))
+        d0 = ds[0]
+        vec = [np.ascontiguousarray(d0[k]).reshape(-1) for k in ("ubar0", "ubar1", "gweight", "tweight")]
+        keep.append(vec)
+        a.ubar0, a.ubar1, a.gweight, a.tweight = [_lib.addr(v) for v in vec]
+        a.cos_theta = d0["cos_theta"]
+        a.single_phase, a.multi_phase, a.toon_coefficients = sp, 0, 0
+        a.frac_a, a.frac_b, a.frac_c = d0["frac_a"], d0["frac_b"], d0["frac_c"]
+        a.constant_back, a.constant_forward = d0["constant_back"], d0["constant_forward"]
+        a.get_toa_intensity, a.get_lvl_flux = 1, 0
+        a.xint_at_top, a.albedo = d_x, d_a
+        args.append(a)
+    fn = ctx.lib.pb_reflected_toon_1d
+    ms = timeit(ctx, lambda i: ctx.check(fn(ctx.h, ctypes.byref(args[i]), PB_DEVICE)), nsets, reps)
+    alg = ((9 * L + 2 * (L + 1) + 2) * 8 + G * 8) * W * batch
+    report("reflected_toon L=%d W=%d G=%d batch=%d sp=%d%s" % (L, W, G, batch, sp, tag), ms, alg,
+           W * batch, "wave-points", {"nsets": nsets})
+    for a in args:
+        for k in lay + lev + wav:
+            ctx.dev_free(getattr(a, k))
+    ctx.dev_free(d_x)
+    ctx.dev_free(d_a)
+
+
+def bench_thermal(ctx, L, W, G, reps, batch=1, calc_type=0, levels=False):
+    per_set = (3 * L + 3) * 8 * W * batch
+    nsets = min(6, max(1, int(np.ceil(2 * L2_BYTES / per_set))))
+    args, keep = [], []
+    V = L + 1
+    d_f = ctx.dev_alloc(batch * G * W * 8)
+    d_t = ctx.dev_alloc(batch * W * 8)
+    d_lv = [ctx.dev_alloc(batch * G * V * W * 8) for _ in range(4)] if levels else None
+    for s in range(nsets):
+        ds = [synth.thermal_inputs(L=L, W=W, seed=70 + s * batch + b, ngauss=G) for b in range(batch)]
+        a = ThermalArgs()
+        a.nlayer, a.nwno, a.numg, a.numt, a.nbatch, a.ld = L, W, G, 1, batch, W
+        for k in ("dtau", "w0", "cosb"):
+            setattr(a, k, ctx.to_device(np.stack([d[k] for d in ds])))
+        d0 = ds[0]
+        a.wno, a.dwno = ctx.to_device(d0["wno"]), ctx.to_device(d0["dwno"])
+        a.surf_reflect = None
+        vec = [np.ascontiguousarray(np.stack([d["tlevel"] for d in ds])),
+               np.ascontiguousarray(np.stack([d["plevel"] for d in ds])),
+               np.ascontiguousarray(d0["ubar1"]).reshape(-1), np.ascontiguousarray(d0["gweight"]),
+               np.ascontiguousarray(d0["tweight"])]
+        keep.append(vec)
+        a.tlevel, a.plevel, a.ubar1, a.gweight, a.tweight = [_lib.addr(v) for v in vec]
+        a.hard_surface, a.calc_type = 0, calc_type
+        a.flux_at_top, a.thermal = d_f, d_t
+        if levels:
+            a.flux_minus, a.flux_plus, a.flux_minus_mdpt, a.flux_plus_mdpt = d_lv
+        args.append(a)
+    fn = ctx.lib.pb_thermal_toon_1d
+    ms = timeit(ctx, lambda i: ctx.check(fn(ctx.h, ctypes.byref(args[i]), PB_DEVICE)), nsets, reps)
+    alg = ((3 * L + 3) * 8 + G * 8 + (4 * G * V * 8 if levels else 0)) * W * batch
+    report("thermal_toon L=%d W=%d G=%d batch=%d calc_type=%d levels=%d" % (L, W, G, batch, calc_type, levels),
+           ms, alg, W * batch, "wave-points", {"nsets": nsets})
+    for a in args:
+        for k in ("dtau", "w0", "cosb", "wno", "dwno"):
+            ctx.dev_free(getattr(a, k))
+    for p in [d_f, d_t] + (d_lv or []):
+        ctx.dev_free(p)
+
+
+def bench_transit(ctx, L, W, reps):
+    per_set = L * 8 * W
+    nsets = min(8, max(1, int(np.ceil(2 * L2_BYTES / per_set))))
+    args, keep = [], []
+    d_F = ctx.dev_alloc(W * 8)
+    for s in range(nsets):
+        d = synth.transit_inputs(L=L, W=W, seed=90 + s)
+        a = TransitArgs()
+        a.nlevel, a.nwno, a.nbatch, a.ld = L + 1, W, 1, W
+        a.DTAU = ctx.to_device(d["DTAU"])
+        vec = [np.ascontiguousarray(d[k], dtype=np.float64) for k in ("z", "dz", "player", "tlayer", "mmw", "colden")]
+        keep.append(vec)
+        a.z, a.dz, a.player, a.tlayer, a.mmw, a.colden = [_lib.addr(v) for v in vec]
+        a.rstar, a.k_b, a.amu, a.F = d["rstar"], d["k_b"], d["amu"], d_F
+        args.append(a)
+    fn = ctx.lib.pb_transit_1d
+    ms = timeit(ctx, lambda i: ctx.check(fn(ctx.h, ctypes.byref(args[i]), PB_DEVICE)), nsets, reps)
+    report("transit L=%d W=%d" % (L, W), ms, (L + 1) * 8 * W, W, "wave-points", {"nsets": nsets})
+    for a in args:
+        ctx.dev_free(a.DTAU)
+    ctx.dev_free(d_F)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=50)
+    ap.add_argument("--only", default="refl,thermal,transit,batch")
+    a = ap.parse_args()
+    only = set(a.only.split(","))
+    ctx = pb.Context(0)
+    print(json.dumps({"device": ctx.device_name(), "hbm_peak_gbs": hbm_peak()}), flush=True)
+    if "refl" in only:
+        bench_reflected(ctx, 60, 300, 5, a.reps, sp=1, tag=" (cfg1)")
+        bench_reflected(ctx, 60, 10000, 5, a.reps, tag=" (headline)")
+        bench_reflected(ctx, 60, 10000, 5, a.reps, sp=1, tag=" (headline OTHG)")
+        bench_reflected(ctx, 60, 196000, 5, max(5, a.reps // 5), tag=" (cfg3 shape, Toon)")
+    if "thermal" in only:
+        bench_thermal(ctx, 90, 10000, 5, a.reps)
+        bench_thermal(ctx, 90, 10000, 5, max(5, a.reps // 5), calc_type=1, levels=True)
+        bench_thermal(ctx, 90, 100000, 5, max(5, a.reps // 5))
+    if "transit" in only:
+        bench_transit(ctx, 80, 50000, a.reps)
+    if "batch" in only:
+        bench_thermal(ctx, 60, 2000, 5, max(5, a.reps // 5), batch=128)
+        bench_reflected(ctx, 60, 10000, 5, max(5, a.reps // 5), batch=8, tag=" (8 spectra/launch)")
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

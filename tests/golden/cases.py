@@ -106,3 +106,50 @@ def transit_args(d):
     """positional argument list of get_transit_1d (fluxes.py:2582-2583)."""
     return (d["z"], d["dz"], d["nlevel"], d["nwno"], d["rstar"], d["mmw"], d["k_b"], d["amu"],
             d["player"], d["tlayer"], d["colden"], d["DTAU"])
+
+
+def sh_cases():
+    """get_reflected_SH (fluxes.py:2675): forms = (w_single_form, w_multi_form, psingle_form,
+    w_single_rayleigh, w_multi_rayleigh, psingle_rayleigh); 0 = TTHG / off, 1 = OTHG / on."""
+    cases = {}
+    forms_list = {"othg": (1, 1, 1, 1, 1, 1), "tthg": (0, 0, 0, 1, 1, 1), "mix1": (1, 0, 0, 0, 0, 0),
+                  "mix2": (0, 1, 1, 1, 0, 1)}
+    for stream in (2, 4):
+        for fname, forms in forms_list.items():
+            for sf in (0, 1):
+                cases[f"sh{stream}_{fname}_sf{sf}"] = dict(
+                    build=dict(L=18, W=24, seed=300 + stream, stream=stream, phase=0.5), forms=forms,
+                    stream=stream, single_form=sf, surf_reflect=0.2)
+        # BASELINE config 3 shape (60 layers, 5 angles, SH, "Raman on" = w0 with a Raman factor) at
+        # reduced wave count; OTHG is drift-free, TTHG is the reference default
+        cases[f"sh{stream}_cfg3_othg"] = dict(build=dict(L=60, W=48, seed=1003, stream=stream),
+                                              forms=(1, 1, 1, 1, 1, 1), stream=stream, single_form=0,
+                                              surf_reflect=0.0)
+        cases[f"sh{stream}_cfg3_tthg"] = dict(build=dict(L=60, W=48, seed=1003, stream=stream),
+                                              forms=(0, 0, 0, 1, 1, 1), stream=stream, single_form=0,
+                                              surf_reflect=0.0)
+        cases[f"sh{stream}_no_deltaM"] = dict(build=dict(L=9, W=33, seed=310, stream=stream,
+                                                         delta_eddington=False, ngauss=7, phase=1.7),
+                                              forms=(0, 0, 0, 1, 1, 1), stream=stream, single_form=0,
+                                              surf_reflect=0.5)
+        cases[f"sh{stream}_one_layer"] = dict(build=dict(L=1, W=3, seed=311, stream=stream),
+                                              forms=(1, 1, 1, 1, 1, 1), stream=stream, single_form=0,
+                                              surf_reflect=0.3)
+    return cases
+
+
+def build_sh(case):
+    d = synth.reflected_inputs(**case["build"])
+    d["surf_reflect"] = np.full(d["nwno"], case["surf_reflect"])
+    return d
+
+
+def sh_args(d, case):
+    """positional argument list of get_reflected_SH (fluxes.py:2675-2679); f_deltaM is copied
+    because the reference modifies it in place."""
+    f = case["forms"]
+    return (d["nlevel"], d["nwno"], d["numg"], d["numt"], d["dtau"], d["tau"], d["w0"], d["cosb"],
+            d["ftau_cld"], d["ftau_ray"], d["f_deltaM"].copy(), d["dtau_og"], d["tau_og"], d["w0_og"],
+            d["cosb_og"], d["surf_reflect"], d["ubar0"], d["ubar1"], d["cos_theta"], d["F0PI"],
+            f[0], f[1], f[2], f[3], f[4], f[5], d["frac_a"], d["frac_b"], d["frac_c"],
+            d["constant_back"], d["constant_forward"], case["stream"], 0.0, 0, case["single_form"])

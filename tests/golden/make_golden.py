@@ -51,6 +51,18 @@ def main():
     print("thermal:", len(out), "arrays")
 
     out = {}
+    for name, case in C.sh_cases().items():
+        d = C.build_sh(case)
+        a = C.sh_args(d, case)
+        xint, _ = F.get_reflected_SH(*a)
+        out[name + "/xint"] = xint
+        out[name + "/albedo"] = D.compress_disco(d["nwno"], d["cos_theta"], xint, d["gweight"],
+                                                 d["tweight"], d["F0PI"])
+        out[name + "/f_deltaM_after"] = a[10]   # the reference scaled it in place (Appendix A1)
+    np.savez_compressed(os.path.join(HERE, "sh.npz"), ref_commit=REF_COMMIT, **out)
+    print("sh:", len(out), "arrays")
+
+    out = {}
     from picaso_b200 import synth
     for name, kw in C.transit_cases().items():
         d = synth.transit_inputs(**kw)

@@ -65,6 +65,21 @@ def test_thermal_vs_golden_and_oracle(name):
                        what="compress_thermal 4-D")
 
 
+@pytest.mark.parametrize("name", sorted(C.sh_cases()))
+def test_reflected_sh_vs_golden_and_oracle(name):
+    g = golden("sh")
+    case = C.sh_cases()[name]
+    d = C.build_sh(case)
+    a = C.sh_args(d, case)
+    xint, flux, alb = pb.get_reflected_SH(*a, gweight=d["gweight"], tweight=d["tweight"], return_albedo=True)
+    assert_close(xint, g[name + "/xint"], RTOL, name + " xint vs reference")
+    assert_close(alb, g[name + "/albedo"], RTOL, name + " fused albedo vs reference")
+    assert_close(a[10], g[name + "/f_deltaM_after"], 1e-13, name + " f_deltaM side effect")
+    assert flux.shape == (d["numg"], d["numt"], case["stream"] * d["nlevel"], d["nwno"]) and not flux.any()
+    ox, _ = oracle.get_reflected_SH(*C.sh_args(d, case))
+    assert_close(xint, ox, RTOL, name + " xint vs oracle")
+
+
 @pytest.mark.parametrize("name", sorted(C.transit_cases()))
 def test_transit_vs_golden_and_oracle(name):
     g = golden("transit")

@@ -39,6 +39,17 @@ def test_thermal(name):
             assert_level_close(a, g[name + "/" + k], what=name + " " + k)
 
 
+@pytest.mark.parametrize("name", sorted(C.sh_cases()))
+def test_reflected_sh(name):
+    g = golden("sh")
+    case = C.sh_cases()[name]
+    d = C.build_sh(case)
+    a = C.sh_args(d, case)
+    xint, _ = oracle.get_reflected_SH(*a)
+    assert_close(xint, g[name + "/xint"], 1e-9, name + " xint")
+    assert_close(a[10], g[name + "/f_deltaM_after"], 1e-14, name + " in-place f_deltaM drift")
+
+
 @pytest.mark.parametrize("name", sorted(C.transit_cases()))
 def test_transit(name):
     g = golden("transit")
