@@ -153,3 +153,98 @@ def transit_inputs(L=80, W=50000, seed=1004):
     dtau, _, _ = _layer_fields(rng, L, W)
     return dict(z=z, dz=dz, nlevel=V, nwno=W, rstar=6.957e10, mmw=mmw, k_b=k_b, amu=amu,
                 player=plevel, tlayer=tlevel, colden=colden, DTAU=dtau)
+
+
+# ---------------------------------------------------------------------------------------
+# synthetic opacity "database" + atmosphere profile for the opacity path (a9-a11)
+# ---------------------------------------------------------------------------------------
+MOLECULES = ["H2O", "CH4", "CO", "CO2", "NH3", "Na", "K", "TiO", "VO", "H2S", "PH3", "FeH"]
+CONTINUUM = [("H2", "H2"), ("H2", "He"), ("H2", "CH4"), ("H-", "bf"), ("H-", "ff"), ("H2-", "")]
+RAYLEIGH = ["H2", "He", "CH4"]
+
+
+def opacity_database(W=200, nmol=4, seed=2001, nT=12, nP=10, nTc=15, ragged=True,
+                     wave_range=(0.3, 1.0)):
+    """Synthetic stand-in for the reference's sqlite opacity DB (opacity_factory.py:622-668):
+    per-molecule cross-section rows on a (T-major, P-minor) grid with `nc_p[it]` pressures per
+    temperature (ragged like the real 1060/1460 grids when `ragged`), continuum tables on their
+    own temperature grid, wavenumber grid ascending in cm^-1."""
+    rng = np.random.default_rng(seed)
+    wno = np.sort(1e4 / np.linspace(wave_range[1], wave_range[0], W))
+    temps = np.round(np.geomspace(75.0, 4000.0, nT), 3)
+    pressures = np.geomspace(1e-6, 3e3, nP)           # bar
+    nc_p = np.full(nT, nP)
+    if ragged:
+        nc_p[-3:] = nP - 2                            # hottest temperatures lack the highest pressures
+        nc_p[0] = nP - 1
+    pt = []                                           # (ptid (1-based), pressure, temperature)
+    for it, T in enumerate(temps):
+        for ip in range(nc_p[it]):
+            pt.append((len(pt) + 1, float(pressures[ip]), float(T)))
+    npt = len(pt)
+    mols = MOLECULES[:nmol]
+    lgT = np.log10(np.array([p[2] for p in pt]))[:, None]
+    lgP = np.log10(np.array([p[1] for p in pt]))[:, None]
+    tables = {}
+    for i, m in enumerate(mols):
+        band = np.sin(np.linspace(0, 6 + i, W) + i)[None, :]
+        lk = -24.0 + 2.5 * band + 0.8 * (lgT - 2.5) + 0.15 * lgP + 0.3 * rng.standard_normal((npt, W))
+        k = 10.0 ** lk
+        k[rng.random((npt, W)) < 0.01] = 0.0          # exercised by the reference's 1e-50 guard
+        tables[m] = k
+    cia_temps = np.round(np.geomspace(75.0, 3500.0, nTc), 2)
+    cont = {}
+    for a, b in CONTINUUM:
+        lk = -7.0 + np.cos(np.linspace(0, 4, W))[None, :] + 0.5 * np.log10(cia_temps / 300.0)[:, None] \
+            + 0.2 * rng.standard_normal((nTc, W))
+        if a in ("H-", "H2-"):
+            lk = lk - 18.0
+        cont[a + b] = 10.0 ** lk
+    return dict(wno=wno, nwno=W, temps=temps, pressures=pressures, nc_p=nc_p, pt_pairs=pt,
+                molecules=mols, tables=tables, cia_temps=cia_temps, continuum=cont,
+                continuum_molecules=list(CONTINUUM), rayleigh_molecules=list(RAYLEIGH))
+
+
+def raman_table(seed=2002, n=56):
+    """Synthetic H2 Raman transitions with the structure of Oklopcic+2016 table 2 (ji, C, deltanu);
+    every fourth row is a Rayleigh (deltanu = 0) term."""
+    rng = np.random.default_rng(seed)
+    ji = np.repeat(np.arange(10), 6)[:n]
+    c = 10.0 ** rng.uniform(-48, -44.5, n)
+    dnu = rng.choice([354.6, 587.4, 814.9, 4161.2, 4500.2, -354.6, -587.4], n)
+    dnu[::4] = 0.0
+    return ji.astype(np.int64), c, dnu
+
+
+def atmosphere_profile(db, L=12, seed=2003, cloudy=True):
+    """Per-layer scalars compute_opacity multiplies by (atmsetup.py: level/layer T,P, mixing
+    ratios, mmw, column density) for a hot-Jupiter-like profile, CGS units."""
+    rng = np.random.default_rng(seed)
+    W = db["nwno"]
+    pconv = 1e6
+    plevel = np.geomspace(3e-6, 80.0, L + 1) * pconv           # dyn/cm2
+    tlevel = 300.0 + 1400.0 * (np.log10(plevel / pconv) + 6) / 8 + 30 * rng.standard_normal(L + 1)
+    tlevel = np.clip(tlevel, 90.0, 3800.0)
+    tlayer = 0.5 * (tlevel[1:] + tlevel[:-1])
+    player = np.sqrt(plevel[1:] * plevel[:-1])
+    gravity = 2500.0                                            # cm/s2
+    mmw = np.full(L, 2.3) + 0.01 * rng.standard_normal(L)
+    colden = (plevel[1:] - plevel[:-1]) / gravity
+    species = sorted(set(db["molecules"]) | {"H2", "He", "CH4", "H", "H-"})
+    mix = {s: 10.0 ** rng.uniform(-8, -3, L) for s in species}
+    mix["H2"] = np.full(L, 0.84)
+    mix["He"] = np.full(L, 0.155)
+    mix["H"] = 10.0 ** rng.uniform(-9, -6, L)
+    mix["H-"] = 10.0 ** rng.uniform(-14, -11, L)
+    electrons = 10.0 ** rng.uniform(-12, -8, L)
+    if cloudy:
+        lgrid = np.arange(L)[:, None] / max(L - 1, 1)
+        opd = 10.0 ** (-3 + 3 * np.exp(-((lgrid - 0.6) / 0.15) ** 2) + 0.1 * rng.standard_normal((L, W)))
+        cw0 = np.clip(0.9 + 0.05 * rng.standard_normal((L, W)), 0.05, 0.999)
+        cg0 = np.clip(0.6 + 0.1 * rng.standard_normal((L, W)), 0.0, 0.9)
+    else:
+        opd = np.zeros((L, W)); cw0 = np.zeros((L, W)); cg0 = np.zeros((L, W))
+    return dict(nlayer=L, nlevel=L + 1, pconv=pconv, rgas=8.31446261815324e7, amu=1.66053906660e-24,
+                k_b=1.380649e-16, plevel=plevel, tlevel=tlevel, player=player, tlayer=tlayer,
+                gravity=gravity, mmw=mmw, colden=colden, mixingratios=mix, electrons=electrons,
+                cloud_opd=opd, cloud_w0=cw0, cloud_g0=cg0)

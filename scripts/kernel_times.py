@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import picaso_b200 as pb  # noqa: E402
 from picaso_b200 import _lib, synth  # noqa: E402
-from picaso_b200._lib import PB_DEVICE, ReflectedArgs, ThermalArgs, TransitArgs  # noqa: E402
+from picaso_b200._lib import PB_DEVICE, ReflectedArgs, ShArgs, ThermalArgs, TransitArgs  # noqa: E402
 
 L2_BYTES = 126e6
 
@@ -80,6 +80,44 @@ def bench_reflected(ctx, L, W, G, reps, sp=3, batch=1, tag=""):
     alg = ((9 * L + 2 * (L + 1) + 2) * 8 + G * 8) * W * batch
     report("reflected_toon L=%d W=%d G=%d batch=%d sp=%d%s" % (L, W, G, batch, sp, tag), ms, alg,
            W * batch, "wave-points", {"nsets": nsets})
+    for a in args:
+        for k in lay + lev + wav:
+            ctx.dev_free(getattr(a, k))
+    ctx.dev_free(d_x)
+    ctx.dev_free(d_a)
+
+
+def bench_sh(ctx, L, W, G, reps, stream=4, forms=(0, 0, 0, 1, 1, 1)):
+    per_set = (9 * L + 2 * (L + 1) + 2) * 8 * W
+    nsets = min(6, max(1, int(np.ceil(2 * L2_BYTES / per_set))))
+    lay = ("dtau", "w0", "ftau_cld", "ftau_ray", "f_deltaM", "dtau_og", "w0_og", "cosb_og")
+    lev = ("tau", "tau_og")
+    wav = ("surf_reflect", "F0PI")
+    args, keep = [], []
+    d_x = ctx.dev_alloc(G * W * 8)
+    d_a = ctx.dev_alloc(W * 8)
+    for s_ in range(nsets):
+        d = synth.reflected_inputs(L=L, W=W, seed=150 + s_, ngauss=G, stream=stream)
+        a = ShArgs()
+        a.nlayer, a.nwno, a.numg, a.numt, a.nbatch, a.ld = L, W, G, 1, 1, W
+        for k in lay + lev + wav:
+            setattr(a, k, ctx.to_device(d[k]))
+        vec = [np.ascontiguousarray(d[k]).reshape(-1) for k in ("ubar0", "ubar1", "gweight", "tweight")]
+        keep.append(vec)
+        a.ubar0, a.ubar1, a.gweight, a.tweight = [_lib.addr(v) for v in vec]
+        a.cos_theta = d["cos_theta"]
+        (a.w_single_form, a.w_multi_form, a.psingle_form, a.w_single_rayleigh, a.w_multi_rayleigh,
+         a.psingle_rayleigh) = forms
+        a.frac_a, a.frac_b, a.frac_c = d["frac_a"], d["frac_b"], d["frac_c"]
+        a.constant_back, a.constant_forward = d["constant_back"], d["constant_forward"]
+        a.stream, a.flx, a.single_form = stream, 0, 0
+        a.xint_at_top, a.albedo = d_x, d_a
+        args.append(a)
+    fn = ctx.lib.pb_reflected_sh
+    ms = timeit(ctx, lambda i: ctx.check(fn(ctx.h, ctypes.byref(args[i]), PB_DEVICE)), nsets, reps)
+    alg = ((9 * L + 2 * (L + 1) + 2) * 8 + G * 8) * W
+    report("reflected_SH%d L=%d W=%d G=%d forms=%s" % (stream, L, W, G, "".join(map(str, forms))), ms, alg,
+           W, "wave-points", {"nsets": nsets})
     for a in args:
         for k in lay + lev + wav:
             ctx.dev_free(getattr(a, k))
@@ -153,7 +191,7 @@ def bench_transit(ctx, L, W, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=50)
-    ap.add_argument("--only", default="refl,thermal,transit,batch")
+    ap.add_argument("--only", default="refl,sh,thermal,transit,batch")
     a = ap.parse_args()
     only = set(a.only.split(","))
     ctx = pb.Context(0)
@@ -163,6 +201,11 @@ def main():
         bench_reflected(ctx, 60, 10000, 5, a.reps, tag=" (headline)")
         bench_reflected(ctx, 60, 10000, 5, a.reps, sp=1, tag=" (headline OTHG)")
         bench_reflected(ctx, 60, 196000, 5, max(5, a.reps // 5), tag=" (cfg3 shape, Toon)")
+    if "sh" in only:
+        bench_sh(ctx, 60, 10000, 5, max(5, a.reps // 5), stream=2)
+        bench_sh(ctx, 60, 10000, 5, max(5, a.reps // 5), stream=4)
+        bench_sh(ctx, 60, 196000, 5, 5, stream=4)
+        bench_sh(ctx, 60, 196000, 5, 5, stream=4, forms=(1, 1, 1, 1, 1, 1))
     if "thermal" in only:
         bench_thermal(ctx, 90, 10000, 5, a.reps)
         bench_thermal(ctx, 90, 10000, 5, max(5, a.reps // 5), calc_type=1, levels=True)

@@ -153,3 +153,17 @@ def sh_args(d, case):
             d["cosb_og"], d["surf_reflect"], d["ubar0"], d["ubar1"], d["cos_theta"], d["F0PI"],
             f[0], f[1], f[2], f[3], f[4], f[5], d["frac_a"], d["frac_b"], d["frac_c"],
             d["constant_back"], d["constant_forward"], case["stream"], 0.0, 0, case["single_form"])
+
+
+def optics_cases():
+    """opacity path (a9-a11): RetrieveOpacities.get_opacities ('linear' = bilinear in 1/T, log10 P;
+    'nearest' = the reference default) + compute_opacity + compute_raman."""
+    return {
+        "opt_linear_raman": dict(db=dict(W=60, nmol=4, seed=2001), atm=dict(L=12, seed=2003), query="linear",
+                                 raman=0, stream=2, dedd=True),
+        "opt_nearest_noraman": dict(db=dict(W=45, nmol=3, seed=2011), atm=dict(L=9, seed=2013), query="nearest",
+                                    raman=2, stream=4, dedd=True),
+        "opt_linear_clear_nodedd": dict(db=dict(W=33, nmol=2, seed=2021, ragged=False),
+                                        atm=dict(L=7, seed=2023, cloudy=False), query="linear", raman=2,
+                                        stream=2, dedd=False),
+    }
