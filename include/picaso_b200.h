@@ -175,6 +175,61 @@ int pb_compress_disco(pb_ctx *ctx, int nwno, double cos_theta, const double *xin
 int pb_compress_thermal(pb_ctx *ctx, int64_t n, const double *flux_at_top, const double *gweight,
                         int ng, const double *tweight, int nt, double *out, int memspace);
 
+/* ---- opacity state + per-layer optical properties -------------------------------------- */
+/* Device-resident replacement of the opacity data the reference re-reads from sqlite on every
+ * call (RetrieveOpacities, picaso/optics.py:1877-2368).  Tables are uploaded once; all are
+ * [rows][nwno] float64 on the wavenumber grid of the connection.
+ *   molecular  : rows = (T,P) grid points in ptid order (T-major), raw cross-sections as stored
+ *                in the DB.  store bit 1 keeps the raw rows (nearest-neighbour queries, the
+ *                reference default), bit 2 keeps log10(k != 0 ? k : 1e-50) rows (bilinear
+ *                queries, optics.py:2281-2293); 3 keeps both.
+ *   continuum  : rows = unique CIA temperatures, ascending (optics.py:2298)
+ *   rayleigh   : one row of cross-sections per scatterer (optics.py:2041-2046)
+ *   raman      : Oklopcic+2016 transitions (c, ji, deltanu) + stellar_shifts[nwno][ntrans]
+ *                (optics.py:467-494, :2370-2402) */
+typedef struct pb_optab pb_optab;
+int pb_optab_create(pb_ctx *ctx, int nwno, int nmol, int ncont, int nray, pb_optab **out);
+int pb_optab_destroy(pb_ctx *ctx, pb_optab *tab);
+int pb_optab_set_molecular(pb_ctx *ctx, pb_optab *tab, int imol, const double *table, int npt, int store);
+int pb_optab_set_continuum(pb_ctx *ctx, pb_optab *tab, int icont, const double *table, int ntemp);
+int pb_optab_set_rayleigh(pb_ctx *ctx, pb_optab *tab, int iray, const double *sigma);
+int pb_optab_set_raman(pb_ctx *ctx, pb_optab *tab, const double *wno, int ntrans, const double *c,
+                       const int *ji, const double *deltanu, const double *stellar_shifts);
+int pb_optab_bytes(const pb_optab *tab, size_t *bytes);
+
+/* replaces get_opacities / get_opacities_nearest (optics.py:2241-2368) + compute_opacity
+ * (optics.py:147-431, ngauss = 1, test_mode = None) + compute_raman (optics.py:435-494) in one
+ * kernel.  All per-layer vectors are HOST pointers (O(nlayer) data); only the optional cloud
+ * arrays, raman_pollack and the 13 outputs follow `memspace`.  Layer multipliers are formed by
+ * the caller exactly as the reference parenthesises them, e.g. mol_scale = colden*x_mol/mmw,
+ * cont_scale = COEF1*x_a*x_b (or the H-, H2- expressions of optics.py:175-213). */
+typedef struct pb_opacity_args {
+    int nlayer;
+    int query;                 /* 0 nearest (pt_index[l][0]), 1 bilinear */
+    const int *pt_index;       /* [nlayer][4] 0-based table rows in the reference's term order:
+                                  (t_low,p_low), (t_hi,p_low), (t_hi,p_hi), (t_low,p_hi) */
+    const double *weights;     /* [nlayer][4] (1-t)(1-p), t(1-p), t p, (1-t) p   (query = 1) */
+    const double *mol_scale;   /* [nmol][nlayer] */
+    const int *cont_index;     /* [nlayer] row of the nearest CIA temperature */
+    const double *cont_scale;  /* [ncont][nlayer] */
+    const double *ray_scale;   /* [nray][nlayer] */
+    int raman;                 /* 0 oklopcic, 1 pollack, 2 none  (justdoit.py:5512-5658) */
+    const double *jfrac;       /* [10][nlayer] j_fraction(J, T_layer), optics.py:570 (raman = 0) */
+    const double *raman_pollack; /* [nwno] (raman = 1), follows memspace */
+    const double *cloud_opd, *cloud_w0, *cloud_g0; /* [nlayer][cloud_ld] or NULL, follow memspace */
+    int64_t cloud_ld;
+    double fthin_cld;
+    int do_holes;
+    int stream;                /* 2 or 4: exponent of the delta-Eddington f = COSB**stream */
+    int delta_eddington;
+    /* outputs in the reference's return order (optics.py:423-431); NULL = not wanted.
+     * TAU, TAU_OG are [nlayer+1][nwno], the others [nlayer][nwno] */
+    double *DTAU, *TAU, *W0, *COSB, *ftau_cld, *ftau_ray, *GCOS2, *DTAU_OG, *TAU_OG, *W0_OG, *COSB_OG,
+        *W0_no_raman, *f_deltaM;
+} pb_opacity_args;
+
+int pb_compute_opacity(pb_ctx *ctx, pb_optab *tab, const pb_opacity_args *args, int memspace);
+
 /* ---- self test ------------------------------------------------------------------------- */
 /* evaluates the kernels' branch-free exp() and 1/x on x[n] (host pointers); test hook */
 int pb_selftest_math(pb_ctx *ctx, const double *x, int n, double *exp_out, double *rcp_out);

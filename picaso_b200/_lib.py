@@ -49,6 +49,17 @@ class ShArgs(ctypes.Structure):
         [(n, c_vp) for n in ("xint_at_top", "albedo", "f_deltaM_out")])
 
 
+class OpacityArgs(ctypes.Structure):
+    _fields_ = (
+        [("nlayer", c_int), ("query", c_int), ("pt_index", c_vp), ("weights", c_vp), ("mol_scale", c_vp),
+         ("cont_index", c_vp), ("cont_scale", c_vp), ("ray_scale", c_vp), ("raman", c_int), ("jfrac", c_vp),
+         ("raman_pollack", c_vp), ("cloud_opd", c_vp), ("cloud_w0", c_vp), ("cloud_g0", c_vp),
+         ("cloud_ld", c_i64), ("fthin_cld", c_dbl), ("do_holes", c_int), ("stream", c_int),
+         ("delta_eddington", c_int)] +
+        [(n, c_vp) for n in ("DTAU", "TAU", "W0", "COSB", "ftau_cld", "ftau_ray", "GCOS2", "DTAU_OG", "TAU_OG",
+                             "W0_OG", "COSB_OG", "W0_no_raman", "f_deltaM")])
+
+
 class ThermalArgs(ctypes.Structure):
     _fields_ = (
         [(n, c_int) for n in ("nlayer", "nwno", "numg", "numt", "nbatch")] + [("ld", c_i64)] +
@@ -95,6 +106,14 @@ SYMBOLS = {
                                   c_int]),
     "pb_compress_thermal": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int]),
     "pb_selftest_math": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
+    "pb_optab_create": (c_int, [c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
+    "pb_optab_destroy": (c_int, [c_vp, c_vp]),
+    "pb_optab_set_molecular": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int]),
+    "pb_optab_set_continuum": (c_int, [c_vp, c_vp, c_int, c_vp, c_int]),
+    "pb_optab_set_rayleigh": (c_int, [c_vp, c_vp, c_int, c_vp]),
+    "pb_optab_set_raman": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "pb_optab_bytes": (c_int, [c_vp, ctypes.POINTER(ctypes.c_size_t)]),
+    "pb_compute_opacity": (c_int, [c_vp, c_vp, ctypes.POINTER(OpacityArgs), c_int]),
 }
 
 _lib = None

@@ -8,7 +8,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import PB_HOST, ReflectedArgs, ShArgs, ThermalArgs, TransitArgs, addr
+from ._lib import PB_DEVICE, PB_HOST, ReflectedArgs, ShArgs, ThermalArgs, TransitArgs, addr
 
 __all__ = ["get_reflected_1d", "get_reflected_SH", "get_thermal_1d", "get_transit_1d"]
 
@@ -39,6 +39,26 @@ def _layer_set(arrs, nrows, nwno):
     return out, lds.pop()
 
 
+def _is_dev(a):
+    return hasattr(a, "ptr") and hasattr(a, "ctx")
+
+
+def _resolve(ctx, arrs, nrows, nwno, wave_vecs=()):
+    """Normalise a group of [rows, nwno] inputs.  Host (numpy) inputs -> (addresses, ld, PB_HOST,
+    wave-vector addresses, keepalive).  DeviceArray inputs (picaso_b200.optics.compute_opacity with
+    device_outputs=True) -> PB_DEVICE pointers; the small per-wavelength vectors are uploaded."""
+    if any(_is_dev(a) for a in arrs):
+        if not all(_is_dev(a) for a in arrs):
+            raise TypeError("either all or none of the layer/level arrays may be DeviceArrays")
+        for a in arrs:
+            if tuple(a.shape[:2]) not in ((nrows, nwno), (nrows + 1, nwno)):
+                raise ValueError("DeviceArray of shape %s does not match (%d|%d, %d)" % (a.shape, nrows, nrows + 1, nwno))
+        from .optics import DeviceArray
+        vecs = [None if v is None else DeviceArray.from_numpy(ctx, v) for v in wave_vecs]
+        return [a.ptr for a in arrs], nwno, PB_DEVICE, [None if v is None else v.ptr for v in vecs], vecs
+    return None
+
+
 def _wvec(x, n):
     """scalar or [n] -> contiguous float64 [n] (surf_reflect/b_top arrive either way)."""
     a = np.asarray(x, dtype=np.float64)
@@ -63,6 +83,12 @@ def get_reflected_1d(nlevel, wno, nwno, numg, numt, dtau, tau, w0, cosb, gcos2, 
     """
     ctx = ctx or _lib.default_context()
     nlayer = nlevel - 1
+    if any(_is_dev(x) for x in (dtau, tau, w0, cosb, gcos2, ftau_cld, ftau_ray, dtau_og, tau_og, w0_og, cosb_og)):
+        return _reflected_device(ctx, nlevel, nwno, numg, numt, [dtau, w0, cosb, gcos2, ftau_cld, ftau_ray,
+                                 dtau_og, w0_og, cosb_og], [tau, tau_og], surf_reflect, ubar0, ubar1, cos_theta,
+                                 F0PI, single_phase, multi_phase, frac_a, frac_b, frac_c, constant_back,
+                                 constant_forward, get_toa_intensity, get_lvl_flux, toon_coefficients, b_top,
+                                 gweight, tweight, return_albedo)
     same = dict(dtau_og=dtau_og is dtau, w0_og=w0_og is w0, cosb_og=cosb_og is cosb,
                 tau_og=tau_og is tau)
     lay, ld = _layer_set([dtau, w0, cosb, gcos2, ftau_cld, ftau_ray, dtau_og, w0_og, cosb_og],
@@ -112,6 +138,59 @@ def get_reflected_1d(nlevel, wno, nwno, numg, numt, dtau, tau, w0, cosb, gcos2, 
         lv = [z, z, z, z]
     if return_albedo:
         return xint, tuple(lv), alb
+    return xint, tuple(lv)
+
+
+def _zero_or_vec(x, n):
+    """None for an all-zero scalar (the C side treats NULL surf_reflect / b_top as 0), else [n]."""
+    a = np.asarray(x, dtype=np.float64)
+    if a.ndim == 0 and float(a) == 0.0:
+        return None
+    return _wvec(x, n)
+
+
+def _reflected_device(ctx, nlevel, nwno, numg, numt, lay, lev, surf_reflect, ubar0, ubar1, cos_theta, F0PI,
+                      single_phase, multi_phase, frac_a, frac_b, frac_c, constant_back, constant_forward,
+                      get_toa_intensity, get_lvl_flux, toon_coefficients, b_top, gweight, tweight,
+                      return_albedo):
+    """get_reflected_1d on DeviceArray inputs: kernels read HBM directly, only [G, W] comes back."""
+    from .optics import DeviceArray
+    nlayer, G = nlevel - 1, numg * numt
+    f0 = np.asarray(F0PI, dtype=np.float64)
+    vecs = [_zero_or_vec(surf_reflect, nwno), None if (f0.ndim == 0 and float(f0) == 1.0) else _wvec(F0PI, nwno),
+            _zero_or_vec(b_top, nwno)]
+    ptrs, ld, memspace, vptr, keep = _resolve(ctx, lay + lev, nlayer, nwno, vecs)
+    u0 = np.ascontiguousarray(ubar0, dtype=np.float64).reshape(-1)
+    u1 = np.ascontiguousarray(ubar1, dtype=np.float64).reshape(-1)
+    gw = tw = None
+    if return_albedo:
+        gw = np.ascontiguousarray(gweight, dtype=np.float64)
+        tw = np.ascontiguousarray(tweight, dtype=np.float64)
+    d_x = DeviceArray(ctx, (numg, numt, nwno))
+    d_a = DeviceArray(ctx, (nwno,)) if return_albedo else None
+    d_lv = [DeviceArray(ctx, (numg, numt, nlevel, nwno)) for _ in range(4)] if get_lvl_flux else None
+    a = ReflectedArgs()
+    a.nlayer, a.nwno, a.numg, a.numt, a.nbatch, a.ld = nlayer, nwno, numg, numt, 1, ld
+    (a.dtau, a.w0, a.cosb, a.gcos2, a.ftau_cld, a.ftau_ray, a.dtau_og, a.w0_og, a.cosb_og, a.tau, a.tau_og) = ptrs
+    a.surf_reflect, a.F0PI, a.b_top = vptr
+    a.ubar0, a.ubar1, a.gweight, a.tweight = addr(u0), addr(u1), addr(gw), addr(tw)
+    a.cos_theta = float(cos_theta)
+    a.single_phase, a.multi_phase, a.toon_coefficients = int(single_phase), int(multi_phase), int(toon_coefficients)
+    a.frac_a, a.frac_b, a.frac_c = float(frac_a), float(frac_b), float(frac_c)
+    a.constant_back, a.constant_forward = float(constant_back), float(constant_forward)
+    a.get_toa_intensity, a.get_lvl_flux = int(get_toa_intensity), int(get_lvl_flux)
+    a.xint_at_top, a.albedo = d_x.ptr, (d_a.ptr if d_a else None)
+    if d_lv:
+        a.flux_minus, a.flux_plus, a.flux_minus_mdpt, a.flux_plus_mdpt = [x.ptr for x in d_lv]
+    ctx.check(ctx.lib.pb_reflected_toon_1d(ctx.h, ctypes.byref(a), memspace))
+    xint = d_x.numpy()
+    if d_lv:
+        lv = [x.numpy() for x in d_lv]
+    else:
+        z = np.broadcast_to(_ZERO, (numg, numt, nlevel, nwno))
+        lv = [z, z, z, z]
+    if return_albedo:
+        return xint, tuple(lv), d_a.numpy()
     return xint, tuple(lv)
 
 
@@ -190,6 +269,14 @@ def get_thermal_1d(nlevel, wno, nwno, numg, numt, tlevel, dtau, w0, cosb, plevel
     """
     ctx = ctx or _lib.default_context()
     nlayer = nlevel - 1
+    dev = None
+    if any(_is_dev(x) for x in (dtau, w0, cosb)):
+        wn_h = np.ascontiguousarray(wno, dtype=np.float64)
+        dw_h = _wvec(dwno, nwno) if (calc_type == 1 or np.ndim(dwno) > 0) else None
+        dev = _resolve(ctx, [dtau, w0, cosb], nlayer, nwno, [wn_h, dw_h, _zero_or_vec(surf_reflect, nwno)])
+    if dev is not None:
+        return _thermal_device(ctx, dev, nlevel, nwno, numg, numt, tlevel, plevel, ubar1, hard_surface, calc_type,
+                               level_fluxes, gweight, tweight, return_thermal)
     lay, ld = _layer_set([dtau, w0, cosb], nlayer, nwno)
     wn = np.ascontiguousarray(wno, dtype=np.float64)
     sr = _wvec(surf_reflect, nwno)
@@ -221,6 +308,36 @@ def get_thermal_1d(nlevel, wno, nwno, numg, numt, tlevel, dtau, w0, cosb, plevel
     return res
 
 
+def _thermal_device(ctx, dev, nlevel, nwno, numg, numt, tlevel, plevel, ubar1, hard_surface, calc_type,
+                    level_fluxes, gweight, tweight, return_thermal):
+    from .optics import DeviceArray
+    ptrs, ld, memspace, vptr, keep = dev
+    tl = np.ascontiguousarray(tlevel, dtype=np.float64)
+    pl = np.ascontiguousarray(plevel, dtype=np.float64)
+    u1 = np.ascontiguousarray(ubar1, dtype=np.float64).reshape(-1)
+    gw = tw = None
+    if return_thermal:
+        gw = np.ascontiguousarray(gweight, dtype=np.float64)
+        tw = np.ascontiguousarray(tweight, dtype=np.float64)
+    d_f = DeviceArray(ctx, (numg, numt, nwno))
+    d_t = DeviceArray(ctx, (nwno,)) if return_thermal else None
+    d_lv = [DeviceArray(ctx, (numg, numt, nlevel, nwno)) for _ in range(4)] if level_fluxes else None
+    a = ThermalArgs()
+    a.nlayer, a.nwno, a.numg, a.numt, a.nbatch, a.ld = nlevel - 1, nwno, numg, numt, 1, ld
+    a.dtau, a.w0, a.cosb = ptrs
+    a.wno, a.dwno, a.surf_reflect = vptr
+    a.tlevel, a.plevel, a.ubar1, a.gweight, a.tweight = addr(tl), addr(pl), addr(u1), addr(gw), addr(tw)
+    a.hard_surface, a.calc_type = int(hard_surface), int(calc_type)
+    a.flux_at_top, a.thermal = d_f.ptr, (d_t.ptr if d_t else None)
+    if d_lv:
+        a.flux_minus, a.flux_plus, a.flux_minus_mdpt, a.flux_plus_mdpt = [x.ptr for x in d_lv]
+    ctx.check(ctx.lib.pb_thermal_toon_1d(ctx.h, ctypes.byref(a), memspace))
+    res = (d_f.numpy(), tuple(x.numpy() for x in d_lv) if d_lv else None)
+    if return_thermal:
+        res = res + (d_t.numpy(),)
+    return res
+
+
 def get_transit_1d(z, dz, nlevel, nwno, rstar, mmw, k_b, amu, player, tlayer, colden, DTAU, *,
                    ctx=None):
     """CUDA replacement of fluxes.get_transit_1d (picaso/fluxes.py:2582-2663): returns
@@ -228,7 +345,11 @@ def get_transit_1d(z, dz, nlevel, nwno, rstar, mmw, k_b, amu, player, tlayer, co
     level pressure/temperature (justdoit.py:392-396); only the first nlevel-1 are read."""
     ctx = ctx or _lib.default_context()
     nlayer = nlevel - 1
-    (dt,), ld = _layer_set([DTAU], nlayer, nwno)
+    dev_in = _is_dev(DTAU)
+    if dev_in:
+        dt, ld = DTAU, nwno
+    else:
+        (dt,), ld = _layer_set([DTAU], nlayer, nwno)
     vec = lambda x, n: np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (n,)))
     z_, dz_ = vec(z, nlevel), vec(dz, nlevel)
     pl = np.zeros(nlevel); tl = np.ones(nlevel)
@@ -239,8 +360,15 @@ def get_transit_1d(z, dz, nlevel, nwno, rstar, mmw, k_b, amu, player, tlayer, co
     F = np.zeros(nwno)
     a = TransitArgs()
     a.nlevel, a.nwno, a.nbatch, a.ld = nlevel, nwno, 1, ld
-    a.DTAU, a.z, a.dz, a.player, a.tlayer, a.mmw, a.colden = [addr(x) for x in (dt, z_, dz_, pl, tl, mm, cd)]
-    a.rstar, a.k_b, a.amu, a.F = float(rstar), float(k_b), float(amu), addr(F)
+    a.z, a.dz, a.player, a.tlayer, a.mmw, a.colden = [addr(x) for x in (z_, dz_, pl, tl, mm, cd)]
+    a.rstar, a.k_b, a.amu = float(rstar), float(k_b), float(amu)
+    if dev_in:
+        from .optics import DeviceArray
+        d_F = DeviceArray(ctx, (nwno,))
+        a.DTAU, a.F = dt.ptr, d_F.ptr
+        ctx.check(ctx.lib.pb_transit_1d(ctx.h, ctypes.byref(a), PB_DEVICE))
+        return d_F.numpy()
+    a.DTAU, a.F = addr(dt), addr(F)
     if nwno > 0:
         ctx.check(ctx.lib.pb_transit_1d(ctx.h, ctypes.byref(a), PB_HOST))
     return F

@@ -1,0 +1,377 @@
+"""Host-side mirror of the opacity half of picaso/optics.py for the GPU path.
+
+* ``DeviceOpacities`` plays the role of ``optics.RetrieveOpacities`` (optics.py:1877-2368): it
+  owns the cross-section tables - but uploaded ONCE into HBM instead of being re-read from
+  sqlite per call - and ``get_opacities(atmosphere)`` only records which table rows / weights
+  each layer needs (O(nlayer) host work; no data moves).
+* ``compute_opacity(atmosphere, opacityclass, ...)`` has the reference's signature and 13-tuple
+  return (optics.py:26-27, :423-431) and runs interpolation + mixing + Raman + delta-Eddington
+  in one kernel.  With ``device_outputs=True`` the 13 arrays stay in HBM as ``DeviceArray``
+  handles that ``picaso_b200.fluxes`` accepts directly, so a whole spectrum needs no
+  O(nlayer x nwno) PCIe traffic.
+
+The ``atmosphere`` argument is duck-typed on the attributes the reference reads from ATMSETUP:
+``c.{nlayer,pconv,rgas,amu,k_b}``, ``level['temperature'|'pressure']``, ``layer['temperature'|
+'pressure'|'colden'|'mmw'|'mixingratios'|'electrons'|'cloud']``, ``planet.gravity``, ``molecules``,
+``continuum_molecules``, ``rayleigh_molecules``.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import PB_DEVICE, PB_HOST, OpacityArgs, addr
+
+__all__ = ["DeviceArray", "DeviceOpacities", "compute_opacity", "j_fraction"]
+
+OUTPUT_NAMES = ("DTAU", "TAU", "W0", "COSB", "ftau_cld", "ftau_ray", "GCOS2", "DTAU_OG", "TAU_OG", "W0_OG",
+                "COSB_OG", "W0_no_raman", "f_deltaM")
+_LEVEL = {"TAU", "TAU_OG"}
+
+
+class DeviceArray:
+    """A float64 C-order array living in HBM (owned unless `owner` is given)."""
+
+    def __init__(self, ctx, shape, ptr=None, owner=None):
+        self.ctx, self.shape = ctx, tuple(int(s) for s in shape)
+        self.nbytes = int(np.prod(self.shape)) * 8
+        self._own = ptr is None
+        self.ptr = ctx.dev_alloc(max(self.nbytes, 8)) if ptr is None else ptr
+        self._owner = owner
+
+    @classmethod
+    def from_numpy(cls, ctx, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        d = cls(ctx, a.shape)
+        ctx.check(ctx.lib.pb_memcpy_h2d(ctx.h, d.ptr, a.ctypes.data, a.nbytes))
+        ctx.sync()
+        return d
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def numpy(self):
+        return self.ctx.from_device(self.ptr, self.shape)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, key):
+        """supports the X[:, :, ig] slices picaso() takes (justdoit.py:275-283) for ngauss = 1"""
+        if (isinstance(key, tuple) and len(key) == 3 and key[0] == slice(None) and key[1] == slice(None)
+                and key[2] in (0, -1) and (self.ndim == 2 or self.shape[2] == 1)):
+            return DeviceArray(self.ctx, self.shape[:2], ptr=self.ptr, owner=self)
+        return self.numpy()[key]
+
+    def free(self):
+        if self._own and self.ptr is not None:
+            self.ctx.dev_free(self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            if self._own and self.ptr is not None and self.ctx.h is not None:
+                self.ctx.dev_free(self.ptr)
+        except Exception:
+            pass
+
+
+def _partition_function(j, T):
+    # optics.py:541-549, as coded (b_energy already carries j(j+1))
+    k, b, c, h = 1.38064852e-16, 60.853, 29979245800, 6.62607004e-27
+    b_energy = (b * (h) * (c) * j * (j + 1) / k)
+    g = (2.0 * j + 1.0) if j % 2 == 0 else 3.0 * (2.0 * j + 1.0)
+    return g * np.exp(-0.5 * b_energy * j * (j + 1) / T)
+
+
+def j_fraction(j, T):
+    """fraction of H2 in rotational level J at temperature(s) T (optics.py:552-581)."""
+    T = np.asarray(T, dtype=np.float64)
+    Z = np.zeros(T.shape)
+    for jj in range(20):
+        Z += _partition_function(jj, T)
+    return _partition_function(j, T) / Z
+
+
+class DeviceOpacities:
+    """GPU-resident stand-in for optics.RetrieveOpacities (monochromatic opacities, ngauss = 1).
+
+    Parameters mirror what the reference reads from its sqlite DB (optics.py:1998-2046):
+    wno [W]; pt_pairs = [(ptid, pressure_bar, temperature), ...] in ptid order (T-major);
+    tables {molecule: [npt, W]}; cia_temps [nTc] + continuum {pair: [nTc, W]}; rayleigh_opa
+    {molecule: [W]}; raman_db = (c, ji, deltanu); query_method 'nearest' (reference default)
+    or 'linear'."""
+
+    ngauss = 1
+
+    def __init__(self, wno, pt_pairs, tables, cia_temps, continuum, rayleigh_opa, raman_db=None,
+                 query_method="nearest", ctx=None):
+        if query_method not in ("nearest", "linear"):
+            raise Exception(f"Do not recognize query method for opacities: {query_method}. Options are nearest or linear")
+        self.ctx = ctx or _lib.default_context()
+        self.query_method = query_method
+        self.wno = np.ascontiguousarray(wno, dtype=np.float64)
+        self.wave = 1e4 / self.wno
+        self.nwno = self.wno.size
+        self.gauss_wts = np.array([1])
+        self.pt_pairs = [(int(p[0]), float(p[1]), float(p[2])) for p in pt_pairs]
+        self._ptid = np.array([p[0] for p in self.pt_pairs])
+        P = np.array([p[1] for p in self.pt_pairs])
+        T = np.array([p[2] for p in self.pt_pairs])
+        self._lnP, self._T = np.log(P), T
+        # grid description as get_available_data builds it (optics.py:2019-2025)
+        self.temps = T[np.sort(np.unique(T, return_index=True)[1])]
+        self.pressures = P[np.sort(np.unique(P, return_index=True)[1])]
+        self.nc_p = np.array([np.sum(T == t) for t in np.unique(T)])
+        self.t_inv_grid = 1 / self.temps
+        self.p_log_grid = np.log10(self.pressures)
+        self.molecules = np.array(list(tables.keys()))
+        self._mol_index = {m: i for i, m in enumerate(tables)}
+        self.cia_temps = np.asarray(cia_temps, dtype=np.float64)
+        self._cia_unique = np.unique(self.cia_temps)
+        self.avail_continuum = list(continuum.keys())
+        self._cont_index = {k: i for i, k in enumerate(continuum)}
+        self.rayleigh_molecules = list(rayleigh_opa.keys())
+        self.rayleigh_opa = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in rayleigh_opa.items()}
+        self._ray_index = {k: i for i, k in enumerate(rayleigh_opa)}
+        self.raman_db = raman_db
+        self._shifts = None
+        self.preload = True
+        lib, h = self.ctx.lib, self.ctx.h
+        tab = ctypes.c_void_p()
+        self.ctx.check(lib.pb_optab_create(h, self.nwno, len(tables), len(continuum), len(rayleigh_opa),
+                                           ctypes.byref(tab)))
+        self._tab = tab
+        store = 3 if query_method == "linear" else 1
+        for m, t in tables.items():
+            t = np.ascontiguousarray(t, dtype=np.float64)
+            if t.shape != (len(self.pt_pairs), self.nwno):
+                raise ValueError(f"table of {m} has shape {t.shape}, expected {(len(self.pt_pairs), self.nwno)}")
+            self.ctx.check(lib.pb_optab_set_molecular(h, tab, self._mol_index[m], addr(t), t.shape[0], store))
+        for k, t in continuum.items():
+            t = np.ascontiguousarray(t, dtype=np.float64)
+            order = np.argsort(self.cia_temps)  # rows in ascending unique-temperature order
+            t = np.ascontiguousarray(t[order])
+            self.ctx.check(lib.pb_optab_set_continuum(h, tab, self._cont_index[k], addr(t), t.shape[0]))
+        for k, s in self.rayleigh_opa.items():
+            self.ctx.check(lib.pb_optab_set_rayleigh(h, tab, self._ray_index[k], addr(s)))
+        self._plan = None
+
+    # ---- Raman stellar shifts (star(), justdoit.py:1756-1913 sets opa.raman_stellar_shifts) ----
+    @property
+    def raman_stellar_shifts(self):
+        return self._shifts
+
+    @raman_stellar_shifts.setter
+    def raman_stellar_shifts(self, shifts):
+        self._shifts = np.ascontiguousarray(shifts, dtype=np.float64)
+        if self.raman_db is None:
+            raise ValueError("raman_db = (c, ji, deltanu) is required before setting raman_stellar_shifts")
+        c, ji, dnu = (np.asarray(self.raman_db[k] if isinstance(self.raman_db, dict) else self.raman_db[i])
+                      for i, k in enumerate(("c", "ji", "deltanu")))
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        dnu = np.ascontiguousarray(dnu, dtype=np.float64)
+        ji = np.ascontiguousarray(ji, dtype=np.int32)
+        if self._shifts.shape != (self.nwno, c.size):
+            raise ValueError("raman_stellar_shifts must be [nwno, ntransitions]")
+        self._raman = (c, ji, dnu)
+        self.ctx.check(self.ctx.lib.pb_optab_set_raman(self.ctx.h, self._tab, addr(self.wno), c.size, addr(c),
+                                                       addr(ji), addr(dnu), addr(self._shifts)))
+
+    def device_bytes(self):
+        n = ctypes.c_size_t(0)
+        self.ctx.lib.pb_optab_bytes(self._tab, ctypes.byref(n))
+        return n.value
+
+    # ---- which rows does an atmosphere need (optics.py:2048-2123, :2330-2332, :2298) ----------
+    def find_needed_pts(self, tlayer, player):
+        """bilinear neighbours in (1/T, log10 P); same return convention as the reference:
+        t_interp[:,None], p_interp[:,None], and the four 0-based row indices."""
+        t_inv = 1 / np.asarray(tlayer, dtype=np.float64)
+        p_log = np.log10(np.asarray(player, dtype=np.float64))
+        nT = self.t_inv_grid.size
+        # last grid temperature strictly below T (t_inv_grid is descending): count of entries > t_inv
+        cnt = np.array([np.count_nonzero(self.t_inv_grid > x) for x in t_inv])
+        t_low = np.where(cnt == 0, 0, cnt - 1)
+        if np.any(np.diff(self.t_inv_grid) > 0):  # non-monotonic grid: fall back to the literal rule
+            t_low = np.array([(np.where(self.t_inv_grid > x)[0][-1] if np.any(self.t_inv_grid > x) else 0)
+                              for x in t_inv])
+        t_low = np.where(t_low == nT - 1, nT - 2, t_low)
+        t_hi = t_low + 1
+        p_low = np.array([(np.where(self.p_log_grid <= x)[0][-1] if np.any(self.p_log_grid <= x) else 0)
+                          for x in p_log])
+        p_low = np.minimum(p_low, self.nc_p[t_hi] - 3)
+        p_hi = p_low + 1
+        off = np.concatenate([[0], np.cumsum(self.nc_p)])
+        t_interp = ((t_inv - self.t_inv_grid[t_low]) / (self.t_inv_grid[t_hi] - self.t_inv_grid[t_low]))[:, np.newaxis]
+        p_interp = ((p_log - self.p_log_grid[p_low]) / (self.p_log_grid[p_hi] - self.p_log_grid[p_low]))[:, np.newaxis]
+        return (t_interp, p_interp, off[t_low] + p_low, off[t_hi] + p_low, off[t_low] + p_hi,
+                off[t_hi] + p_hi)
+
+    def get_opacities(self, atmosphere, exclude_mol=1):
+        """Record the table rows / weights for this atmosphere; nothing is fetched or copied.
+        Sets atmosphere.layer['pt_opa_index'] like the reference (optics.py:2265, :2333)."""
+        tlayer = np.asarray(atmosphere.layer["temperature"], dtype=np.float64)
+        pbar = np.asarray(atmosphere.layer["pressure"], dtype=np.float64) / atmosphere.c.pconv
+        L = tlayer.size
+        idx = np.zeros((L, 4), dtype=np.int32)
+        wts = np.zeros((L, 4))
+        if self.query_method == "linear":
+            t, p, ill, ihl, ilh, ihh = self.find_needed_pts(tlayer, pbar)
+            t, p = t[:, 0], p[:, 0]
+            idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3] = ill, ihl, ihh, ilh
+            wts[:, 0], wts[:, 1], wts[:, 2], wts[:, 3] = (1 - t) * (1 - p), t * (1 - p), t * p, (1 - t) * p
+            atmosphere.layer["pt_opa_index"] = 1 + np.unique(np.concatenate([ill, ihl, ilh, ihh]))
+        else:
+            rows = np.array([int(np.argmin(np.hypot(self._lnP - np.log(p), self._T - t)))
+                             for p, t in zip(pbar, tlayer)])
+            idx[:, 0] = rows
+            atmosphere.layer["pt_opa_index"] = [int(self._ptid[r]) for r in rows]
+        cia = np.array([int(np.abs(self._cia_unique - t).argmin()) for t in tlayer], dtype=np.int32)
+        fac = {}
+        for m in atmosphere.molecules:
+            fac[m] = 1 if (np.isscalar(exclude_mol) and exclude_mol == 1) else exclude_mol[m]
+        self._plan = dict(idx=idx, wts=wts, cia=cia, fac=fac, nlayer=L)
+        # the reference exposes dicts of [nlayer, nwno] arrays here; on this path they never exist
+        self.molecular_opa = None
+        self.continuum_opa = None
+
+    def close(self):
+        if getattr(self, "_tab", None) is not None and self.ctx.h is not None:
+            self.ctx.lib.pb_optab_destroy(self.ctx.h, self._tab)
+        self._tab = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _layer_scalars(atm, opa):
+    """per-layer multipliers exactly as compute_opacity parenthesises them (optics.py:147-271)."""
+    L = atm.c.nlayer
+    tlevel = np.asarray(atm.level["temperature"], dtype=np.float64)
+    plevel = np.asarray(atm.level["pressure"], dtype=np.float64) / atm.c.pconv
+    tlayer = np.asarray(atm.layer["temperature"], dtype=np.float64)
+    gravity = atm.planet.gravity / 100.0
+    mmw = np.asarray(atm.layer["mmw"], dtype=np.float64)
+    colden = np.asarray(atm.layer["colden"], dtype=np.float64)
+    player = np.asarray(atm.layer["pressure"], dtype=np.float64)
+    mix = atm.layer["mixingratios"]
+    x = lambda s: np.asarray(mix[s].values if hasattr(mix[s], "values") else mix[s], dtype=np.float64)
+    ACOEF = (tlayer / (tlevel[:-1] * tlevel[1:])) * (
+        tlevel[1:] * plevel[1:] - tlevel[:-1] * plevel[:-1]) / (plevel[1:] - plevel[:-1])
+    BCOEF = (tlayer / (tlevel[:-1] * tlevel[1:])) * (tlevel[:-1] - tlevel[1:]) / (plevel[1:] - plevel[:-1])
+    COEF1 = atm.c.rgas * 273.15 ** 2 * .5E5 * (
+        ACOEF * (plevel[1:] ** 2 - plevel[:-1] ** 2) + BCOEF * (2. / 3.) * (plevel[1:] ** 3 - plevel[:-1] ** 3)) / (
+        1.01325 ** 2 * gravity * tlayer * mmw)
+    cont = np.zeros((len(opa._cont_index), L))
+    used = set()
+    for m in atm.continuum_molecules:
+        key = m[0] + m[1]
+        if key not in opa._cont_index:
+            raise KeyError(f"continuum pair {key} is not in the uploaded tables")
+        used.add(key)
+        if m[0] == "H-" and m[1] == "bf":
+            s = (x("H-") * colden / (mmw * atm.c.amu))
+        elif m[0] == "H-" and m[1] == "ff":
+            s = (player * x("H") * np.asarray(atm.layer["electrons"]) * colden / (tlayer * mmw * atm.c.amu * atm.c.k_b))
+        elif m[0] == "H2-" and m[1] == "":
+            s = (player * x("H2") * np.asarray(atm.layer["electrons"]) * colden / (mmw * atm.c.amu))
+        else:
+            s = (COEF1 * x(m[0]) * x(m[1]))
+        cont[opa._cont_index[key]] = s
+    mol = np.zeros((len(opa._mol_index), L))
+    for m in atm.molecules:
+        if m not in opa._mol_index:
+            raise KeyError(f"molecule {m} is not in the uploaded tables")
+        mol[opa._mol_index[m]] = opa._plan["fac"][m] * (colden * x(m) / mmw)
+    ray = np.zeros((len(opa._ray_index), L))
+    for m in atm.rayleigh_molecules:
+        ray[opa._ray_index[m]] = (colden * x(m) / mmw)
+    return mol, cont, ray
+
+
+def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddington=True, test_mode=False,
+                    raman=0, plot_opacity=False, full_output=False, return_mode=False, fthin_cld=None,
+                    do_holes=False, *, device_outputs=False, outputs=None):
+    """CUDA replacement of optics.compute_opacity (optics.py:26-431) for a ``DeviceOpacities``
+    connection: returns the reference's 13-tuple (DTAU, TAU, W0, COSB, ftau_cld, ftau_ray, GCOS2,
+    DTAU_OG, TAU_OG, W0_OG, COSB_OG, W0_no_raman, f_deltaM), each [nlayer|nlevel, nwno, 1] like the
+    reference's ngauss axis.  ``device_outputs=True`` returns ``DeviceArray`` handles instead
+    (2-D, sliceable with [:, :, 0]); ``outputs`` restricts the computed set to the given names
+    (others are returned as None).
+
+    Not supported on this path: ngauss > 1 (correlated-k), test_mode strings, plot_opacity,
+    return_mode, full_output.  ``test_mode`` None/False both mean "normal run": the reference's
+    own default False would enter its test branch (optics.py:372), real callers pass None."""
+    if not isinstance(opacityclass, DeviceOpacities):
+        raise TypeError("picaso_b200.compute_opacity needs a picaso_b200.DeviceOpacities connection")
+    if ngauss != 1:
+        raise NotImplementedError("correlated-k (ngauss > 1) opacities are not on the GPU path yet")
+    if test_mode not in (None, False):
+        raise NotImplementedError("compute_opacity test modes are not implemented on the GPU path")
+    if plot_opacity or return_mode or full_output:
+        raise NotImplementedError("plot_opacity / return_mode / full_output are host-side diagnostics")
+    opa, atm = opacityclass, atmosphere
+    ctx = opa.ctx
+    if opa._plan is None or opa._plan["nlayer"] != atm.c.nlayer:
+        raise RuntimeError("call opacityclass.get_opacities(atmosphere) first (justdoit.py:236)")
+    L, W = atm.c.nlayer, opa.nwno
+    mol, cont, ray = _layer_scalars(atm, opa)
+    a = OpacityArgs()
+    a.nlayer = L
+    a.query = 1 if opa.query_method == "linear" else 0
+    idx, wts, cia = opa._plan["idx"], opa._plan["wts"], opa._plan["cia"]
+    a.pt_index, a.weights, a.cont_index = addr(idx), addr(wts), addr(cia)
+    a.mol_scale, a.cont_scale, a.ray_scale = addr(mol), addr(cont), addr(ray)
+    a.raman = int(raman)
+    keep = [idx, wts, cia, mol, cont, ray]
+    if raman == 0:
+        if opa.raman_stellar_shifts is None:
+            raise RuntimeError("raman=0 needs opacityclass.raman_stellar_shifts (set by star())")
+        jf = np.ascontiguousarray([j_fraction(j, np.asarray(atm.layer["temperature"])) for j in range(10)])
+        a.jfrac = addr(jf)
+        keep.append(jf)
+    elif raman == 1:
+        raise NotImplementedError("raman='pollack' needs the reference's raman_fortran.txt table; pass raman=0 or 2")
+    cloud = atm.layer.get("cloud") if isinstance(atm.layer, dict) else atm.layer["cloud"]
+    memspace = PB_DEVICE if device_outputs else PB_HOST
+    tmp_dev = []
+    if cloud is not None and np.any(np.asarray(cloud["opd"]) != 0):
+        cl = [np.ascontiguousarray(np.broadcast_to(np.asarray(cloud[k], dtype=np.float64), (L, W)))
+              for k in ("opd", "w0", "g0")]
+        if device_outputs:
+            cl = [DeviceArray.from_numpy(ctx, c) for c in cl]
+            tmp_dev += cl
+            a.cloud_opd, a.cloud_w0, a.cloud_g0 = [c.ptr for c in cl]
+        else:
+            a.cloud_opd, a.cloud_w0, a.cloud_g0 = [addr(c) for c in cl]
+            keep += cl
+        a.cloud_ld = W
+    a.fthin_cld = float(fthin_cld) if fthin_cld is not None else 0.0
+    a.do_holes = int(bool(do_holes))
+    a.stream, a.delta_eddington = int(stream), int(bool(delta_eddington))
+    want = set(OUTPUT_NAMES if outputs is None else outputs)
+    res = {}
+    for n in OUTPUT_NAMES:
+        if n not in want:
+            res[n] = None
+            continue
+        shape = (L + 1, W) if n in _LEVEL else (L, W)
+        if device_outputs:
+            res[n] = DeviceArray(ctx, shape)
+            setattr(a, n, res[n].ptr)
+        else:
+            res[n] = np.zeros(shape)
+            setattr(a, n, addr(res[n]))
+    ctx.check(ctx.lib.pb_compute_opacity(ctx.h, opa._tab, ctypes.byref(a), memspace))
+    if device_outputs:
+        ctx.sync()   # temporaries (cloud uploads) may be released after this point
+        for t in tmp_dev:
+            t.free()
+        return tuple(res[n] for n in OUTPUT_NAMES)
+    return tuple(None if res[n] is None else res[n][:, :, np.newaxis] for n in OUTPUT_NAMES)

@@ -20,3 +20,29 @@ def load_case(name):
                raman_c=g[f"{name}/in/raman_c"], raman_ji=g[f"{name}/in/raman_ji"],
                raman_deltanu=g[f"{name}/in/raman_deltanu"], stellar_shifts=g[f"{name}/in/stellar_shifts"])
     return case, g, db, atm, ins
+
+
+def duck_atmosphere(db, atm):
+    """what compute_opacity / get_opacities read from the reference's ATMSETUP object"""
+    import types
+    a = types.SimpleNamespace()
+    a.c = types.SimpleNamespace(nlayer=atm["nlayer"], pconv=atm["pconv"], rgas=atm["rgas"], amu=atm["amu"],
+                                k_b=atm["k_b"])
+    a.level = {"temperature": atm["tlevel"], "pressure": atm["plevel"]}
+    a.layer = {"temperature": atm["tlayer"], "pressure": atm["player"], "colden": atm["colden"],
+               "mmw": atm["mmw"], "mixingratios": atm["mixingratios"], "electrons": atm["electrons"],
+               "cloud": {"opd": atm["cloud_opd"], "w0": atm["cloud_w0"], "g0": atm["cloud_g0"]}}
+    a.planet = types.SimpleNamespace(gravity=atm["gravity"])
+    a.molecules = list(db["molecules"])
+    a.continuum_molecules = [list(x) for x in db["continuum_molecules"]]
+    a.rayleigh_molecules = list(db["rayleigh_molecules"])
+    return a
+
+
+def device_opacities(pb, case, db, ins):
+    opa = pb.DeviceOpacities(db["wno"], db["pt_pairs"], db["tables"], db["cia_temps"], db["continuum"],
+                             ins["rayleigh"], raman_db=(ins["raman_c"], ins["raman_ji"], ins["raman_deltanu"]),
+                             query_method=case["query"])
+    if case["raman"] == 0:
+        opa.raman_stellar_shifts = ins["stellar_shifts"]
+    return opa

@@ -1,0 +1,75 @@
+"""GPU: device-resident opacity path (pb_optab_* + pb_compute_opacity through
+picaso_b200.DeviceOpacities / compute_opacity) against the reference golden vectors, and the
+fully device-resident chain opacity -> flux solvers against the CPU oracle."""
+import numpy as np
+import pytest
+
+import cases as C
+import oracle
+import picaso_b200 as pb
+from optics_util import OUT_NAMES, device_opacities, duck_atmosphere, load_case
+from picaso_b200 import synth
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6          # north_star tolerance; the opacity arrays actually agree to ~1e-13
+
+
+@pytest.mark.parametrize("name", sorted(C.optics_cases()))
+def test_compute_opacity_vs_reference(name):
+    case, g, db, atm, ins = load_case(name)
+    opa = device_opacities(pb, case, db, ins)
+    a = duck_atmosphere(db, atm)
+    opa.get_opacities(a)
+    assert np.array_equal(np.asarray(a.layer["pt_opa_index"]), g[f"{name}/pt_opa_index"])
+    res = pb.compute_opacity(a, opa, ngauss=1, stream=case["stream"], delta_eddington=case["dedd"],
+                             test_mode=None, raman=case["raman"])
+    assert len(res) == 13
+    for n, arr in zip(OUT_NAMES, res):
+        want = g[f"{name}/out/{n}"]
+        assert arr.shape == want.shape + (1,)
+        assert_close(arr[:, :, 0], want, 1e-10, name + " " + n)
+    # restricted output set (what transit needs) gives the same DTAU_OG
+    only = pb.compute_opacity(a, opa, stream=case["stream"], delta_eddington=case["dedd"], test_mode=None,
+                              raman=case["raman"], outputs=("DTAU_OG",))
+    assert only[0] is None and np.array_equal(only[7], res[7])
+    opa.close()
+
+
+def test_device_resident_chain_matches_oracle():
+    """profile -> opacity kernel -> reflected / thermal / transit kernels without any
+    O(nlayer x nwno) host transfer, against oracle flux solvers fed the golden opacity arrays."""
+    name = "opt_linear_raman"
+    case, g, db, atm, ins = load_case(name)
+    opa = device_opacities(pb, case, db, ins)
+    a = duck_atmosphere(db, atm)
+    opa.get_opacities(a)
+    dev = pb.compute_opacity(a, opa, stream=2, delta_eddington=True, test_mode=None, raman=0, device_outputs=True)
+    (DTAU, TAU, W0, COSB, ftau_cld, ftau_ray, GCOS2, DTAU_OG, TAU_OG, W0_OG, COSB_OG, W0_no_raman, f_deltaM) = dev
+    ref = {n: g[f"{name}/out/{n}"] for n in OUT_NAMES}
+    L, W = atm["nlayer"], db["nwno"]
+    gangle, gweight, tangle, tweight, ubar0, ubar1, cos_theta = synth.geometry_1d(5, 0.0)
+    F0PI = np.ones(W)
+    args_tail = (0, ubar0, ubar1, cos_theta, F0PI, 3, 0, 1.0, -1.0, 2.0, -0.5, 1.0)
+    xint, _, alb = pb.get_reflected_1d(L + 1, db["wno"], W, 5, 1, DTAU[:, :, 0], TAU[:, :, 0], W0[:, :, 0],
+                                       COSB[:, :, 0], GCOS2[:, :, 0], ftau_cld[:, :, 0], ftau_ray[:, :, 0],
+                                       DTAU_OG[:, :, 0], TAU_OG[:, :, 0], W0_OG[:, :, 0], COSB_OG[:, :, 0],
+                                       *args_tail, gweight=gweight, tweight=tweight, return_albedo=True)
+    ox, _ = oracle.get_reflected_1d(L + 1, db["wno"], W, 5, 1, ref["DTAU"], ref["TAU"], ref["W0"], ref["COSB"],
+                                    ref["GCOS2"], ref["ftau_cld"], ref["ftau_ray"], ref["DTAU_OG"], ref["TAU_OG"],
+                                    ref["W0_OG"], ref["COSB_OG"], *args_tail)
+    assert_close(xint, ox, RTOL, "chain reflected")
+    assert_close(alb, oracle.compress_disco(W, cos_theta, ox, gweight, tweight, F0PI), RTOL, "chain albedo")
+    ft, none, th = pb.get_thermal_1d(L + 1, db["wno"], W, 5, 1, atm["tlevel"], DTAU_OG, W0_no_raman, COSB_OG,
+                                     atm["plevel"], ubar1, 0, 0, 0.0, 0, level_fluxes=False, gweight=gweight,
+                                     tweight=tweight, return_thermal=True)
+    oft, _ = oracle.get_thermal_1d(L + 1, db["wno"], W, 5, 1, atm["tlevel"], ref["DTAU_OG"], ref["W0_no_raman"],
+                                   ref["COSB_OG"], atm["plevel"], ubar1, 0, 0, np.zeros(W), 0, level_fluxes=False)
+    assert_close(ft, oft, RTOL, "chain thermal")
+    z = np.linspace(8.0e9, 7.0e9, L + 1)
+    dz = np.full(L + 1, (z[0] - z[1]))
+    tr_args = (z, dz, L + 1, W, 6.957e10, atm["mmw"], atm["k_b"], atm["amu"], atm["plevel"], atm["tlevel"],
+               atm["colden"])
+    F = pb.get_transit_1d(*tr_args, DTAU_OG)
+    assert_close(F, oracle.get_transit_1d(*tr_args, ref["DTAU_OG"]), RTOL, "chain transit")
+    opa.close()
