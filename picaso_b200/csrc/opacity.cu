@@ -14,11 +14,13 @@
 // R ~ 1e5 database) - both raw (nearest lookups) and as log10(max-guarded) rows so that the
 // bilinear interpolation needs no log per call - and a call ships only O(nlayer) scalars:
 // table-row indices, interpolation weights and the per-layer multipliers
-// colden * x_mol / mmw etc.  One kernel, one wavelength per thread marching down the layers:
-// it gathers 4 table rows per molecule (coalesced 256-B segments; consecutive layers share
-// rows, which L2 serves), applies 10**bilinear, mixes continuum + molecular + Rayleigh + cloud,
-// the Raman factor, delta-Eddington and the running optical depth, and writes only the
-// outputs the caller asked for (transit needs 1 array, thermal 3, reflected 11).
+// colden * x_mol / mmw etc.  One thread per (layer, wavelength) - 4 M threads at 80 x 50 000 -
+// gathers 4 table rows per molecule (coalesced 256-B segments; layers sharing (T, P) neighbours
+// share rows through L2), applies 10**bilinear, mixes continuum + molecular + Rayleigh + cloud,
+// the Raman factor and delta-Eddington, and writes only the outputs the caller asked for
+// (transit needs 1 array, thermal 3, reflected 11).  A second, tiny kernel accumulates the
+// running optical depths in the reference's summation order.  Per-wavelength Raman sums are
+// built once per star (pb_optab_set_raman), not per call.
 #include <string>
 #include <vector>
 
@@ -36,6 +38,7 @@ struct pb_optab {
     double *shifts = nullptr;                // [W][ntrans]
     double *raman_c = nullptr, *raman_dnu = nullptr;
     int *raman_ji = nullptr;
+    double *RA = nullptr, *RB = nullptr;       // [10][W] per-level Raman sums
     // device-side pointer tables rebuilt when a table changes
     const double **d_mol_raw = nullptr, **d_mol_log = nullptr, **d_cont = nullptr, **d_ray = nullptr;
     bool dirty = true;
@@ -58,8 +61,7 @@ struct OpaParams {
     const double *ray_scale;   // [nray][L]
     int raman;                 // 0 oklopcic, 1 pollack, 2 none
     const double *jfrac;       // [10][L]
-    const double *wno, *shifts, *raman_c, *raman_dnu, *pollack;
-    const int *raman_ji;
+    const double *RA, *RB, *pollack;
     const double *cld_opd, *cld_w0, *cld_g0;  // [L][ld] or null
     int64_t ld;
     double fthin;
@@ -76,119 +78,129 @@ __global__ void log_table_kernel(int64_t n, const double *raw, double *lg)
     lg[i] = log10(a != 0 ? a : 1e-50);  // optics.py:2282
 }
 
-__global__ void __launch_bounds__(128) opacity_kernel(OpaParams p)
+// per-wavelength Raman sums grouped by initial rotational level (optics.py:478-491); they depend
+// only on the wavenumber grid and the stellar shifts, so they are built once per star:
+// RA[j][w] = sum_{i: ji=j} Q_i * (deltanu_i == 0 ? 1 : shift_i),  RB[j][w] = sum_{i: ji=j} Q_i
+__global__ void raman_sums_kernel(int W, int ntrans, const double *wno, const double *shifts, const double *c,
+                                  const double *dnu_, const int *ji_, double *RA, double *RB)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    double ra[kMaxJ], rb[kMaxJ];
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j) ra[j] = rb[j] = 0.0;
+    const double wn = wno[w];
+    const double w3 = wn * wn * wn;
+    const double *sh = shifts + (int64_t)w * ntrans;
+    for (int i = 0; i < ntrans; ++i) {
+        const double dnu = dnu_[i];
+        const double Q = c[i] / w3 / (wn + dnu);
+        const int ji = ji_[i];
+        const double qa = (dnu == 0.0) ? Q : Q * sh[i];
+#pragma unroll
+        for (int j = 0; j < kMaxJ; ++j)
+            if (j == ji) { ra[j] += qa; rb[j] += Q; }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j) { RA[(int64_t)j * W + w] = ra[j]; RB[(int64_t)j * W + w] = rb[j]; }
+}
+
+// One thread per (layer, wavelength): blockIdx.y = layer, so every per-layer scalar (row indices,
+// weights, multipliers) is CTA-uniform; table rows are read as coalesced 256-B segments.
+__global__ void __launch_bounds__(256) opacity_layer_kernel(OpaParams p)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
     if (w >= p.W) return;
     const int L = p.L, W = p.W;
     const double N_A = 6.02214086e+23;
-    // Raman (optics.py:478-494): per-wavelength sums grouped by initial rotational level
-    double RA[kMaxJ], RB[kMaxJ];  // (rayleigh + shifted), (rayleigh + unshifted) per ji
-    if (p.raman == 0) {
-#pragma unroll
-        for (int j = 0; j < kMaxJ; ++j) RA[j] = RB[j] = 0.0;
-        const double wn = p.wno[w];
-        const double w3 = wn * wn * wn;
-        const double *sh = p.shifts + (int64_t)w * p.ntrans;
-        for (int i = 0; i < p.ntrans; ++i) {
-            const double dnu = p.raman_dnu[i];
-            const double Q = p.raman_c[i] / w3 / (wn + dnu);
-            const int ji = p.raman_ji[i];
-            const double qa = (dnu == 0.0) ? Q : Q * sh[i];
-#pragma unroll
-            for (int j = 0; j < kMaxJ; ++j)
-                if (j == ji) { RA[j] += qa; RB[j] += Q; }
+    double taugas = 0.0;
+    // continuum (optics.py:172-233): table row of the nearest CIA temperature x layer factor
+    const int64_t crow = (int64_t)p.cont_index[l] * W + w;
+    for (int c = 0; c < p.ncont; ++c) taugas += __ldg(p.cont[c] + crow) * p.cont_scale[c * L + l];
+    // molecular (optics.py:243-250)
+    if (p.query == 1) {
+        const int *ix = p.pt_index + 4 * l;
+        const double w1 = p.wts[4 * l], w2 = p.wts[4 * l + 1], w3 = p.wts[4 * l + 2], w4 = p.wts[4 * l + 3];
+        const int64_t r1 = (int64_t)ix[0] * W + w, r2 = (int64_t)ix[1] * W + w, r3 = (int64_t)ix[2] * W + w,
+                      r4 = (int64_t)ix[3] * W + w;
+        for (int m = 0; m < p.nmol; ++m) {
+            const double *t = p.mol_log[m];
+            // 10**((1-t)(1-p) l1 + t(1-p) l2 + t p l3 + (1-t) p l4), optics.py:2290-2293
+            const double e = ((w1 * __ldg(t + r1)) + (w2 * __ldg(t + r2)) + (w3 * __ldg(t + r3)) +
+                              (w4 * __ldg(t + r4)));
+            taugas += (exp10(e) * N_A) * p.mol_scale[m * L + l];
         }
+    } else {
+        const int64_t r1 = (int64_t)p.pt_index[4 * l] * W + w;
+        for (int m = 0; m < p.nmol; ++m) taugas += (__ldg(p.mol_raw[m] + r1) * N_A) * p.mol_scale[m * L + l];
     }
-    const double pol = (p.raman == 1) ? p.pollack[w] : 0.0;
-    double tau = 0.0, tau_d = 0.0;
-    if (p.o[1]) p.o[1][w] = 0.0;
-    if (p.o[8]) p.o[8][w] = 0.0;
-    for (int l = 0; l < L; ++l) {
-        double taugas = 0.0;
-        // continuum (optics.py:172-233): table row of the nearest CIA temperature x layer factor
-        const int64_t crow = (int64_t)p.cont_index[l] * W + w;
-        for (int c = 0; c < p.ncont; ++c) taugas += __ldg(p.cont[c] + crow) * p.cont_scale[c * L + l];
-        // molecular (optics.py:243-250)
-        if (p.query == 1) {
-            const int *ix = p.pt_index + 4 * l;
-            const double w1 = p.wts[4 * l], w2 = p.wts[4 * l + 1], w3 = p.wts[4 * l + 2], w4 = p.wts[4 * l + 3];
-            const int64_t r1 = (int64_t)ix[0] * W + w, r2 = (int64_t)ix[1] * W + w, r3 = (int64_t)ix[2] * W + w,
-                          r4 = (int64_t)ix[3] * W + w;
-            for (int m = 0; m < p.nmol; ++m) {
-                const double *t = p.mol_log[m];
-                // 10**((1-t)(1-p) l1 + t(1-p) l2 + t p l3 + (1-t) p l4), optics.py:2290-2293
-                const double e = ((w1 * __ldg(t + r1)) + (w2 * __ldg(t + r2)) + (w3 * __ldg(t + r3)) +
-                                  (w4 * __ldg(t + r4)));
-                taugas += (exp10(e) * N_A) * p.mol_scale[m * L + l];
-            }
-        } else {
-            const int64_t r1 = (int64_t)p.pt_index[4 * l] * W + w;
-            for (int m = 0; m < p.nmol; ++m)
-                taugas += (__ldg(p.mol_raw[m] + r1) * N_A) * p.mol_scale[m * L + l];
-        }
-        // Rayleigh (optics.py:265-271)
-        double tauray = 0.0;
-        for (int m = 0; m < p.nray; ++m) tauray += __ldg(p.ray[m] + w) * p.ray_scale[m * L + l];
-        // Raman factor (optics.py:287-306), capped at 0.99999
-        double rf = 0.99999;
-        if (p.raman == 0) {
-            double num = 0.0, den = 0.0;
+    // Rayleigh (optics.py:265-271)
+    double tauray = 0.0;
+    for (int m = 0; m < p.nray; ++m) tauray += __ldg(p.ray[m] + w) * p.ray_scale[m * L + l];
+    // Raman factor (optics.py:287-306), capped at 0.99999
+    double rf = 0.99999;
+    if (p.raman == 0) {
+        double num = 0.0, den = 0.0;
 #pragma unroll
-            for (int j = 0; j < kMaxJ; ++j) {
-                const double f = p.jfrac[j * L + l];
-                num = fma(f, RA[j], num);
-                den = fma(f, RB[j], den);
-            }
-            rf = fmin(num / den, 0.99999);
-        } else if (p.raman == 1) {
-            rf = fmin(pol, 0.99999);
+        for (int j = 0; j < kMaxJ; ++j) {
+            const double f = p.jfrac[j * L + l];
+            num = fma(f, __ldg(p.RA + (int64_t)j * W + w), num);
+            den = fma(f, __ldg(p.RB + (int64_t)j * W + w), den);
         }
-        // cloud (optics.py:309-315)
-        double taucld = 0.0, w0c = 0.0, g0 = 0.0;
-        if (p.cld_opd) {
-            const int64_t ic = (int64_t)l * p.ld + w;
-            taucld = __ldg(p.cld_opd + ic);
-            w0c = __ldg(p.cld_w0 + ic);
-            g0 = __ldg(p.cld_g0 + ic);
-            if (p.do_holes) taucld = p.fthin * taucld;
-        }
-        // totals (optics.py:329-350)
-        const double dtau = taugas + tauray + taucld;
-        const double sc = w0c * taucld;
-        const double fcld = sc / (sc + tauray);
-        const double fray = tauray / (tauray + sc);
-        const double gcos2 = 0.5 * fray;
-        const double w0 = (tauray * rf + taucld * w0c) / dtau;
-        const double w0nr = (tauray * 0.99999 + taucld * w0c) / dtau;
-        const int64_t io = (int64_t)l * W + w, iv = (int64_t)(l + 1) * W + w;
-        tau += dtau;
-        if (p.o[4]) p.o[4][io] = fcld;
-        if (p.o[5]) p.o[5][io] = fray;
-        if (p.o[6]) p.o[6][io] = gcos2;
-        if (p.o[7]) p.o[7][io] = dtau;
-        if (p.o[8]) p.o[8][iv] = tau;
-        if (p.o[9]) p.o[9][io] = w0;
-        if (p.o[10]) p.o[10][io] = g0;
-        if (p.o[11]) p.o[11][io] = w0nr;
-        if (p.dedd) {
-            // delta-Eddington (optics.py:412-420)
-            double f = 1.0;
-            for (int s = 0; s < p.stream; ++s) f *= g0;
-            const double dt_d = dtau * (1. - w0 * f);
-            tau_d += dt_d;
-            if (p.o[0]) p.o[0][io] = dt_d;
-            if (p.o[1]) p.o[1][iv] = tau_d;
-            if (p.o[2]) p.o[2][io] = w0 * (1. - f) / (1.0 - w0 * f);
-            if (p.o[3]) p.o[3][io] = (g0 - f) / (1. - f);
-            if (p.o[12]) p.o[12][io] = f;
-        } else {
-            if (p.o[0]) p.o[0][io] = dtau;
-            if (p.o[1]) p.o[1][iv] = tau;
-            if (p.o[2]) p.o[2][io] = w0;
-            if (p.o[3]) p.o[3][io] = g0;
-            if (p.o[12]) p.o[12][io] = 0 * g0;
-        }
+        rf = fmin(num / den, 0.99999);
+    } else if (p.raman == 1) {
+        rf = fmin(p.pollack[w], 0.99999);
+    }
+    // cloud (optics.py:309-315)
+    double taucld = 0.0, w0c = 0.0, g0 = 0.0;
+    if (p.cld_opd) {
+        const int64_t ic = (int64_t)l * p.ld + w;
+        taucld = __ldg(p.cld_opd + ic);
+        w0c = __ldg(p.cld_w0 + ic);
+        g0 = __ldg(p.cld_g0 + ic);
+        if (p.do_holes) taucld = p.fthin * taucld;
+    }
+    // totals (optics.py:329-350)
+    const double dtau = taugas + tauray + taucld;
+    const double sc = w0c * taucld;
+    const double w0 = (tauray * rf + taucld * w0c) / dtau;
+    const int64_t io = (int64_t)l * W + w;
+    if (p.o[4]) p.o[4][io] = sc / (sc + tauray);
+    const double fray = tauray / (tauray + sc);
+    if (p.o[5]) p.o[5][io] = fray;
+    if (p.o[6]) p.o[6][io] = 0.5 * fray;
+    if (p.o[7]) p.o[7][io] = dtau;
+    if (p.o[9]) p.o[9][io] = w0;
+    if (p.o[10]) p.o[10][io] = g0;
+    if (p.o[11]) p.o[11][io] = (tauray * 0.99999 + taucld * w0c) / dtau;
+    if (p.dedd) {
+        // delta-Eddington (optics.py:412-420)
+        double f = 1.0;
+        for (int s = 0; s < p.stream; ++s) f *= g0;
+        if (p.o[0]) p.o[0][io] = dtau * (1. - w0 * f);
+        if (p.o[2]) p.o[2][io] = w0 * (1. - f) / (1.0 - w0 * f);
+        if (p.o[3]) p.o[3][io] = (g0 - f) / (1. - f);
+        if (p.o[12]) p.o[12][io] = f;
+    } else {
+        if (p.o[0]) p.o[0][io] = dtau;
+        if (p.o[2]) p.o[2][io] = w0;
+        if (p.o[3]) p.o[3][io] = g0;
+        if (p.o[12]) p.o[12][io] = 0 * g0;
+    }
+}
+
+// TAU[0] = 0, TAU[l+1] = TAU[l] + DTAU[l]  (numba_cumsum, optics.py:353-354, :419-420): one
+// wavelength per thread, sequential in l so that the summation order is the reference's
+__global__ void opacity_cumsum_kernel(int L, int W, const double *dtau, double *tau)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    double acc = 0.0;
+    tau[w] = 0.0;
+    for (int l = 0; l < L; ++l) {
+        acc += __ldg(dtau + (int64_t)l * W + w);
+        tau[(int64_t)(l + 1) * W + w] = acc;
     }
 }
 
@@ -254,6 +266,8 @@ extern "C" int pb_optab_destroy(pb_ctx *ctx, pb_optab *t)
     if (t->raman_c) cudaFree(t->raman_c);
     if (t->raman_dnu) cudaFree(t->raman_dnu);
     if (t->raman_ji) cudaFree(t->raman_ji);
+    if (t->RA) cudaFree(t->RA);
+    if (t->RB) cudaFree(t->RB);
     if (t->d_mol_raw) cudaFree((void *)t->d_mol_raw);
     if (t->d_mol_log) cudaFree((void *)t->d_mol_log);
     if (t->d_cont) cudaFree((void *)t->d_cont);
@@ -323,6 +337,15 @@ extern "C" int pb_optab_set_raman(pb_ctx *ctx, pb_optab *t, const double *wno, i
     PB_CUDA(ctx, cudaMalloc((void **)&t->raman_ji, ntrans * sizeof(int)));
     PB_CUDA(ctx, cudaMemcpy(t->raman_ji, ji, ntrans * sizeof(int), cudaMemcpyHostToDevice));
     t->ntrans = ntrans;
+    if (!t->RA) {
+        PB_CUDA(ctx, cudaMalloc((void **)&t->RA, (size_t)kMaxJ * t->W * sizeof(double)));
+        PB_CUDA(ctx, cudaMalloc((void **)&t->RB, (size_t)kMaxJ * t->W * sizeof(double)));
+        t->bytes += 2 * (size_t)kMaxJ * t->W * sizeof(double);
+    }
+    raman_sums_kernel<<<(t->W + 127) / 128, 128, 0, ctx->stream>>>(t->W, ntrans, t->wno, t->shifts, t->raman_c,
+                                                                    t->raman_dnu, t->raman_ji, t->RA, t->RB);
+    PB_CHECK_LAUNCH(ctx);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB_OK;
 }
 
@@ -371,7 +394,7 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
     double *const outs[13] = {a->DTAU, a->TAU, a->W0, a->COSB, a->ftau_cld, a->ftau_ray, a->GCOS2, a->DTAU_OG,
                               a->TAU_OG, a->W0_OG, a->COSB_OG, a->W0_no_raman, a->f_deltaM};
     const bool is_level[13] = {false, true, false, false, false, false, false, false, true, false, false, false, false};
-    size_t need = 64 * 256 + pb_align(4 * (size_t)L * 12) + pb_align((size_t)L * 8) +
+    size_t need = 64 * 256 + 2 * pb_align((size_t)L * nW) + pb_align(4 * (size_t)L * 12) + pb_align((size_t)L * 8) +
                   (size_t)(t->nmol + t->ncont + t->nray + kMaxJ + 4) * pb_align((size_t)L * 8);
     if (host) {
         if (cloud) need += 3 * pb_align((size_t)L * nW);
@@ -404,7 +427,7 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
     p.raman = a->raman;
     if (a->raman == 0) {
         PB_TRY(pb_upload_small(ctx, a->jfrac, (size_t)kMaxJ * L, &p.jfrac));
-        p.wno = t->wno; p.shifts = t->shifts; p.raman_c = t->raman_c; p.raman_dnu = t->raman_dnu; p.raman_ji = t->raman_ji;
+        p.RA = t->RA; p.RB = t->RB;
     }
     int64_t ldo;
     if (a->raman == 1) PB_TRY(pb_stage_in(ctx, a->raman_pollack, memspace, 1, W, W, &p.pollack, &ldo));
@@ -423,8 +446,21 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
         if (host) PB_TRY(pb_arena_alloc(ctx, (size_t)(L + (is_level[k] ? 1 : 0)) * nW, (void **)&p.o[k]));
         else p.o[k] = outs[k];
     }
-    opacity_kernel<<<(W + 127) / 128, 128, 0, ctx->stream>>>(p);
+    // the running optical depths need the per-layer values even if the caller did not ask for them
+    double *dtau_d = p.o[0], *dtau_og = p.o[7];
+    if (p.o[1] && !dtau_d) { PB_TRY(pb_arena_alloc(ctx, (size_t)L * nW, (void **)&dtau_d)); p.o[0] = dtau_d; }
+    if (p.o[8] && !dtau_og) { PB_TRY(pb_arena_alloc(ctx, (size_t)L * nW, (void **)&dtau_og)); p.o[7] = dtau_og; }
+    dim3 grid((W + 255) / 256, L);
+    opacity_layer_kernel<<<grid, 256, 0, ctx->stream>>>(p);
     PB_CHECK_LAUNCH(ctx);
+    if (p.o[1]) {
+        opacity_cumsum_kernel<<<(W + 127) / 128, 128, 0, ctx->stream>>>(L, W, dtau_d, p.o[1]);
+        PB_CHECK_LAUNCH(ctx);
+    }
+    if (p.o[8]) {
+        opacity_cumsum_kernel<<<(W + 127) / 128, 128, 0, ctx->stream>>>(L, W, dtau_og, p.o[8]);
+        PB_CHECK_LAUNCH(ctx);
+    }
     if (host) {
         for (int k = 0; k < 13; ++k)
             if (outs[k])

@@ -158,6 +158,17 @@ class DeviceOpacities:
         for k, s in self.rayleigh_opa.items():
             self.ctx.check(lib.pb_optab_set_rayleigh(h, tab, self._ray_index[k], addr(s)))
         self._plan = None
+        self._ws = {}   # pooled device buffers for compute_opacity(device_outputs=True)
+
+    def _buffer(self, name, shape):
+        """pooled DeviceArray: reused by the next call on this connection (no cudaMalloc churn)"""
+        d = self._ws.get(name)
+        if d is None or d.shape != tuple(shape) or d.ptr is None:
+            if d is not None:
+                d.free()
+            d = DeviceArray(self.ctx, shape)
+            self._ws[name] = d
+        return d
 
     # ---- Raman stellar shifts (star(), justdoit.py:1756-1913 sets opa.raman_stellar_shifts) ----
     @property
@@ -239,6 +250,9 @@ class DeviceOpacities:
         self.continuum_opa = None
 
     def close(self):
+        for d in getattr(self, "_ws", {}).values():
+            d.free()
+        self._ws = {}
         if getattr(self, "_tab", None) is not None and self.ctx.h is not None:
             self.ctx.lib.pb_optab_destroy(self.ctx.h, self._tab)
         self._tab = None
@@ -302,8 +316,9 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
     connection: returns the reference's 13-tuple (DTAU, TAU, W0, COSB, ftau_cld, ftau_ray, GCOS2,
     DTAU_OG, TAU_OG, W0_OG, COSB_OG, W0_no_raman, f_deltaM), each [nlayer|nlevel, nwno, 1] like the
     reference's ngauss axis.  ``device_outputs=True`` returns ``DeviceArray`` handles instead
-    (2-D, sliceable with [:, :, 0]); ``outputs`` restricts the computed set to the given names
-    (others are returned as None).
+    (2-D, sliceable with [:, :, 0]) that live in buffers pooled on the connection - they are
+    overwritten by the next compute_opacity call on the same ``DeviceOpacities``; ``outputs``
+    restricts the computed set to the given names (others are returned as None).
 
     Not supported on this path: ngauss > 1 (correlated-k), test_mode strings, plot_opacity,
     return_mode, full_output.  ``test_mode`` None/False both mean "normal run": the reference's
@@ -342,12 +357,15 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
     memspace = PB_DEVICE if device_outputs else PB_HOST
     tmp_dev = []
     if cloud is not None and np.any(np.asarray(cloud["opd"]) != 0):
-        cl = [np.ascontiguousarray(np.broadcast_to(np.asarray(cloud[k], dtype=np.float64), (L, W)))
-              for k in ("opd", "w0", "g0")]
+        cl = [np.asarray(cloud[k], dtype=np.float64) for k in ("opd", "w0", "g0")]
+        cl = [c if (c.shape == (L, W) and c.flags.c_contiguous) else
+              np.ascontiguousarray(np.broadcast_to(c, (L, W))) for c in cl]
         if device_outputs:
-            cl = [DeviceArray.from_numpy(ctx, c) for c in cl]
-            tmp_dev += cl
-            a.cloud_opd, a.cloud_w0, a.cloud_g0 = [c.ptr for c in cl]
+            dcl = [opa._buffer("cloud_" + k, (L, W)) for k in ("opd", "w0", "g0")]
+            for d, c in zip(dcl, cl):
+                ctx.check(ctx.lib.pb_memcpy_h2d(ctx.h, d.ptr, c.ctypes.data, c.nbytes))
+            keep += cl
+            a.cloud_opd, a.cloud_w0, a.cloud_g0 = [d.ptr for d in dcl]
         else:
             a.cloud_opd, a.cloud_w0, a.cloud_g0 = [addr(c) for c in cl]
             keep += cl
@@ -363,15 +381,13 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
             continue
         shape = (L + 1, W) if n in _LEVEL else (L, W)
         if device_outputs:
-            res[n] = DeviceArray(ctx, shape)
+            res[n] = opa._buffer(n, shape)
             setattr(a, n, res[n].ptr)
         else:
             res[n] = np.zeros(shape)
             setattr(a, n, addr(res[n]))
     ctx.check(ctx.lib.pb_compute_opacity(ctx.h, opa._tab, ctypes.byref(a), memspace))
     if device_outputs:
-        ctx.sync()   # temporaries (cloud uploads) may be released after this point
-        for t in tmp_dev:
-            t.free()
+        ctx.sync()   # the host staging arrays in `keep` may be released after this point
         return tuple(res[n] for n in OUTPUT_NAMES)
     return tuple(None if res[n] is None else res[n][:, :, np.newaxis] for n in OUTPUT_NAMES)

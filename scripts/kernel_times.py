@@ -125,6 +125,74 @@ def bench_sh(ctx, L, W, G, reps, stream=4, forms=(0, 0, 0, 1, 1, 1)):
     ctx.dev_free(d_a)
 
 
+def bench_opacity(ctx, L, W, nmol, reps, query="linear", raman=2, outputs=None, tag=""):
+    """cfg4: opacity-interpolation-dominated path.  Tables resident in HBM; per call only O(L) scalars."""
+    import time
+    import types
+    from picaso_b200 import optics as po
+    from picaso_b200._lib import OpacityArgs
+    db = synth.opacity_database(W=W, nmol=nmol, seed=4001, nT=20, nP=18, nTc=30, wave_range=(0.3, 5.0))
+    atm = synth.atmosphere_profile(db, L=L, seed=4003, cloudy=True)
+    rng = np.random.default_rng(1)
+    ray = {m: 10.0 ** rng.uniform(-27, -25, W) for m in db["rayleigh_molecules"]}
+    ji, c, dnu = synth.raman_table()
+    t0 = time.perf_counter()
+    opa = pb.DeviceOpacities(db["wno"], db["pt_pairs"], db["tables"], db["cia_temps"], db["continuum"], ray,
+                             raman_db=(c, ji, dnu), query_method=query, ctx=ctx)
+    if raman == 0:
+        opa.raman_stellar_shifts = 0.6 + 0.8 * rng.random((W, c.size))
+    t_up = time.perf_counter() - t0
+    a = types.SimpleNamespace()
+    a.c = types.SimpleNamespace(nlayer=L, pconv=atm["pconv"], rgas=atm["rgas"], amu=atm["amu"], k_b=atm["k_b"])
+    a.level = {"temperature": atm["tlevel"], "pressure": atm["plevel"]}
+    a.layer = {"temperature": atm["tlayer"], "pressure": atm["player"], "colden": atm["colden"], "mmw": atm["mmw"],
+               "mixingratios": atm["mixingratios"], "electrons": atm["electrons"],
+               "cloud": {"opd": atm["cloud_opd"], "w0": atm["cloud_w0"], "g0": atm["cloud_g0"]}}
+    a.planet = types.SimpleNamespace(gravity=atm["gravity"])
+    a.molecules, a.rayleigh_molecules = list(db["molecules"]), list(db["rayleigh_molecules"])
+    a.continuum_molecules = [list(x) for x in db["continuum_molecules"]]
+    opa.get_opacities(a)
+    names = po.OUTPUT_NAMES if outputs is None else outputs
+    # wall-clock of the public call (host scalars + launch + sync), outputs staying in HBM
+    res = pb.compute_opacity(a, opa, stream=2, delta_eddington=True, test_mode=None, raman=raman,
+                             device_outputs=True, outputs=names)
+    t0 = time.perf_counter()
+    n_api = 10
+    for _ in range(n_api):
+        res = pb.compute_opacity(a, opa, stream=2, delta_eddington=True, test_mode=None, raman=raman,
+                                 device_outputs=True, outputs=names)
+    api_ms = (time.perf_counter() - t0) / n_api * 1e3
+    # kernel-only: prebuilt argument block, device-resident cloud arrays and outputs
+    mol, cont, rays = po._layer_scalars(a, opa)
+    idx, wts, cia = opa._plan["idx"], opa._plan["wts"], opa._plan["cia"]
+    oa = OpacityArgs()
+    oa.nlayer, oa.query = L, (1 if query == "linear" else 0)
+    oa.pt_index, oa.weights, oa.cont_index = _lib.addr(idx), _lib.addr(wts), _lib.addr(cia)
+    oa.mol_scale, oa.cont_scale, oa.ray_scale = _lib.addr(mol), _lib.addr(cont), _lib.addr(rays)
+    oa.raman = raman
+    jf = np.ascontiguousarray([po.j_fraction(j, atm["tlayer"]) for j in range(10)])
+    oa.jfrac = _lib.addr(jf)
+    cl = [po.DeviceArray.from_numpy(ctx, atm[k]) for k in ("cloud_opd", "cloud_w0", "cloud_g0")]
+    oa.cloud_opd, oa.cloud_w0, oa.cloud_g0 = [x.ptr for x in cl]
+    oa.cloud_ld, oa.stream, oa.delta_eddington = W, 2, 1
+    outs = {n: po.DeviceArray(ctx, (L + (1 if n in ("TAU", "TAU_OG") else 0), W)) for n in names}
+    for n, dv in outs.items():
+        setattr(oa, n, dv.ptr)
+    fn = ctx.lib.pb_compute_opacity
+    ms = timeit(ctx, lambda i: ctx.check(fn(ctx.h, opa._tab, ctypes.byref(oa), PB_DEVICE)), 1, reps)
+    # algorithmic bytes: every distinct table row touched once + cloud arrays + requested outputs
+    nrows = len(np.unique(idx if query == "linear" else idx[:, :1]))
+    ncont_rows = len(np.unique(cia))
+    alg = (nmol * nrows + len(db["continuum"]) * ncont_rows + len(ray) + 3 * L) * W * 8
+    alg += sum((L + (1 if n in ("TAU", "TAU_OG") else 0)) * W * 8 for n in names)
+    if raman == 0:
+        alg += (c.size + 1) * W * 8
+    report("compute_opacity L=%d W=%d nmol=%d query=%s raman=%d outputs=%d%s" % (L, W, nmol, query, raman, len(names), tag),
+           ms, alg, W, "wave-points", {"distinct_rows_per_molecule": nrows, "api_ms": api_ms,
+                                       "table_bytes": opa.device_bytes(), "table_upload_s": t_up})
+    opa.close()
+
+
 def bench_thermal(ctx, L, W, G, reps, batch=1, calc_type=0, levels=False):
     per_set = (3 * L + 3) * 8 * W * batch
     nsets = min(6, max(1, int(np.ceil(2 * L2_BYTES / per_set))))
@@ -191,7 +259,7 @@ def bench_transit(ctx, L, W, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=50)
-    ap.add_argument("--only", default="refl,sh,thermal,transit,batch")
+    ap.add_argument("--only", default="refl,sh,opacity,thermal,transit,batch")
     a = ap.parse_args()
     only = set(a.only.split(","))
     ctx = pb.Context(0)
@@ -206,6 +274,11 @@ def main():
         bench_sh(ctx, 60, 10000, 5, max(5, a.reps // 5), stream=4)
         bench_sh(ctx, 60, 196000, 5, 5, stream=4)
         bench_sh(ctx, 60, 196000, 5, 5, stream=4, forms=(1, 1, 1, 1, 1, 1))
+    if "opacity" in only:
+        bench_opacity(ctx, 80, 50000, 12, a.reps, outputs=("DTAU_OG",), tag=" (cfg4: transit needs DTAU only)")
+        bench_opacity(ctx, 80, 50000, 12, a.reps, tag=" (cfg4, all 13 outputs)")
+        bench_opacity(ctx, 80, 50000, 12, a.reps, query="nearest", tag=" (reference default query)")
+        bench_opacity(ctx, 60, 10000, 12, a.reps, raman=0, tag=" (headline shape, Raman on)")
     if "thermal" in only:
         bench_thermal(ctx, 90, 10000, 5, a.reps)
         bench_thermal(ctx, 90, 10000, 5, max(5, a.reps // 5), calc_type=1, levels=True)
