@@ -133,6 +133,25 @@ typedef struct pb_sh_args {
 
 int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *args, int memspace);
 
+/* replaces get_thermal_SH, fluxes.py:2979-3186 (flx = 0) and, optionally, compress_thermal.
+ * The reference accepts but never reads tau, dtau_og, tau_og, w0_og and w0_no_raman; they are
+ * not part of this struct.  `cosb` is only compared with `cosb_og` (np.array_equal decides
+ * whether the delta-M fraction is 0, fluxes.py:3044-3047). */
+typedef struct pb_thermal_sh_args {
+    int nlayer, nwno, numg, numt, nbatch;
+    int64_t ld;
+    const double *dtau, *w0, *cosb, *cosb_og;  /* layer arrays */
+    const double *wno;                          /* [nwno] */
+    const double *surf_reflect;                 /* [nwno] or NULL */
+    const double *tlevel, *plevel;              /* host, [nbatch][nlevel] */
+    const double *ubar1, *gweight, *tweight;    /* host */
+    int stream, hard_surface, flx;
+    double *xint_at_top;                        /* [numg*numt][nwno] or NULL */
+    double *thermal;                            /* [nwno] fused compress_thermal, or NULL */
+} pb_thermal_sh_args;
+
+int pb_thermal_sh(pb_ctx *ctx, const pb_thermal_sh_args *args, int memspace);
+
 /* ---- thermal emission, Toon89 two-stream + source function ------------------------- */
 /* replaces get_thermal_1d, fluxes.py:1683-1912 (blackbody :1661, blackbody_integrated
  * :1609) and, when `thermal` is given, compress_thermal, disco.py:152-180 */

@@ -81,6 +81,14 @@ void orc_get_reflected_SH(
     double frac_a, double frac_b, double frac_c, double constant_back, double constant_forward,
     int stream, const double *b_top, int single_form, double *xint_at_top, int nthreads);
 
+/* follows fluxes.py:2979-3186 (get_thermal_SH, flx = 0).  Arguments the reference accepts
+ * but never reads (tau, dtau_og, tau_og, w0_og, w0_no_raman) are not part of this signature. */
+void orc_get_thermal_SH(
+    int nlevel, const double *wno, int nwno, int numg, int numt, const double *tlevel,
+    const double *dtau, const double *w0, const double *cosb, const double *cosb_og,
+    const double *plevel, const double *ubar1, const double *surf_reflect, int stream,
+    int hard_surface, double *xint_at_top, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

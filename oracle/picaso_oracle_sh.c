@@ -417,3 +417,217 @@ void ORC_NAME(orc_get_reflected_SH)(
         free(ab); free(B); free(ipiv); free(lay);
     }
 }
+
+
+/* blackbody(t, 1/wno), fluxes.py:1676-1680 */
+static inline real sh_planck(real t, real wno)
+{
+    const real h = 6.62607004e-27, c = 2.99792458e+10, k = 1.38064852e-16;
+    real w = 1.0 / wno;
+    return ((2.0 * h * c * c) / R_POW(w, (real)5.0)) * (1.0 / (R_EXP((h * c) / (t * (w * k))) - 1.0));
+}
+
+/* get_thermal_SH, fluxes.py:2979-3186 with the calculation == 1 branches of
+ * setup_2_stream_fluxes (:3266-3270) and setup_4_stream_fluxes (:3451-3459); flx = 0.
+ * The banded system does not depend on the viewing angle and is solved once per wavelength. */
+void ORC_NAME(orc_get_thermal_SH)(
+    int nlevel, const f64 *wno, int nwno, int numg, int numt, const f64 *tlevel,
+    const f64 *dtau, const f64 *w0, const f64 *cosb, const f64 *cosb_og, const f64 *plevel,
+    const f64 *ubar1, const f64 *surf_reflect, int stream, int hard_surface,
+    f64 *xint_at_top, int nthreads)
+{
+    const int L = nlevel - 1, W = nwno, G = numg * numt, S = stream;
+    const int n = S * L, k = 3 * S / 2 - 1, ldab = 3 * k + 1;
+    const real mu1 = 0.5;
+    /* ff = 0 when cosb equals cosb_og everywhere (np.array_equal), else cosb_og**stream (:3044-3047) */
+    int same = 1;
+    for (size_t i = 0; i < (size_t)L * W && same; ++i) same = (cosb[i] == cosb_og[i]);
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+    {
+        real *ab = (real *)malloc(sizeof(real) * (size_t)ldab * n);
+        real *B = (real *)malloc(sizeof(real) * (size_t)n);
+        int *ipiv = (int *)malloc(sizeof(int) * (size_t)n);
+        real *lay = (real *)malloc(sizeof(real) * (size_t)(L + 1) * 40);
+        real *bb = lay, *b0 = bb + (L + 1), *b1 = b0 + L, *a_ = b1 + L, *wm = a_ + 4 * L, *lam1 = wm + 4 * L,
+             *lam2 = lam1 + L, *qv = lam2 + L, *pq = qv + L /* 8L */, *ex = pq + 8 * L /* 2L */,
+             *zz = ex + 2 * L /* 8L */, *RQS = zz + 8 * L /* 6L */;
+#pragma omp for schedule(static)
+        for (int w = 0; w < W; ++w) {
+#define LW(arr, l) ((real)(arr)[(size_t)(l) * W + w])
+            const real r = surf_reflect[w];
+            for (int i = 0; i <= L; ++i) bb[i] = sh_planck(tlevel[i], wno[w]);
+            for (int l = 0; l < L; ++l) {
+                b0[l] = bb[l];
+                b1[l] = (bb[l + 1] - b0[l]) / LW(dtau, l);
+                real g = LW(cosb_og, l);
+                real ff = same ? 0. * g : R_POW(g, (real)S);
+                for (int m = 0; m < S; ++m) {
+                    wm[m * L + l] = (2 * m + 1) * (R_POW(g, (real)m) - ff) / (1 - ff);
+                    a_[m * L + l] = (2 * m + 1) - LW(w0, l) * wm[m * L + l];
+                }
+            }
+            real tau_top = LW(dtau, 0) * plevel[0] / (plevel[1] - plevel[0]);
+            real b_top = PI * (1.0 - R_EXP(-tau_top / mu1)) * bb[0];
+            real b_surface = hard_surface ? PI * bb[L] : PI * (bb[L] + b1[L - 1] * mu1);
+            real b_surface_SH4 = (-PI * bb[L] / 4);
+            memset(ab, 0, sizeof(real) * (size_t)ldab * n);
+            memset(B, 0, sizeof(real) * (size_t)n);
+            if (S == 2) {
+                real *Q1 = pq, *Q2 = pq + L, *em = ex, *zmu = zz, *zpu = zz + L, *zmd = zz + 2 * L, *zpd = zz + 3 * L;
+                for (int l = 0; l < L; ++l) {
+                    real a0 = a_[l], a1 = a_[L + l], om = LW(w0, l), dt = LW(dtau, l);
+                    lam1[l] = R_SQRT(a0 * a1);
+                    em[l] = R_EXP(-clip35(lam1[l] * dt));
+                    qv[l] = lam1[l] / a1;
+                    Q1[l] = (0.5 + qv[l]) * 2 * PI;
+                    Q2[l] = (0.5 - qv[l]) * 2 * PI;
+                    zmd[l] = ((1 - om) / a0 * (b0[l] / 2 - b1[l] / a1)) * 2 * PI;
+                    zmu[l] = ((1 - om) / a0 * (b0[l] / 2 - b1[l] / a1 + b1[l] * dt / 2)) * 2 * PI;
+                    zpd[l] = ((1 - om) / a0 * (b0[l] / 2 + b1[l] / a1)) * 2 * PI;
+                    zpu[l] = ((1 - om) / a0 * (b0[l] / 2 + b1[l] / a1 + b1[l] * dt / 2)) * 2 * PI;
+                }
+                MB(2, 0) = Q1[0];
+                MB(1, 1) = Q2[0];
+                B[0] = b_top - zmd[0];
+                int nn = L - 1;
+                MB(3, 2 * L - 2) = Q2[nn] * em[nn] - r * (Q1[nn] * em[nn]);
+                MB(2, 2 * L - 1) = Q1[nn] / em[nn] - r * (Q2[nn] / em[nn]);
+                B[2 * L - 1] = b_surface - zpu[nn] + r * zmu[nn];
+                for (int kk = 0; kk < L - 1; ++kk) {
+                    MB(0, 2 * kk + 3) = -Q2[kk + 1];
+                    MB(1, 2 * kk + 2) = -Q1[kk + 1];
+                    MB(1, 2 * kk + 3) = -Q1[kk + 1];
+                    MB(2, 2 * kk + 1) = Q2[kk] / em[kk];
+                    MB(2, 2 * kk + 2) = -Q2[kk + 1];
+                    MB(3, 2 * kk) = Q1[kk] * em[kk];
+                    MB(3, 2 * kk + 1) = Q1[kk] / em[kk];
+                    MB(4, 2 * kk) = Q2[kk] * em[kk];
+                    B[2 * kk + 1] = zmd[kk + 1] - zmu[kk];
+                    B[2 * kk + 2] = zpd[kk + 1] - zpu[kk];
+                }
+            } else {
+                for (int l = 0; l < L; ++l) {
+                    real a0 = a_[l], a1 = a_[L + l], a2 = a_[2 * L + l], a3 = a_[3 * L + l];
+                    real om = LW(w0, l), dt = LW(dtau, l);
+                    real beta = a0 * a1 + 4 * a0 * a3 / 9 + a2 * a3 / 9;
+                    real gama = a0 * a1 * a2 * a3 / 9;
+                    real l1 = R_SQRT((beta + R_SQRT(beta * beta - 4 * gama)) / 2);
+                    real l2 = R_SQRT((beta - R_SQRT(beta * beta - 4 * gama)) / 2);
+                    lam1[l] = l1; lam2[l] = l2;
+                    ex[l] = R_EXP(-clip35(l1 * dt));
+                    ex[L + l] = R_EXP(-clip35(l2 * dt));
+                    real R1 = -a0 / l1, R2 = -a0 / l2;
+                    real Q1 = 0.5 * (a0 * a1 / (l1 * l1) - 1), Q2 = 0.5 * (a0 * a1 / (l2 * l2) - 1);
+                    real S1 = -3 / (2 * a3) * (a0 * a1 / l1 - l1), S2 = -3 / (2 * a3) * (a0 * a1 / l2 - l2);
+                    RQS[l] = R1; RQS[L + l] = R2; RQS[2 * L + l] = Q1; RQS[3 * L + l] = Q2;
+                    RQS[4 * L + l] = S1; RQS[5 * L + l] = S2;
+                    pq[0 * L + l] = (0.5 + R1 + 5 * Q1 / 8) * 2 * PI;
+                    pq[1 * L + l] = (0.5 + R2 + 5 * Q2 / 8) * 2 * PI;
+                    pq[2 * L + l] = (-0.125 + 5 * Q1 / 8 + S1) * 2 * PI;
+                    pq[3 * L + l] = (-0.125 + 5 * Q2 / 8 + S2) * 2 * PI;
+                    pq[4 * L + l] = (0.5 - R1 + 5 * Q1 / 8) * 2 * PI;
+                    pq[5 * L + l] = (0.5 - R2 + 5 * Q2 / 8) * 2 * PI;
+                    pq[6 * L + l] = (-0.125 + 5 * Q1 / 8 - S1) * 2 * PI;
+                    pq[7 * L + l] = (-0.125 + 5 * Q2 / 8 - S2) * 2 * PI;
+                    /* fluxes.py:3452-3459; order (z1mn, z2mn, z1pl, z2pl), up then down */
+                    zz[0 * L + l] = (1 - om) / a0 * (b0[l] / 2 - b1[l] / a1 + b1[l] * dt / 2) * 2 * PI;
+                    zz[1 * L + l] = -0.5 * (1 - om) / (4 * a0) * (b0[l] + b1[l] * dt) * 2 * PI;
+                    zz[2 * L + l] = (1 - om) / a0 * (b0[l] / 2 + b1[l] / a1 + b1[l] * dt / 2) * 2 * PI;
+                    zz[3 * L + l] = -0.5 * (1 - om) / (4 * a0) * (b0[l] + b1[l] * dt) * 2 * PI;
+                    zz[4 * L + l] = (1 - om) / a0 * (b0[l] / 2 - b1[l] / a1) * 2 * PI;
+                    zz[5 * L + l] = -0.5 * (1 - om) / (4 * a0) * (b0[l]) * 2 * PI;
+                    zz[6 * L + l] = (1 - om) / a0 * (b0[l] / 2 + b1[l] / a1) * 2 * PI;
+                    zz[7 * L + l] = -0.5 * (1 - om) / (4 * a0) * (b0[l]) * 2 * PI;
+                }
+                MB(5, 0) = P1MN(0); MB(5, 1) = Q1PL(0); MB(4, 1) = P1PL(0); MB(4, 2) = Q2MN(0);
+                MB(3, 2) = P2MN(0); MB(3, 3) = Q2PL(0); MB(2, 3) = P2PL(0); MB(6, 0) = Q1MN(0);
+                B[0] = b_top - zz[4 * L + 0];
+                B[1] = -b_top / 4 - zz[5 * L + 0];
+                int nn = L - 1;
+                MB(5, 4 * L - 2) = F22(nn) - r * F02(nn);
+                MB(5, 4 * L - 1) = F33(nn) - r * F13(nn);
+                MB(4, 4 * L - 1) = F23(nn) - r * F03(nn);
+                MB(6, 4 * L - 3) = F21(nn) - r * F01(nn);
+                MB(6, 4 * L - 2) = F32(nn) - r * F12(nn);
+                MB(7, 4 * L - 4) = F20(nn) - r * F00(nn);
+                MB(7, 4 * L - 3) = F31(nn) - r * F11(nn);
+                MB(8, 4 * L - 4) = F30(nn) - r * F10(nn);
+                B[4 * L - 2] = b_surface - zz[2 * L + nn] + r * zz[0 * L + nn];
+                B[4 * L - 1] = b_surface_SH4 - zz[3 * L + nn] + r * zz[1 * L + nn];
+                for (int kk = 0; kk < L - 1; ++kk) {
+                    int c = 4 * kk;
+                    MB(5, c + 2) = F02(kk); MB(5, c + 3) = F13(kk);
+                    MB(5, c + 4) = -P1PL(kk + 1); MB(5, c + 5) = -Q1MN(kk + 1);
+                    MB(4, c + 3) = F03(kk); MB(4, c + 4) = -Q1MN(kk + 1);
+                    MB(4, c + 5) = -P1MN(kk + 1); MB(4, c + 6) = -Q2PL(kk + 1);
+                    MB(3, c + 4) = -P1MN(kk + 1); MB(3, c + 5) = -Q1PL(kk + 1);
+                    MB(3, c + 6) = -P2PL(kk + 1); MB(3, c + 7) = -Q2MN(kk + 1);
+                    MB(2, c + 5) = -P1PL(kk + 1); MB(2, c + 6) = -Q2MN(kk + 1); MB(2, c + 7) = -P2MN(kk + 1);
+                    MB(1, c + 6) = -P2MN(kk + 1); MB(1, c + 7) = -Q2PL(kk + 1);
+                    MB(0, c + 7) = -P2PL(kk + 1);
+                    MB(6, c + 1) = F01(kk); MB(6, c + 2) = F12(kk); MB(6, c + 3) = F23(kk);
+                    MB(6, c + 4) = -Q1PL(kk + 1);
+                    MB(7, c) = F00(kk); MB(7, c + 1) = F11(kk); MB(7, c + 2) = F22(kk); MB(7, c + 3) = F33(kk);
+                    MB(8, c) = F10(kk); MB(8, c + 1) = F21(kk); MB(8, c + 2) = F32(kk);
+                    MB(9, c) = F20(kk); MB(9, c + 1) = F31(kk);
+                    MB(10, c) = F30(kk);
+                    B[c + 2] = zz[4 * L + kk + 1] - zz[0 * L + kk];
+                    B[c + 3] = zz[5 * L + kk + 1] - zz[1 * L + kk];
+                    B[c + 4] = zz[6 * L + kk + 1] - zz[2 * L + kk];
+                    B[c + 5] = zz[7 * L + kk + 1] - zz[3 * L + kk];
+                }
+            }
+            band_solve(n, k, ab, ldab, ipiv, B);
+            /* per-angle source-function integration, fluxes.py:3105-3182 */
+            for (int ai = 0; ai < G; ++ai) {
+                const real u1 = ubar1[ai];
+                real Pu1[4];
+                legp(u1, Pu1);
+                real xi = hard_surface ? bb[L] * 2 * PI : (bb[L] + b1[L - 1] * u1) * 2 * PI;
+                for (int l = L - 1; l >= 0; --l) {
+                    real dt = LW(dtau, l), om = LW(w0, l);
+                    real a0 = a_[l], a1 = a_[L + l];
+                    real multi;
+                    if (S == 2) {
+                        real alpha = 1 / u1 + lam1[l], beta = 1 / u1 - lam1[l];
+                        real ea = (1 - R_EXP(-clip35(alpha * dt))) / alpha;
+                        real eb = (1 - R_EXP(-clip35(beta * dt))) / beta;
+                        real wm0 = wm[l], wm1 = wm[L + l];
+                        real A0 = B[2 * l] * (wm0 - wm1 * Pu1[1] * qv[l]) * ea;
+                        real A1 = B[2 * l + 1] * (wm0 + wm1 * Pu1[1] * qv[l]) * eb;
+                        real ed = R_EXP(-dt / u1);
+                        real N0 = wm0 * ((1 - om) * u1 / a0 * (b0[l] * (1 - ed) + b1[l] * (u1 - (dt + u1) * ed)));
+                        real N1 = wm1 * Pu1[1] * ((1 - om) * u1 / a0 * (b1[l] * (1 - ed) / a1));
+                        multi = A0 + N0 + A1 + N1;
+                    } else {
+                        real R1 = RQS[l], R2 = RQS[L + l], Q1 = RQS[2 * L + l], Q2 = RQS[3 * L + l];
+                        real S1 = RQS[4 * L + l], S2 = RQS[5 * L + l];
+                        real al1 = 1 / u1 + lam1[l], al2 = 1 / u1 + lam2[l];
+                        real be1 = 1 / u1 - lam1[l], be2 = 1 / u1 - lam2[l];
+                        real et[4];
+                        et[0] = (1 - R_EXP(-clip35(al1 * dt))) / al1 * B[4 * l];
+                        et[1] = (1 - R_EXP(-clip35(be1 * dt))) / be1 * B[4 * l + 1];
+                        et[2] = (1 - R_EXP(-clip35(al2 * dt))) / al2 * B[4 * l + 2];
+                        et[3] = (1 - R_EXP(-clip35(be2 * dt))) / be2 * B[4 * l + 3];
+                        real Arow[4][4] = {{1, 1, 1, 1}, {R1, -R1, R2, -R2}, {Q1, Q1, Q2, Q2}, {S1, -S1, S2, -S2}};
+                        real Aint[4] = {0, 0, 0, 0};
+                        for (int j = 0; j < 4; ++j)
+                            for (int c = 0; c < 4; ++c) Aint[c] = Aint[c] + wm[j * L + l] * Pu1[j] * Arow[j][c];
+                        for (int c = 0; c < 4; ++c) Aint[c] = Aint[c] * et[c];
+                        real ed = R_EXP(-clip35(dt / u1));
+                        real N0 = wm[l] * ((1 - om) * u1 / a0 * (b0[l] * (1 - ed) + b1[l] * (u1 - (dt + u1) * ed)));
+                        real N1 = wm[L + l] * u1 * ((1 - om) * u1 / a0 * (b1[l] * (1 - ed) / a1));
+                        multi = Aint[0] + Aint[1] + Aint[2] + Aint[3] + N0 + N1 + 0 + 0;
+                    }
+                    real ed = R_EXP(-(dt / u1));
+                    real integ = (om * multi * 2 * PI +
+                                  2 * PI * (1 - om) * u1 * (b0[l] * (1 - ed) + b1[l] * (u1 - (dt + u1) * ed)));
+                    xi = xi * R_EXP(-dt / u1) + integ / u1;
+                }
+                xint_at_top[(size_t)ai * W + w] = (f64)xi;
+            }
+#undef LW
+        }
+        free(ab); free(B); free(ipiv); free(lay);
+    }
+}

@@ -49,6 +49,15 @@ class ShArgs(ctypes.Structure):
         [(n, c_vp) for n in ("xint_at_top", "albedo", "f_deltaM_out")])
 
 
+class ThermalShArgs(ctypes.Structure):
+    _fields_ = (
+        [(n, c_int) for n in ("nlayer", "nwno", "numg", "numt", "nbatch")] + [("ld", c_i64)] +
+        [(n, c_vp) for n in ("dtau", "w0", "cosb", "cosb_og", "wno", "surf_reflect", "tlevel", "plevel",
+                             "ubar1", "gweight", "tweight")] +
+        [("stream", c_int), ("hard_surface", c_int), ("flx", c_int)] +
+        [(n, c_vp) for n in ("xint_at_top", "thermal")])
+
+
 class OpacityArgs(ctypes.Structure):
     _fields_ = (
         [("nlayer", c_int), ("query", c_int), ("pt_index", c_vp), ("weights", c_vp), ("mol_scale", c_vp),
@@ -100,6 +109,7 @@ SYMBOLS = {
     "pb_launch_count": (ctypes.c_uint64, [c_vp]),
     "pb_reflected_toon_1d": (c_int, [c_vp, ctypes.POINTER(ReflectedArgs), c_int]),
     "pb_reflected_sh": (c_int, [c_vp, ctypes.POINTER(ShArgs), c_int]),
+    "pb_thermal_sh": (c_int, [c_vp, ctypes.POINTER(ThermalShArgs), c_int]),
     "pb_thermal_toon_1d": (c_int, [c_vp, ctypes.POINTER(ThermalArgs), c_int]),
     "pb_transit_1d": (c_int, [c_vp, ctypes.POINTER(TransitArgs), c_int]),
     "pb_compress_disco": (c_int, [c_vp, c_int, c_dbl, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp,

@@ -412,6 +412,258 @@ __global__ void __launch_bounds__(128) sh_reflected_kernel(ShParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Thermal SH (get_thermal_SH, fluxes.py:2979-3186): same block structure with the linear-in-tau
+// Planck particular solution (calculation == 1 branches, :3266-3270 / :3451-3459); the upward
+// intensity starts from the surface emission instead of flux_bot/pi.
+// ---------------------------------------------------------------------------------------
+struct ShThermParams {
+    int L, W, G, nt;
+    int64_t ld, bs_layer, bs_wave;
+    const double *dtau, *w0, *cosb_og;
+    const double *wno, *surf;
+    const double *tlevel, *plevel;  // [B][V]
+    const double *ubar1, *gweight, *tweight;
+    const int *ff_zero;  // device flag: 1 when cosb == cosb_og everywhere (ff = 0, fluxes.py:3044)
+    int hard_surface;
+    double *xint, *thermal;
+    int fuse;
+};
+
+__global__ void arrays_equal_kernel(int64_t n, const double *a, const double *b, int *flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !(a[i] == b[i])) *flag = 0;
+}
+
+template <int S>
+__device__ __forceinline__ void sh_thermal_layer(double om, double dt, double g, bool ff_zero, double B0,
+                                                 double B1, double u1, const double (&Pu1)[4], Layer<S> &o)
+{
+    const double TWO_PI = 2 * PB_PI;
+    double wm[4], a[4];
+    {
+        double ff = 0. * g;
+        if (!ff_zero) {
+            ff = 1.0;
+#pragma unroll
+            for (int m = 0; m < S; ++m) ff *= g;
+        }
+        double gm = 1.0;
+#pragma unroll
+        for (int m = 0; m < S; ++m) {
+            wm[m] = (2 * m + 1) * (gm - ff) / (1 - ff);
+            a[m] = (2 * m + 1) - om * wm[m];
+            gm *= g;
+        }
+    }
+    const double inv_u1 = 1.0 / u1;
+    const double src = (1 - om) * pbm::krcp(a[0]);  // (1 - w0)/a[0]
+    double c[S], wgt[S];
+    if (S == 2) {
+        const double lam = sqrt(a[0] * a[1]);
+        const double e = pbm::kexp(-clip35(lam * dt));
+        const double q = lam * pbm::krcp(a[1]);
+        const double Q1 = (0.5 + q) * TWO_PI, Q2 = (0.5 - q) * TWO_PI;
+        o.T[0][0] = Q1; o.T[0][1] = Q2;
+        o.T[1][0] = Q2; o.T[1][1] = Q1;
+        o.cs[0] = e; o.cs[1] = pbm::krcp(e);
+        const double ia1 = pbm::krcp(a[1]);
+        o.Zd[0] = (src * (B0 / 2 - B1 * ia1)) * TWO_PI;
+        o.Zu[0] = (src * (B0 / 2 - B1 * ia1 + B1 * dt / 2)) * TWO_PI;
+        o.Zd[1] = (src * (B0 / 2 + B1 * ia1)) * TWO_PI;
+        o.Zu[1] = (src * (B0 / 2 + B1 * ia1 + B1 * dt / 2)) * TWO_PI;
+        c[0] = inv_u1 + lam; c[1] = inv_u1 - lam;
+        wgt[0] = wm[0] - wm[1] * Pu1[1] * q;
+        wgt[1] = wm[0] + wm[1] * Pu1[1] * q;
+    } else {
+        const double beta = a[0] * a[1] + 4 * a[0] * a[3] / 9 + a[2] * a[3] / 9;
+        const double gama = a[0] * a[1] * a[2] * a[3] / 9;
+        const double disc = sqrt(beta * beta - 4 * gama);
+        const double l1 = sqrt((beta + disc) / 2), l2 = sqrt((beta - disc) / 2);
+        const double x1 = pbm::kexp(-clip35(l1 * dt)), xx2 = pbm::kexp(-clip35(l2 * dt));
+        const double il1 = pbm::krcp(l1), il2 = pbm::krcp(l2);
+        const double R1 = -a[0] * il1, R2 = -a[0] * il2;
+        const double Q1 = 0.5 * (a[0] * a[1] * il1 * il1 - 1), Q2 = 0.5 * (a[0] * a[1] * il2 * il2 - 1);
+        const double m3 = -3 * pbm::krcp(2 * a[3]);
+        const double S1 = m3 * (a[0] * a[1] * il1 - l1), S2 = m3 * (a[0] * a[1] * il2 - l2);
+        const double p1pl = (0.5 + R1 + 5 * Q1 / 8) * TWO_PI, p2pl = (0.5 + R2 + 5 * Q2 / 8) * TWO_PI;
+        const double q1pl = (-0.125 + 5 * Q1 / 8 + S1) * TWO_PI, q2pl = (-0.125 + 5 * Q2 / 8 + S2) * TWO_PI;
+        const double p1mn = (0.5 - R1 + 5 * Q1 / 8) * TWO_PI, p2mn = (0.5 - R2 + 5 * Q2 / 8) * TWO_PI;
+        const double q1mn = (-0.125 + 5 * Q1 / 8 - S1) * TWO_PI, q2mn = (-0.125 + 5 * Q2 / 8 - S2) * TWO_PI;
+        o.T[0][0] = p1mn; o.T[0][1] = p1pl; o.T[0][2] = p2mn; o.T[0][3] = p2pl;
+        o.T[1][0] = q1mn; o.T[1][1] = q1pl; o.T[1][2] = q2mn; o.T[1][3] = q2pl;
+        o.T[2][0] = p1pl; o.T[2][1] = p1mn; o.T[2][2] = p2pl; o.T[2][3] = p2mn;
+        o.T[3][0] = q1pl; o.T[3][1] = q1mn; o.T[3][2] = q2pl; o.T[3][3] = q2mn;
+        o.cs[0] = x1; o.cs[1] = pbm::krcp(x1); o.cs[2] = xx2; o.cs[3] = pbm::krcp(xx2);
+        const double ia1 = pbm::krcp(a[1]);
+        const double s4 = -0.5 * (1 - om) / (4 * a[0]);
+        o.Zu[0] = src * (B0 / 2 - B1 * ia1 + B1 * dt / 2) * TWO_PI;
+        o.Zu[1] = s4 * (B0 + B1 * dt) * TWO_PI;
+        o.Zu[2] = src * (B0 / 2 + B1 * ia1 + B1 * dt / 2) * TWO_PI;
+        o.Zu[3] = o.Zu[1];
+        o.Zd[0] = src * (B0 / 2 - B1 * ia1) * TWO_PI;
+        o.Zd[1] = s4 * (B0)*TWO_PI;
+        o.Zd[2] = src * (B0 / 2 + B1 * ia1) * TWO_PI;
+        o.Zd[3] = o.Zd[1];
+        c[0] = inv_u1 + l1; c[1] = inv_u1 - l1; c[2] = inv_u1 + l2; c[3] = inv_u1 - l2;
+        const double w1 = wm[1] * Pu1[1], w2 = wm[2] * Pu1[2], w3 = wm[3] * Pu1[3], w0_ = wm[0] * Pu1[0];
+        wgt[0] = w0_ + w1 * R1 + w2 * Q1 + w3 * S1;
+        wgt[1] = w0_ - w1 * R1 + w2 * Q1 - w3 * S1;
+        wgt[2] = w0_ + w1 * R2 + w2 * Q2 + w3 * S2;
+        wgt[3] = w0_ - w1 * R2 + w2 * Q2 - w3 * S2;
+    }
+    // source function, fluxes.py:3105-3182
+    const double ed = pbm::kexp(-dt * inv_u1);                  // exp(-dtau/u1)
+    const double ed_n = (S == 4) ? fmax(ed, 6.305116760146989e-16) : ed;  // SH4 clips dtau/u1 at 35 in Nint
+    const double pl = B0 * (1 - ed) + B1 * (u1 - (dt + u1) * ed);
+    const double pl_n = B0 * (1 - ed_n) + B1 * (u1 - (dt + u1) * ed_n);
+    const double N0 = wm[0] * (src * u1 * pl_n);
+    const double N1 = wm[1] * Pu1[1] * (src * u1 * (B1 * (1 - ed_n) * pbm::krcp(a[1])));
+#pragma unroll
+    for (int k = 0; k < S; ++k)
+        o.sw[k] = om * TWO_PI * wgt[k] * ((1 - pbm::kexp(-clip35(c[k] * dt))) * pbm::krcp(c[k])) * inv_u1;
+    o.sconst = (om * (N0 + N1) * TWO_PI + TWO_PI * (1 - om) * u1 * pl) * inv_u1;
+    o.xa = ed;
+}
+
+template <int S>
+__global__ void __launch_bounds__(128) sh_thermal_kernel(ShThermParams p)
+{
+    constexpr int H = S / 2, NR = H + S, NC = 2 * S + 1;
+    extern __shared__ double s_int[];
+    const int lane = threadIdx.x;
+    const int w = blockIdx.x * kWaves + lane;
+    const int a = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    const bool active = (w < p.W) && (a < p.G);
+    double result = 0.0;
+    if (active) {
+        const int L = p.L, V = p.L + 1;
+        const int64_t ld = p.ld;
+        const int64_t ol = (int64_t)b * p.bs_layer + w;
+        const double *tl = p.tlevel + (int64_t)b * V, *pl = p.plevel + (int64_t)b * V;
+        const double u1 = p.ubar1[a];
+        const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + w] : 0.0;
+        const bool ff_zero = *p.ff_zero != 0;
+        const double kMu = 0.5;
+        double Pu1[4];
+        Pu1[0] = 1; Pu1[1] = u1; Pu1[2] = (3 * u1 * u1 - 1) / 2; Pu1[3] = (5 * u1 * u1 * u1 - 3 * u1) / 2;
+        // blackbody(t, 1/wno), fluxes.py:1676-1680
+        const double h = 6.62607004e-27, c = 2.99792458e+10, k = 1.38064852e-16;
+        const double wl = 1.0 / p.wno[w];
+        const double c1w = (2.0 * h * c * c) / pow(wl, 5.0), c2w = (h * c) / (wl * k);
+        double Bbot = c1w * (1.0 / (exp(c2w / tl[L]) - 1.0));
+        const double BL = Bbot;
+        double C[H][S + 1], J[S + 1], Tn[S][S], Zdn[S];
+        for (int l = L - 1; l >= 0; --l) {
+            const int64_t il = ol + (int64_t)l * ld;
+            const double dt = __ldg(p.dtau + il);
+            const double Btop = c1w * (1.0 / (exp(c2w / tl[l]) - 1.0));
+            const double B1 = (Bbot - Btop) / dt;
+            Layer<S> y;
+            sh_thermal_layer<S>(__ldg(p.w0 + il), dt, __ldg(p.cosb_og + il), ff_zero, Btop, B1, u1, Pu1, y);
+            if (l == L - 1) {
+                const double b_surface = p.hard_surface ? PB_PI * BL : PB_PI * (BL + B1 * kMu);
+                const double b_surface4 = (-PB_PI * BL / 4);
+#pragma unroll
+                for (int hh = 0; hh < H; ++hh) {
+#pragma unroll
+                    for (int cc = 0; cc < S; ++cc)
+                        C[hh][cc] = y.T[H + hh][cc] * y.cs[cc] - r * (y.T[hh][cc] * y.cs[cc]);
+                    C[hh][S] = ((hh == 0) ? b_surface : b_surface4) - y.Zu[H + hh] + r * y.Zu[hh];
+                }
+#pragma unroll
+                for (int cc = 0; cc < S; ++cc) J[cc] = 0.0;
+                J[S] = p.hard_surface ? BL * 2 * PB_PI : (BL + B1 * u1) * 2 * PB_PI;  // fluxes.py:3171-3174
+            } else {
+                double R[NR][NC], F[NC];
+#pragma unroll
+                for (int hh = 0; hh < H; ++hh) {
+#pragma unroll
+                    for (int cc = 0; cc < S; ++cc) { R[hh][cc] = C[hh][cc]; R[hh][S + cc] = 0.0; }
+                    R[hh][2 * S] = C[hh][S];
+                }
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+#pragma unroll
+                    for (int cc = 0; cc < S; ++cc) { R[H + i][cc] = -Tn[i][cc]; R[H + i][S + cc] = y.T[i][cc] * y.cs[cc]; }
+                    R[H + i][2 * S] = Zdn[i] - y.Zu[i];
+                }
+#pragma unroll
+                for (int cc = 0; cc < S; ++cc) { F[cc] = J[cc]; F[S + cc] = 0.0; }
+                F[2 * S] = J[S];
+                eliminate<S, NR, NC>(R, F);
+#pragma unroll
+                for (int hh = 0; hh < H; ++hh) {
+#pragma unroll
+                    for (int cc = 0; cc < S; ++cc) C[hh][cc] = R[S + hh][S + cc];
+                    C[hh][S] = R[S + hh][2 * S];
+                }
+#pragma unroll
+                for (int cc = 0; cc < S; ++cc) J[cc] = F[S + cc];
+                J[S] = F[2 * S];
+            }
+#pragma unroll
+            for (int cc = 0; cc < S; ++cc) J[cc] = fma(y.xa, J[cc], y.sw[cc]);
+            J[S] = fma(y.xa, J[S], y.sconst);
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+#pragma unroll
+                for (int cc = 0; cc < S; ++cc) Tn[i][cc] = y.T[i][cc];
+                Zdn[i] = y.Zd[i];
+            }
+            Bbot = Btop;
+        }
+        {
+            // top boundary (fluxes.py:3034-3035): isothermal overburden above the model top
+            const double tau_top = __ldg(p.dtau + ol) * pl[0] / (pl[1] - pl[0]);
+            const double b_top = PB_PI * (1.0 - exp(-tau_top / kMu)) * Bbot;
+            double R[S][S + 1], F[S + 1];
+#pragma unroll
+            for (int hh = 0; hh < H; ++hh) {
+#pragma unroll
+                for (int cc = 0; cc <= S; ++cc) R[hh][cc] = C[hh][cc];
+#pragma unroll
+                for (int cc = 0; cc < S; ++cc) R[H + hh][cc] = Tn[hh][cc];
+                R[H + hh][S] = ((hh == 0) ? b_top : -b_top / 4) - Zdn[hh];
+            }
+#pragma unroll
+            for (int cc = 0; cc <= S; ++cc) F[cc] = J[cc];
+            eliminate<S, S, S + 1>(R, F);
+            result = F[S];
+        }
+        if (p.xint) p.xint[((int64_t)b * p.G + a) * p.W + w] = result;
+    }
+    if (p.fuse) {
+        s_int[threadIdx.y * kWaves + lane] = result;
+        __syncthreads();
+        if (threadIdx.y == 0 && w < p.W) {
+            double acc = 0.0;
+            for (int aa = 0; aa < p.G; ++aa) {
+                const int ig = aa / p.nt, it = aa - ig * p.nt;
+                acc = acc + s_int[aa * kWaves + lane] * p.gweight[ig] * p.tweight[it];
+            }
+            const double sym = (p.nt == 1) ? 1.0 : 1 / (2 * PB_PI);
+            p.thermal[(int64_t)b * p.W + w] = acc * sym;
+        }
+    }
+}
+
+__global__ void sh_compress_thermal_kernel(int W, int G, int nt, const double *flux, const double *gweight,
+                                           const double *tweight, double *out)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (w >= W) return;
+    double acc = 0.0;
+    for (int a = 0; a < G; ++a) {
+        const int ig = a / nt, it = a - ig * nt;
+        acc = acc + flux[((int64_t)b * G + a) * W + w] * gweight[ig] * tweight[it];
+    }
+    out[(int64_t)b * W + w] = acc * ((nt == 1) ? 1.0 : 1 / (2 * PB_PI));
+}
+
 __global__ void sh_compress_kernel(int W, int G, int nt, double cos_theta, const double *xint,
                                    const double *gweight, const double *tweight, const double *f0pi,
                                    int64_t bs_wave, double *albedo)
@@ -522,6 +774,98 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
         if (a->xint_at_top) PB_CUDA(ctx, cudaMemcpyAsync(a->xint_at_top, d_xint, (size_t)B * G * nW, cudaMemcpyDeviceToHost, ctx->stream));
         if (a->albedo) PB_CUDA(ctx, cudaMemcpyAsync(a->albedo, d_alb, B * nW, cudaMemcpyDeviceToHost, ctx->stream));
         if (a->f_deltaM_out) PB_CUDA(ctx, cudaMemcpyAsync(a->f_deltaM_out, d_fdm, (size_t)B * L * nW, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_thermal_sh(pb_ctx *ctx, const pb_thermal_sh_args *a, int memspace)
+{
+    if (!ctx || !a) return PB_ERR_ARG;
+    const int L = a->nlayer, W = a->nwno, G = a->numg * a->numt, V = L + 1;
+    const int B = a->nbatch > 0 ? a->nbatch : 1;
+    if (L < 1 || W < 0 || G < 1) return pb_fail(ctx, PB_ERR_ARG, "thermal_sh: bad sizes L=%d W=%d G=%d", L, W, G);
+    if (a->stream != 2 && a->stream != 4) return pb_fail(ctx, PB_ERR_ARG, "thermal_sh: stream must be 2 or 4");
+    if (a->flx != 0) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "thermal_sh: flx=1 is not implemented (it raises in the reference too)");
+    if (W == 0) return PB_OK;
+    if (a->ld < W) return pb_fail(ctx, PB_ERR_ARG, "thermal_sh: ld < nwno");
+    if (!a->dtau || !a->w0 || !a->cosb || !a->cosb_og || !a->wno || !a->tlevel || !a->plevel || !a->ubar1)
+        return pb_fail(ctx, PB_ERR_ARG, "thermal_sh: NULL input array");
+    if (a->thermal && (!a->gweight || !a->tweight)) return pb_fail(ctx, PB_ERR_ARG, "thermal_sh: thermal output needs gweight/tweight");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool host = memspace == PB_HOST;
+    const size_t nW = (size_t)W * sizeof(double);
+    const bool fuse = a->thermal && G <= 4;
+    const bool need_x = a->xint_at_top || (a->thermal && !fuse);
+    size_t need = 32 * 256 + 2 * pb_align((size_t)B * V * 8) + 3 * pb_align((size_t)G * 8);
+    if (host) need += 4 * pb_align((size_t)B * L * nW) + 2 * pb_align(nW) + pb_align(B * nW) + pb_align((size_t)B * G * nW) + pb_align(B * nW);
+    else need += pb_align((size_t)B * G * nW);
+    pb_arena_reset(ctx);
+    PB_TRY(pb_arena_reserve(ctx, need));
+    PB_TRY(pb_pinned_reserve(ctx, (2 * (size_t)B * V + 3 * (size_t)G + 64) * sizeof(double)));
+    ShThermParams p;
+    memset(&p, 0, sizeof(p));
+    p.L = L; p.W = W; p.G = G; p.nt = a->numt;
+    int64_t ldo;
+    const double *d_cosb;
+    PB_TRY(pb_stage_in(ctx, a->dtau, memspace, (int64_t)B * L, W, a->ld, &p.dtau, &ldo));
+    PB_TRY(pb_stage_in(ctx, a->w0, memspace, (int64_t)B * L, W, a->ld, &p.w0, &ldo));
+    PB_TRY(pb_stage_in(ctx, a->cosb_og, memspace, (int64_t)B * L, W, a->ld, &p.cosb_og, &ldo));
+    if (a->cosb == a->cosb_og) d_cosb = p.cosb_og;
+    else PB_TRY(pb_stage_in(ctx, a->cosb, memspace, (int64_t)B * L, W, a->ld, &d_cosb, &ldo));
+    PB_TRY(pb_stage_in(ctx, a->wno, memspace, 1, W, W, &p.wno, &ldo));
+    PB_TRY(pb_stage_in(ctx, a->surf_reflect, memspace, B, W, W, &p.surf, &ldo));
+    p.ld = host ? W : a->ld;
+    p.bs_layer = (int64_t)L * p.ld; p.bs_wave = W;
+    PB_TRY(pb_upload_small(ctx, a->tlevel, (size_t)B * V, &p.tlevel));
+    PB_TRY(pb_upload_small(ctx, a->plevel, (size_t)B * V, &p.plevel));
+    PB_TRY(pb_upload_small(ctx, a->ubar1, G, &p.ubar1));
+    if (a->gweight) PB_TRY(pb_upload_small(ctx, a->gweight, a->numg, &p.gweight));
+    if (a->tweight) PB_TRY(pb_upload_small(ctx, a->tweight, a->numt, &p.tweight));
+    p.hard_surface = a->hard_surface;
+    // ff = 0 iff cosb == cosb_og everywhere (np.array_equal, fluxes.py:3044): decided on the device
+    int *d_flag;
+    PB_TRY(pb_arena_alloc(ctx, sizeof(int), (void **)&d_flag));
+    {
+        const int one = 1;
+        const double *tmp;
+        double pad = 0;
+        memcpy(&pad, &one, sizeof(int));
+        PB_TRY(pb_upload_small(ctx, &pad, 1, &tmp));
+        PB_CUDA(ctx, cudaMemcpyAsync(d_flag, tmp, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (d_cosb != p.cosb_og) {
+        if (p.ld != W && !host) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "thermal_sh: padded device arrays need cosb == cosb_og aliasing");
+        const int64_t n = (int64_t)B * L * W;
+        arrays_equal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, d_cosb, p.cosb_og, d_flag);
+        PB_CHECK_LAUNCH(ctx);
+    }
+    p.ff_zero = d_flag;
+    double *d_x = nullptr, *d_th = nullptr;
+    if (host) {
+        if (need_x) PB_TRY(pb_arena_alloc(ctx, (size_t)B * G * nW, (void **)&d_x));
+        if (a->thermal) PB_TRY(pb_arena_alloc(ctx, B * nW, (void **)&d_th));
+    } else {
+        d_x = a->xint_at_top;
+        if (!d_x && need_x) PB_TRY(pb_arena_alloc(ctx, (size_t)B * G * nW, (void **)&d_x));
+        d_th = a->thermal;
+    }
+    p.xint = d_x; p.thermal = d_th; p.fuse = fuse ? 1 : 0;
+    const int ay = G < 4 ? G : 4;
+    dim3 block(kWaves, ay, 1);
+    dim3 grid((W + kWaves - 1) / kWaves, (G + ay - 1) / ay, B);
+    const size_t smem = fuse ? (size_t)ay * kWaves * sizeof(double) : 0;
+    if (a->stream == 2) sh_thermal_kernel<2><<<grid, block, smem, ctx->stream>>>(p);
+    else sh_thermal_kernel<4><<<grid, block, smem, ctx->stream>>>(p);
+    PB_CHECK_LAUNCH(ctx);
+    if (a->thermal && !fuse) {
+        dim3 g2((W + 127) / 128, B);
+        sh_compress_thermal_kernel<<<g2, 128, 0, ctx->stream>>>(W, G, a->numt, d_x, p.gweight, p.tweight, d_th);
+        PB_CHECK_LAUNCH(ctx);
+    }
+    if (host) {
+        if (a->xint_at_top) PB_CUDA(ctx, cudaMemcpyAsync(a->xint_at_top, d_x, (size_t)B * G * nW, cudaMemcpyDeviceToHost, ctx->stream));
+        if (a->thermal) PB_CUDA(ctx, cudaMemcpyAsync(a->thermal, d_th, B * nW, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return PB_OK;

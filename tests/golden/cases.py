@@ -167,3 +167,33 @@ def optics_cases():
                                         atm=dict(L=7, seed=2023, cloudy=False), query="linear", raman=2,
                                         stream=2, dedd=False),
     }
+
+
+def thermal_sh_cases():
+    """get_thermal_SH (fluxes.py:2979): stream x hard_surface x (cosb == cosb_og ?)"""
+    cases = {}
+    for stream in (2, 4):
+        for hs in (0, 1):
+            for same in (0, 1):
+                cases[f"thsh{stream}_hs{hs}_same{same}"] = dict(build=dict(L=22, W=26, seed=400 + stream + hs),
+                                                               stream=stream, hard_surface=hs, same=same,
+                                                               surf_reflect=0.25 * hs)
+        cases[f"thsh{stream}_cfg2_small"] = dict(build=dict(L=90, W=40, seed=1002), stream=stream,
+                                                 hard_surface=0, same=0, surf_reflect=0.0)
+        cases[f"thsh{stream}_one_layer"] = dict(build=dict(L=1, W=4, seed=411), stream=stream, hard_surface=0,
+                                                same=1, surf_reflect=0.0)
+    return cases
+
+
+def build_thermal_sh(case):
+    d = synth.thermal_inputs(**case["build"])
+    d["cosb_og"] = d["cosb"].copy() if case["same"] else np.clip(d["cosb"] * 1.15 + 0.01, 0.0, 0.95)
+    d["surf_reflect"] = np.full(d["nwno"], case["surf_reflect"])
+    return d
+
+
+def thermal_sh_args(d, case):
+    """positional argument list of get_thermal_SH (fluxes.py:2979-2981)"""
+    return (d["nlevel"], d["wno"], d["nwno"], d["numg"], d["numt"], d["tlevel"], d["dtau"], None, d["w0"],
+            d["cosb"], None, None, None, d["w0"], d["cosb_og"], d["plevel"], d["ubar1"], d["surf_reflect"],
+            case["stream"], case["hard_surface"])
