@@ -446,6 +446,7 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
         if (host) PB_TRY(pb_arena_alloc(ctx, (size_t)(L + (is_level[k] ? 1 : 0)) * nW, (void **)&p.o[k]));
         else p.o[k] = outs[k];
     }
+    PB_TRY(pb_upload_flush(ctx));
     // the running optical depths need the per-layer values even if the caller did not ask for them
     double *dtau_d = p.o[0], *dtau_og = p.o[7];
     if (p.o[1] && !dtau_d) { PB_TRY(pb_arena_alloc(ctx, (size_t)L * nW, (void **)&dtau_d)); p.o[0] = dtau_d; }

@@ -72,7 +72,11 @@ void pb_destroy(pb_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->arena) cudaFree(ctx->arena);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto &sl : ctx->pin) {
+        if (sl.host) cudaFreeHost(sl.host);
+        if (sl.dev) cudaFree(sl.dev);
+        if (sl.ev) cudaEventDestroy(sl.ev);
+    }
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
     cudaEventDestroy(ctx->ev_copy);
@@ -198,7 +202,15 @@ uint64_t pb_launch_count(const pb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void pb_arena_reset(pb_ctx *ctx)
 {
     ctx->arena_off = 0;
-    ctx->pinned_off = 0;
+    // next pinned slot; wait (normally a no-op) until the copy that last used it has finished
+    ctx->pin_cur = (ctx->pin_cur + 1) % pb_ctx::kPinSlots;
+    pb_ctx::PinSlot &sl = ctx->pin[ctx->pin_cur];
+    if (sl.pending) {
+        cudaEventSynchronize(sl.ev);
+        sl.pending = false;
+    }
+    ctx->pin_off = 0;
+    ctx->pin_flushed = 0;
 }
 
 int pb_arena_reserve(pb_ctx *ctx, size_t bytes)
@@ -231,32 +243,45 @@ int pb_arena_alloc(pb_ctx *ctx, size_t bytes, void **out)
 
 int pb_pinned_reserve(pb_ctx *ctx, size_t bytes)
 {
-    if (bytes <= ctx->pinned_cap) return PB_OK;
-    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->pinned) PB_CUDA(ctx, cudaFreeHost(ctx->pinned));
-    ctx->pinned = nullptr;
-    ctx->pinned_cap = 0;
-    size_t cap = pb_align(bytes * 2, 1 << 16);
-    cudaError_t e = cudaHostAlloc((void **)&ctx->pinned, cap, cudaHostAllocDefault);
+    pb_ctx::PinSlot &sl = ctx->pin[ctx->pin_cur];
+    if (!sl.ev) PB_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    if (bytes <= sl.cap) return PB_OK;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // kernels may still read the old device block
+    if (sl.host) PB_CUDA(ctx, cudaFreeHost(sl.host));
+    if (sl.dev) PB_CUDA(ctx, cudaFree(sl.dev));
+    sl.host = sl.dev = nullptr;
+    sl.cap = 0;
+    const size_t cap = pb_align(bytes * 2, 1 << 16);
+    cudaError_t e = cudaHostAlloc((void **)&sl.host, cap, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&sl.dev, cap);
     if (e != cudaSuccess)
-        return pb_fail(ctx, PB_ERR_NOMEM, "pinned bounce cudaHostAlloc(%zu) -> %s", cap,
-                       cudaGetErrorString(e));
-    ctx->pinned_cap = cap;
+        return pb_fail(ctx, PB_ERR_NOMEM, "pinned slot allocation (%zu bytes) -> %s", cap, cudaGetErrorString(e));
+    sl.cap = cap;
     return PB_OK;
 }
 
 int pb_upload_small(pb_ctx *ctx, const double *host, size_t n, const double **dev_out)
 {
-    void *d = nullptr;
-    size_t bytes = n * sizeof(double);
-    PB_TRY(pb_arena_alloc(ctx, bytes, &d));
-    size_t off = pb_align(ctx->pinned_off, 64);
-    if (off + bytes > ctx->pinned_cap)
-        return pb_fail(ctx, PB_ERR_NOMEM, "pinned bounce overflow (reserve bug)");
-    memcpy(ctx->pinned + off, host, bytes);
-    ctx->pinned_off = off + bytes;
-    PB_CUDA(ctx, cudaMemcpyAsync(d, ctx->pinned + off, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    *dev_out = (const double *)d;
+    pb_ctx::PinSlot &sl = ctx->pin[ctx->pin_cur];
+    const size_t bytes = n * sizeof(double);
+    const size_t off = pb_align(ctx->pin_off, 64);
+    if (off + bytes > sl.cap) return pb_fail(ctx, PB_ERR_NOMEM, "pinned slot overflow (reserve bug)");
+    memcpy(sl.host + off, host, bytes);
+    ctx->pin_off = off + bytes;
+    *dev_out = (const double *)(sl.dev + off);
+    return PB_OK;
+}
+
+int pb_upload_flush(pb_ctx *ctx)
+{
+    pb_ctx::PinSlot &sl = ctx->pin[ctx->pin_cur];
+    if (ctx->pin_off > ctx->pin_flushed) {
+        PB_CUDA(ctx, cudaMemcpyAsync(sl.dev + ctx->pin_flushed, sl.host + ctx->pin_flushed,
+                                     ctx->pin_off - ctx->pin_flushed, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaEventRecord(sl.ev, ctx->stream));
+        sl.pending = true;
+        ctx->pin_flushed = ctx->pin_off;
+    }
     return PB_OK;
 }
 

@@ -28,8 +28,19 @@ struct pb_ctx {
     size_t arena_cap = 0, arena_off = 0;
     // grow-only pinned bounce buffer for small host vectors (geometry) so that their
     // H2D copies are truly asynchronous
-    char *pinned = nullptr;
-    size_t pinned_cap = 0, pinned_off = 0;
+    // H2D copies are truly asynchronous and ONE copy per API call carries all of them.  A ring
+    // of slots (each with an event recorded after its copy) keeps a later asynchronous call
+    // from overwriting host bytes a pending copy still reads.
+    struct PinSlot {
+        char *host = nullptr, *dev = nullptr;
+        size_t cap = 0;
+        cudaEvent_t ev = nullptr;
+        bool pending = false;
+    };
+    static constexpr int kPinSlots = 8;
+    PinSlot pin[kPinSlots];
+    int pin_cur = 0;
+    size_t pin_off = 0, pin_flushed = 0;
 };
 
 int pb_fail(pb_ctx *ctx, int code, const char *fmt, ...);
@@ -59,8 +70,10 @@ int pb_fail(pb_ctx *ctx, int code, const char *fmt, ...);
 int pb_arena_reserve(pb_ctx *ctx, size_t bytes);
 void pb_arena_reset(pb_ctx *ctx);
 int pb_arena_alloc(pb_ctx *ctx, size_t bytes, void **out);
-// copy a small host vector into the arena through the pinned bounce buffer
+// stage a small host vector in the current pinned slot; the returned device pointer becomes
+// valid after pb_upload_flush (which every entry point calls before its first launch)
 int pb_upload_small(pb_ctx *ctx, const double *host, size_t n, const double **dev_out);
+int pb_upload_flush(pb_ctx *ctx);
 // reserve pinned bounce space (call before the first pb_upload_small of an API call)
 int pb_pinned_reserve(pb_ctx *ctx, size_t bytes);
 

@@ -757,6 +757,7 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
         d_fdm = a->f_deltaM_out;
     }
     p.xint = d_xint; p.albedo = d_alb; p.fdm_out = d_fdm; p.fuse_albedo = fuse ? 1 : 0;
+    PB_TRY(pb_upload_flush(ctx));
     const int ay = G < 4 ? G : 4;
     dim3 block(kWaves, ay, 1);
     dim3 grid((W + kWaves - 1) / kWaves, (G + ay - 1) / ay, B);
@@ -823,6 +824,7 @@ extern "C" int pb_thermal_sh(pb_ctx *ctx, const pb_thermal_sh_args *a, int memsp
     if (a->gweight) PB_TRY(pb_upload_small(ctx, a->gweight, a->numg, &p.gweight));
     if (a->tweight) PB_TRY(pb_upload_small(ctx, a->tweight, a->numt, &p.tweight));
     p.hard_surface = a->hard_surface;
+    PB_TRY(pb_upload_flush(ctx));
     // ff = 0 iff cosb == cosb_og everywhere (np.array_equal, fluxes.py:3044): decided on the device
     int *d_flag;
     PB_TRY(pb_arena_alloc(ctx, sizeof(int), (void **)&d_flag));
@@ -832,6 +834,7 @@ extern "C" int pb_thermal_sh(pb_ctx *ctx, const pb_thermal_sh_args *a, int memsp
         double pad = 0;
         memcpy(&pad, &one, sizeof(int));
         PB_TRY(pb_upload_small(ctx, &pad, 1, &tmp));
+        PB_TRY(pb_upload_flush(ctx));
         PB_CUDA(ctx, cudaMemcpyAsync(d_flag, tmp, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     if (d_cosb != p.cosb_og) {

@@ -575,6 +575,7 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             else d_lv[k] = h_lv[k];
         }
 
+    PB_TRY(pb_upload_flush(ctx));
     const int ay = G < 8 ? G : 8;
     dim3 block(kWavesPerCta, ay, 1);
     dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
@@ -637,6 +638,7 @@ extern "C" int pb_compress_disco(pb_ctx *ctx, int nwno, double cos_theta, const 
     PB_TRY(pb_upload_small(ctx, tweight, nt, &d_tw));
     double *d_alb = albedo;
     if (memspace == PB_HOST) PB_TRY(pb_arena_alloc(ctx, nW, (void **)&d_alb));
+    PB_TRY(pb_upload_flush(ctx));
     dim3 grid((W + 127) / 128, 1);
     compress_disco_kernel<<<grid, 128, 0, ctx->stream>>>(W, G, nt, cos_theta, d_x, d_gw, d_tw, d_f0, W, d_alb);
     PB_CHECK_LAUNCH(ctx);

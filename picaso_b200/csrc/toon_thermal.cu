@@ -519,6 +519,7 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
         d_th = a->thermal;
         for (int k = 0; k < 4; ++k) d_lv[k] = h_lv[k];
     }
+    PB_TRY(pb_upload_flush(ctx));
     const int ay = G < 8 ? G : 8;
     dim3 block(kWavesPerCta, ay, 1);
     dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
@@ -570,6 +571,7 @@ extern "C" int pb_compress_thermal(pb_ctx *ctx, int64_t n, const double *flux, c
     PB_TRY(pb_upload_small(ctx, tweight, nt, &d_tw));
     double *d_out = out;
     if (memspace == PB_HOST) PB_TRY(pb_arena_alloc(ctx, nb, (void **)&d_out));
+    PB_TRY(pb_upload_flush(ctx));
     dim3 grid((unsigned)((n + 127) / 128), 1);
     compress_thermal_kernel<<<grid, 128, 0, ctx->stream>>>(n, G, nt, d_x, d_gw, d_tw, d_out);
     PB_CHECK_LAUNCH(ctx);

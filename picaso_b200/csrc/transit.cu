@@ -2,31 +2,34 @@
 //
 // Replaces picaso/fluxes.py:2582-2663 (get_transit_1d, Brown 2001 eq. 11).
 //
-// Two kernels: a tiny one builds the chord matrix M[i][k] = 2 * delta_length[i, i-k-1]
-// (the path through layer k seen from the tangent level i, already doubled for the two
-// halves of the chord, fluxes.py:2624-2644, :2656) plus z*dz; the main kernel assigns
-// one wavelength per thread, stages its sigma_k = DTAU_k / colden_k * mmw_k * amu column
-// slice in shared memory (coalesced, read from HBM once) and evaluates the
-// lower-triangular contraction tau_i = sum_{k<i} sigma_k M[i][k] four tangent levels at
-// a time for ILP, M being broadcast through L1.
+// Two kernels.  A tiny one builds the TRANSPOSED chord matrix MT[k][i] = 2 * delta_length[i, i-k-1]
+// (path through layer k along the chord tangent at level i, doubled for the two halves,
+// fluxes.py:2624-2644, :2656; zero for k >= i) plus z*dz.  The main kernel assigns one
+// wavelength per thread and evaluates the lower-triangular contraction
+//     tau_i = sum_{k<i} sigma_k MT[k][i],   sigma_k = DTAU_k / colden_k * mmw_k * amu
+// eight tangent levels at a time in registers: per k one coalesced sigma load (L1-resident
+// after the first pass over the tile) and one 64-byte shared-memory broadcast of
+// MT[k][i0..i0+7] feed eight DFMAs.  The reference is compiled with fastmath, so the
+// summation order is free.
 #include "pb_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 64;
+constexpr int kThreads = 128;
+constexpr int kBlk = 8;
 
-__global__ void transit_path_kernel(int V, const double *z, const double *dz, const double *player,
-                                    const double *tlayer, double k_b, double *M, double *zdz)
+__global__ void transit_path_kernel(int V, int Vp, const double *z, const double *dz, const double *player,
+                                    const double *tlayer, double k_b, double *MT, double *zdz)
 {
     const int b = blockIdx.y;
     z += (int64_t)b * V; dz += (int64_t)b * V; player += (int64_t)b * V; tlayer += (int64_t)b * V;
-    M += (int64_t)b * V * V; zdz += (int64_t)b * V;
+    MT += (int64_t)b * V * Vp; zdz += (int64_t)b * Vp;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < V) zdz[idx] = z[idx] * dz[idx];
-    if (idx >= V * V) return;
-    const int i = idx / V, k = idx - i * V;
+    if (idx < Vp) zdz[idx] = idx < V ? z[idx] * dz[idx] : 0.0;
+    if (idx >= V * Vp) return;
+    const int k = idx / Vp, i = idx - k * Vp;
     double m = 0.0;
-    if (k < i) {
+    if (i < V && k < i) {
         const int j = i - k - 1;
         const double ref = z[i], inner = z[i - j], outer = z[i - j - 1];
         double seg = 0.0;
@@ -37,60 +40,40 @@ __global__ void transit_path_kernel(int V, const double *z, const double *dz, co
             seg = sqrt(outer * outer - ref * ref);
         m = 2.0 * (seg * player[k] / tlayer[k] / k_b);
     }
-    M[idx] = m;
+    MT[idx] = m;
 }
 
-__global__ void __launch_bounds__(kThreads) transit_kernel(int V, int W, int64_t ld, int64_t bs_layer,
+__global__ void __launch_bounds__(kThreads) transit_kernel(int V, int Vp, int W, int64_t ld, int64_t bs_layer,
                                                          const double *DTAU, const double *scale /*[B][L]*/,
-                                                         const double *M, const double *zdz,
+                                                         const double *MT, const double *zdz,
                                                          const double *zmin, double rstar, double *F)
 {
-    extern __shared__ double s_sig[];  // [L][kThreads]
+    extern __shared__ double s_mt[];  // [L][Vp] then zdz[Vp]
     const int L = V - 1;
     const int b = blockIdx.y;
+    const double *mt = MT + (int64_t)b * V * Vp;
+    for (int i = threadIdx.x; i < L * Vp; i += kThreads) s_mt[i] = mt[i];
+    double *s_zdz = s_mt + L * Vp;
+    for (int i = threadIdx.x; i < Vp; i += kThreads) s_zdz[i] = zdz[(int64_t)b * Vp + i];
+    __syncthreads();
     const int w = blockIdx.x * kThreads + threadIdx.x;
-    const bool active = w < W;
-    const double *Mb = M + (int64_t)b * V * V;
-    const double *zb = zdz + (int64_t)b * V;
+    if (w >= W) return;
+    const double *col = DTAU + (int64_t)b * bs_layer + w;
     const double *sc = scale + (int64_t)b * L;
-    if (active) {
-        const double *col = DTAU + (int64_t)b * bs_layer + w;
-        for (int k = 0; k < L; ++k) s_sig[k * kThreads + threadIdx.x] = col[(int64_t)k * ld] * sc[k];
-    }
-    // each thread only reads back its own column: no barrier needed
-    if (!active) return;
     double acc = 0.0;
-    int i = 1;
-    for (; i + 3 < V; i += 4) {
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-        const double *m0 = Mb + (int64_t)i * V, *m1 = m0 + V, *m2 = m1 + V, *m3 = m2 + V;
-        for (int k = 0; k < i; ++k) {
-            const double s = s_sig[k * kThreads + threadIdx.x];
-            t0 = fma(s, __ldg(m0 + k), t0);
-            t1 = fma(s, __ldg(m1 + k), t1);
-            t2 = fma(s, __ldg(m2 + k), t2);
-            t3 = fma(s, __ldg(m3 + k), t3);
+    for (int i0 = 0; i0 < V; i0 += kBlk) {
+        double t[kBlk];
+#pragma unroll
+        for (int u = 0; u < kBlk; ++u) t[u] = 0.0;
+        const int kend = (i0 + kBlk - 1 < L) ? i0 + kBlk - 1 : L;  // rows k < i <= i0+7
+        for (int k = 0; k < kend; ++k) {
+            const double s = __ldg(col + (int64_t)k * ld) * sc[k];
+            const double *m = s_mt + k * Vp + i0;
+#pragma unroll
+            for (int u = 0; u < kBlk; ++u) t[u] = fma(s, m[u], t[u]);
         }
-        // remaining triangle entries of the 4-row block
-        {
-            const double s0 = s_sig[i * kThreads + threadIdx.x];
-            t1 = fma(s0, __ldg(m1 + i), t1);
-            t2 = fma(s0, __ldg(m2 + i), t2);
-            t3 = fma(s0, __ldg(m3 + i), t3);
-            const double s1 = s_sig[(i + 1) * kThreads + threadIdx.x];
-            t2 = fma(s1, __ldg(m2 + i + 1), t2);
-            t3 = fma(s1, __ldg(m3 + i + 1), t3);
-            const double s2 = s_sig[(i + 2) * kThreads + threadIdx.x];
-            t3 = fma(s2, __ldg(m3 + i + 2), t3);
-        }
-        acc += (1.0 - exp(-t0)) * zb[i] + (1.0 - exp(-t1)) * zb[i + 1] +
-               (1.0 - exp(-t2)) * zb[i + 2] + (1.0 - exp(-t3)) * zb[i + 3];
-    }
-    for (; i < V; ++i) {
-        double t0 = 0.0;
-        const double *m0 = Mb + (int64_t)i * V;
-        for (int k = 0; k < i; ++k) t0 = fma(s_sig[k * kThreads + threadIdx.x], __ldg(m0 + k), t0);
-        acc += (1.0 - exp(-t0)) * zb[i];
+#pragma unroll
+        for (int u = 0; u < kBlk; ++u) acc += (1.0 - exp(-t[u])) * s_zdz[i0 + u];  // padded levels carry zdz = 0
     }
     const double q = zmin[b] / rstar;
     F[(int64_t)b * W + w] = q * q + 2.0 / (rstar * rstar) * acc;
@@ -108,12 +91,14 @@ extern "C" int pb_transit_1d(pb_ctx *ctx, const pb_transit_args *a, int memspace
     if (a->ld < W) return pb_fail(ctx, PB_ERR_ARG, "transit: ld < nwno");
     if (!a->DTAU || !a->z || !a->dz || !a->player || !a->tlayer || !a->mmw || !a->colden || !a->F)
         return pb_fail(ctx, PB_ERR_ARG, "transit: NULL argument");
-    const size_t smem = (size_t)L * kThreads * sizeof(double);
-    if (smem > 200 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "transit: nlevel=%d exceeds the shared-memory tile (max 400 layers)", V);
+    const int Vp = (V + kBlk - 1) / kBlk * kBlk;
+    const size_t smem = ((size_t)L * Vp + Vp) * sizeof(double);
+    if (smem > 220 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "transit: nlevel=%d exceeds the shared-memory chord matrix (max ~165 levels)", V);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool host = memspace == PB_HOST;
     const size_t nW = (size_t)W * sizeof(double);
-    size_t need = 16 * 256 + 6 * pb_align((size_t)B * V * 8) + pb_align((size_t)B * V * V * 8) + pb_align((size_t)B * 8);
+    size_t need = 16 * 256 + 6 * pb_align((size_t)B * V * 8) + pb_align((size_t)B * V * Vp * 8) +
+                  pb_align((size_t)B * Vp * 8) + pb_align((size_t)B * 8);
     if (host) need += pb_align((size_t)B * L * nW) + pb_align(B * nW);
     pb_arena_reset(ctx);
     PB_TRY(pb_arena_reserve(ctx, need));
@@ -126,7 +111,8 @@ extern "C" int pb_transit_1d(pb_ctx *ctx, const pb_transit_args *a, int memspace
     // per-layer scale  mmw*amu/colden  (fluxes.py:2622, :2650) and min(z) on the host: O(nlevel)
     std::vector<double> scale((size_t)B * L), zmin(B);
     for (int b = 0; b < B; ++b) {
-        for (int k = 0; k < L; ++k) scale[(size_t)b * L + k] = 1.0 / a->colden[(size_t)b * L + k] * (a->mmw[(size_t)b * L + k] * a->amu);
+        for (int k = 0; k < L; ++k)
+            scale[(size_t)b * L + k] = 1.0 / a->colden[(size_t)b * L + k] * (a->mmw[(size_t)b * L + k] * a->amu);
         double m = a->z[(size_t)b * V];
         for (int i = 1; i < V; ++i) m = a->z[(size_t)b * V + i] < m ? a->z[(size_t)b * V + i] : m;
         zmin[b] = m;
@@ -138,18 +124,20 @@ extern "C" int pb_transit_1d(pb_ctx *ctx, const pb_transit_args *a, int memspace
     PB_TRY(pb_upload_small(ctx, a->tlayer, (size_t)B * V, &d_t));
     PB_TRY(pb_upload_small(ctx, scale.data(), (size_t)B * L, &d_scale));
     PB_TRY(pb_upload_small(ctx, zmin.data(), (size_t)B, &d_zmin));
-    double *d_M, *d_zdz, *d_F = a->F;
-    PB_TRY(pb_arena_alloc(ctx, (size_t)B * V * V * 8, (void **)&d_M));
-    PB_TRY(pb_arena_alloc(ctx, (size_t)B * V * 8, (void **)&d_zdz));
+    double *d_MT, *d_zdz, *d_F = a->F;
+    PB_TRY(pb_arena_alloc(ctx, (size_t)B * V * Vp * 8, (void **)&d_MT));
+    PB_TRY(pb_arena_alloc(ctx, (size_t)B * Vp * 8, (void **)&d_zdz));
     if (host) PB_TRY(pb_arena_alloc(ctx, B * nW, (void **)&d_F));
 
-    dim3 gp((V * V + 127) / 128, B);
-    transit_path_kernel<<<gp, 128, 0, ctx->stream>>>(V, d_z, d_dz, d_p, d_t, a->k_b, d_M, d_zdz);
+    PB_TRY(pb_upload_flush(ctx));
+    dim3 gp((V * Vp + 127) / 128, B);
+    transit_path_kernel<<<gp, 128, 0, ctx->stream>>>(V, Vp, d_z, d_dz, d_p, d_t, a->k_b, d_MT, d_zdz);
     PB_CHECK_LAUNCH(ctx);
     if (smem > 48 * 1024)
         PB_CUDA(ctx, cudaFuncSetAttribute(transit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((W + kThreads - 1) / kThreads, B);
-    transit_kernel<<<grid, kThreads, smem, ctx->stream>>>(V, W, ld, (int64_t)L * ld, d_dtau, d_scale, d_M, d_zdz, d_zmin, a->rstar, d_F);
+    transit_kernel<<<grid, kThreads, smem, ctx->stream>>>(V, Vp, W, ld, (int64_t)L * ld, d_dtau, d_scale, d_MT, d_zdz,
+                                                          d_zmin, a->rstar, d_F);
     PB_CHECK_LAUNCH(ctx);
     if (host) {
         PB_CUDA(ctx, cudaMemcpyAsync(a->F, d_F, B * nW, cudaMemcpyDeviceToHost, ctx->stream));
