@@ -21,6 +21,8 @@
 //  * level fluxes (get_lvl_flux=1, the climate path) need every X[n]: a second kernel
 //    stores the elimination coefficients in the caller's four output arrays (they are
 //    exactly 4 doubles per level) and overwrites them with fluxes on the way down.
+#include <cstdlib>
+
 #include "pb_common.cuh"
 #include "pb_math.cuh"
 
@@ -143,6 +145,8 @@ __device__ __forceinline__ void refl_produce(const ReflParams &p, const ReflInpu
     q[Q_TAUO * 32] = x.tauo;
     q[Q_DTO * 32] = x.dto;
 }
+
+#include "toon_reflected_toa3.cuh"
 
 template <int MP /*multi_phase*/>
 __global__ void __launch_bounds__(256) refl_toa_kernel(ReflParams p)
@@ -581,13 +585,25 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
     dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
     if (want_toa) {
         p.xint = d_xint; p.albedo = d_alb; p.fuse_albedo = fuse ? 1 : 0;
-        const size_t smem = (size_t)2 * ay * NQ * 32 * sizeof(double);
-        if (smem > 48 * 1024) {
-            PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // PB_REFL_KERNEL=2 selects the previous generation (one layer per consume step) for A/B runs
+        static const int variant = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 3; }();
+        if (variant == 2) {
+            const size_t smem = (size_t)2 * ay * NQ * 32 * sizeof(double);
+            if (smem > 48 * 1024) {
+                PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
+            if (p.mp == 0) refl_toa_kernel<0><<<grid, block, smem, ctx->stream>>>(p);
+            else refl_toa_kernel<1><<<grid, block, smem, ctx->stream>>>(p);
+        } else {
+            const size_t smem = (size_t)2 * (2 * ay) * NQ * 32 * sizeof(double);
+            if (smem > 48 * 1024) {
+                PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
+            if (p.mp == 0) refl_toa_kernel3<0><<<grid, block, smem, ctx->stream>>>(p);
+            else refl_toa_kernel3<1><<<grid, block, smem, ctx->stream>>>(p);
         }
-        if (p.mp == 0) refl_toa_kernel<0><<<grid, block, smem, ctx->stream>>>(p);
-        else refl_toa_kernel<1><<<grid, block, smem, ctx->stream>>>(p);
         PB_CHECK_LAUNCH(ctx);
         if (a->albedo && !fuse) {
             dim3 g2((W + 127) / 128, B);
