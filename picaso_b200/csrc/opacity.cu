@@ -105,89 +105,193 @@ __global__ void raman_sums_kernel(int W, int ntrans, const double *wno, const do
     for (int j = 0; j < kMaxJ; ++j) { RA[(int64_t)j * W + w] = ra[j]; RB[(int64_t)j * W + w] = rb[j]; }
 }
 
-// One thread per (layer, wavelength): blockIdx.y = layer, so every per-layer scalar (row indices,
-// weights, multipliers) is CTA-uniform; table rows are read as coalesced 256-B segments.
-__global__ void __launch_bounds__(256) opacity_layer_kernel(OpaParams p)
+// One thread per (layer, VEC consecutive wavelengths): blockIdx.y = layer, so everything that
+// depends on the layer only - table-row base pointers, interpolation weights, multipliers,
+// j-fractions - is resolved ONCE per CTA into shared memory; a thread then issues one 16-byte
+// (VEC = 2) load per table row.  VEC = 2 needs an even nwno (rows are then 16-byte aligned).
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<1> {
+    double v[1];
+    __device__ __forceinline__ void load(const double *p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void store(double *p) const { p[0] = v[0]; }
+};
+template <>
+struct Vec<2> {
+    double v[2];
+    __device__ __forceinline__ void load(const double *p)
+    {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+        v[0] = t.x; v[1] = t.y;
+    }
+    __device__ __forceinline__ void store(double *p) const { *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]); }
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
 {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    const int l = blockIdx.y;
-    if (w >= p.W) return;
-    const int L = p.L, W = p.W;
+    extern __shared__ unsigned char s_raw[];
+    const int L = p.L, W = p.W, l = blockIdx.y;
+    const int nrow = (p.query == 1) ? 4 : 1;
+    // shared layout: row pointers [nmol*nrow + ncont + nray], then doubles [4 + nmol + ncont + nray + 10]
+    const double **s_ptr = reinterpret_cast<const double **>(s_raw);
+    const int nptr = p.nmol * nrow + p.ncont + p.nray;
+    double *s_d = reinterpret_cast<double *>(s_raw + sizeof(double *) * (size_t)nptr);
+    double *s_w = s_d, *s_ms = s_d + 4, *s_cs = s_ms + p.nmol, *s_rs = s_cs + p.ncont, *s_jf = s_rs + p.nray;
+    for (int i = threadIdx.x; i < nptr; i += blockDim.x) {
+        if (i < p.nmol * nrow) {
+            const int m = i / nrow, k = i - m * nrow;
+            const double *base = (p.query == 1) ? p.mol_log[m] : p.mol_raw[m];
+            s_ptr[i] = base + (int64_t)p.pt_index[4 * l + k] * W;
+        } else if (i < p.nmol * nrow + p.ncont) {
+            s_ptr[i] = p.cont[i - p.nmol * nrow] + (int64_t)p.cont_index[l] * W;
+        } else {
+            s_ptr[i] = p.ray[i - p.nmol * nrow - p.ncont];
+        }
+    }
+    for (int i = threadIdx.x; i < 4 + p.nmol + p.ncont + p.nray + kMaxJ; i += blockDim.x) {
+        double v;
+        if (i < 4) v = (p.query == 1) ? p.wts[4 * l + i] : 0.0;
+        else if (i < 4 + p.nmol) v = p.mol_scale[(i - 4) * L + l];
+        else if (i < 4 + p.nmol + p.ncont) v = p.cont_scale[(i - 4 - p.nmol) * L + l];
+        else if (i < 4 + p.nmol + p.ncont + p.nray) v = p.ray_scale[(i - 4 - p.nmol - p.ncont) * L + l];
+        else v = (p.raman == 0) ? p.jfrac[(i - 4 - p.nmol - p.ncont - p.nray) * L + l] : 0.0;
+        s_d[i] = v;
+    }
+    __syncthreads();
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (w >= W) return;
     const double N_A = 6.02214086e+23;
-    double taugas = 0.0;
+    double taugas[VEC], tauray[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) taugas[v] = tauray[v] = 0.0;
     // continuum (optics.py:172-233): table row of the nearest CIA temperature x layer factor
-    const int64_t crow = (int64_t)p.cont_index[l] * W + w;
-    for (int c = 0; c < p.ncont; ++c) taugas += __ldg(p.cont[c] + crow) * p.cont_scale[c * L + l];
+    const double **cp = s_ptr + p.nmol * nrow;
+    for (int c = 0; c < p.ncont; ++c) {
+        Vec<VEC> k;
+        k.load(cp[c] + w);
+        const double sc = s_cs[c];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) taugas[v] += k.v[v] * sc;
+    }
     // molecular (optics.py:243-250)
     if (p.query == 1) {
-        const int *ix = p.pt_index + 4 * l;
-        const double w1 = p.wts[4 * l], w2 = p.wts[4 * l + 1], w3 = p.wts[4 * l + 2], w4 = p.wts[4 * l + 3];
-        const int64_t r1 = (int64_t)ix[0] * W + w, r2 = (int64_t)ix[1] * W + w, r3 = (int64_t)ix[2] * W + w,
-                      r4 = (int64_t)ix[3] * W + w;
+        const double w1 = s_w[0], w2 = s_w[1], w3 = s_w[2], w4 = s_w[3];
         for (int m = 0; m < p.nmol; ++m) {
-            const double *t = p.mol_log[m];
-            // 10**((1-t)(1-p) l1 + t(1-p) l2 + t p l3 + (1-t) p l4), optics.py:2290-2293
-            const double e = ((w1 * __ldg(t + r1)) + (w2 * __ldg(t + r2)) + (w3 * __ldg(t + r3)) +
-                              (w4 * __ldg(t + r4)));
-            taugas += (exp10(e) * N_A) * p.mol_scale[m * L + l];
+            Vec<VEC> a1, a2, a3, a4;
+            a1.load(s_ptr[4 * m] + w);
+            a2.load(s_ptr[4 * m + 1] + w);
+            a3.load(s_ptr[4 * m + 2] + w);
+            a4.load(s_ptr[4 * m + 3] + w);
+            const double sc = s_ms[m];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                // 10**((1-t)(1-p) l1 + t(1-p) l2 + t p l3 + (1-t) p l4), optics.py:2290-2293
+                const double e = ((w1 * a1.v[v]) + (w2 * a2.v[v]) + (w3 * a3.v[v]) + (w4 * a4.v[v]));
+                // 10**e as exp(e ln 10): |e ln 10| < 120 adds < 2e-14 relative error, far inside 1e-6
+                taugas[v] += (exp(e * 2.302585092994045684) * N_A) * sc;
+            }
         }
     } else {
-        const int64_t r1 = (int64_t)p.pt_index[4 * l] * W + w;
-        for (int m = 0; m < p.nmol; ++m) taugas += (__ldg(p.mol_raw[m] + r1) * N_A) * p.mol_scale[m * L + l];
+        for (int m = 0; m < p.nmol; ++m) {
+            Vec<VEC> k;
+            k.load(s_ptr[m] + w);
+            const double sc = s_ms[m];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) taugas[v] += (k.v[v] * N_A) * sc;
+        }
     }
     // Rayleigh (optics.py:265-271)
-    double tauray = 0.0;
-    for (int m = 0; m < p.nray; ++m) tauray += __ldg(p.ray[m] + w) * p.ray_scale[m * L + l];
+    const double **rp = cp + p.ncont;
+    for (int m = 0; m < p.nray; ++m) {
+        Vec<VEC> k;
+        k.load(rp[m] + w);
+        const double sc = s_rs[m];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) tauray[v] += k.v[v] * sc;
+    }
     // Raman factor (optics.py:287-306), capped at 0.99999
-    double rf = 0.99999;
+    double rf[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) rf[v] = 0.99999;
     if (p.raman == 0) {
-        double num = 0.0, den = 0.0;
+        double num[VEC], den[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) num[v] = den[v] = 0.0;
 #pragma unroll
         for (int j = 0; j < kMaxJ; ++j) {
-            const double f = p.jfrac[j * L + l];
-            num = fma(f, __ldg(p.RA + (int64_t)j * W + w), num);
-            den = fma(f, __ldg(p.RB + (int64_t)j * W + w), den);
+            Vec<VEC> ra, rb;
+            ra.load(p.RA + (int64_t)j * W + w);
+            rb.load(p.RB + (int64_t)j * W + w);
+            const double f = s_jf[j];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { num[v] = fma(f, ra.v[v], num[v]); den[v] = fma(f, rb.v[v], den[v]); }
         }
-        rf = fmin(num / den, 0.99999);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) rf[v] = fmin(num[v] / den[v], 0.99999);
     } else if (p.raman == 1) {
-        rf = fmin(p.pollack[w], 0.99999);
+        Vec<VEC> pl;
+        pl.load(p.pollack + w);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) rf[v] = fmin(pl.v[v], 0.99999);
     }
     // cloud (optics.py:309-315)
-    double taucld = 0.0, w0c = 0.0, g0 = 0.0;
+    Vec<VEC> opd, cw0, cg0;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) opd.v[v] = cw0.v[v] = cg0.v[v] = 0.0;
     if (p.cld_opd) {
         const int64_t ic = (int64_t)l * p.ld + w;
-        taucld = __ldg(p.cld_opd + ic);
-        w0c = __ldg(p.cld_w0 + ic);
-        g0 = __ldg(p.cld_g0 + ic);
-        if (p.do_holes) taucld = p.fthin * taucld;
+        if (VEC == 1 || (p.ld & 1) == 0) {
+            opd.load(p.cld_opd + ic); cw0.load(p.cld_w0 + ic); cg0.load(p.cld_g0 + ic);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { opd.v[v] = __ldg(p.cld_opd + ic + v); cw0.v[v] = __ldg(p.cld_w0 + ic + v); cg0.v[v] = __ldg(p.cld_g0 + ic + v); }
+        }
+        if (p.do_holes) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) opd.v[v] = p.fthin * opd.v[v];
+        }
     }
-    // totals (optics.py:329-350)
-    const double dtau = taugas + tauray + taucld;
-    const double sc = w0c * taucld;
-    const double w0 = (tauray * rf + taucld * w0c) / dtau;
+    // totals (optics.py:329-350) and delta-Eddington (optics.py:412-420)
+    Vec<VEC> o0, o2, o3, o4, o5, o6, o7, o9, o10, o11, o12;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const double taucld = opd.v[v], w0c = cw0.v[v], g0 = cg0.v[v];
+        const double dtau = taugas[v] + tauray[v] + taucld;
+        const double sc = w0c * taucld;
+        const double w0 = (tauray[v] * rf[v] + taucld * w0c) / dtau;
+        const double fray = tauray[v] / (tauray[v] + sc);
+        o4.v[v] = sc / (sc + tauray[v]);
+        o5.v[v] = fray;
+        o6.v[v] = 0.5 * fray;
+        o7.v[v] = dtau;
+        o9.v[v] = w0;
+        o10.v[v] = g0;
+        o11.v[v] = (tauray[v] * 0.99999 + taucld * w0c) / dtau;
+        if (p.dedd) {
+            double f = 1.0;
+            for (int s = 0; s < p.stream; ++s) f *= g0;
+            o0.v[v] = dtau * (1. - w0 * f);
+            o2.v[v] = w0 * (1. - f) / (1.0 - w0 * f);
+            o3.v[v] = (g0 - f) / (1. - f);
+            o12.v[v] = f;
+        } else {
+            o0.v[v] = dtau; o2.v[v] = w0; o3.v[v] = g0; o12.v[v] = 0 * g0;
+        }
+    }
     const int64_t io = (int64_t)l * W + w;
-    if (p.o[4]) p.o[4][io] = sc / (sc + tauray);
-    const double fray = tauray / (tauray + sc);
-    if (p.o[5]) p.o[5][io] = fray;
-    if (p.o[6]) p.o[6][io] = 0.5 * fray;
-    if (p.o[7]) p.o[7][io] = dtau;
-    if (p.o[9]) p.o[9][io] = w0;
-    if (p.o[10]) p.o[10][io] = g0;
-    if (p.o[11]) p.o[11][io] = (tauray * 0.99999 + taucld * w0c) / dtau;
-    if (p.dedd) {
-        // delta-Eddington (optics.py:412-420)
-        double f = 1.0;
-        for (int s = 0; s < p.stream; ++s) f *= g0;
-        if (p.o[0]) p.o[0][io] = dtau * (1. - w0 * f);
-        if (p.o[2]) p.o[2][io] = w0 * (1. - f) / (1.0 - w0 * f);
-        if (p.o[3]) p.o[3][io] = (g0 - f) / (1. - f);
-        if (p.o[12]) p.o[12][io] = f;
-    } else {
-        if (p.o[0]) p.o[0][io] = dtau;
-        if (p.o[2]) p.o[2][io] = w0;
-        if (p.o[3]) p.o[3][io] = g0;
-        if (p.o[12]) p.o[12][io] = 0 * g0;
-    }
+    if (p.o[0]) o0.store(p.o[0] + io);
+    if (p.o[2]) o2.store(p.o[2] + io);
+    if (p.o[3]) o3.store(p.o[3] + io);
+    if (p.o[4]) o4.store(p.o[4] + io);
+    if (p.o[5]) o5.store(p.o[5] + io);
+    if (p.o[6]) o6.store(p.o[6] + io);
+    if (p.o[7]) o7.store(p.o[7] + io);
+    if (p.o[9]) o9.store(p.o[9] + io);
+    if (p.o[10]) o10.store(p.o[10] + io);
+    if (p.o[11]) o11.store(p.o[11] + io);
+    if (p.o[12]) o12.store(p.o[12] + io);
 }
 
 // TAU[0] = 0, TAU[l+1] = TAU[l] + DTAU[l]  (numba_cumsum, optics.py:353-354, :419-420): one
@@ -451,9 +555,25 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
     double *dtau_d = p.o[0], *dtau_og = p.o[7];
     if (p.o[1] && !dtau_d) { PB_TRY(pb_arena_alloc(ctx, (size_t)L * nW, (void **)&dtau_d)); p.o[0] = dtau_d; }
     if (p.o[8] && !dtau_og) { PB_TRY(pb_arena_alloc(ctx, (size_t)L * nW, (void **)&dtau_og)); p.o[7] = dtau_og; }
-    dim3 grid((W + 255) / 256, L);
-    opacity_layer_kernel<<<grid, 256, 0, ctx->stream>>>(p);
-    PB_CHECK_LAUNCH(ctx);
+    {
+        const int nrow = a->query == 1 ? 4 : 1;
+        const size_t smem = sizeof(double *) * (size_t)(t->nmol * nrow + t->ncont + t->nray) +
+                            sizeof(double) * (size_t)(4 + t->nmol + t->ncont + t->nray + kMaxJ);
+        if (smem > 48 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "compute_opacity: too many species for the per-layer shared table");
+        // 16-byte vector path: even nwno (every table row and output row is then 16-byte aligned)
+        bool vec2 = (W % 2 == 0);
+        for (int k = 0; k < 13; ++k) if (p.o[k] && ((uintptr_t)p.o[k] & 15)) vec2 = false;
+        if (p.pollack && ((uintptr_t)p.pollack & 15)) vec2 = false;
+        if (p.cld_opd && (((uintptr_t)p.cld_opd | (uintptr_t)p.cld_w0 | (uintptr_t)p.cld_g0) & 15)) vec2 = false;
+        if (vec2) {
+            dim3 grid((W / 2 + 127) / 128, L);
+            opacity_layer_kernel<2><<<grid, 128, smem, ctx->stream>>>(p);
+        } else {
+            dim3 grid((W + 127) / 128, L);
+            opacity_layer_kernel<1><<<grid, 128, smem, ctx->stream>>>(p);
+        }
+        PB_CHECK_LAUNCH(ctx);
+    }
     if (p.o[1]) {
         opacity_cumsum_kernel<<<(W + 127) / 128, 128, 0, ctx->stream>>>(L, W, dtau_d, p.o[1]);
         PB_CHECK_LAUNCH(ctx);
