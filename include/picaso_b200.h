@@ -100,6 +100,11 @@ typedef struct pb_reflected_args {
     double *xint_at_top;                                        /* [numg*numt][nwno] */
     double *albedo;                                             /* [nwno], fused compress_disco */
     double *flux_minus, *flux_plus, *flux_minus_mdpt, *flux_plus_mdpt; /* [numg*numt][nlevel][nwno] */
+    /* 0: get_reflected_1d.  1: the per-facet formulas of get_reflected_3d (fluxes.py:355-660): the
+     * nbatch entries are the ng*nt facets (each with its own opacities), numg = numt = 1, ubar0/ubar1
+     * hold one value per facet, |ubar| is used, exponents clip at 40, quadrature coefficients, 3-D
+     * 'cahoy' phase function; TOA intensity only. */
+    int variant;
 } pb_reflected_args;
 
 int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *args, int memspace);
@@ -167,6 +172,10 @@ typedef struct pb_thermal_args {
     double *flux_at_top;                   /* [numg*numt][nwno] or NULL */
     double *thermal;                       /* [nwno] fused compress_thermal, or NULL */
     double *flux_minus, *flux_plus, *flux_minus_mdpt, *flux_plus_mdpt; /* [numg*numt][nlevel][nwno] or NULL */
+    /* 0: get_thermal_1d.  1: get_thermal_3d (fluxes.py:2148-2352): nbatch = ng*nt facets with their own
+     * tlevel/plevel/opacities, numg = numt = 1, ubar1 one value per facet, pi-based boundary terms,
+     * calc_type 0, TOA only. */
+    int variant;
 } pb_thermal_args;
 
 int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *args, int memspace);

@@ -39,6 +39,11 @@ typedef double real;
 
 #define PI 3.14159265358979323846
 
+/* 0: the 1-D reference functions; 1: the per-facet formulas of get_reflected_3d / get_thermal_3d
+ * (fluxes.py:355-660, :2148-2352): |ubar|, exponent clip 40, the 3-D 'cahoy' phase function, and the
+ * pi-based thermal boundary terms.  Set only by the *_3d entry points below. */
+static int g_variant = 0;
+
 /* tri_diag_solve, fluxes.py:311-323: eliminate from the last row upwards, then
  * substitute from the first row downwards. */
 static void tri_solve(int n, const real *a, const real *b, const real *c, const real *d,
@@ -153,7 +158,8 @@ void ORC_NAME(orc_get_reflected_1d)(
             }
             const real f0 = F0PI[w], r = surf_reflect[w], bt = b_top ? b_top[w] : 0.0;
             for (int a = 0; a < G; ++a) {
-                const real u0 = ubar0[a], u1 = ubar1[a];
+                const real u0 = g_variant ? (real)fabs(ubar0[a]) : (real)ubar0[a];
+                const real u1 = g_variant ? (real)fabs(ubar1[a]) : (real)ubar1[a];
                 /* fluxes.py:1146-1183 */
                 for (int l = 0; l < L; ++l) {
                     real om = LW(w0, l), fc = LW(ftau_cld, l), g = LW(cosb, l);
@@ -168,7 +174,7 @@ void ORC_NAME(orc_get_reflected_1d)(
                     cmd[l] = a_minus * xd; cpd[l] = a_plus * xd;
                     apl[l] = a_plus; ex[l] = a_minus; /* keep a+- for the midpoint terms */
                     real e = lam[l] * LW(dtau, l);
-                    if (e > 35.0) e = 35.0;
+                    if (e > (g_variant ? 40.0 : 35.0)) e = (g_variant ? 40.0 : 35.0);
                     ep[l] = R_EXP(e);
                     em[l] = 1.0 / ep[l];
                 }
@@ -189,7 +195,7 @@ void ORC_NAME(orc_get_reflected_1d)(
                         flux_minus[base + (size_t)l * W + w] = fm;
                         flux_plus[base + (size_t)l * W + w] = fp;
                         real e = lam[l] * LW(dtau, l);
-                        if (e > 35.0) e = 35.0;
+                        if (e > (g_variant ? 40.0 : 35.0)) e = (g_variant ? 40.0 : 35.0);
                         real epm = R_EXP(0.5 * e), emm = 1.0 / epm;
                         real taumid = LW(tau, l) + 0.5 * LW(dtau, l);
                         real xm = R_EXP(-taumid / u0);
@@ -234,7 +240,15 @@ void ORC_NAME(orc_get_reflected_1d)(
                             gb = constant_back * go;
                             f = frac_a + frac_b * R_POW(gb, frac_c);
                         }
-                        if (single_phase == 0)
+                        if (single_phase == 0 && g_variant) {
+                            /* get_reflected_3d's 'cahoy' (fluxes.py:582-588): denominators use cosb_og
+                             * and -cosb_og/2 instead of g_forward / g_back */
+                            real tf = 1 + go * go + 2 * go * cos_theta;
+                            real hb = -go / 2.;
+                            real tb = 1 + hb * hb + 2 * hb * cos_theta;
+                            ps = f * (1 - gf * gf) / R_SQRT(tf * tf * tf) +
+                                 (1 - f) * (1 - gb * gb) / R_SQRT(tb * tb * tb) + (LW(gcos2, l));
+                        } else if (single_phase == 0)
                             ps = f * hg_down(gf, cos_theta) + (1.0 - f) * hg_down(gb, cos_theta) +
                                  LW(gcos2, l);
                         else if (single_phase == 1)
@@ -246,7 +260,7 @@ void ORC_NAME(orc_get_reflected_1d)(
                                        (1.0 - f) * hg_down(gb, cos_theta)) +
                                  LW(ftau_ray, l) * (0.75 * (1.0 + cos_theta * cos_theta));
                         real e = lam[l] * LW(dtau, l);
-                        if (e > 35.0) e = 35.0;
+                        if (e > (g_variant ? 40.0 : 35.0)) e = (g_variant ? 40.0 : 35.0);
                         real dt = LW(dtau, l);
                         xint[l] = xint[l + 1] * R_EXP(-dt / u1) +
                                   (LW(w0_og, l) * f0 / (4.0 * PI)) * ps * R_EXP(-LW(tau_og, l) / u0) *
@@ -342,7 +356,7 @@ void ORC_NAME(orc_get_thermal_1d)(
             real tau_top = LW(dtau, 0) * plevel[0] / (plevel[1] - plevel[0]);
             real b_top = (1.0 - R_EXP(-tau_top / mu1)) * bb[0] * PI;
             real r = surf_reflect[w];
-            real b_surface = hard_surface ? (1.0 - r) * bb[L] * PI
+            real b_surface = hard_surface ? (g_variant ? PI * bb[L] : (1.0 - r) * bb[L] * PI)
                                             : (bb[L] + b1[L - 1] * mu1) * PI;
             build_tridiag(L, cpu, cmu, cpd, cmd, b_top, b_surface, r, gam, ep, em, A, B, C, D);
             tri_solve(2 * L, A, B, C, D, AS, DS, X);
@@ -363,9 +377,14 @@ void ORC_NAME(orc_get_thermal_1d)(
             for (int a = 0; a < G; ++a) {
                 real u = ubar1[a];
                 for (int i = 0; i < V; ++i) fm[i] = fp[i] = fmm[i] = fpm[i] = 0.0;
-                fp[L] = hard_surface ? (1.0 - r) * bb[L] * 2 * PI
-                                     : (bb[L] + b1[L - 1] * u) * 2 * PI;
-                fm[0] = (1 - R_EXP(-tau_top / u)) * bb[0] * 2 * PI;
+                if (g_variant) { /* get_thermal_3d, fluxes.py:2302-2306 */
+                    fp[L] = hard_surface ? PI * (b_surface) : PI * (bb[L] + b1[L - 1] * u);
+                    fm[0] = PI * (1 - R_EXP(-tau_top / u)) * bb[0];
+                } else {
+                    fp[L] = hard_surface ? (1.0 - r) * bb[L] * 2 * PI
+                                         : (bb[L] + b1[L - 1] * u) * 2 * PI;
+                    fm[0] = (1 - R_EXP(-tau_top / u)) * bb[0] * 2 * PI;
+                }
                 for (int it = 0; it < L; ++it) {
                     real dt = LW(dtau, it);
                     real xa = R_EXP(-dt / u), xh = R_EXP(-0.5 * dt / u);
@@ -470,4 +489,43 @@ void ORC_NAME(orc_compress_thermal)(int n, const f64 *flux_at_top, const f64 *gw
                 s = s + flux_at_top[((size_t)ig * nt + it) * n + w] * gweight[ig] * tweight[it];
         flux[w] = s * sym;
     }
+}
+
+
+/* get_reflected_3d, fluxes.py:355-660.  Facet-major inputs: every layer/level array is
+ * [numg*numt][nlayer|nlevel][nwno] (the Python wrapper transposes the reference's [.., nwno, ng, nt]). */
+void ORC_NAME(orc_get_reflected_3d)(
+    int nlevel, int nwno, int numg, int numt,
+    const f64 *dtau, const f64 *tau, const f64 *w0, const f64 *cosb, const f64 *gcos2,
+    const f64 *ftau_cld, const f64 *ftau_ray, const f64 *dtau_og, const f64 *tau_og,
+    const f64 *w0_og, const f64 *cosb_og, const f64 *surf_reflect, const f64 *ubar0,
+    const f64 *ubar1, f64 cos_theta, const f64 *F0PI, int single_phase, int multi_phase,
+    f64 frac_a, f64 frac_b, f64 frac_c, f64 constant_back, f64 constant_forward,
+    f64 *xint_at_top, int nthreads)
+{
+    const size_t nl = (size_t)(nlevel - 1) * nwno, nv = (size_t)nlevel * nwno;
+    g_variant = 1;
+    for (int a = 0; a < numg * numt; ++a)
+        ORC_NAME(orc_get_reflected_1d)(nlevel, nwno, 1, 1, dtau + a * nl, tau + a * nv, w0 + a * nl, cosb + a * nl,
+                             gcos2 + a * nl, ftau_cld + a * nl, ftau_ray + a * nl, dtau_og + a * nl,
+                             tau_og + a * nv, w0_og + a * nl, cosb_og + a * nl, surf_reflect, ubar0 + a,
+                             ubar1 + a, cos_theta, F0PI, single_phase, multi_phase, frac_a, frac_b, frac_c,
+                             constant_back, constant_forward, 1, 0, 0, NULL, xint_at_top + (size_t)a * nwno,
+                             NULL, NULL, NULL, NULL, nthreads);
+    g_variant = 0;
+}
+
+/* get_thermal_3d, fluxes.py:2148-2352.  Facet-major inputs; tlevel/plevel are [numg*numt][nlevel]. */
+void ORC_NAME(orc_get_thermal_3d)(
+    int nlevel, const f64 *wno, int nwno, int numg, int numt, const f64 *tlevel, const f64 *dtau,
+    const f64 *w0, const f64 *cosb, const f64 *plevel, const f64 *ubar1, const f64 *surf_reflect,
+    int hard_surface, f64 *int_at_top, int nthreads)
+{
+    const size_t nl = (size_t)(nlevel - 1) * nwno;
+    g_variant = 1;
+    for (int a = 0; a < numg * numt; ++a)
+        ORC_NAME(orc_get_thermal_1d)(nlevel, wno, nwno, 1, 1, tlevel + (size_t)a * nlevel, dtau + a * nl, w0 + a * nl,
+                           cosb + a * nl, plevel + (size_t)a * nlevel, ubar1 + a, surf_reflect, hard_surface,
+                           NULL, 0, int_at_top + (size_t)a * nwno, NULL, NULL, NULL, NULL, nthreads);
+    g_variant = 0;
 }

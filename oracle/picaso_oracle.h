@@ -89,6 +89,22 @@ void orc_get_thermal_SH(
     const double *plevel, const double *ubar1, const double *surf_reflect, int stream,
     int hard_surface, double *xint_at_top, int nthreads);
 
+/* follow fluxes.py:355-660 (get_reflected_3d) and :2148-2352 (get_thermal_3d); facet-major
+ * inputs [numg*numt][nlayer|nlevel][nwno] (tlevel/plevel [numg*numt][nlevel]). */
+void orc_get_reflected_3d(
+    int nlevel, int nwno, int numg, int numt,
+    const double *dtau, const double *tau, const double *w0, const double *cosb, const double *gcos2,
+    const double *ftau_cld, const double *ftau_ray, const double *dtau_og, const double *tau_og,
+    const double *w0_og, const double *cosb_og, const double *surf_reflect, const double *ubar0,
+    const double *ubar1, double cos_theta, const double *F0PI, int single_phase, int multi_phase,
+    double frac_a, double frac_b, double frac_c, double constant_back, double constant_forward,
+    double *xint_at_top, int nthreads);
+void orc_get_thermal_3d(
+    int nlevel, const double *wno, int nwno, int numg, int numt, const double *tlevel,
+    const double *dtau, const double *w0, const double *cosb, const double *plevel,
+    const double *ubar1, const double *surf_reflect, int hard_surface, double *int_at_top,
+    int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ class ReflectedArgs(ctypes.Structure):
         [(n, c_dbl) for n in ("frac_a", "frac_b", "frac_c", "constant_back", "constant_forward")] +
         [("get_toa_intensity", c_int), ("get_lvl_flux", c_int)] +
         [(n, c_vp) for n in ("xint_at_top", "albedo", "flux_minus", "flux_plus", "flux_minus_mdpt",
-                             "flux_plus_mdpt")])
+                             "flux_plus_mdpt")] + [("variant", c_int)])
 
 
 class ShArgs(ctypes.Structure):
@@ -76,7 +76,7 @@ class ThermalArgs(ctypes.Structure):
                              "plevel", "ubar1", "gweight", "tweight")] +
         [("hard_surface", c_int), ("calc_type", c_int)] +
         [(n, c_vp) for n in ("flux_at_top", "thermal", "flux_minus", "flux_plus",
-                             "flux_minus_mdpt", "flux_plus_mdpt")])
+                             "flux_minus_mdpt", "flux_plus_mdpt")] + [("variant", c_int)])
 
 
 class TransitArgs(ctypes.Structure):

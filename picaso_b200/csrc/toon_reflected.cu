@@ -39,6 +39,8 @@ struct ReflParams {
     double *xint, *albedo;
     double *fm, *fp, *fmm, *fpm;
     int fuse_albedo;
+    int variant;   // 1: per-facet get_reflected_3d semantics (geometry indexed by batch entry)
+    double clip;   // exponent clip: 35 (1-D, fluxes.py:1174) or 40 (3-D, fluxes.py:516)
 };
 
 constexpr int kWavesPerCta = 32;
@@ -61,6 +63,13 @@ __device__ __forceinline__ double p_single(const ReflParams &p, double g_og, dou
     const double gbc = (p.frac_c == 2.0) ? gb * gb : pow(gb, p.frac_c);
     double f = p.frac_a + p.frac_b * gbc;
     double tt = f * hg_down(gf, p.cos_theta) + (1.0 - f) * hg_down(gb, p.cos_theta);
+    if (p.sp == 0 && p.variant) {
+        // get_reflected_3d's 'cahoy' (fluxes.py:582-588): denominators use cosb_og and -cosb_og/2
+        const double tf = 1 + g_og * g_og + 2 * g_og * p.cos_theta;
+        const double hb = -g_og / 2.;
+        const double tb = 1 + hb * hb + 2 * hb * p.cos_theta;
+        return f * (1 - gf * gf) / sqrt(tf * tf * tf) + (1 - f) * (1 - gb * gb) / sqrt(tb * tb * tb) + (gcos2);
+    }
     if (p.sp == 0) return tt + gcos2;
     if (p.sp == 2) return tt;
     return fcld * tt + fray * (0.75 * (1.0 + p.cos_theta * p.cos_theta));
@@ -127,7 +136,7 @@ __device__ __forceinline__ void refl_produce(const ReflParams &p, const ReflInpu
     toon_g(p.tc, x.om, g, g1, g2);
     const double lam = sqrt(g1 * g1 - g2 * g2);
     const double gam = (g1 - lam) * pbm::krcp(g2);
-    const double E = fmin(lam * x.dt, 35.0);  // slice_gt(exptrm, 35), fluxes.py:1174
+    const double E = fmin(lam * x.dt, p.clip);  // slice_gt(exptrm, 35 | 40), fluxes.py:1174, :516
     const double EP = pbm::kexp(E);
     const double ps = p_single(p, x.cbo, x.gc2, x.fc, x.fr);
     q[Q_G * 32] = g;
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(256) refl_toa_kernel(ReflParams p)
     const int64_t ol = (int64_t)b * p.bs_layer + wc;
     const int64_t ov = (int64_t)b * p.bs_level + wc;
     const int64_t ow = (int64_t)b * p.bs_wave + wc;
-    const double u0 = p.ubar0[ac], u1 = p.ubar1[ac];
+    const double u0 = p.variant ? fabs(p.ubar0[b]) : p.ubar0[ac], u1 = p.variant ? fabs(p.ubar1[b]) : p.ubar1[ac];
     const double f0 = p.f0pi ? p.f0pi[ow] : 1.0;
     const double r = p.surf ? p.surf[ow] : 0.0;
     const double btop = p.btop ? p.btop[ow] : 0.0;
@@ -498,6 +507,9 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
         return pb_fail(ctx, PB_ERR_ARG, "reflected: unsupported enum (single_phase=%d multi_phase=%d toon=%d)",
                        a->single_phase, a->multi_phase, a->toon_coefficients);
     const bool want_lvl = a->get_lvl_flux != 0;
+    if (a->variant != 0 && a->variant != 1) return pb_fail(ctx, PB_ERR_ARG, "reflected: variant must be 0 or 1");
+    if (a->variant == 1 && (G != 1 || want_lvl || a->albedo || a->toon_coefficients != 0))
+        return pb_fail(ctx, PB_ERR_ARG, "reflected: variant 1 (3-D facets) needs numg=numt=1 per facet, quadrature, TOA intensity only");
     if (want_lvl && (!a->flux_minus || !a->flux_plus || !a->flux_minus_mdpt || !a->flux_plus_mdpt))
         return pb_fail(ctx, PB_ERR_ARG, "reflected: get_lvl_flux without the four level arrays");
     const bool want_toa = a->get_toa_intensity != 0 && (a->xint_at_top || a->albedo);
@@ -519,7 +531,7 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
     }
     pb_arena_reset(ctx);
     PB_TRY(pb_arena_reserve(ctx, need));
-    PB_TRY(pb_pinned_reserve(ctx, 4 * ((size_t)G + 16) * sizeof(double)));
+    PB_TRY(pb_pinned_reserve(ctx, 4 * ((size_t)G + (size_t)B + 16) * sizeof(double)));
 
     ReflParams p;
     memset(&p, 0, sizeof(p));
@@ -545,20 +557,23 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
         PB_TRY(pb_stage_in(ctx, a->tau, memspace, rowsV, W, a->ld, &p.tau, &ldo));
         if (a->tau_og == a->tau) p.tau_og = p.tau;
         else PB_TRY(pb_stage_in(ctx, a->tau_og, memspace, rowsV, W, a->ld, &p.tau_og, &ldo));
-        PB_TRY(pb_stage_in(ctx, a->surf_reflect, memspace, B, W, W, &p.surf, &ldo));
-        PB_TRY(pb_stage_in(ctx, a->F0PI, memspace, B, W, W, &p.f0pi, &ldo));
-        PB_TRY(pb_stage_in(ctx, a->b_top, memspace, B, W, W, &p.btop, &ldo));
+        const int64_t nvec = a->variant ? 1 : B;
+        PB_TRY(pb_stage_in(ctx, a->surf_reflect, memspace, nvec, W, W, &p.surf, &ldo));
+        PB_TRY(pb_stage_in(ctx, a->F0PI, memspace, nvec, W, W, &p.f0pi, &ldo));
+        PB_TRY(pb_stage_in(ctx, a->b_top, memspace, nvec, W, W, &p.btop, &ldo));
     }
     if (host) ld = W;
     p.ld = ld;
-    p.bs_layer = (int64_t)L * ld; p.bs_level = (int64_t)V * ld; p.bs_wave = W;
-    PB_TRY(pb_upload_small(ctx, a->ubar0, G, &p.ubar0));
-    PB_TRY(pb_upload_small(ctx, a->ubar1, G, &p.ubar1));
+    p.bs_layer = (int64_t)L * ld; p.bs_level = (int64_t)V * ld;
+    p.bs_wave = a->variant ? 0 : W;  // 3-D facets share surf_reflect / F0PI / b_top
+    PB_TRY(pb_upload_small(ctx, a->ubar0, a->variant ? B : G, &p.ubar0));
+    PB_TRY(pb_upload_small(ctx, a->ubar1, a->variant ? B : G, &p.ubar1));
     if (a->gweight) PB_TRY(pb_upload_small(ctx, a->gweight, a->numg, &p.gweight));
     if (a->tweight) PB_TRY(pb_upload_small(ctx, a->tweight, a->numt, &p.tweight));
     p.cos_theta = a->cos_theta; p.frac_a = a->frac_a; p.frac_b = a->frac_b; p.frac_c = a->frac_c;
     p.cback = a->constant_back; p.cfwd = a->constant_forward;
     p.sp = a->single_phase; p.mp = a->multi_phase; p.tc = a->toon_coefficients;
+    p.variant = a->variant; p.clip = a->variant ? 40.0 : 35.0;
 
     // ---- outputs ----
     double *d_xint = nullptr, *d_alb = nullptr, *d_lv[4] = {nullptr, nullptr, nullptr, nullptr};

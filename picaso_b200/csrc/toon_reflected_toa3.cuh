@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(256) refl_toa_kernel3(ReflParams p)
     const int64_t ov = (int64_t)b * p.bs_level + wc;
     const int64_t ow = (int64_t)b * p.bs_wave + wc;
     ReflAngle g;
-    g.u0 = p.ubar0[ac]; g.u1 = p.ubar1[ac];
+    g.u0 = p.variant ? fabs(p.ubar0[b]) : p.ubar0[ac];  // 3-D facets: geometry per batch entry, |ubar|
+    g.u1 = p.variant ? fabs(p.ubar1[b]) : p.ubar1[ac];
     g.f0 = p.f0pi ? p.f0pi[ow] : 1.0;
     const double r = p.surf ? p.surf[ow] : 0.0;
     const double btop = p.btop ? p.btop[ow] : 0.0;

@@ -26,6 +26,7 @@ struct ThermParams {
     double *ftop, *thermal;
     double *fm, *fp, *fmm, *fpm;
     int fuse;
+    int variant;  // 1: get_thermal_3d per-facet semantics (fluxes.py:2148-2352)
 };
 
 constexpr int kWavesPerCta = 32;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
     const int64_t ol = (int64_t)b * p.bs_layer + wc;
     const double *tl = p.tlevel + (int64_t)b * V;
     const double *pl = p.plevel + (int64_t)b * V;
-    const double u = p.ubar1[ac];
+    const double u = p.variant ? p.ubar1[b] : p.ubar1[ac];
     const double inv_u = 1.0 / u;
     const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + wc] : 0.0;
     double *sB = smem;
@@ -216,13 +217,16 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
             if (l == L - 1) {
                 // surface boundary, fluxes.py:1802-1806, :1869-1873, last row :178-181
                 const double b1 = q[T_B1 * 32];
-                const double b_surface = p.hard_surface ? (1.0 - r) * BL * PB_PI : (BL + b1 * kMu1) * PB_PI;
+                // 3-D variant: b_surface = pi B_L without emissivity, int_plus[L] = pi b_surface | pi (B_L + b1 u)
+                const double b_surface = p.hard_surface ? (p.variant ? PB_PI * BL : (1.0 - r) * BL * PB_PI)
+                                                        : (BL + b1 * kMu1) * PB_PI;
                 const double a_ = e1 - r * e3, b_ = e2 - r * e4;
                 const double d_ = b_surface - cpd + r * cmd;
                 const double ib = pbm::krcp(b_);
                 AS = a_ * ib;
                 DS = d_ * ib;
-                alpha = p.hard_surface ? (1.0 - r) * BL * 2 * PB_PI : (BL + b1 * u) * 2 * PB_PI;
+                if (p.variant) alpha = p.hard_surface ? PB_PI * b_surface : PB_PI * (BL + b1 * u);
+                else alpha = p.hard_surface ? (1.0 - r) * BL * 2 * PB_PI : (BL + b1 * u) * 2 * PB_PI;
                 beta = 0.0;
             } else {
                 const double gm1 = gam_n - 1.0;
@@ -468,6 +472,9 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
     if (a->calc_type == 1 && !a->dwno) return pb_fail(ctx, PB_ERR_ARG, "thermal: calc_type=1 needs dwno");
     if (a->thermal && (!a->gweight || !a->tweight)) return pb_fail(ctx, PB_ERR_ARG, "thermal: thermal output needs gweight/tweight");
     const bool want_lvl = a->flux_minus || a->flux_plus || a->flux_minus_mdpt || a->flux_plus_mdpt;
+    if (a->variant != 0 && a->variant != 1) return pb_fail(ctx, PB_ERR_ARG, "thermal: variant must be 0 or 1");
+    if (a->variant == 1 && (G != 1 || want_lvl || a->thermal || a->calc_type != 0))
+        return pb_fail(ctx, PB_ERR_ARG, "thermal: variant 1 (3-D facets) needs numg=numt=1 per facet, calc_type 0, TOA only");
     if (want_lvl && (!a->flux_minus || !a->flux_plus || !a->flux_minus_mdpt || !a->flux_plus_mdpt))
         return pb_fail(ctx, PB_ERR_ARG, "thermal: level fluxes need all four arrays");
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -486,7 +493,7 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
     }
     pb_arena_reset(ctx);
     PB_TRY(pb_arena_reserve(ctx, need));
-    PB_TRY(pb_pinned_reserve(ctx, (2 * (size_t)B * V + 3 * (size_t)G + 64) * sizeof(double)));
+    PB_TRY(pb_pinned_reserve(ctx, (2 * (size_t)B * V + 3 * (size_t)G + (size_t)B + 64) * sizeof(double)));
 
     ThermParams p;
     memset(&p, 0, sizeof(p));
@@ -497,15 +504,16 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
     PB_TRY(pb_stage_in(ctx, a->cosb, memspace, (int64_t)B * L, W, a->ld, &p.cosb, &ldo));
     PB_TRY(pb_stage_in(ctx, a->wno, memspace, 1, W, W, &p.wno, &ldo));
     PB_TRY(pb_stage_in(ctx, a->dwno, memspace, 1, W, W, &p.dwno, &ldo));
-    PB_TRY(pb_stage_in(ctx, a->surf_reflect, memspace, B, W, W, &p.surf, &ldo));
+    PB_TRY(pb_stage_in(ctx, a->surf_reflect, memspace, a->variant ? 1 : B, W, W, &p.surf, &ldo));
     p.ld = host ? W : a->ld;
     p.bs_layer = (int64_t)L * p.ld; p.bs_wave = W;
     PB_TRY(pb_upload_small(ctx, a->tlevel, (size_t)B * V, &p.tlevel));
     PB_TRY(pb_upload_small(ctx, a->plevel, (size_t)B * V, &p.plevel));
-    PB_TRY(pb_upload_small(ctx, a->ubar1, G, &p.ubar1));
+    PB_TRY(pb_upload_small(ctx, a->ubar1, a->variant ? B : G, &p.ubar1));
     if (a->gweight) PB_TRY(pb_upload_small(ctx, a->gweight, a->numg, &p.gweight));
     if (a->tweight) PB_TRY(pb_upload_small(ctx, a->tweight, a->numt, &p.tweight));
-    p.hard_surface = a->hard_surface; p.calc_type = a->calc_type;
+    p.hard_surface = a->hard_surface; p.calc_type = a->calc_type; p.variant = a->variant;
+    if (a->variant) p.bs_wave = 0;  // facets share surf_reflect
 
     double *d_ftop = nullptr, *d_th = nullptr, *d_lv[4] = {nullptr, nullptr, nullptr, nullptr};
     double *h_lv[4] = {a->flux_minus, a->flux_plus, a->flux_minus_mdpt, a->flux_plus_mdpt};

@@ -197,3 +197,69 @@ def thermal_sh_args(d, case):
     return (d["nlevel"], d["wno"], d["nwno"], d["numg"], d["numt"], d["tlevel"], d["dtau"], None, d["w0"],
             d["cosb"], None, None, None, d["w0"], d["cosb_og"], d["plevel"], d["ubar1"], d["surf_reflect"],
             case["stream"], case["hard_surface"])
+
+
+def facet_geometry(ng, nt, phase):
+    """get_angles_3d + compute_disco (disco.py:92-115, :36-50) in plain numpy"""
+    i = np.linspace(1, nt, nt)
+    tangle = np.cos(i * np.pi / (nt + 1))
+    tweight = np.pi / (nt + 1) * np.sin(i * np.pi / (nt + 1)) ** 2.0
+    gangle, gweight = np.polynomial.legendre.leggauss(ng)
+    ct = np.cos(phase)
+    lon = np.arcsin((gangle - (ct - 1.0) / (ct + 1.0)) / (2.0 / (ct + 1)))
+    f = np.sin(np.arccos(tangle))
+    return np.outer(np.cos(lon - phase), f), np.outer(np.cos(lon), f), float(ct), gweight, tweight
+
+
+REFL_KEYS = ("dtau", "tau", "w0", "cosb", "gcos2", "ftau_cld", "ftau_ray", "dtau_og", "tau_og", "w0_og", "cosb_og")
+
+
+def facets_cases():
+    """get_reflected_3d / get_thermal_3d (fluxes.py:355, :2148): per-facet opacities [rows, nwno, ng, nt]"""
+    cases = {}
+    for sp in (0, 1, 2, 3):
+        cases[f"refl3d_sp{sp}"] = dict(kind="refl", ng=3, nt=2, L=14, W=21, seed=500 + sp, phase=0.7, sp=sp,
+                                       mp=sp % 2, surf=0.2)
+    cases["refl3d_10x10ish"] = dict(kind="refl", ng=4, nt=3, L=30, W=40, seed=520, phase=1.9, sp=3, mp=0, surf=0.0)
+    for hs in (0, 1):
+        cases[f"therm3d_hs{hs}"] = dict(kind="therm", ng=3, nt=2, L=16, W=23, seed=540 + hs, phase=0.0, hs=hs,
+                                        surf=0.3 * hs)
+    return cases
+
+
+def build_facets(case):
+    ng, nt, L, W = case["ng"], case["nt"], case["L"], case["W"]
+    ubar0, ubar1, ct, gweight, tweight = facet_geometry(ng, nt, case["phase"])
+    out = dict(ng=ng, nt=nt, nlevel=L + 1, nwno=W, ubar0=ubar0, ubar1=ubar1, cos_theta=ct, gweight=gweight,
+               tweight=tweight, surf_reflect=np.full(W, case["surf"]))
+    if case["kind"] == "refl":
+        arrs = {k: np.zeros((L + 1 if k in ("tau", "tau_og") else L, W, ng, nt)) for k in REFL_KEYS}
+        for ig in range(ng):
+            for it in range(nt):
+                d = synth.reflected_inputs(L=L, W=W, seed=case["seed"] + 17 * ig + it)
+                for k in REFL_KEYS:
+                    arrs[k][:, :, ig, it] = d[k]
+        out.update(arrs)
+        out.update(wno=d["wno"], F0PI=d["F0PI"])
+    else:
+        arrs = {k: np.zeros((L, W, ng, nt)) for k in ("dtau", "w0", "cosb")}
+        tl = np.zeros((L + 1, ng, nt))
+        pl = np.zeros((L + 1, ng, nt))
+        for ig in range(ng):
+            for it in range(nt):
+                d = synth.thermal_inputs(L=L, W=W, seed=case["seed"] + 17 * ig + it)
+                for k in arrs:
+                    arrs[k][:, :, ig, it] = d[k]
+                tl[:, ig, it] = d["tlevel"] * (1 + 0.04 * ig - 0.02 * it)
+                pl[:, ig, it] = d["plevel"] * (1 + 0.1 * it)
+        out.update(arrs)
+        out.update(wno=d["wno"], tlevel=tl, plevel=pl)
+    return out
+
+
+def facets_args(d, case):
+    if case["kind"] == "refl":
+        return (d["nlevel"], d["wno"], d["nwno"], d["ng"], d["nt"], *[d[k] for k in REFL_KEYS], d["surf_reflect"],
+                d["ubar0"], d["ubar1"], d["cos_theta"], d["F0PI"], case["sp"], case["mp"], 1.0, -1.0, 2.0, -0.5, 1.0)
+    return (d["nlevel"], d["wno"], d["nwno"], d["ng"], d["nt"], d["tlevel"], d["dtau"], d["w0"], d["cosb"],
+            d["plevel"], d["ubar1"], d["surf_reflect"], case["hs"])

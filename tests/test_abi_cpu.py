@@ -39,8 +39,8 @@ def test_version(lib):
 
 def test_struct_sizes_match_header():
     # 5 ints + pad, i64, 18 pointers, double, 3 ints (+pad), 5 doubles, 2 ints, 6 pointers
-    assert ctypes.sizeof(_lib.ReflectedArgs) == 24 + 8 + 18 * 8 + 8 + 16 + 40 + 8 + 48
-    assert ctypes.sizeof(_lib.ThermalArgs) == 24 + 8 + 11 * 8 + 8 + 6 * 8
+    assert ctypes.sizeof(_lib.ReflectedArgs) == 24 + 8 + 18 * 8 + 8 + 16 + 40 + 8 + 48 + 8
+    assert ctypes.sizeof(_lib.ThermalArgs) == 24 + 8 + 11 * 8 + 8 + 6 * 8 + 8
     assert ctypes.sizeof(_lib.TransitArgs) == 16 + 8 + 7 * 8 + 24 + 8
 
 
