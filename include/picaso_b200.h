@@ -223,6 +223,8 @@ int pb_optab_set_continuum(pb_ctx *ctx, pb_optab *tab, int icont, const double *
 int pb_optab_set_rayleigh(pb_ctx *ctx, pb_optab *tab, int iray, const double *sigma);
 int pb_optab_set_raman(pb_ctx *ctx, pb_optab *tab, const double *wno, int ntrans, const double *c,
                        const int *ji, const double *deltanu, const double *stellar_shifts);
+/* pre-mixed correlated-k table of RetrieveCKs (optics.py:737-753): ln(kappa) [npress][ntemp][nwno][ngauss] */
+int pb_optab_set_ck(pb_ctx *ctx, pb_optab *tab, const double *lnkappa, int npress, int ntemp, int ngauss);
 int pb_optab_bytes(const pb_optab *tab, size_t *bytes);
 
 /* replaces get_opacities / get_opacities_nearest (optics.py:2241-2368) + compute_opacity
@@ -254,6 +256,18 @@ typedef struct pb_opacity_args {
      * TAU, TAU_OG are [nlayer+1][nwno], the others [nlayer][nwno] */
     double *DTAU, *TAU, *W0, *COSB, *ftau_cld, *ftau_ray, *GCOS2, *DTAU_OG, *TAU_OG, *W0_OG, *COSB_OG,
         *W0_no_raman, *f_deltaM;
+    /* correlated-k (ngauss > 1; RetrieveCKs.get_pre_mix_ck optics.py:1081-1161, compute_opacity :257-262):
+     * outputs become [nlayer|nlevel][nwno][ngauss] (gauss point fastest, the reference's layout) */
+    int ngauss;                /* 0/1 monochromatic, else must equal the ngauss of pb_optab_set_ck */
+    const int *ck_index;       /* [nlayer][4] flat rows p*ntemp + t in the reference's term order:
+                                  (p_low,t_low), (p_low,t_hi), (p_hi,t_hi), (p_hi,t_low) */
+    const double *ck_weights;  /* [nlayer][4] (1-t)(1-p), t(1-p), t p, (1-t) p */
+    const double *ck_scale;    /* [nlayer] colden/mmw */
+    /* continuum lookup: 0 nearest temperature (RetrieveOpacities), 1 log-linear in 1/T between rows
+     * cont_index and cont_index_hi with weight cont_t (RetrieveCKs.get_continuum, optics.py:1471-1497) */
+    int cont_mode;
+    const int *cont_index_hi;  /* [nlayer] */
+    const double *cont_t;      /* [nlayer] */
 } pb_opacity_args;
 
 int pb_compute_opacity(pb_ctx *ctx, pb_optab *tab, const pb_opacity_args *args, int memspace);

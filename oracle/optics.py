@@ -183,3 +183,104 @@ def compute_opacity(atm, molecular_opa, continuum_opa, rayleigh_opa, raman_facto
             return (dtau_d, tau_d, w0_d, cosb_d, ftau_cld, ftau_ray, GCOS2, DTAU, TAU, W0, COSB,
                     W0_no_raman, f)
     return (DTAU, TAU, W0, COSB, ftau_cld, ftau_ray, GCOS2, DTAU, TAU, W0, COSB, W0_no_raman, 0 * COSB)
+
+
+# ---- correlated-k (RetrieveCKs, pre-mixed tables) ---------------------------------------------------
+def ck_find_pts(pressures, temps, nc_p, tlayer, player_bar):
+    """index / weight logic of RetrieveCKs.get_pre_mix_ck (optics.py:1086-1149)."""
+    t_inv = 1 / np.asarray(tlayer, dtype=np.float64)
+    p_log = np.log10(np.asarray(player_bar, dtype=np.float64))
+    p_grid = np.unique(pressures)
+    p_log_grid = np.log10(p_grid[p_grid > 0])
+    t_inv_grid = 1 / np.array(np.unique(temps))
+    L = t_inv.size
+    t_low = np.zeros(L, dtype=np.int64)
+    for i in range(L):
+        find = np.where(t_inv_grid > t_inv[i])[0]
+        t_low[i] = 0 if len(find) == 0 else find[-1]
+    t_low[t_low == (len(t_inv_grid) - 1)] = len(t_inv_grid) - 2
+    t_hi = t_low + 1
+    p_low = np.zeros(L, dtype=np.int64)
+    for i in range(L):
+        find = np.where(p_log_grid <= p_log[i])[0]
+        p_low[i] = 0 if len(find) == 0 else find[-1]
+        p_low[i] = min(p_low[i], nc_p[t_hi[i]] - 3)
+    p_hi = p_low + 1
+    t_interp = (t_inv - t_inv_grid[t_low]) / (t_inv_grid[t_hi] - t_inv_grid[t_low])
+    p_interp = (p_log - p_log_grid[p_low]) / (p_log_grid[p_hi] - p_log_grid[p_low])
+    return t_interp, p_interp, p_low, t_low, p_hi, t_hi
+
+
+def premix_ck(ln_kappa, t_interp, p_interp, p_low, t_low, p_hi, t_hi):
+    """optics.py:1151-1161: ln_kappa [nP, nT, W, K] -> molecular_opa [L, W, K]."""
+    t = np.asarray(t_interp)[:, None, None]
+    p = np.asarray(p_interp)[:, None, None]
+    out = np.exp(((1 - t) * (1 - p) * ln_kappa[p_low, t_low, :, :]) + ((t) * (1 - p) * ln_kappa[p_low, t_hi, :, :]) +
+                 ((t) * (p) * ln_kappa[p_hi, t_hi, :, :]) + ((1 - t) * (p) * ln_kappa[p_hi, t_low, :, :]))
+    return out * N_A
+
+
+def continuum_loglinear(cia_temps, table, tlayer):
+    """RetrieveCKs.get_continuum (optics.py:1410-1497) for one CIA pair: table [nTc, W] in the order of
+    cia_temps -> [L, W]; returns also the (low, high) row indices into the ascending-sorted table and t."""
+    order = np.argsort(cia_temps)
+    st = np.asarray(cia_temps, dtype=np.float64)[order]
+    tab = np.asarray(table)[order]
+    L = len(tlayer)
+    lo = np.zeros(L, dtype=np.int64)
+    hi = np.zeros(L, dtype=np.int64)
+    for i, t in enumerate(tlayer):
+        if t <= st[0]:
+            lo[i], hi[i] = 0, 1
+        elif t >= st[-1]:
+            lo[i], hi[i] = len(st) - 2, len(st) - 1
+        else:
+            lo[i] = np.where(st - t <= 0)[0][-1]
+            hi[i] = np.where(st - t > 0)[0][0]
+    t_inv = 1 / np.asarray(tlayer, dtype=np.float64)
+    ti = (t_inv - 1 / st[lo]) / (1 / st[hi] - 1 / st[lo])
+    out = np.exp(((1 - ti)[:, None] * np.log(tab[lo])) + ((ti)[:, None] * np.log(tab[hi])))
+    return out, lo, hi, ti
+
+
+def compute_opacity_ck(atm, molecular_opa, continuum_opa, rayleigh_opa, stream=2, delta_eddington=True):
+    """optics.py:147-431 for ngauss > 1 (pre-mixed CK), raman = 2, test_mode = None: molecular_opa
+    [L, W, K] (already x N_A); returns the 13-tuple of [L|V, W, K] arrays."""
+    L, W, K = molecular_opa.shape
+    # continuum, Rayleigh and cloud terms are identical for every gauss point (optics.py:238, :277, :309-312):
+    # run the monochromatic assembly once without molecules / Rayleigh / cloud to get the continuum sum
+    bare = dict(atm, cloud_opd=np.zeros((L, W)), cloud_w0=np.zeros((L, W)), cloud_g0=np.zeros((L, W)))
+    zero_ray = {m: np.zeros(W) for m in rayleigh_opa}
+    with np.errstate(all="ignore"):
+        TAUGAS0 = compute_opacity(bare, {}, continuum_opa, zero_ray, None, stream=stream, delta_eddington=False)[7]
+    colden = atm["colden"][:, None, None]
+    mmw = atm["mmw"][:, None, None]
+    TAURAY = np.zeros((L, W))
+    for m, sig in rayleigh_opa.items():
+        TAURAY += np.array([sig] * L) * (atm["colden"][:, None] * atm["mixingratios"][m][:, None] / atm["mmw"][:, None])
+    TAUCLD = atm["cloud_opd"]
+    TAUGAS = TAUGAS0[:, :, None] + molecular_opa * (colden / mmw)
+    TAURAY = np.repeat(TAURAY[:, :, None], K, axis=2)
+    TAUCLD = np.repeat(TAUCLD[:, :, None], K, axis=2)
+    w0c = np.repeat(atm["cloud_w0"][:, :, None], K, axis=2)
+    g0 = np.repeat(atm["cloud_g0"][:, :, None], K, axis=2)
+    rf = 0.99999
+    with np.errstate(all="ignore"):
+        DTAU = TAUGAS + TAURAY + TAUCLD
+        ftau_cld = (w0c * TAUCLD) / (w0c * TAUCLD + TAURAY)
+        ftau_ray = TAURAY / (TAURAY + w0c * TAUCLD)
+        GCOS2 = 0.5 * ftau_ray
+        W0 = (TAURAY * rf + TAUCLD * w0c) / (TAUGAS + TAURAY + TAUCLD)
+        W0nr = (TAURAY * 0.99999 + TAUCLD * w0c) / (TAUGAS + TAURAY + TAUCLD)
+        TAU = np.zeros((L + 1, W, K))
+        TAU[1:] = np.cumsum(DTAU, axis=0)
+        COSB = g0
+        if delta_eddington:
+            f = COSB ** stream
+            w0_d = W0 * (1. - f) / (1.0 - W0 * f)
+            cosb_d = (COSB - f) / (1. - f)
+            dtau_d = DTAU * (1. - W0 * f)
+            tau_d = np.zeros((L + 1, W, K))
+            tau_d[1:] = np.cumsum(dtau_d, axis=0)
+            return (dtau_d, tau_d, w0_d, cosb_d, ftau_cld, ftau_ray, GCOS2, DTAU, TAU, W0, COSB, W0nr, f)
+    return (DTAU, TAU, W0, COSB, ftau_cld, ftau_ray, GCOS2, DTAU, TAU, W0, COSB, W0nr, 0 * COSB)

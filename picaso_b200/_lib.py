@@ -66,7 +66,9 @@ class OpacityArgs(ctypes.Structure):
          ("cloud_ld", c_i64), ("fthin_cld", c_dbl), ("do_holes", c_int), ("stream", c_int),
          ("delta_eddington", c_int)] +
         [(n, c_vp) for n in ("DTAU", "TAU", "W0", "COSB", "ftau_cld", "ftau_ray", "GCOS2", "DTAU_OG", "TAU_OG",
-                             "W0_OG", "COSB_OG", "W0_no_raman", "f_deltaM")])
+                             "W0_OG", "COSB_OG", "W0_no_raman", "f_deltaM")] +
+        [("ngauss", c_int), ("ck_index", c_vp), ("ck_weights", c_vp), ("ck_scale", c_vp), ("cont_mode", c_int),
+         ("cont_index_hi", c_vp), ("cont_t", c_vp)])
 
 
 class ThermalArgs(ctypes.Structure):
@@ -122,6 +124,7 @@ SYMBOLS = {
     "pb_optab_set_continuum": (c_int, [c_vp, c_vp, c_int, c_vp, c_int]),
     "pb_optab_set_rayleigh": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "pb_optab_set_raman": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "pb_optab_set_ck": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int]),
     "pb_optab_bytes": (c_int, [c_vp, ctypes.POINTER(ctypes.c_size_t)]),
     "pb_compute_opacity": (c_int, [c_vp, c_vp, ctypes.POINTER(OpacityArgs), c_int]),
 }

@@ -32,6 +32,9 @@ struct pb_optab {
     std::vector<double *> mol_raw, mol_log;  // [npt][W] device
     std::vector<int> mol_npt;
     std::vector<double *> cont;              // [ntemp][W]
+    std::vector<double *> cont_ln;           // ln of the same rows (log-linear interpolation in 1/T)
+    double *ck = nullptr;                    // pre-mixed correlated-k ln(kappa) [nP][nT][W][K]
+    int ck_np = 0, ck_nt = 0, K = 1;
     std::vector<int> cont_nt;
     std::vector<double *> ray;               // [W]
     double *wno = nullptr;                   // [W]
@@ -40,7 +43,8 @@ struct pb_optab {
     int *raman_ji = nullptr;
     double *RA = nullptr, *RB = nullptr;       // [10][W] per-level Raman sums
     // device-side pointer tables rebuilt when a table changes
-    const double **d_mol_raw = nullptr, **d_mol_log = nullptr, **d_cont = nullptr, **d_ray = nullptr;
+    const double **d_mol_raw = nullptr, **d_mol_log = nullptr, **d_cont = nullptr, **d_ray = nullptr,
+                 **d_cont_ln = nullptr;
     bool dirty = true;
     size_t bytes = 0;
 };
@@ -52,7 +56,15 @@ constexpr int kMaxJ = 10;
 struct OpaParams {
     int L, W, nmol, ncont, nray, ntrans;
     int query;  // 0 nearest, 1 bilinear
-    const double *const *mol_raw, *const *mol_log, *const *cont, *const *ray;
+    const double *const *mol_raw, *const *mol_log, *const *cont, *const *ray, *const *cont_ln;
+    int K;                     // gauss points per wavelength (1 = monochromatic)
+    const double *ck;          // ln kappa [nP*nT][W*K] or null
+    const int *ck_index;       // [L][4]
+    const double *ck_wts;      // [L][4]
+    const double *ck_scale;    // [L] colden/mmw
+    int cont_mode;             // 0 nearest row, 1 log-linear between cont_index and cont_index_hi
+    const int *cont_index_hi;  // [L]
+    const double *cont_t;      // [L]
     const int *pt_index;       // [L][4]
     const double *wts;         // [L][4] bilinear weights in the reference's term order
     const double *mol_scale;   // [nmol][L]
@@ -76,6 +88,12 @@ __global__ void log_table_kernel(int64_t n, const double *raw, double *lg)
     if (i >= n) return;
     const double a = raw[i];
     lg[i] = log10(a != 0 ? a : 1e-50);  // optics.py:2282
+}
+
+__global__ void ln_table_kernel(int64_t n, const double *raw, double *ln)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ln[i] = log(raw[i]);  // optics.py:1483-1484
 }
 
 // per-wavelength Raman sums grouped by initial rotational level (optics.py:478-491); they depend
@@ -136,44 +154,83 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
     const int nrow = (p.query == 1) ? 4 : 1;
     // shared layout: row pointers [nmol*nrow + ncont + nray], then doubles [4 + nmol + ncont + nray + 10]
     const double **s_ptr = reinterpret_cast<const double **>(s_raw);
-    const int nptr = p.nmol * nrow + p.ncont + p.nray;
+    const int K = p.K, C = W * K;
+    const int ncp = p.ncont * (p.cont_mode ? 2 : 1);  // continuum rows per pair: nearest | (low, high)
+    const int nptr = p.nmol * nrow + ncp + p.nray + 4;
     double *s_d = reinterpret_cast<double *>(s_raw + sizeof(double *) * (size_t)nptr);
-    double *s_w = s_d, *s_ms = s_d + 4, *s_cs = s_ms + p.nmol, *s_rs = s_cs + p.ncont, *s_jf = s_rs + p.nray;
+    double *s_w = s_d, *s_ms = s_d + 4, *s_cs = s_ms + p.nmol, *s_rs = s_cs + p.ncont, *s_jf = s_rs + p.nray,
+           *s_ck = s_jf + kMaxJ;  // 4 ck weights, ck scale, continuum t
     for (int i = threadIdx.x; i < nptr; i += blockDim.x) {
         if (i < p.nmol * nrow) {
             const int m = i / nrow, k = i - m * nrow;
             const double *base = (p.query == 1) ? p.mol_log[m] : p.mol_raw[m];
             s_ptr[i] = base + (int64_t)p.pt_index[4 * l + k] * W;
-        } else if (i < p.nmol * nrow + p.ncont) {
-            s_ptr[i] = p.cont[i - p.nmol * nrow] + (int64_t)p.cont_index[l] * W;
+        } else if (i < p.nmol * nrow + ncp) {
+            const int c = i - p.nmol * nrow;
+            if (p.cont_mode == 0) s_ptr[i] = p.cont[c] + (int64_t)p.cont_index[l] * W;
+            else s_ptr[i] = p.cont_ln[c >> 1] + (int64_t)((c & 1) ? p.cont_index_hi[l] : p.cont_index[l]) * W;
+        } else if (i < p.nmol * nrow + ncp + p.nray) {
+            s_ptr[i] = p.ray[i - p.nmol * nrow - ncp];
         } else {
-            s_ptr[i] = p.ray[i - p.nmol * nrow - p.ncont];
+            const int k = i - (p.nmol * nrow + ncp + p.nray);
+            s_ptr[i] = p.ck ? p.ck + (int64_t)p.ck_index[4 * l + k] * C : nullptr;
         }
     }
-    for (int i = threadIdx.x; i < 4 + p.nmol + p.ncont + p.nray + kMaxJ; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 4 + p.nmol + p.ncont + p.nray + kMaxJ + 6; i += blockDim.x) {
         double v;
-        if (i < 4) v = (p.query == 1) ? p.wts[4 * l + i] : 0.0;
+        const int base_ck = 4 + p.nmol + p.ncont + p.nray + kMaxJ;
+        if (i < 4) v = (p.query == 1 && p.nmol) ? p.wts[4 * l + i] : 0.0;
         else if (i < 4 + p.nmol) v = p.mol_scale[(i - 4) * L + l];
         else if (i < 4 + p.nmol + p.ncont) v = p.cont_scale[(i - 4 - p.nmol) * L + l];
         else if (i < 4 + p.nmol + p.ncont + p.nray) v = p.ray_scale[(i - 4 - p.nmol - p.ncont) * L + l];
-        else v = (p.raman == 0) ? p.jfrac[(i - 4 - p.nmol - p.ncont - p.nray) * L + l] : 0.0;
+        else if (i < base_ck) v = (p.raman == 0) ? p.jfrac[(i - 4 - p.nmol - p.ncont - p.nray) * L + l] : 0.0;
+        else if (i < base_ck + 4) v = p.ck ? p.ck_wts[4 * l + (i - base_ck)] : 0.0;
+        else if (i == base_ck + 4) v = p.ck ? p.ck_scale[l] : 0.0;
+        else v = p.cont_mode ? p.cont_t[l] : 0.0;
         s_d[i] = v;
     }
     __syncthreads();
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (w >= W) return;
+    // column j runs over (wavelength, gauss point) with the gauss point fastest, the reference's
+    // [nlayer, nwno, ngauss] layout; per-wavelength tables are read at w = j / K
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (j >= C) return;
+    const int w = (K == 1) ? j : j / K;
     const double N_A = 6.02214086e+23;
     double taugas[VEC], tauray[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) taugas[v] = tauray[v] = 0.0;
     // continuum (optics.py:172-233): table row of the nearest CIA temperature x layer factor
     const double **cp = s_ptr + p.nmol * nrow;
-    for (int c = 0; c < p.ncont; ++c) {
-        Vec<VEC> k;
-        k.load(cp[c] + w);
-        const double sc = s_cs[c];
+    if (p.cont_mode == 0) {
+        for (int c = 0; c < p.ncont; ++c) {
+            Vec<VEC> k;
+            k.load(cp[c] + w);
+            const double sc = s_cs[c];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) taugas[v] += k.v[v] * sc;
+            for (int v = 0; v < VEC; ++v) taugas[v] += k.v[v] * sc;
+        }
+    } else {
+        // RetrieveCKs.get_continuum (optics.py:1471-1497): log-linear in 1/T between the bracketing rows
+        const double t = s_ck[5];
+        for (int c = 0; c < p.ncont; ++c) {
+            Vec<VEC> lo, hi;
+            lo.load(cp[2 * c] + w);
+            hi.load(cp[2 * c + 1] + w);
+            const double sc = s_cs[c];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) taugas[v] += exp(((1 - t) * lo.v[v]) + ((t)*hi.v[v])) * sc;
+        }
+    }
+    // pre-mixed correlated-k (RetrieveCKs.get_pre_mix_ck, optics.py:1151-1161; compute_opacity :257-262)
+    if (p.ck) {
+        const double **kp = s_ptr + p.nmol * nrow + ncp + p.nray;
+        Vec<VEC> a1, a2, a3, a4;
+        a1.load(kp[0] + j); a2.load(kp[1] + j); a3.load(kp[2] + j); a4.load(kp[3] + j);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double e = ((s_ck[0] * a1.v[v]) + (s_ck[1] * a2.v[v]) + (s_ck[2] * a3.v[v]) + (s_ck[3] * a4.v[v]));
+            taugas[v] += (exp(e) * N_A) * s_ck[4];
+        }
     }
     // molecular (optics.py:243-250)
     if (p.query == 1) {
@@ -203,7 +260,7 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
         }
     }
     // Rayleigh (optics.py:265-271)
-    const double **rp = cp + p.ncont;
+    const double **rp = cp + ncp;
     for (int m = 0; m < p.nray; ++m) {
         Vec<VEC> k;
         k.load(rp[m] + w);
@@ -280,7 +337,7 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
             o0.v[v] = dtau; o2.v[v] = w0; o3.v[v] = g0; o12.v[v] = 0 * g0;
         }
     }
-    const int64_t io = (int64_t)l * W + w;
+    const int64_t io = (int64_t)l * C + j;
     if (p.o[0]) o0.store(p.o[0] + io);
     if (p.o[2]) o2.store(p.o[2] + io);
     if (p.o[3]) o3.store(p.o[3] + io);
@@ -337,6 +394,7 @@ int sync_pointer_tables(pb_ctx *ctx, pb_optab *t)
     PB_TRY(push(t->mol_raw, &t->d_mol_raw));
     PB_TRY(push(t->mol_log, &t->d_mol_log));
     PB_TRY(push(t->cont, &t->d_cont));
+    PB_TRY(push(t->cont_ln, &t->d_cont_ln));
     PB_TRY(push(t->ray, &t->d_ray));
     t->dirty = false;
     return PB_OK;
@@ -350,7 +408,7 @@ extern "C" int pb_optab_create(pb_ctx *ctx, int nwno, int nmol, int ncont, int n
     pb_optab *t = new pb_optab();
     t->W = nwno; t->nmol = nmol; t->ncont = ncont; t->nray = nray;
     t->mol_raw.assign(nmol, nullptr); t->mol_log.assign(nmol, nullptr); t->mol_npt.assign(nmol, 0);
-    t->cont.assign(ncont, nullptr); t->cont_nt.assign(ncont, 0);
+    t->cont.assign(ncont, nullptr); t->cont_nt.assign(ncont, 0); t->cont_ln.assign(ncont, nullptr);
     t->ray.assign(nray, nullptr);
     *out = t;
     return PB_OK;
@@ -364,6 +422,9 @@ extern "C" int pb_optab_destroy(pb_ctx *ctx, pb_optab *t)
     for (auto p : t->mol_raw) if (p) cudaFree(p);
     for (auto p : t->mol_log) if (p) cudaFree(p);
     for (auto p : t->cont) if (p) cudaFree(p);
+    for (auto p : t->cont_ln) if (p) cudaFree(p);
+    if (t->ck) cudaFree(t->ck);
+    if (t->d_cont_ln) cudaFree((void *)t->d_cont_ln);
     for (auto p : t->ray) if (p) cudaFree(p);
     if (t->wno) cudaFree(t->wno);
     if (t->shifts) cudaFree(t->shifts);
@@ -410,8 +471,15 @@ extern "C" int pb_optab_set_continuum(pb_ctx *ctx, pb_optab *t, int icont, const
 {
     if (!ctx || !t || !table || icont < 0 || icont >= t->ncont || ntemp < 1) return pb_fail(ctx, PB_ERR_ARG, "optab_set_continuum: bad arguments");
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
-    PB_TRY(upload_table(ctx, table, (size_t)ntemp * t->W, &t->cont[icont], &t->bytes));
+    const size_t n = (size_t)ntemp * t->W;
+    PB_TRY(upload_table(ctx, table, n, &t->cont[icont], &t->bytes));
     t->cont_nt[icont] = ntemp;
+    if (t->cont_ln[icont]) { PB_CUDA(ctx, cudaFree(t->cont_ln[icont])); t->cont_ln[icont] = nullptr; }
+    PB_CUDA(ctx, cudaMalloc((void **)&t->cont_ln[icont], n * sizeof(double)));
+    ln_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int64_t)n, t->cont[icont], t->cont_ln[icont]);
+    PB_CHECK_LAUNCH(ctx);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    t->bytes += n * sizeof(double);
     t->dirty = true;
     return PB_OK;
 }
@@ -453,6 +521,16 @@ extern "C" int pb_optab_set_raman(pb_ctx *ctx, pb_optab *t, const double *wno, i
     return PB_OK;
 }
 
+extern "C" int pb_optab_set_ck(pb_ctx *ctx, pb_optab *t, const double *lnkappa, int npress, int ntemp, int ngauss)
+{
+    if (!ctx || !t || !lnkappa || npress < 2 || ntemp < 2 || ngauss < 1)
+        return pb_fail(ctx, PB_ERR_ARG, "optab_set_ck: bad arguments");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PB_TRY(upload_table(ctx, lnkappa, (size_t)npress * ntemp * t->W * ngauss, &t->ck, &t->bytes));
+    t->ck_np = npress; t->ck_nt = ntemp; t->K = ngauss;
+    return PB_OK;
+}
+
 extern "C" int pb_optab_bytes(const pb_optab *t, size_t *bytes)
 {
     if (!t || !bytes) return PB_ERR_ARG;
@@ -464,13 +542,19 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
 {
     if (!ctx || !t || !a) return PB_ERR_ARG;
     const int L = a->nlayer, W = t->W;
+    const bool ck = a->ngauss > 1 || (t->ck && t->nmol == 0 && a->ck_index);
+    const int K = ck ? t->K : 1;
+    if (a->ngauss > 1 && (!t->ck || a->ngauss != t->K)) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: ngauss=%d needs pb_optab_set_ck tables with the same number of gauss points", a->ngauss);
+    if (ck && (!a->ck_index || !a->ck_weights || !a->ck_scale)) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: correlated-k call needs ck_index, ck_weights, ck_scale");
+    if (a->cont_mode != 0 && a->cont_mode != 1) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: cont_mode must be 0 or 1");
+    if (a->cont_mode == 1 && (!a->cont_index_hi || !a->cont_t)) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: cont_mode=1 needs cont_index_hi and cont_t");
     if (L < 1) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: nlayer < 1");
     if (a->query != 0 && a->query != 1) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: query must be 0 (nearest) or 1 (bilinear)");
     if (a->raman < 0 || a->raman > 2) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: raman must be 0, 1 or 2");
     if (a->stream != 2 && a->stream != 4) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: stream must be 2 or 4");
-    if (!a->pt_index || !a->cont_index || (t->nmol && !a->mol_scale) || (t->ncont && !a->cont_scale) || (t->nray && !a->ray_scale))
+    if ((t->nmol && !a->pt_index) || !a->cont_index || (t->nmol && !a->mol_scale) || (t->ncont && !a->cont_scale) || (t->nray && !a->ray_scale))
         return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: NULL per-layer vector");
-    if (a->query == 1 && !a->weights) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: bilinear query needs weights");
+    if (a->query == 1 && t->nmol && !a->weights) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: bilinear query needs weights");
     if (a->raman == 0 && (!t->shifts || !a->jfrac)) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: raman=0 needs pb_optab_set_raman and jfrac");
     if (a->raman == 1 && !a->raman_pollack) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: raman=1 needs raman_pollack[nwno]");
     const bool cloud = a->cloud_opd != nullptr;
@@ -487,44 +571,68 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
     for (int c = 0; c < t->ncont; ++c) {
         if (!t->cont[c]) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: continuum table %d not set", c);
         for (int l = 0; l < L; ++l)
-            if (a->cont_index[l] < 0 || a->cont_index[l] >= t->cont_nt[c]) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: cont_index[%d] out of range", l);
+            if (a->cont_index[l] < 0 || a->cont_index[l] >= t->cont_nt[c] ||
+                (a->cont_mode == 1 && (a->cont_index_hi[l] < 0 || a->cont_index_hi[l] >= t->cont_nt[c])))
+                return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: cont_index[%d] out of range", l);
     }
     for (int m = 0; m < t->nray; ++m)
         if (!t->ray[m]) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: rayleigh table %d not set", m);
+    if (ck)
+        for (int l = 0; l < L; ++l)
+            for (int k = 0; k < 4; ++k)
+                if (a->ck_index[4 * l + k] < 0 || a->ck_index[4 * l + k] >= t->ck_np * t->ck_nt)
+                    return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: ck_index[%d][%d] out of range", l, k);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     PB_TRY(sync_pointer_tables(ctx, t));
     const bool host = memspace == PB_HOST;
     const size_t nW = (size_t)W * sizeof(double);
+    const size_t nC = nW * K;  // one output row: (wavelength, gauss point) columns
     double *const outs[13] = {a->DTAU, a->TAU, a->W0, a->COSB, a->ftau_cld, a->ftau_ray, a->GCOS2, a->DTAU_OG,
                               a->TAU_OG, a->W0_OG, a->COSB_OG, a->W0_no_raman, a->f_deltaM};
     const bool is_level[13] = {false, true, false, false, false, false, false, false, true, false, false, false, false};
-    size_t need = 64 * 256 + 2 * pb_align((size_t)L * nW) + pb_align(4 * (size_t)L * 12) + pb_align((size_t)L * 8) +
+    size_t need = 96 * 256 + 2 * pb_align((size_t)L * nC) + 8 * pb_align((size_t)L * 8) + pb_align(4 * (size_t)L * 12) + pb_align((size_t)L * 8) +
                   (size_t)(t->nmol + t->ncont + t->nray + kMaxJ + 4) * pb_align((size_t)L * 8);
     if (host) {
         if (cloud) need += 3 * pb_align((size_t)L * nW);
         if (a->raman == 1) need += pb_align(nW);
         for (int k = 0; k < 13; ++k)
-            if (outs[k]) need += pb_align((size_t)(L + (is_level[k] ? 1 : 0)) * nW);
+            if (outs[k]) need += pb_align((size_t)(L + (is_level[k] ? 1 : 0)) * nC);
     }
     pb_arena_reset(ctx);
     PB_TRY(pb_arena_reserve(ctx, need));
-    PB_TRY(pb_pinned_reserve(ctx, (size_t)(t->nmol + t->ncont + t->nray + kMaxJ + 16) * ((size_t)L * 8 + 64)));
+    PB_TRY(pb_pinned_reserve(ctx, (size_t)(t->nmol + t->ncont + t->nray + kMaxJ + 32) * ((size_t)L * 8 + 64)));
     OpaParams p;
     memset(&p, 0, sizeof(p));
     p.L = L; p.W = W; p.nmol = t->nmol; p.ncont = t->ncont; p.nray = t->nray; p.ntrans = t->ntrans;
     p.query = a->query;
     p.mol_raw = t->d_mol_raw; p.mol_log = t->d_mol_log; p.cont = t->d_cont; p.ray = t->d_ray;
+    p.cont_ln = t->d_cont_ln; p.K = K; p.ck = ck ? t->ck : nullptr; p.cont_mode = a->cont_mode;
     const double *tmp;
     // ints travel through the same pinned bounce as doubles (sizes rounded up to 8 bytes)
-    PB_TRY(pb_upload_small(ctx, (const double *)a->pt_index, ((size_t)4 * L * sizeof(int) + 7) / 8, &tmp));
-    p.pt_index = (const int *)tmp;
+    if (t->nmol) {
+        PB_TRY(pb_upload_small(ctx, (const double *)a->pt_index, ((size_t)4 * L * sizeof(int) + 7) / 8, &tmp));
+        p.pt_index = (const int *)tmp;
+    }
+    if (ck) {
+        PB_TRY(pb_upload_small(ctx, (const double *)a->ck_index, ((size_t)4 * L * sizeof(int) + 7) / 8, &tmp));
+        p.ck_index = (const int *)tmp;
+        PB_TRY(pb_upload_small(ctx, a->ck_weights, (size_t)4 * L, &p.ck_wts));
+        PB_TRY(pb_upload_small(ctx, a->ck_scale, (size_t)L, &p.ck_scale));
+    }
+    if (a->cont_mode == 1) {
+        std::vector<int> ci(a->cont_index_hi, a->cont_index_hi + L);
+        if (ci.size() & 1) ci.push_back(0);
+        PB_TRY(pb_upload_small(ctx, (const double *)ci.data(), ci.size() / 2, &tmp));
+        p.cont_index_hi = (const int *)tmp;
+        PB_TRY(pb_upload_small(ctx, a->cont_t, (size_t)L, &p.cont_t));
+    }
     {
         std::vector<int> ci(a->cont_index, a->cont_index + L);
         if (ci.size() & 1) ci.push_back(0);
         PB_TRY(pb_upload_small(ctx, (const double *)ci.data(), ci.size() / 2, &tmp));
         p.cont_index = (const int *)tmp;
     }
-    if (a->query == 1) PB_TRY(pb_upload_small(ctx, a->weights, (size_t)4 * L, &p.wts));
+    if (a->query == 1 && t->nmol) PB_TRY(pb_upload_small(ctx, a->weights, (size_t)4 * L, &p.wts));
     if (t->nmol) PB_TRY(pb_upload_small(ctx, a->mol_scale, (size_t)t->nmol * L, &p.mol_scale));
     if (t->ncont) PB_TRY(pb_upload_small(ctx, a->cont_scale, (size_t)t->ncont * L, &p.cont_scale));
     if (t->nray) PB_TRY(pb_upload_small(ctx, a->ray_scale, (size_t)t->nray * L, &p.ray_scale));
@@ -547,21 +655,22 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
     for (int k = 0; k < 13; ++k) {
         p.o[k] = nullptr;
         if (!outs[k]) continue;
-        if (host) PB_TRY(pb_arena_alloc(ctx, (size_t)(L + (is_level[k] ? 1 : 0)) * nW, (void **)&p.o[k]));
+        if (host) PB_TRY(pb_arena_alloc(ctx, (size_t)(L + (is_level[k] ? 1 : 0)) * nC, (void **)&p.o[k]));
         else p.o[k] = outs[k];
     }
     PB_TRY(pb_upload_flush(ctx));
     // the running optical depths need the per-layer values even if the caller did not ask for them
     double *dtau_d = p.o[0], *dtau_og = p.o[7];
-    if (p.o[1] && !dtau_d) { PB_TRY(pb_arena_alloc(ctx, (size_t)L * nW, (void **)&dtau_d)); p.o[0] = dtau_d; }
-    if (p.o[8] && !dtau_og) { PB_TRY(pb_arena_alloc(ctx, (size_t)L * nW, (void **)&dtau_og)); p.o[7] = dtau_og; }
+    if (p.o[1] && !dtau_d) { PB_TRY(pb_arena_alloc(ctx, (size_t)L * nC, (void **)&dtau_d)); p.o[0] = dtau_d; }
+    if (p.o[8] && !dtau_og) { PB_TRY(pb_arena_alloc(ctx, (size_t)L * nC, (void **)&dtau_og)); p.o[7] = dtau_og; }
     {
         const int nrow = a->query == 1 ? 4 : 1;
-        const size_t smem = sizeof(double *) * (size_t)(t->nmol * nrow + t->ncont + t->nray) +
-                            sizeof(double) * (size_t)(4 + t->nmol + t->ncont + t->nray + kMaxJ);
+        const size_t smem = sizeof(double *) * (size_t)(t->nmol * nrow + 2 * t->ncont + t->nray + 4) +
+                            sizeof(double) * (size_t)(4 + t->nmol + t->ncont + t->nray + kMaxJ + 6);
         if (smem > 48 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "compute_opacity: too many species for the per-layer shared table");
         // 16-byte vector path: even nwno (every table row and output row is then 16-byte aligned)
-        bool vec2 = (W % 2 == 0);
+        const int C = W * K;
+        bool vec2 = (W % 2 == 0) && K == 1;
         for (int k = 0; k < 13; ++k) if (p.o[k] && ((uintptr_t)p.o[k] & 15)) vec2 = false;
         if (p.pollack && ((uintptr_t)p.pollack & 15)) vec2 = false;
         if (p.cld_opd && (((uintptr_t)p.cld_opd | (uintptr_t)p.cld_w0 | (uintptr_t)p.cld_g0) & 15)) vec2 = false;
@@ -569,23 +678,23 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
             dim3 grid((W / 2 + 127) / 128, L);
             opacity_layer_kernel<2><<<grid, 128, smem, ctx->stream>>>(p);
         } else {
-            dim3 grid((W + 127) / 128, L);
+            dim3 grid((C + 127) / 128, L);
             opacity_layer_kernel<1><<<grid, 128, smem, ctx->stream>>>(p);
         }
         PB_CHECK_LAUNCH(ctx);
     }
     if (p.o[1]) {
-        opacity_cumsum_kernel<<<(W + 127) / 128, 128, 0, ctx->stream>>>(L, W, dtau_d, p.o[1]);
+        opacity_cumsum_kernel<<<(W * K + 127) / 128, 128, 0, ctx->stream>>>(L, W * K, dtau_d, p.o[1]);
         PB_CHECK_LAUNCH(ctx);
     }
     if (p.o[8]) {
-        opacity_cumsum_kernel<<<(W + 127) / 128, 128, 0, ctx->stream>>>(L, W, dtau_og, p.o[8]);
+        opacity_cumsum_kernel<<<(W * K + 127) / 128, 128, 0, ctx->stream>>>(L, W * K, dtau_og, p.o[8]);
         PB_CHECK_LAUNCH(ctx);
     }
     if (host) {
         for (int k = 0; k < 13; ++k)
             if (outs[k])
-                PB_CUDA(ctx, cudaMemcpyAsync(outs[k], p.o[k], (size_t)(L + (is_level[k] ? 1 : 0)) * nW,
+                PB_CUDA(ctx, cudaMemcpyAsync(outs[k], p.o[k], (size_t)(L + (is_level[k] ? 1 : 0)) * nC,
                                              cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }

@@ -323,15 +323,24 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
     Not supported on this path: ngauss > 1 (correlated-k), test_mode strings, plot_opacity,
     return_mode, full_output.  ``test_mode`` None/False both mean "normal run": the reference's
     own default False would enter its test branch (optics.py:372), real callers pass None."""
-    if not isinstance(opacityclass, DeviceOpacities):
-        raise TypeError("picaso_b200.compute_opacity needs a picaso_b200.DeviceOpacities connection")
-    if ngauss != 1:
-        raise NotImplementedError("correlated-k (ngauss > 1) opacities are not on the GPU path yet")
+    from .optics_ck import DeviceCKs, compute_opacity_ck
+    if not isinstance(opacityclass, (DeviceOpacities, DeviceCKs)):
+        raise TypeError("picaso_b200.compute_opacity needs a DeviceOpacities or DeviceCKs connection")
+    if isinstance(opacityclass, DeviceOpacities) and ngauss != 1:
+        raise ValueError("monochromatic DeviceOpacities have ngauss = 1")
+    if isinstance(opacityclass, DeviceCKs) and ngauss != opacityclass.ngauss:
+        raise ValueError("ngauss must equal the number of gauss points of the DeviceCKs table")
     if test_mode not in (None, False):
         raise NotImplementedError("compute_opacity test modes are not implemented on the GPU path")
     if plot_opacity or return_mode or full_output:
         raise NotImplementedError("plot_opacity / return_mode / full_output are host-side diagnostics")
     opa, atm = opacityclass, atmosphere
+    if isinstance(opa, DeviceCKs):
+        import copy
+        atm_ck = copy.copy(atm)
+        atm_ck.molecules = []   # pre-mixed tables already contain every molecule (optics.py:257-262)
+        return compute_opacity_ck(atm_ck, opa, stream, delta_eddington, raman, fthin_cld, do_holes,
+                                  device_outputs, outputs)
     ctx = opa.ctx
     if opa._plan is None or opa._plan["nlayer"] != atm.c.nlayer:
         raise RuntimeError("call opacityclass.get_opacities(atmosphere) first (justdoit.py:236)")

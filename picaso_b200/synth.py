@@ -248,3 +248,30 @@ def atmosphere_profile(db, L=12, seed=2003, cloudy=True):
                 k_b=1.380649e-16, plevel=plevel, tlevel=tlevel, player=player, tlayer=tlayer,
                 gravity=gravity, mmw=mmw, colden=colden, mixingratios=mix, electrons=electrons,
                 cloud_opd=opd, cloud_w0=cw0, cloud_g0=cg0)
+
+
+def ck_database(W=40, K=8, seed=2101, nT=9, nP=8, nTc=12):
+    """Synthetic pre-mixed correlated-k table in the layout RetrieveCKs keeps it (optics.py:737-753):
+    ln(kappa) [nP, nT, W, K], K double-Gauss points per wavenumber bin, monotone in the gauss index."""
+    rng = np.random.default_rng(seed)
+    wno = np.sort(1e4 / np.linspace(30.0, 0.3, W))
+    temps = np.round(np.geomspace(75.0, 4000.0, nT), 3)
+    pressures = np.geomspace(1e-6, 3e3, nP)
+    nc_p = np.full(nT, nP)
+    base = -26.0 + 2.0 * np.sin(np.linspace(0, 7, W))[None, None, :, None] + \
+        0.7 * (np.log10(temps) - 2.5)[None, :, None, None] + 0.2 * np.log10(pressures)[:, None, None, None]
+    spread = np.sort(rng.uniform(0.0, 4.0, (nP, nT, W, K)), axis=3)
+    lnk = (base + spread) * np.log(10.0)
+    gauss_wts = np.array([0.16523105, 0.30976895, 0.30976895, 0.16523105, 0.00869637, 0.01630363, 0.01630363,
+                          0.00869637])[:K]
+    cia_temps = np.round(np.geomspace(75.0, 3500.0, nTc), 2)
+    cont = {}
+    for a, b in CONTINUUM:
+        lk = -7.0 + np.cos(np.linspace(0, 4, W))[None, :] + 0.5 * np.log10(cia_temps / 300.0)[:, None] \
+            + 0.2 * rng.standard_normal((nTc, W))
+        if a in ("H-", "H2-"):
+            lk = lk - 18.0
+        cont[a + b] = 10.0 ** lk
+    return dict(wno=wno, nwno=W, ngauss=K, temps=temps, pressures=pressures, nc_p=nc_p, kappa=lnk,
+                gauss_wts=gauss_wts, cia_temps=cia_temps, continuum=cont, continuum_molecules=list(CONTINUUM),
+                rayleigh_molecules=list(RAYLEIGH), molecules=[])

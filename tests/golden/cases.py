@@ -263,3 +263,11 @@ def facets_args(d, case):
                 d["ubar0"], d["ubar1"], d["cos_theta"], d["F0PI"], case["sp"], case["mp"], 1.0, -1.0, 2.0, -0.5, 1.0)
     return (d["nlevel"], d["wno"], d["nwno"], d["ng"], d["nt"], d["tlevel"], d["dtau"], d["w0"], d["cosb"],
             d["plevel"], d["ubar1"], d["surf_reflect"], case["hs"])
+
+
+def ck_cases():
+    """pre-mixed correlated-k: RetrieveCKs.get_pre_mix_ck + get_continuum + compute_opacity(ngauss=K)"""
+    return {
+        "ck8_dedd": dict(db=dict(W=40, K=8, seed=2101), atm=dict(L=11, seed=2103), stream=2, dedd=True),
+        "ck4_clear": dict(db=dict(W=25, K=4, seed=2111), atm=dict(L=8, seed=2113, cloudy=False), stream=4, dedd=False),
+    }
