@@ -268,9 +268,32 @@ typedef struct pb_opacity_args {
     int cont_mode;
     const int *cont_index_hi;  /* [nlayer] */
     const double *cont_t;      /* [nlayer] */
+    /* resort-rebin path: molecular_opa [nlayer][nwno][ngauss] written by pb_ck_mix with PB_DEVICE
+     * (ALWAYS a device pointer), used instead of the pre-mixed table; needs ck_scale */
+    const double *ck_direct;
 } pb_opacity_args;
 
 int pb_compute_opacity(pb_ctx *ctx, pb_optab *tab, const pb_opacity_args *args, int memspace);
+
+/* ---- resort-rebin mixing of per-gas correlated-k tables ----------------------------------
+ * Replaces deq_chem.mix_all_gases_gasesfly / do_mixing_mono_gasesfly / mix_2_gases
+ * (deq_chem.py:334-386, :388-432, :538-597) and the interpolation + exp * N_A of
+ * optics.RetrieveCKs.mix_my_opacities_gasesfly (optics.py:1164-1197).  The per-gas tables stay
+ * resident in HBM (pb_dev_alloc + pb_memcpy_h2d); the small per-layer vectors are host memory;
+ * the outputs follow `memspace`. */
+typedef struct pb_ck_mix_args {
+    int nlayer, nwno, ngauss, ngas; /* ngauss <= 8, ngas <= 32 */
+    int np, nt;                     /* table grid: kappas[g] is ln(kappa) [np][nt][nwno][ngauss] */
+    const double *const *kappas;    /* HOST array of ngas DEVICE pointers, in gases_fly order */
+    const double *mixes;            /* HOST [ngas][nlayer] volume mixing ratios */
+    const int *indices;             /* HOST [4][nlayer]: p_low, p_hi, t_low, t_hi (get_mixing_indices, optics.py:1199-1277) */
+    const double *t_interp, *p_interp; /* HOST [nlayer] */
+    const double *gauss_pts, *gauss_wts; /* HOST [ngauss] */
+    double *molecular_opa;          /* out [nlayer][nwno][ngauss] = exp(bilinear ln kappa_mixed) * N_A */
+    double *ln_mixed;               /* out, optional [nlayer][nwno][ngauss][4] = ln kappa_mixed (deq_chem.py:386) */
+} pb_ck_mix_args;
+
+int pb_ck_mix(pb_ctx *ctx, const pb_ck_mix_args *args, int memspace);
 
 /* ---- self test ------------------------------------------------------------------------- */
 /* evaluates the kernels' branch-free exp() and 1/x on x[n] (host pointers); test hook */

@@ -13,7 +13,7 @@ from .fluxes import get_reflected_1d, get_reflected_SH, get_thermal_1d, get_tran
 from .fluxes_sh_thermal import get_thermal_SH  # noqa: F401
 from .fluxes_3d import get_reflected_3d, get_thermal_3d  # noqa: F401
 from .optics import DeviceArray, DeviceOpacities, compute_opacity  # noqa: F401
-from .optics_ck import DeviceCKs  # noqa: F401
+from .optics_ck import DeviceCKs, DeviceGasCKs  # noqa: F401
 from .disco import compress_disco, compress_thermal, get_angles_1d, get_angles_3d, compute_disco  # noqa: F401
 
 __version__ = "0.1.0"

@@ -68,7 +68,13 @@ class OpacityArgs(ctypes.Structure):
         [(n, c_vp) for n in ("DTAU", "TAU", "W0", "COSB", "ftau_cld", "ftau_ray", "GCOS2", "DTAU_OG", "TAU_OG",
                              "W0_OG", "COSB_OG", "W0_no_raman", "f_deltaM")] +
         [("ngauss", c_int), ("ck_index", c_vp), ("ck_weights", c_vp), ("ck_scale", c_vp), ("cont_mode", c_int),
-         ("cont_index_hi", c_vp), ("cont_t", c_vp)])
+         ("cont_index_hi", c_vp), ("cont_t", c_vp), ("ck_direct", c_vp)])
+
+
+class CkMixArgs(ctypes.Structure):
+    _fields_ = ([(n, c_int) for n in ("nlayer", "nwno", "ngauss", "ngas", "np", "nt")] +
+                [(n, c_vp) for n in ("kappas", "mixes", "indices", "t_interp", "p_interp", "gauss_pts", "gauss_wts",
+                                     "molecular_opa", "ln_mixed")])
 
 
 class ThermalArgs(ctypes.Structure):
@@ -127,6 +133,7 @@ SYMBOLS = {
     "pb_optab_set_ck": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int]),
     "pb_optab_bytes": (c_int, [c_vp, ctypes.POINTER(ctypes.c_size_t)]),
     "pb_compute_opacity": (c_int, [c_vp, c_vp, ctypes.POINTER(OpacityArgs), c_int]),
+    "pb_ck_mix": (c_int, [c_vp, ctypes.POINTER(CkMixArgs), c_int]),
 }
 
 _lib = None

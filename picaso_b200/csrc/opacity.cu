@@ -62,6 +62,7 @@ struct OpaParams {
     const int *ck_index;       // [L][4]
     const double *ck_wts;      // [L][4]
     const double *ck_scale;    // [L] colden/mmw
+    const double *ck_direct;   // molecular_opa [L][W*K] from pb_ck_mix, or null
     int cont_mode;             // 0 nearest row, 1 log-linear between cont_index and cont_index_hi
     const int *cont_index_hi;  // [L]
     const double *cont_t;      // [L]
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
         else if (i < 4 + p.nmol + p.ncont + p.nray) v = p.ray_scale[(i - 4 - p.nmol - p.ncont) * L + l];
         else if (i < base_ck) v = (p.raman == 0) ? p.jfrac[(i - 4 - p.nmol - p.ncont - p.nray) * L + l] : 0.0;
         else if (i < base_ck + 4) v = p.ck ? p.ck_wts[4 * l + (i - base_ck)] : 0.0;
-        else if (i == base_ck + 4) v = p.ck ? p.ck_scale[l] : 0.0;
+        else if (i == base_ck + 4) v = (p.ck || p.ck_direct) ? p.ck_scale[l] : 0.0;
         else v = p.cont_mode ? p.cont_t[l] : 0.0;
         s_d[i] = v;
     }
@@ -231,6 +232,13 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
             const double e = ((s_ck[0] * a1.v[v]) + (s_ck[1] * a2.v[v]) + (s_ck[2] * a3.v[v]) + (s_ck[3] * a4.v[v]));
             taugas[v] += (exp(e) * N_A) * s_ck[4];
         }
+    }
+    // resort-rebin mixed k-coefficients (optics.py:1197 molecular_opa, compute_opacity :257-262)
+    if (p.ck_direct) {
+        Vec<VEC> k;
+        k.load(p.ck_direct + (int64_t)l * C + j);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) taugas[v] += k.v[v] * s_ck[4];
     }
     // molecular (optics.py:243-250)
     if (p.query == 1) {
@@ -542,9 +550,11 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
 {
     if (!ctx || !t || !a) return PB_ERR_ARG;
     const int L = a->nlayer, W = t->W;
-    const bool ck = a->ngauss > 1 || (t->ck && t->nmol == 0 && a->ck_index);
-    const int K = ck ? t->K : 1;
-    if (a->ngauss > 1 && (!t->ck || a->ngauss != t->K)) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: ngauss=%d needs pb_optab_set_ck tables with the same number of gauss points", a->ngauss);
+    const bool direct = a->ck_direct != nullptr;
+    const bool ck = !direct && (a->ngauss > 1 || (t->ck && t->nmol == 0 && a->ck_index));
+    const int K = direct ? (a->ngauss > 1 ? a->ngauss : 1) : ck ? t->K : 1;
+    if (direct && !a->ck_scale) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: ck_direct needs ck_scale");
+    if (!direct && a->ngauss > 1 && (!t->ck || a->ngauss != t->K)) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: ngauss=%d needs pb_optab_set_ck tables with the same number of gauss points", a->ngauss);
     if (ck && (!a->ck_index || !a->ck_weights || !a->ck_scale)) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: correlated-k call needs ck_index, ck_weights, ck_scale");
     if (a->cont_mode != 0 && a->cont_mode != 1) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: cont_mode must be 0 or 1");
     if (a->cont_mode == 1 && (!a->cont_index_hi || !a->cont_t)) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: cont_mode=1 needs cont_index_hi and cont_t");
@@ -617,6 +627,10 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
         PB_TRY(pb_upload_small(ctx, (const double *)a->ck_index, ((size_t)4 * L * sizeof(int) + 7) / 8, &tmp));
         p.ck_index = (const int *)tmp;
         PB_TRY(pb_upload_small(ctx, a->ck_weights, (size_t)4 * L, &p.ck_wts));
+        PB_TRY(pb_upload_small(ctx, a->ck_scale, (size_t)L, &p.ck_scale));
+    }
+    if (direct) {
+        p.ck_direct = a->ck_direct;
         PB_TRY(pb_upload_small(ctx, a->ck_scale, (size_t)L, &p.ck_scale));
     }
     if (a->cont_mode == 1) {

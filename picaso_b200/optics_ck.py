@@ -9,9 +9,9 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import PB_DEVICE, PB_HOST, OpacityArgs, addr
+from ._lib import PB_DEVICE, PB_HOST, CkMixArgs, OpacityArgs, addr
 
-__all__ = ["DeviceCKs"]
+__all__ = ["DeviceCKs", "DeviceGasCKs"]
 
 
 class DeviceCKs:
@@ -29,10 +29,11 @@ class DeviceCKs:
         self.pressures = np.asarray(pressures, dtype=np.float64)
         self.temps = np.asarray(temps, dtype=np.float64)
         self.nc_p = np.asarray(nc_p)
-        kappa = np.ascontiguousarray(kappa, dtype=np.float64)
-        if kappa.ndim != 4 or kappa.shape[2] != self.nwno:
-            raise ValueError("kappa must be ln(kappa) [nP, nT, nwno, ngauss]")
-        self._np, self._nt, _, self.ngauss = kappa.shape
+        if kappa is not None:
+            kappa = np.ascontiguousarray(kappa, dtype=np.float64)
+            if kappa.ndim != 4 or kappa.shape[2] != self.nwno:
+                raise ValueError("kappa must be ln(kappa) [nP, nT, nwno, ngauss]")
+            self._np, self._nt, _, self.ngauss = kappa.shape
         self.gauss_wts = np.asarray(gauss_wts, dtype=np.float64)
         self.cia_temps = np.asarray(cia_temps, dtype=np.float64)
         self._cia_sorted = np.sort(self.cia_temps)
@@ -47,7 +48,8 @@ class DeviceCKs:
         tab = ctypes.c_void_p()
         self.ctx.check(lib.pb_optab_create(h, self.nwno, 0, len(continuum), len(rayleigh_opa), ctypes.byref(tab)))
         self._tab = tab
-        self.ctx.check(lib.pb_optab_set_ck(h, tab, addr(kappa), self._np, self._nt, self.ngauss))
+        if kappa is not None:
+            self.ctx.check(lib.pb_optab_set_ck(h, tab, addr(kappa), self._np, self._nt, self.ngauss))
         order = np.argsort(self.cia_temps)
         for k, t in continuum.items():
             t = np.ascontiguousarray(np.asarray(t, dtype=np.float64)[order])
@@ -68,17 +70,15 @@ class DeviceCKs:
             self._ws[name] = d
         return d
 
-    def get_opacities(self, atmosphere, exclude_mol=1):
-        """get_opacities_preweighted (optics.py:1500-1511) = get_continuum + get_pre_mix_ck, recorded as a
-        plan of table rows and weights (nothing is fetched)."""
+    def _grid_neighbours(self, atmosphere, unique_temps):
+        """the (1/T, log10 P) bracketing shared by get_pre_mix_ck (optics.py:1086-1149, unique temps) and
+        get_mixing_indices (optics.py:1199-1277, temps as stored)"""
         t = np.asarray(atmosphere.layer["temperature"], dtype=np.float64)
         p = np.asarray(atmosphere.layer["pressure"], dtype=np.float64) / atmosphere.c.pconv
-        L = t.size
-        # --- get_pre_mix_ck, optics.py:1086-1149
         t_inv, p_log = 1 / t, np.log10(p)
         pg = np.unique(self.pressures)
         p_log_grid = np.log10(pg[pg > 0])
-        t_inv_grid = 1 / np.array(np.unique(self.temps))
+        t_inv_grid = 1 / np.array(np.unique(self.temps) if unique_temps else self.temps)
         cnt = np.array([np.count_nonzero(t_inv_grid > x) for x in t_inv])
         t_low = np.where(cnt == 0, 0, cnt - 1)
         t_low = np.where(t_low == t_inv_grid.size - 1, t_inv_grid.size - 2, t_low)
@@ -88,12 +88,12 @@ class DeviceCKs:
         p_hi = p_low + 1
         ti = (t_inv - t_inv_grid[t_low]) / (t_inv_grid[t_hi] - t_inv_grid[t_low])
         pi = (p_log - p_log_grid[p_low]) / (p_log_grid[p_hi] - p_log_grid[p_low])
-        idx = np.zeros((L, 4), dtype=np.int32)
-        idx[:, 0], idx[:, 1] = p_low * self._nt + t_low, p_low * self._nt + t_hi
-        idx[:, 2], idx[:, 3] = p_hi * self._nt + t_hi, p_hi * self._nt + t_low
-        wts = np.stack([(1 - ti) * (1 - pi), ti * (1 - pi), ti * pi, (1 - ti) * pi], axis=1)
-        # --- get_continuum, optics.py:1410-1424: bracketing CIA temperatures, log-linear in 1/T
+        return t, t_inv, p_low, p_hi, t_low, t_hi, ti, pi
+
+    def _continuum_plan(self, t, t_inv):
+        """get_continuum, optics.py:1410-1424: bracketing CIA temperatures, log-linear in 1/T"""
         st = self._cia_sorted
+        L = t.size
         lo = np.zeros(L, dtype=np.int32)
         hi = np.zeros(L, dtype=np.int32)
         for i, tt in enumerate(t):
@@ -105,6 +105,18 @@ class DeviceCKs:
                 lo[i] = np.where(st - tt <= 0)[0][-1]
                 hi[i] = np.where(st - tt > 0)[0][0]
         ct = (t_inv - 1 / st[lo]) / (1 / st[hi] - 1 / st[lo])
+        return lo, hi, np.ascontiguousarray(ct)
+
+    def get_opacities(self, atmosphere, exclude_mol=1):
+        """get_opacities_preweighted (optics.py:1500-1511) = get_continuum + get_pre_mix_ck, recorded as a
+        plan of table rows and weights (nothing is fetched)."""
+        t, t_inv, p_low, p_hi, t_low, t_hi, ti, pi = self._grid_neighbours(atmosphere, unique_temps=True)
+        L = t.size
+        idx = np.zeros((L, 4), dtype=np.int32)
+        idx[:, 0], idx[:, 1] = p_low * self._nt + t_low, p_low * self._nt + t_hi
+        idx[:, 2], idx[:, 3] = p_hi * self._nt + t_hi, p_hi * self._nt + t_low
+        wts = np.stack([(1 - ti) * (1 - pi), ti * (1 - pi), ti * pi, (1 - ti) * pi], axis=1)
+        lo, hi, ct = self._continuum_plan(t, t_inv)
         self._plan = dict(nlayer=L, idx=np.ascontiguousarray(idx), wts=np.ascontiguousarray(wts), lo=lo, hi=hi,
                           ct=np.ascontiguousarray(ct), fac={})
         self.molecular_opa = None
@@ -123,6 +135,91 @@ class DeviceCKs:
             self.close()
         except Exception:
             pass
+
+
+class DeviceGasCKs(DeviceCKs):
+    """GPU-resident stand-in for optics.RetrieveCKs(..., method='resortrebin') (optics.py:700-760):
+    one ln(kappa) table [nP, nT, W, K] per gas kept in HBM and mixed on the fly per layer with the
+    resort-rebin random-overlap rule (deq_chem.py:334-597).
+
+    kappas = {molecule: ln(kappa)}; gauss_pts/gauss_wts [K] on (0, 1)."""
+
+    def __init__(self, wno, pressures, temps, nc_p, kappas, gauss_pts, gauss_wts, cia_temps, continuum, rayleigh_opa,
+                 ctx=None):
+        super().__init__(wno, pressures, temps, nc_p, None, gauss_wts, cia_temps, continuum, rayleigh_opa, ctx=ctx)
+        from .optics import DeviceArray
+        self.gauss_pts = np.ascontiguousarray(gauss_pts, dtype=np.float64)
+        self.gauss_wts = np.ascontiguousarray(gauss_wts, dtype=np.float64)
+        self.ngauss = self.gauss_wts.size
+        self.kappas = {}
+        shape = None
+        for m, k in kappas.items():
+            k = np.ascontiguousarray(k, dtype=np.float64)
+            if shape is None:
+                shape = k.shape
+            if k.shape != shape or k.ndim != 4 or k.shape[2] != self.nwno or k.shape[3] != self.ngauss:
+                raise ValueError("kappas[%s] must be ln(kappa) [nP, nT, nwno, ngauss] on one grid" % m)
+            d = DeviceArray(self.ctx, k.shape)
+            self.ctx.check(self.ctx.lib.pb_memcpy_h2d(self.ctx.h, d.ptr, k.ctypes.data, k.nbytes))
+            self.kappas[m] = d
+        self._np, self._nt = shape[0], shape[1]
+        self.ctx.sync()
+
+    def get_mixing_indices(self, atmosphere):
+        """optics.py:1199-1277: ([p_low, p_hi, t_low, t_hi], t_interp, p_interp)"""
+        _, _, p_low, p_hi, t_low, t_hi, ti, pi = self._grid_neighbours(atmosphere, unique_temps=False)
+        return np.array([p_low, p_hi, t_low, t_hi]), ti, pi
+
+    def mix_my_opacities_gasesfly(self, atmosphere, exclude_mol=1, device_output=False, return_ln_mixed=False):
+        """optics.py:1164-1197: sets self.molecular_opa [nlayer, nwno, ngauss] (a DeviceArray with
+        device_output=True).  Gases are folded in the order of atmosphere.molecules, skipping those whose
+        exclude_mol entry is not 1 (optics.py:1177-1181); a gas without a table raises KeyError as there."""
+        indices, ti, pi = self.get_mixing_indices(atmosphere)
+        mr = atmosphere.layer["mixingratios"]
+        gases = [m for m in atmosphere.molecules if exclude_mol == 1 or exclude_mol[m] == 1]
+        for m in gases:
+            self.kappas[m]
+        L = ti.size
+        mixes = np.ascontiguousarray([np.asarray(mr[m], dtype=np.float64) for m in gases])
+        ptrs = (ctypes.c_void_p * len(gases))(*[self.kappas[m].ptr for m in gases])
+        ind = np.ascontiguousarray(indices, dtype=np.int32)
+        ti, pi = np.ascontiguousarray(ti), np.ascontiguousarray(pi)
+        a = CkMixArgs(nlayer=L, nwno=self.nwno, ngauss=self.ngauss, ngas=len(gases), np=self._np, nt=self._nt)
+        a.kappas = ctypes.cast(ptrs, ctypes.c_void_p)
+        a.mixes, a.indices, a.t_interp, a.p_interp = addr(mixes), addr(ind), addr(ti), addr(pi)
+        a.gauss_pts, a.gauss_wts = addr(self.gauss_pts), addr(self.gauss_wts)
+        shape = (L, self.nwno, self.ngauss)
+        ln_mixed = None
+        if device_output:
+            out = self._buffer("molecular_opa", shape)
+            a.molecular_opa = out.ptr
+            if return_ln_mixed:
+                ln_mixed = self._buffer("ln_mixed", shape + (4,))
+                a.ln_mixed = ln_mixed.ptr
+        else:
+            out = np.zeros(shape)
+            a.molecular_opa = addr(out)
+            if return_ln_mixed:
+                ln_mixed = np.zeros(shape + (4,))
+                a.ln_mixed = addr(ln_mixed)
+        self.ctx.check(self.ctx.lib.pb_ck_mix(self.ctx.h, ctypes.byref(a), PB_DEVICE if device_output else PB_HOST))
+        self.molecular_opa = out
+        return (out, ln_mixed) if return_ln_mixed else out
+
+    def get_opacities(self, atmosphere, exclude_mol=1):
+        """get_opacities_deq_onfly (optics.py:1513-1520) = get_continuum + mix_my_opacities_gasesfly; the mixed
+        k-coefficients stay in HBM for compute_opacity."""
+        t = np.asarray(atmosphere.layer["temperature"], dtype=np.float64)
+        lo, hi, ct = self._continuum_plan(t, 1 / t)
+        self.mix_my_opacities_gasesfly(atmosphere, exclude_mol=exclude_mol, device_output=True)
+        self._plan = dict(nlayer=t.size, lo=lo, hi=hi, ct=ct, direct=self.molecular_opa)
+        self.continuum_opa = None
+
+    def close(self):
+        for d in getattr(self, "kappas", {}).values():
+            d.free()
+        self.kappas = {}
+        super().close()
 
 
 def compute_opacity_ck(atm, opa, stream, delta_eddington, raman, fthin_cld, do_holes, device_outputs, outputs):
@@ -145,7 +242,11 @@ def compute_opacity_ck(atm, opa, stream, delta_eddington, raman, fthin_cld, do_h
     a.nlayer, a.query, a.raman = L, 1, 2
     a.cont_index, a.cont_index_hi, a.cont_t, a.cont_mode = addr(pl["lo"]), addr(pl["hi"]), addr(pl["ct"]), 1
     a.cont_scale, a.ray_scale = addr(cont), addr(ray)
-    a.ngauss, a.ck_index, a.ck_weights, a.ck_scale = K, addr(pl["idx"]), addr(pl["wts"]), addr(ck_scale)
+    a.ngauss, a.ck_scale = K, addr(ck_scale)
+    if "direct" in pl:
+        a.ck_direct = pl["direct"].ptr
+    else:
+        a.ck_index, a.ck_weights = addr(pl["idx"]), addr(pl["wts"])
     keep = [cont, ray, ck_scale]
     cloud = atm.layer.get("cloud") if isinstance(atm.layer, dict) else atm.layer["cloud"]
     if cloud is not None and np.any(np.asarray(cloud["opd"]) != 0):

@@ -256,10 +256,38 @@ def bench_transit(ctx, L, W, reps):
     ctx.dev_free(d_F)
 
 
+def bench_mix(ctx, L, W, K, ngas, reps):
+    """resort-rebin mixing at the climate solver's shape (661 bins x 8 gauss points, ~a dozen gases)"""
+    from picaso_b200._lib import CkMixArgs
+    nP, nT = 8, 9
+    rng = np.random.default_rng(5)
+    dk = [ctx.to_device(np.sort(rng.uniform(-70.0, -45.0, (nP, nT, W, K)), axis=3)) for _ in range(ngas)]
+    ptrs = (ctypes.c_void_p * ngas)(*dk)
+    mixes = np.ascontiguousarray(10.0 ** rng.uniform(-8, -0.5, (ngas, L)))
+    ind = np.ascontiguousarray(np.stack([rng.integers(0, nP - 1, L), rng.integers(1, nP, L), rng.integers(0, nT - 1, L),
+                                         rng.integers(1, nT, L)]), dtype=np.int32)
+    ti, pi = rng.uniform(0, 1, L), rng.uniform(0, 1, L)
+    x, w = np.polynomial.legendre.leggauss(K)
+    gp, gw = np.ascontiguousarray(0.5 * (x + 1)), np.ascontiguousarray(0.5 * w)
+    out = ctx.dev_alloc(L * W * K * 8)
+    a = CkMixArgs(nlayer=L, nwno=W, ngauss=K, ngas=ngas, np=nP, nt=nT)
+    a.kappas = ctypes.cast(ptrs, ctypes.c_void_p)
+    a.mixes, a.indices, a.t_interp, a.p_interp = _lib.addr(mixes), _lib.addr(ind), _lib.addr(ti), _lib.addr(pi)
+    a.gauss_pts, a.gauss_wts, a.molecular_opa = _lib.addr(gp), _lib.addr(gw), out
+    fn = ctx.lib.pb_ck_mix
+    ms = timeit(ctx, lambda i: ctx.check(fn(ctx.h, ctypes.byref(a), PB_DEVICE)), 1, reps)
+    nmix = L * W * 4 * (ngas - 1)
+    report("ck_mix L=%d W=%d K=%d ngas=%d" % (L, W, K, ngas), ms, (4 * ngas + 1) * L * W * K * 8, nmix, "pair-mixes",
+           {"ns_per_pair_mix": ms * 1e6 / nmix})
+    for d in dk:
+        ctx.dev_free(d)
+    ctx.dev_free(out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=50)
-    ap.add_argument("--only", default="refl,sh,opacity,thermal,transit,batch")
+    ap.add_argument("--only", default="refl,sh,opacity,thermal,transit,mix,batch")
     a = ap.parse_args()
     only = set(a.only.split(","))
     ctx = pb.Context(0)
@@ -285,6 +313,8 @@ def main():
         bench_thermal(ctx, 90, 100000, 5, max(5, a.reps // 5))
     if "transit" in only:
         bench_transit(ctx, 80, 50000, a.reps)
+    if "mix" in only:
+        bench_mix(ctx, 90, 661, 8, 12, max(5, a.reps // 5))
     if "batch" in only:
         bench_thermal(ctx, 60, 2000, 5, max(5, a.reps // 5), batch=128)
         bench_reflected(ctx, 60, 10000, 5, max(5, a.reps // 5), batch=8, tag=" (8 spectra/launch)")

@@ -271,3 +271,26 @@ def ck_cases():
         "ck8_dedd": dict(db=dict(W=40, K=8, seed=2101), atm=dict(L=11, seed=2103), stream=2, dedd=True),
         "ck4_clear": dict(db=dict(W=25, K=4, seed=2111), atm=dict(L=8, seed=2113, cloudy=False), stream=4, dedd=False),
     }
+
+
+def mix_cases():
+    """resort-rebin mixing (deq_chem.mix_all_gases_gasesfly + optics.mix_my_opacities_gasesfly)"""
+    return {
+        "mix_4gas_nk8": dict(W=6, K=8, ngas=4, L=5, seed=2201),
+        "mix_2gas_nk8": dict(W=4, K=8, ngas=2, L=3, seed=2211),
+        "mix_6gas_nk4": dict(W=5, K=4, ngas=6, L=4, seed=2221),
+    }
+
+
+def build_mix(case):
+    """per-gas ln(kappa) tables [nP, nT, W, K] sharing one (P, T) grid + an atmosphere profile"""
+    rng = np.random.default_rng(case["seed"])
+    dbs = [synth.ck_database(W=case["W"], K=case["K"], seed=case["seed"] + 7 * g, nT=6, nP=6) for g in range(case["ngas"])]
+    db = dbs[0]
+    gases = synth.MOLECULES[:case["ngas"]]
+    kappas = {m: d["kappa"] + 0.5 * g for g, (m, d) in enumerate(zip(gases, dbs))}
+    atm = synth.atmosphere_profile(dict(db, molecules=gases), L=case["L"], seed=case["seed"] + 3, cloudy=False)
+    # Gauss-Legendre points/weights on (0, 1), as opacity_factory.g_w_2gauss style arrays would provide
+    x, w = np.polynomial.legendre.leggauss(case["K"])
+    gauss_pts, gauss_wts = 0.5 * (x + 1.0), 0.5 * w
+    return db, gases, kappas, atm, gauss_pts, gauss_wts
