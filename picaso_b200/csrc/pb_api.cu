@@ -61,6 +61,7 @@ int pb_create(int device, pb_ctx **out)
     CREATE_CUDA(cudaEventCreate(&ctx->ev_start));
     CREATE_CUDA(cudaEventCreate(&ctx->ev_stop));
     CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    for (auto &e : ctx->ev_chunk) CREATE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 #undef CREATE_CUDA
     *out = ctx;
     return PB_OK;
@@ -80,6 +81,8 @@ void pb_destroy(pb_ctx *ctx)
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
     cudaEventDestroy(ctx->ev_copy);
+    for (auto &e : ctx->ev_chunk)
+        if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own_stream);
     cudaStreamDestroy(ctx->copy_stream);
     delete ctx;

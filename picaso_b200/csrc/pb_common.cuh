@@ -21,6 +21,8 @@ struct pb_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy = nullptr;
+    static constexpr int kChunkEvents = 16;
+    cudaEvent_t ev_chunk[kChunkEvents] = {};  // copy-stream -> compute-stream hand-off per wavelength chunk
     uint64_t launches = 0;
     char err[512] = {0};
     // grow-only device arena used to stage PB_HOST calls and small geometry vectors

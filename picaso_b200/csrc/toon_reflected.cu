@@ -538,29 +538,35 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
     p.L = L; p.W = W; p.G = G; p.nt = a->numt;
     int64_t ld = a->ld;
     const int64_t rowsL = (int64_t)B * L, rowsV = (int64_t)B * V;
-    // og arrays may alias the corrected ones when delta-Eddington is off (optics.py:429-431)
-    auto stage_layer = [&](const double *src, const double **dst) -> int {
-        int64_t ldo;
-        return pb_stage_in(ctx, src, memspace, rowsL, W, a->ld, dst, &ldo);
+    // PB_HOST: every input gets a dense [rows][W] device block; the copies themselves are issued
+    // below, per wavelength chunk, so that chunk c+1 crosses PCIe while chunk c is being solved
+    struct Staged { const double *src; double *dst; int64_t rows, ld; };
+    std::vector<Staged> staged;
+    auto stage = [&](const double *src, int64_t rows, int64_t src_ld, const double **dst) -> int {
+        if (!src || !host) { *dst = src; return PB_OK; }
+        void *d = nullptr;
+        PB_TRY(pb_arena_alloc(ctx, (size_t)rows * nW, &d));
+        staged.push_back({src, (double *)d, rows, src_ld});
+        *dst = (const double *)d;
+        return PB_OK;
     };
-    PB_TRY(stage_layer(a->dtau, &p.dtau));
-    PB_TRY(stage_layer(a->w0, &p.w0));
-    PB_TRY(stage_layer(a->cosb, &p.cosb));
-    PB_TRY(stage_layer(a->gcos2, &p.gcos2));
-    PB_TRY(stage_layer(a->ftau_cld, &p.fcld));
-    PB_TRY(stage_layer(a->ftau_ray, &p.fray));
-    if (a->dtau_og == a->dtau) p.dtau_og = p.dtau; else PB_TRY(stage_layer(a->dtau_og, &p.dtau_og));
-    if (a->w0_og == a->w0) p.w0_og = p.w0; else PB_TRY(stage_layer(a->w0_og, &p.w0_og));
-    if (a->cosb_og == a->cosb) p.cosb_og = p.cosb; else PB_TRY(stage_layer(a->cosb_og, &p.cosb_og));
+    PB_TRY(stage(a->dtau, rowsL, a->ld, &p.dtau));
+    PB_TRY(stage(a->w0, rowsL, a->ld, &p.w0));
+    PB_TRY(stage(a->cosb, rowsL, a->ld, &p.cosb));
+    PB_TRY(stage(a->gcos2, rowsL, a->ld, &p.gcos2));
+    PB_TRY(stage(a->ftau_cld, rowsL, a->ld, &p.fcld));
+    PB_TRY(stage(a->ftau_ray, rowsL, a->ld, &p.fray));
+    // og arrays may alias the corrected ones when delta-Eddington is off (optics.py:429-431)
+    if (a->dtau_og == a->dtau) p.dtau_og = p.dtau; else PB_TRY(stage(a->dtau_og, rowsL, a->ld, &p.dtau_og));
+    if (a->w0_og == a->w0) p.w0_og = p.w0; else PB_TRY(stage(a->w0_og, rowsL, a->ld, &p.w0_og));
+    if (a->cosb_og == a->cosb) p.cosb_og = p.cosb; else PB_TRY(stage(a->cosb_og, rowsL, a->ld, &p.cosb_og));
+    PB_TRY(stage(a->tau, rowsV, a->ld, &p.tau));
+    if (a->tau_og == a->tau) p.tau_og = p.tau; else PB_TRY(stage(a->tau_og, rowsV, a->ld, &p.tau_og));
     {
-        int64_t ldo;
-        PB_TRY(pb_stage_in(ctx, a->tau, memspace, rowsV, W, a->ld, &p.tau, &ldo));
-        if (a->tau_og == a->tau) p.tau_og = p.tau;
-        else PB_TRY(pb_stage_in(ctx, a->tau_og, memspace, rowsV, W, a->ld, &p.tau_og, &ldo));
         const int64_t nvec = a->variant ? 1 : B;
-        PB_TRY(pb_stage_in(ctx, a->surf_reflect, memspace, nvec, W, W, &p.surf, &ldo));
-        PB_TRY(pb_stage_in(ctx, a->F0PI, memspace, nvec, W, W, &p.f0pi, &ldo));
-        PB_TRY(pb_stage_in(ctx, a->b_top, memspace, nvec, W, W, &p.btop, &ldo));
+        PB_TRY(stage(a->surf_reflect, nvec, W, &p.surf));
+        PB_TRY(stage(a->F0PI, nvec, W, &p.f0pi));
+        PB_TRY(stage(a->b_top, nvec, W, &p.btop));
     }
     if (host) ld = W;
     p.ld = ld;
@@ -597,9 +603,19 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
     PB_TRY(pb_upload_flush(ctx));
     const int ay = G < 8 ? G : 8;
     dim3 block(kWavesPerCta, ay, 1);
-    dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
-    if (want_toa) {
-        p.xint = d_xint; p.albedo = d_alb; p.fuse_albedo = fuse ? 1 : 0;
+
+    // TOA kernel over the wavelength range [w0, w0 + wc) of batch-dense inputs (ld stays W);
+    // its outputs are chunk-dense: xo [B][G][wc], ao [B][wc]
+    auto launch_toa = [&](int w0, int wc, double *xo, double *ao) -> int {
+        ReflParams q = p;
+        q.W = wc;
+        q.dtau += w0; q.w0 += w0; q.cosb += w0; q.gcos2 += w0; q.fcld += w0; q.fray += w0;
+        q.dtau_og += w0; q.w0_og += w0; q.cosb_og += w0; q.tau += w0; q.tau_og += w0;
+        if (q.surf) q.surf += w0;
+        if (q.f0pi) q.f0pi += w0;
+        if (q.btop) q.btop += w0;
+        q.xint = xo; q.albedo = ao; q.fuse_albedo = fuse ? 1 : 0;
+        dim3 grid((wc + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
         // PB_REFL_KERNEL=2 selects the previous generation (one layer per consume step) for A/B runs
         static const int variant = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 3; }();
         if (variant == 2) {
@@ -608,24 +624,75 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
                 PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             }
-            if (p.mp == 0) refl_toa_kernel<0><<<grid, block, smem, ctx->stream>>>(p);
-            else refl_toa_kernel<1><<<grid, block, smem, ctx->stream>>>(p);
+            if (q.mp == 0) refl_toa_kernel<0><<<grid, block, smem, ctx->stream>>>(q);
+            else refl_toa_kernel<1><<<grid, block, smem, ctx->stream>>>(q);
         } else {
             const size_t smem = (size_t)2 * (2 * ay) * NQ * 32 * sizeof(double);
             if (smem > 48 * 1024) {
                 PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             }
-            if (p.mp == 0) refl_toa_kernel3<0><<<grid, block, smem, ctx->stream>>>(p);
-            else refl_toa_kernel3<1><<<grid, block, smem, ctx->stream>>>(p);
+            if (q.mp == 0) refl_toa_kernel3<0><<<grid, block, smem, ctx->stream>>>(q);
+            else refl_toa_kernel3<1><<<grid, block, smem, ctx->stream>>>(q);
         }
         PB_CHECK_LAUNCH(ctx);
-        if (a->albedo && !fuse) {
-            dim3 g2((W + 127) / 128, B);
-            compress_disco_kernel<<<g2, 128, 0, ctx->stream>>>(W, G, a->numt, a->cos_theta, d_xint,
-                                                               p.gweight, p.tweight, p.f0pi, p.bs_wave, d_alb);
+        if (ao && !fuse) {
+            dim3 g2((wc + 127) / 128, B);
+            compress_disco_kernel<<<g2, 128, 0, ctx->stream>>>(wc, G, a->numt, a->cos_theta, xo, q.gweight,
+                                                               q.tweight, q.f0pi, q.bs_wave, ao);
             PB_CHECK_LAUNCH(ctx);
         }
+        return PB_OK;
+    };
+    auto copy_in = [&](int w0, int wc, cudaStream_t cs) -> int {
+        for (const Staged &s : staged) {
+            if (s.ld == W && wc == W)
+                PB_CUDA(ctx, cudaMemcpyAsync(s.dst, s.src, (size_t)s.rows * nW, cudaMemcpyHostToDevice, cs));
+            else
+                PB_CUDA(ctx, cudaMemcpy2DAsync(s.dst + w0, nW, s.src + w0, (size_t)s.ld * sizeof(double),
+                                               (size_t)wc * sizeof(double), s.rows, cudaMemcpyHostToDevice, cs));
+        }
+        return PB_OK;
+    };
+
+    // A PB_HOST spectrum is PCIe-bound (11 arrays in, G+1 vectors out).  Opt-in (PB_REFL_CHUNKS=n):
+    // split the wavelength axis into n chunks, copy on the copy stream, solve on the compute stream.
+    // Measured on B200 / PCIe gen5 (60 x 10 000 x 5): 1.31 ms unchunked, 1.70 ms with 4 chunks,
+    // 2.24 ms with 8 - the strided 2-D copies (one DMA descriptor per row) cost more than the
+    // 0.09 ms of kernel time they hide, so the default stays one contiguous copy per array.
+    const char *chunk_env = getenv("PB_REFL_CHUNKS");
+    const int want_chunks = chunk_env ? atoi(chunk_env) : 1;
+    int nchunk = 1;
+    if (host && want_toa && !want_lvl && B == 1 && want_chunks > 1 && W >= 1024 * want_chunks) nchunk = want_chunks;
+    if (nchunk > 1) {
+        if (nchunk > pb_ctx::kChunkEvents) nchunk = pb_ctx::kChunkEvents;
+        const int cw = ((W + nchunk - 1) / nchunk + kWavesPerCta - 1) / kWavesPerCta * kWavesPerCta;
+        // the copy stream must not overwrite arena bytes that work already queued on the compute stream uses
+        PB_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+        int c = 0;
+        for (int w0 = 0; w0 < W; w0 += cw, ++c) {
+            const int wc = W - w0 < cw ? W - w0 : cw;
+            PB_TRY(copy_in(w0, wc, ctx->copy_stream));
+            PB_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+            PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0));
+            double *xo = d_xint ? d_xint + (size_t)G * w0 : nullptr;
+            double *ao = d_alb ? d_alb + w0 : nullptr;
+            PB_TRY(launch_toa(w0, wc, xo, ao));
+            if (a->xint_at_top)
+                PB_CUDA(ctx, cudaMemcpy2DAsync(a->xint_at_top + w0, nW, xo, (size_t)wc * sizeof(double),
+                                               (size_t)wc * sizeof(double), G, cudaMemcpyDeviceToHost, ctx->stream));
+            if (a->albedo)
+                PB_CUDA(ctx, cudaMemcpyAsync(a->albedo + w0, ao, (size_t)wc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return PB_OK;
+    }
+
+    if (host) PB_TRY(copy_in(0, W, ctx->stream));
+    dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
+    if (want_toa) {
+        PB_TRY(launch_toa(0, W, d_xint, d_alb));
     } else if (a->xint_at_top && memspace == PB_DEVICE) {
         PB_CUDA(ctx, cudaMemsetAsync(a->xint_at_top, 0, (size_t)B * G * nW, ctx->stream));
     }

@@ -164,6 +164,30 @@ def test_full_size_properties():
     assert np.array_equal(xp, xint[..., perm]), "wavelengths are not independent"
 
 
+def test_chunked_host_pipeline_ragged_padded(monkeypatch):
+    """Opt-in PB_REFL_CHUNKS: PB_HOST calls split into wavelength chunks (copy stream / compute
+    stream, toon_reflected.cu); ragged last chunk, padded leading dimension, xint-only and albedo."""
+    monkeypatch.setenv("PB_REFL_CHUNKS", "4")
+    W = 4099
+    d = synth.reflected_inputs(L=12, W=W, seed=77)
+    kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
+    ox, _ = oracle.get_reflected_1d(*C.reflected_args(d, kw), nthreads=8)
+    oalb = oracle.compress_disco(W, d["cos_theta"], ox, d["gweight"], d["tweight"], d["F0PI"])
+    d2 = dict(d)
+    for k in ("dtau", "tau", "w0", "cosb", "gcos2", "ftau_cld", "ftau_ray", "dtau_og", "tau_og",
+              "w0_og", "cosb_og"):
+        big = np.full((d[k].shape[0], W + 61), np.nan)
+        big[:, :W] = d[k]
+        d2[k] = big[:, :W]
+    for dd in (d, d2):
+        xint, _, alb = pb.get_reflected_1d(*C.reflected_args(dd, kw), gweight=d["gweight"],
+                                           tweight=d["tweight"], return_albedo=True)
+        assert_close(xint, ox, RTOL, "chunked xint")
+        assert_close(alb, oalb, RTOL, "chunked albedo")
+    x_only, _ = pb.get_reflected_1d(*C.reflected_args(d2, kw))
+    assert np.array_equal(x_only, xint)
+
+
 def test_kernel_math_primitives():
     """branch-free exp / reciprocal used inside the kernels vs numpy (libm)."""
     from picaso_b200 import _lib
