@@ -156,6 +156,7 @@ __device__ __forceinline__ void refl_produce(const ReflParams &p, const ReflInpu
 }
 
 #include "toon_reflected_toa3.cuh"
+#include "toon_reflected_toa4.cuh"
 
 template <int MP /*multi_phase*/>
 __global__ void __launch_bounds__(256) refl_toa_kernel(ReflParams p)
@@ -616,8 +617,8 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
         if (q.btop) q.btop += w0;
         q.xint = xo; q.albedo = ao; q.fuse_albedo = fuse ? 1 : 0;
         dim3 grid((wc + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
-        // PB_REFL_KERNEL=2 selects the previous generation (one layer per consume step) for A/B runs
-        static const int variant = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 3; }();
+        // PB_REFL_KERNEL=2|3 select the previous generations (bottom-up sweeps) for A/B runs
+        static const int variant = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 4; }();
         if (variant == 2) {
             const size_t smem = (size_t)2 * ay * NQ * 32 * sizeof(double);
             if (smem > 48 * 1024) {
@@ -626,7 +627,7 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             }
             if (q.mp == 0) refl_toa_kernel<0><<<grid, block, smem, ctx->stream>>>(q);
             else refl_toa_kernel<1><<<grid, block, smem, ctx->stream>>>(q);
-        } else {
+        } else if (variant == 3) {
             const size_t smem = (size_t)2 * (2 * ay) * NQ * 32 * sizeof(double);
             if (smem > 48 * 1024) {
                 PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -634,6 +635,14 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             }
             if (q.mp == 0) refl_toa_kernel3<0><<<grid, block, smem, ctx->stream>>>(q);
             else refl_toa_kernel3<1><<<grid, block, smem, ctx->stream>>>(q);
+        } else {
+            const size_t smem = (size_t)2 * (2 * ay) * NR * 32 * sizeof(double);
+            if (smem > 48 * 1024) {
+                PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
+            if (q.mp == 0) refl_toa_kernel4<0><<<grid, block, smem, ctx->stream>>>(q);
+            else refl_toa_kernel4<1><<<grid, block, smem, ctx->stream>>>(q);
         }
         PB_CHECK_LAUNCH(ctx);
         if (ao && !fuse) {

@@ -164,6 +164,27 @@ def test_full_size_properties():
     assert np.array_equal(xp, xint[..., perm]), "wavelengths are not independent"
 
 
+def test_tau_not_cumsum_of_dtau():
+    """tau / tau_og are independent arguments of the reference signature.  The top-down kernel
+    (toon_reflected_toa4.cuh) replaces exp(-tau/u0) by running products only where
+    tau[l+1] == tau[l] + dtau[l]; everywhere else it must follow the caller's arrays exactly."""
+    kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
+    rng = np.random.default_rng(5)
+    for phase in (0.0, 0.7):
+        d = synth.reflected_inputs(L=23, W=97, seed=61, phase=phase)
+        d = dict(d)
+        d["tau"] = d["tau"] * 1.07 + 0.01                      # inconsistent everywhere, tau[0] != 0
+        tau_og = d["tau_og"].copy()
+        rows = rng.integers(1, 24, size=40)
+        cols = rng.integers(0, 97, size=40)
+        tau_og[rows, cols] *= 1.0 + 1e-9                        # inconsistent at scattered levels only
+        d["tau_og"] = tau_og
+        args = C.reflected_args(d, kw)
+        xint, _ = pb.get_reflected_1d(*args)
+        ox, _ = oracle.get_reflected_1d(*args)
+        assert_close(xint, ox, RTOL, "inconsistent tau, phase %.1f" % phase)
+
+
 def test_chunked_host_pipeline_ragged_padded(monkeypatch):
     """Opt-in PB_REFL_CHUNKS: PB_HOST calls split into wavelength chunks (copy stream / compute
     stream, toon_reflected.cu); ragged last chunk, padded leading dimension, xint-only and albedo."""
