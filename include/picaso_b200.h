@@ -295,6 +295,37 @@ typedef struct pb_ck_mix_args {
 
 int pb_ck_mix(pb_ctx *ctx, const pb_ck_mix_args *args, int memspace);
 
+/* ---- climate solver: level fluxes of all correlated-k gauss points in one call ------- */
+/* replaces get_fluxes, picaso/climate.py:1686-1952 (the cloudy or the clear column of it; the
+ * do_holes mix (1-fhole)*cloudy + fhole*clear is linear in the outputs and done by the caller).
+ * Opacity arrays are [nlayer | nlevel][nwno][ngauss], gauss point fastest - the reference's layout
+ * (optics.py:423-431) - in `memspace`; every other pointer (gauss_wts, wno, dwno, surf_reflect, F0PI,
+ * tlevel, plevel, geometry) and ALL outputs are host pointers in both memory spaces: the solver
+ * consumes the fluxes on the host.  reflected: one mu0 = mu1 = 0.5 stream, quadrature coefficients,
+ * b_top = 0 (climate.py:1797-1816).  thermal: DTAU_OG / W0_no_raman / COSB_OG, hard_surface = 0,
+ * calc_type = 1 over the numg x numt disk angles, then compress_thermal (climate.py:1887-1932). */
+typedef struct pb_climate_args {
+    int nlayer, nwno, ngauss, numg, numt;
+    int reflected, thermal;
+    const double *DTAU, *TAU, *W0, *COSB, *ftau_cld, *ftau_ray, *GCOS2, *W0_no_raman; /* OpacityWEd */
+    const double *DTAU_OG, *TAU_OG, *W0_OG, *COSB_OG;                                  /* OpacityNoEd */
+    const double *gauss_wts;            /* [ngauss] */
+    const double *wno, *dwno;           /* [nwno]; dwno = Opagrid.delta_wno */
+    const double *surf_reflect, *F0PI;  /* [nwno] or NULL (0 / 1) */
+    const double *tlevel, *plevel;      /* [nlevel] */
+    const double *ubar1, *gweight, *tweight; /* [numg*numt], [numg], [numt] (thermal disk angles) */
+    double cos_theta;
+    int single_phase, multi_phase;
+    double frac_a, frac_b, frac_c, constant_back, constant_forward;
+    /* outputs; the reference broadcasts the visible ones over (ng, nt): here one copy */
+    double *flux_net_v_layer, *flux_net_v;   /* [nlevel] */
+    double *flux_plus_v, *flux_minus_v;      /* [nlevel][nwno] */
+    double *flux_net_ir_layer, *flux_net_ir; /* [nlevel] */
+    double *flux_plus_ir, *flux_minus_ir;    /* [nlevel][nwno] */
+} pb_climate_args;
+
+int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *args, int memspace);
+
 /* ---- self test ------------------------------------------------------------------------- */
 /* evaluates the kernels' branch-free exp() and 1/x on x[n] (host pointers); test hook */
 int pb_selftest_math(pb_ctx *ctx, const double *x, int n, double *exp_out, double *rcp_out);

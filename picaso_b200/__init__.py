@@ -14,13 +14,14 @@ from .fluxes_sh_thermal import get_thermal_SH  # noqa: F401
 from .fluxes_3d import get_reflected_3d, get_thermal_3d  # noqa: F401
 from .optics import DeviceArray, DeviceOpacities, compute_opacity  # noqa: F401
 from .optics_ck import DeviceCKs, DeviceGasCKs  # noqa: F401
+from .climate import get_fluxes  # noqa: F401
 from .disco import compress_disco, compress_thermal, get_angles_1d, get_angles_3d, compute_disco  # noqa: F401
 
 __version__ = "0.1.0"
 
 _PATCHED = ("get_reflected_1d", "get_reflected_3d", "get_reflected_SH", "get_thermal_1d", "get_thermal_3d",
             "get_thermal_SH", "get_transit_1d", "compress_disco",
-            "compress_thermal")
+            "compress_thermal", "get_fluxes")
 
 
 def patch(module):

@@ -87,6 +87,18 @@ class ThermalArgs(ctypes.Structure):
                              "flux_minus_mdpt", "flux_plus_mdpt")] + [("variant", c_int)])
 
 
+class ClimateArgs(ctypes.Structure):
+    _fields_ = (
+        [(n, c_int) for n in ("nlayer", "nwno", "ngauss", "numg", "numt", "reflected", "thermal")] +
+        [(n, c_vp) for n in ("DTAU", "TAU", "W0", "COSB", "ftau_cld", "ftau_ray", "GCOS2", "W0_no_raman",
+                             "DTAU_OG", "TAU_OG", "W0_OG", "COSB_OG", "gauss_wts", "wno", "dwno",
+                             "surf_reflect", "F0PI", "tlevel", "plevel", "ubar1", "gweight", "tweight")] +
+        [("cos_theta", c_dbl), ("single_phase", c_int), ("multi_phase", c_int)] +
+        [(n, c_dbl) for n in ("frac_a", "frac_b", "frac_c", "constant_back", "constant_forward")] +
+        [(n, c_vp) for n in ("flux_net_v_layer", "flux_net_v", "flux_plus_v", "flux_minus_v",
+                             "flux_net_ir_layer", "flux_net_ir", "flux_plus_ir", "flux_minus_ir")])
+
+
 class TransitArgs(ctypes.Structure):
     _fields_ = (
         [(n, c_int) for n in ("nlevel", "nwno", "nbatch")] + [("ld", c_i64)] +
@@ -134,6 +146,7 @@ SYMBOLS = {
     "pb_optab_bytes": (c_int, [c_vp, ctypes.POINTER(ctypes.c_size_t)]),
     "pb_compute_opacity": (c_int, [c_vp, c_vp, ctypes.POINTER(OpacityArgs), c_int]),
     "pb_ck_mix": (c_int, [c_vp, ctypes.POINTER(CkMixArgs), c_int]),
+    "pb_climate_get_fluxes": (c_int, [c_vp, ctypes.POINTER(ClimateArgs), c_int]),
 }
 
 _lib = None

@@ -1,0 +1,332 @@
+// climate.cu - the radiative-transfer call of the climate solver, on the device in one call.
+//
+// Replaces picaso/climate.py:1686-1952 (get_fluxes): for every correlated-k gauss point the
+// reference slices X[:, :, ig] out of the [nlayer, nwno, ngauss] opacity arrays, calls
+// get_reflected_1d(get_lvl_flux=1) with a single mu = 0.5 stream and get_thermal_1d(calc_type=1),
+// weights the four level arrays by gauss_wts[ig] and reduces them over wavelength
+// (np.sum(axis=3) for the visible net fluxes, a sequential dwni-weighted loop for the IR ones,
+// compress_thermal over the disk angles in between).
+//
+// Here: one de-interleave pass turns [rows][nwno][ngauss] into ngauss dense [rows][nwno] blocks
+// (wavelength fastest, what the flux kernels coalesce on), the level-flux kernels run ONCE with
+// nbatch = ngauss, and two reduction kernels fold gauss weights, disk weights, dwni and the
+// wavelength sums.  Level arrays never leave HBM; what returns to the host is 4 [nlevel] vectors
+// and 4 [nlevel][nwno] arrays.
+#include <cstdlib>
+
+#include "pb_common.cuh"
+
+namespace {
+
+// [rows][W][K] -> [K][rows][W]
+__global__ void deinterleave_kernel(int64_t n /* rows*W */, int K, const double *__restrict__ in,
+                                    double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *src = in + i * K;
+    for (int k = 0; k < K; ++k) out[(int64_t)k * n + i] = src[k];
+}
+
+// out[k][w] = in[w]
+__global__ void replicate_kernel(int W, int K, const double *__restrict__ in, double fill, double *__restrict__ out)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const double v = in ? in[w] : fill;
+    for (int k = 0; k < K; ++k) out[(int64_t)k * W + w] = v;
+}
+
+constexpr int kRedThreads = 256;
+
+// deterministic CTA-wide sum (fixed shuffle tree + fixed order over warps)
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < kRedThreads / 32; ++i) t += sh[i];
+    return t;  // valid on thread 0
+}
+
+// Visible part (climate.py:1838-1840, :1872-1873).  Level arrays [K][V][W] (one mu = 0.5 stream).
+// One CTA per level.
+__global__ void __launch_bounds__(kRedThreads) climate_visible_reduce(
+    int V, int W, int K, const double *__restrict__ fm, const double *__restrict__ fp,
+    const double *__restrict__ fmm, const double *__restrict__ fpm, const double *__restrict__ gw,
+    double *__restrict__ plus_v, double *__restrict__ minus_v, double *__restrict__ net_layer,
+    double *__restrict__ net)
+{
+    __shared__ double sh[kRedThreads / 32];
+    const int v = blockIdx.x;
+    double nl = 0.0, nn = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const int64_t base = ((int64_t)k * V + v) * W;
+        double s_fm = 0.0, s_fp = 0.0, s_fmm = 0.0, s_fpm = 0.0;
+        for (int w = threadIdx.x; w < W; w += kRedThreads) {
+            s_fm += fm[base + w];
+            s_fp += fp[base + w];
+            s_fmm += fmm[base + w];
+            s_fpm += fpm[base + w];
+        }
+        const double t_fpm = block_sum(s_fpm, sh), t_fmm = block_sum(s_fmm, sh);
+        const double t_fp = block_sum(s_fp, sh), t_fm = block_sum(s_fm, sh);
+        if (threadIdx.x == 0) {
+            nl += (t_fpm - t_fmm) * gw[k];
+            nn += (t_fp - t_fm) * gw[k];
+        }
+    }
+    if (threadIdx.x == 0) {
+        net_layer[v] = nl;
+        net[v] = nn;
+    }
+    for (int w = threadIdx.x; w < W; w += kRedThreads) {
+        double ap = 0.0, am = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const int64_t i = ((int64_t)k * V + v) * W + w;
+            ap += fp[i] * gw[k];
+            am += fm[i] * gw[k];
+        }
+        plus_v[(int64_t)v * W + w] = ap;
+        minus_v[(int64_t)v * W + w] = am;
+    }
+}
+
+// IR part (climate.py:1916-1942): gauss-weighted accumulation, compress_thermal (disco.py:152-180)
+// over the G = ng*nt disk angles, dwni-weighted wavelength sums.  Level arrays [K][G][V][W].
+__global__ void __launch_bounds__(kRedThreads) climate_ir_reduce(
+    int V, int W, int K, int G, int nt, const double *__restrict__ fm, const double *__restrict__ fp,
+    const double *__restrict__ fmm, const double *__restrict__ fpm, const double *__restrict__ gw,
+    const double *__restrict__ gweight, const double *__restrict__ tweight, const double *__restrict__ dwni,
+    double *__restrict__ plus_ir, double *__restrict__ minus_ir, double *__restrict__ net_layer,
+    double *__restrict__ net)
+{
+    __shared__ double sh[kRedThreads / 32];
+    const int v = blockIdx.x;
+    const double sym = (nt == 1) ? 1.0 : 1.0 / (2.0 * PB_PI);
+    double s_net = 0.0, s_lay = 0.0;
+    for (int w = threadIdx.x; w < W; w += kRedThreads) {
+        double c_fm = 0.0, c_fp = 0.0, c_fmm = 0.0, c_fpm = 0.0;
+        for (int a = 0; a < G; ++a) {
+            double a_fm = 0.0, a_fp = 0.0, a_fmm = 0.0, a_fpm = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const int64_t i = (((int64_t)k * G + a) * V + v) * W + w;
+                a_fm += fm[i] * gw[k];
+                a_fp += fp[i] * gw[k];
+                a_fmm += fmm[i] * gw[k];
+                a_fpm += fpm[i] * gw[k];
+            }
+            const int ig = a / nt, it = a - ig * nt;
+            const double wgt_g = gweight[ig], wgt_t = tweight[it];
+            c_fm = c_fm + a_fm * wgt_g * wgt_t;
+            c_fp = c_fp + a_fp * wgt_g * wgt_t;
+            c_fmm = c_fmm + a_fmm * wgt_g * wgt_t;
+            c_fpm = c_fpm + a_fpm * wgt_g * wgt_t;
+        }
+        c_fm *= sym; c_fp *= sym; c_fmm *= sym; c_fpm *= sym;
+        const double dw = dwni[w];
+        s_lay += (c_fpm - c_fmm) * dw;
+        s_net += (c_fp - c_fm) * dw;
+        plus_ir[(int64_t)v * W + w] = c_fp * dw;
+        minus_ir[(int64_t)v * W + w] = c_fm * dw;
+    }
+    const double t_lay = block_sum(s_lay, sh), t_net = block_sum(s_net, sh);
+    if (threadIdx.x == 0) {
+        net_layer[v] = t_lay;
+        net[v] = t_net;
+    }
+}
+
+int aux_reserve(pb_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->aux_cap) return PB_OK;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->aux) PB_CUDA(ctx, cudaFree(ctx->aux));
+    ctx->aux = nullptr;
+    ctx->aux_cap = 0;
+    const size_t cap = pb_align(bytes + bytes / 8, 1 << 20);
+    cudaError_t e = cudaMalloc((void **)&ctx->aux, cap);
+    if (e != cudaSuccess) return pb_fail(ctx, PB_ERR_NOMEM, "climate scratch cudaMalloc(%zu) -> %s", cap, cudaGetErrorString(e));
+    ctx->aux_cap = cap;
+    return PB_OK;
+}
+
+} // namespace
+
+extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int memspace)
+{
+    if (!ctx || !a) return PB_ERR_ARG;
+    const int L = a->nlayer, W = a->nwno, K = a->ngauss, G = a->numg * a->numt;
+    const int V = L + 1;
+    if (L < 1 || W < 1 || K < 1 || G < 1) return pb_fail(ctx, PB_ERR_ARG, "climate: bad sizes L=%d W=%d K=%d G=%d", L, W, K, G);
+    if (!a->gauss_wts) return pb_fail(ctx, PB_ERR_ARG, "climate: gauss_wts missing");
+    if (a->reflected) {
+        if (!a->DTAU || !a->TAU || !a->W0 || !a->COSB || !a->GCOS2 || !a->ftau_cld || !a->ftau_ray ||
+            !a->DTAU_OG || !a->TAU_OG || !a->W0_OG || !a->COSB_OG)
+            return pb_fail(ctx, PB_ERR_ARG, "climate: reflected needs the 11 opacity arrays");
+        if (!a->flux_net_v_layer || !a->flux_net_v || !a->flux_plus_v || !a->flux_minus_v)
+            return pb_fail(ctx, PB_ERR_ARG, "climate: reflected outputs missing");
+    }
+    if (a->thermal) {
+        if (!a->DTAU_OG || !a->W0_no_raman || !a->COSB_OG || !a->tlevel || !a->plevel || !a->wno || !a->dwno ||
+            !a->ubar1 || !a->gweight || !a->tweight)
+            return pb_fail(ctx, PB_ERR_ARG, "climate: thermal needs DTAU_OG, W0_no_raman, COSB_OG, tlevel, plevel, wno, dwno, ubar1, gweight, tweight");
+        if (!a->flux_net_ir_layer || !a->flux_net_ir || !a->flux_plus_ir || !a->flux_minus_ir)
+            return pb_fail(ctx, PB_ERR_ARG, "climate: thermal outputs missing");
+    }
+    if (!a->reflected && !a->thermal) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool host = memspace == PB_HOST;
+    const size_t nLW = (size_t)L * W * sizeof(double), nVW = (size_t)V * W * sizeof(double), nW = (size_t)W * sizeof(double);
+
+    // ---- scratch layout (context-owned, survives the arena resets of the flux entry points) ----
+    const bool restage = host || K > 1;
+    const int n_lay = restage ? ((a->reflected ? 9 : 0) + (a->thermal ? (a->reflected ? 1 : 3) : 0)) : 0;
+    const int n_lev = (restage && a->reflected) ? 2 : 0;
+    const int Gmax = a->thermal ? (G > 1 ? G : 1) : 1;
+    size_t need = 64 * 256;
+    need += (size_t)n_lay * pb_align(K * nLW) + (size_t)n_lev * pb_align(K * nVW);
+    if (host) need += pb_align(K * nVW);                        // raw [rows][W][K] staging
+    need += 2 * pb_align(K * nW) + 2 * pb_align(nW);             // surf, F0PI replicated; wno, dwno
+    need += 4 * pb_align((size_t)K * Gmax * nVW);                // level arrays
+    need += 4 * pb_align(nVW) + 8 * pb_align((size_t)V * 8);     // reduced outputs
+    need += pb_align((size_t)(K + G + 16) * 8 * 4);
+    PB_TRY(aux_reserve(ctx, need));
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> double * {
+        double *ptr = (double *)(ctx->aux + off);
+        off += pb_align(bytes);
+        return ptr;
+    };
+    double *raw = host ? take(K * nVW) : nullptr;
+    auto stage = [&](const double *src, int rows, const double **dst) -> int {
+        if (!src) { *dst = nullptr; return PB_OK; }
+        if (!restage) { *dst = src; return PB_OK; }
+        const int64_t n = (int64_t)rows * W;
+        double *d = take((size_t)K * n * sizeof(double));
+        const double *in = src;
+        if (host) {
+            PB_CUDA(ctx, cudaMemcpyAsync(raw, src, (size_t)K * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            in = raw;
+        }
+        if (K == 1) {
+            PB_CUDA(ctx, cudaMemcpyAsync(d, in, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, K, in, d);
+            PB_CHECK_LAUNCH(ctx);
+        }
+        *dst = d;
+        return PB_OK;
+    };
+    auto small_to_dev = [&](const double *src, size_t n, const double **dst) -> int {
+        // O(K), O(G), O(W) vectors: host pointers in both memory spaces (pageable copy is synchronous
+        // with respect to the host buffer)
+        double *d = take(n * sizeof(double));
+        PB_CUDA(ctx, cudaMemcpyAsync(d, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        *dst = d;
+        return PB_OK;
+    };
+
+    const double *d_dtau = nullptr, *d_tau = nullptr, *d_w0 = nullptr, *d_cosb = nullptr, *d_gcos2 = nullptr,
+                 *d_fcld = nullptr, *d_fray = nullptr, *d_dtau_og = nullptr, *d_tau_og = nullptr, *d_w0_og = nullptr,
+                 *d_cosb_og = nullptr, *d_w0nr = nullptr;
+    if (a->reflected) {
+        PB_TRY(stage(a->DTAU, L, &d_dtau));
+        PB_TRY(stage(a->TAU, V, &d_tau));
+        PB_TRY(stage(a->W0, L, &d_w0));
+        PB_TRY(stage(a->COSB, L, &d_cosb));
+        PB_TRY(stage(a->GCOS2, L, &d_gcos2));
+        PB_TRY(stage(a->ftau_cld, L, &d_fcld));
+        PB_TRY(stage(a->ftau_ray, L, &d_fray));
+        PB_TRY(stage(a->TAU_OG, V, &d_tau_og));
+        PB_TRY(stage(a->W0_OG, L, &d_w0_og));
+    }
+    PB_TRY(stage(a->DTAU_OG, L, &d_dtau_og));
+    PB_TRY(stage(a->COSB_OG, L, &d_cosb_og));
+    if (a->thermal) PB_TRY(stage(a->W0_no_raman, L, &d_w0nr));
+
+    const double *d_gw = nullptr;
+    PB_TRY(small_to_dev(a->gauss_wts, K, &d_gw));
+    double *d_surf = take(K * nW), *d_f0 = take(K * nW);
+    {
+        // per-wave vectors are host pointers (they come from the solver's tuples), shared by all gauss points
+        const double *d_s1 = nullptr, *d_f1 = nullptr;
+        if (a->surf_reflect) PB_TRY(small_to_dev(a->surf_reflect, W, &d_s1));
+        if (a->F0PI) PB_TRY(small_to_dev(a->F0PI, W, &d_f1));
+        replicate_kernel<<<(W + 255) / 256, 256, 0, ctx->stream>>>(W, K, d_s1, 0.0, d_surf);
+        PB_CHECK_LAUNCH(ctx);
+        replicate_kernel<<<(W + 255) / 256, 256, 0, ctx->stream>>>(W, K, d_f1, 1.0, d_f0);
+        PB_CHECK_LAUNCH(ctx);
+    }
+    double *lv[4];
+    for (int i = 0; i < 4; ++i) lv[i] = take((size_t)K * Gmax * nVW);
+    double *o_plus = take(nVW), *o_minus = take(nVW), *o_lay = take((size_t)V * 8), *o_net = take((size_t)V * 8);
+    double *o_plus_ir = take(nVW), *o_minus_ir = take(nVW), *o_lay_ir = take((size_t)V * 8), *o_net_ir = take((size_t)V * 8);
+    if (off > ctx->aux_cap) return pb_fail(ctx, PB_ERR_NOMEM, "climate: scratch layout overflow (%zu > %zu)", off, ctx->aux_cap);
+
+    if (a->reflected) {
+        // climate.py:1803-1816: one stream at mu0 = mu1 = 0.5, fluxes only
+        pb_reflected_args r;
+        memset(&r, 0, sizeof(r));
+        r.nlayer = L; r.nwno = W; r.numg = 1; r.numt = 1; r.nbatch = K; r.ld = W;
+        r.dtau = d_dtau; r.w0 = d_w0; r.cosb = d_cosb; r.gcos2 = d_gcos2; r.ftau_cld = d_fcld; r.ftau_ray = d_fray;
+        r.dtau_og = d_dtau_og; r.w0_og = d_w0_og; r.cosb_og = d_cosb_og; r.tau = d_tau; r.tau_og = d_tau_og;
+        r.surf_reflect = d_surf; r.F0PI = d_f0; r.b_top = nullptr;
+        const double half = 0.5, one = 1.0;
+        r.ubar0 = &half; r.ubar1 = &half; r.gweight = &one; r.tweight = &one;
+        r.cos_theta = a->cos_theta;
+        r.single_phase = a->single_phase; r.multi_phase = a->multi_phase; r.toon_coefficients = 0;
+        r.frac_a = a->frac_a; r.frac_b = a->frac_b; r.frac_c = a->frac_c;
+        r.constant_back = a->constant_back; r.constant_forward = a->constant_forward;
+        r.get_toa_intensity = 0; r.get_lvl_flux = 1;
+        r.flux_minus = lv[0]; r.flux_plus = lv[1]; r.flux_minus_mdpt = lv[2]; r.flux_plus_mdpt = lv[3];
+        PB_TRY(pb_reflected_toon_1d(ctx, &r, PB_DEVICE));
+        climate_visible_reduce<<<V, kRedThreads, 0, ctx->stream>>>(V, W, K, lv[0], lv[1], lv[2], lv[3], d_gw, o_plus,
+                                                                   o_minus, o_lay, o_net);
+        PB_CHECK_LAUNCH(ctx);
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_v, o_plus, nVW, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_v, o_minus, nVW, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_v_layer, o_lay, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_v, o_net, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (a->thermal) {
+        // climate.py:1887-1892: OG optical depths, W0_no_raman, hard_surface = 0, calc_type = 1
+        std::vector<double> tl((size_t)K * V), pl((size_t)K * V);
+        for (int k = 0; k < K; ++k)
+            for (int v = 0; v < V; ++v) {
+                tl[(size_t)k * V + v] = a->tlevel[v];
+                pl[(size_t)k * V + v] = a->plevel[v];
+            }
+        const double *d_wno = nullptr, *d_dwno = nullptr, *d_gweight = nullptr, *d_tweight = nullptr;
+        PB_TRY(small_to_dev(a->wno, W, &d_wno));
+        PB_TRY(small_to_dev(a->dwno, W, &d_dwno));
+        PB_TRY(small_to_dev(a->gweight, a->numg, &d_gweight));
+        PB_TRY(small_to_dev(a->tweight, a->numt, &d_tweight));
+        pb_thermal_args t;
+        memset(&t, 0, sizeof(t));
+        t.nlayer = L; t.nwno = W; t.numg = a->numg; t.numt = a->numt; t.nbatch = K; t.ld = W;
+        t.dtau = d_dtau_og; t.w0 = d_w0nr; t.cosb = d_cosb_og;
+        t.wno = d_wno; t.dwno = d_dwno; t.surf_reflect = d_surf;
+        t.tlevel = tl.data(); t.plevel = pl.data();
+        t.ubar1 = a->ubar1; t.gweight = a->gweight; t.tweight = a->tweight;
+        t.hard_surface = 0; t.calc_type = 1;
+        t.flux_minus = lv[0]; t.flux_plus = lv[1]; t.flux_minus_mdpt = lv[2]; t.flux_plus_mdpt = lv[3];
+        PB_TRY(pb_thermal_toon_1d(ctx, &t, PB_DEVICE));
+        climate_ir_reduce<<<V, kRedThreads, 0, ctx->stream>>>(V, W, K, G, a->numt, lv[0], lv[1], lv[2], lv[3], d_gw,
+                                                              d_gweight, d_tweight, d_dwno, o_plus_ir, o_minus_ir,
+                                                              o_lay_ir, o_net_ir);
+        PB_CHECK_LAUNCH(ctx);
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_ir, o_plus_ir, nVW, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_ir, o_minus_ir, nVW, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_ir_layer, o_lay_ir, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_ir, o_net_ir, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        // tl / pl are consumed by pb_thermal_toon_1d's packed pinned upload before it returns
+    }
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}

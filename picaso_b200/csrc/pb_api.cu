@@ -73,6 +73,7 @@ void pb_destroy(pb_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->aux) cudaFree(ctx->aux);
     for (auto &sl : ctx->pin) {
         if (sl.host) cudaFreeHost(sl.host);
         if (sl.dev) cudaFree(sl.dev);

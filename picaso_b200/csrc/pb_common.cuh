@@ -28,6 +28,9 @@ struct pb_ctx {
     // grow-only device arena used to stage PB_HOST calls and small geometry vectors
     char *arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
+    // second grow-only block for entry points that call other entry points (climate.cu): survives arena resets
+    char *aux = nullptr;
+    size_t aux_cap = 0;
     // grow-only pinned bounce buffer for small host vectors (geometry) so that their
     // H2D copies are truly asynchronous
     // H2D copies are truly asynchronous and ONE copy per API call carries all of them.  A ring

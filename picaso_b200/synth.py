@@ -7,7 +7,7 @@ Used by tests/, bench.py and tests/golden/make_golden.py; pure numpy.
 import numpy as np
 
 __all__ = ["geometry_1d", "reflected_inputs", "thermal_inputs", "transit_inputs",
-           "adversarial_reflected"]
+           "adversarial_reflected", "climate_inputs"]
 
 # Abramowitz & Stegun 25.8 half-sphere Gauss points used by the reference for
 # 1-D geometry (picaso/disco.py:67-87).
@@ -275,3 +275,69 @@ def ck_database(W=40, K=8, seed=2101, nT=9, nP=8, nTc=12):
     return dict(wno=wno, nwno=W, ngauss=K, temps=temps, pressures=pressures, nc_p=nc_p, kappa=lnk,
                 gauss_wts=gauss_wts, cia_temps=cia_temps, continuum=cont, continuum_molecules=list(CONTINUUM),
                 rayleigh_molecules=list(RAYLEIGH), molecules=[])
+
+
+def climate_inputs(L=40, W=120, K=4, seed=3001, ng=1, nt=1, surf=0.0, clear=False):
+    """The namedtuples picaso.climate.get_fluxes takes (climate.py:1962-1966, justdoit.py:5038),
+    with [nlayer, nwno, ngauss] opacity arrays (gauss point fastest, optics.py:423-431).
+    Gauss point k is optically thicker by ~10^k/2 (a k-distribution); clear=True builds the
+    cloud-free column of the same atmosphere for the do_holes path."""
+    from collections import namedtuple
+    rng = np.random.default_rng(seed)
+    wed = {k: np.zeros(((L + 1) if k == "TAU" else L, W, K)) for k in
+           ("DTAU", "TAU", "W0", "COSB", "ftau_cld", "ftau_ray", "GCOS2", "W0_no_raman", "f_deltaM")}
+    noed = {k: np.zeros(((L + 1) if k == "TAU" else L, W, K)) for k in ("DTAU", "TAU", "W0", "COSB")}
+    for k in range(K):
+        dtau_og, w0_og, cosb_og = _layer_fields(rng, L, W)
+        dtau_og = dtau_og * 10.0 ** (0.5 * k - 1.0)
+        ftau_cld = rng.uniform(0.05, 0.95, size=(L, W))
+        if clear:
+            ftau_cld = ftau_cld * 0.0
+            cosb_og = cosb_og * 0.0
+        ftau_ray = 1.0 - ftau_cld
+        f = cosb_og ** 2
+        wed["W0"][:, :, k] = w0_og * (1.0 - f) / (1.0 - w0_og * f)
+        wed["COSB"][:, :, k] = (cosb_og - f) / (1.0 - f)
+        wed["DTAU"][:, :, k] = dtau_og * (1.0 - w0_og * f)
+        wed["TAU"][1:, :, k] = np.cumsum(wed["DTAU"][:, :, k], axis=0)
+        wed["ftau_cld"][:, :, k] = ftau_cld
+        wed["ftau_ray"][:, :, k] = ftau_ray
+        wed["GCOS2"][:, :, k] = 0.5 * ftau_ray
+        wed["W0_no_raman"][:, :, k] = np.clip(w0_og * rng.uniform(0.97, 1.0, size=(L, W)), 0.0, 0.999)
+        wed["f_deltaM"][:, :, k] = f
+        noed["DTAU"][:, :, k] = dtau_og
+        noed["TAU"][1:, :, k] = np.cumsum(dtau_og, axis=0)
+        noed["W0"][:, :, k] = w0_og
+        noed["COSB"][:, :, k] = cosb_og
+    wno = np.linspace(300.0, 30000.0, W)
+    dwno = np.gradient(wno) if W > 1 else np.ones(1)
+    gpts, gw = np.polynomial.legendre.leggauss(K)
+    gauss_wts = 0.5 * gw
+    Atmosphere = namedtuple("Atmosphere_Tuple", ["dtdp", "mmw_layer", "nlevel", "t_level", "p_level", "condensables",
+                                                 "condensable_abundances", "condensable_weights", "scale_height"])
+    OpacityWEd = namedtuple("OpacityWEd_Tuple", ["DTAU", "TAU", "W0", "COSB", "ftau_cld", "ftau_ray", "GCOS2",
+                                                 "W0_no_raman", "f_deltaM"])
+    OpacityNoEd = namedtuple("OpacityNoEd_Tuple", ["DTAU", "TAU", "W0", "COSB"])
+    ScatteringPhase = namedtuple("ScatteringPhase_Tuple", ["surf_reflect", "single_phase", "multi_phase", "frac_a",
+                                                           "frac_b", "frac_c", "constant_back", "constant_forward"])
+    Disco = namedtuple("Disco_Tuple", ["ng", "nt", "gweight", "tweight", "ubar0", "ubar1", "cos_theta"])
+    Opagrid = namedtuple("Opagrid", ["nwno", "delta_wno", "wno", "ngauss", "gauss_wts", "tmin", "tmax"])
+    if nt == 1:
+        gangle, gweight, tangle, tweight, ubar0, ubar1, cos_theta = geometry_1d(ng if ng in _GAUSS else 5, 0.0)
+        if ng not in _GAUSS:  # ng = 1: the climate default single stream
+            ubar0, ubar1 = np.full((ng, 1), 0.5), np.full((ng, 1), 0.5)
+            gweight, tweight = np.full(ng, 1.0 / ng), np.array([1.0])
+    else:
+        ubar1 = rng.uniform(0.1, 1.0, size=(ng, nt))
+        ubar0 = ubar1.copy()
+        gweight, tweight, cos_theta = rng.uniform(0.1, 0.4, size=ng), rng.uniform(0.2, 1.0, size=nt), 1.0
+    tlevel = np.linspace(150.0, 1800.0, L + 1) + 20.0 * np.sin(np.arange(L + 1))
+    plevel = np.logspace(-6, 2, L + 1) * 1e6
+    return dict(
+        Atmosphere=Atmosphere(np.zeros(L), np.full(L, 2.3), L + 1, tlevel, plevel, (), np.zeros((1, 1)),
+                              np.zeros(1), np.zeros(L + 1)),
+        OpacityWEd=OpacityWEd(**wed), OpacityNoEd=OpacityNoEd(**noed),
+        ScatteringPhase=ScatteringPhase(np.full(W, float(surf)), 3, 0, 1.0, -1.0, 2.0, -0.5, 1.0),
+        Disco=Disco(ng, nt, gweight, tweight, ubar0, ubar1, float(cos_theta)),
+        Opagrid=Opagrid(W, dwno, wno, K, gauss_wts, 100.0, 4000.0),
+        F0PI=rng.uniform(0.5, 2.0, size=W))

@@ -294,3 +294,35 @@ def build_mix(case):
     x, w = np.polynomial.legendre.leggauss(case["K"])
     gauss_pts, gauss_wts = 0.5 * (x + 1.0), 0.5 * w
     return db, gases, kappas, atm, gauss_pts, gauss_wts
+
+
+def climate_cases():
+    """picaso.climate.get_fluxes (climate.py:1686-1952): all gauss points, visible + IR, cloud holes"""
+    return {
+        "clim_k4": dict(build=dict(L=24, W=70, K=4, seed=3001), reflected=True, thermal=True),
+        "clim_k8_disk5": dict(build=dict(L=30, W=45, K=8, seed=3011, ng=5), reflected=True, thermal=True),
+        "clim_k1_surf": dict(build=dict(L=12, W=33, K=1, seed=3021, surf=0.3), reflected=True, thermal=True),
+        "clim_thermal_only_3d": dict(build=dict(L=10, W=20, K=2, seed=3031, ng=3, nt=2), reflected=False, thermal=True),
+        "clim_reflected_only": dict(build=dict(L=16, W=50, K=3, seed=3041), reflected=True, thermal=False),
+        "clim_holes": dict(build=dict(L=14, W=40, K=2, seed=3051), reflected=True, thermal=True, fhole=0.35),
+    }
+
+
+def build_climate(case):
+    d = synth.climate_inputs(**case["build"])
+    if "fhole" in case:
+        c = synth.climate_inputs(**dict(case["build"], clear=True))
+        d["hole_OpacityWEd"], d["hole_OpacityNoEd"] = c["OpacityWEd"], c["OpacityNoEd"]
+    return d
+
+
+def climate_args(d, case):
+    args = [d["Atmosphere"], d["OpacityWEd"], d["OpacityNoEd"], d["ScatteringPhase"], d["Disco"], d["Opagrid"],
+            d["F0PI"], case["reflected"], case["thermal"]]
+    if "fhole" in case:
+        args += [True, case["fhole"], d["hole_OpacityWEd"], d["hole_OpacityNoEd"]]
+    return args
+
+
+CLIMATE_OUT = ("flux_net_v_layer", "flux_net_v", "flux_plus_v", "flux_minus_v", "flux_net_ir_layer",
+               "flux_net_ir", "flux_plus_ir", "flux_minus_ir")
