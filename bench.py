@@ -341,6 +341,14 @@ def main():
             traffic = json.load(open(tpath)).get("refl_toa_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    fpath = os.path.join(ROOT, "profiles", "r1_refl_toa_v4.summary.json")
+    fp64_pct = None
+    if os.path.isfile(fpath):
+        try:
+            fp64_pct = json.load(open(fpath))["launches"][0][
+                "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]["value"]
+        except Exception:
+            fp64_pct = None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -355,9 +363,11 @@ def main():
                 "steps": ke, "ms_per_step": 1e3 * e2e_dt / ke,
                 "api": "picaso_b200.get_reflected_1d(..., return_albedo=True), pinned host inputs"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel": "refl_toa_kernel",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": "refl_toa_kernel4",
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                     "note": "fp64-pipe-bound kernel (~50 flop/B); see DESIGN.md and profiles/"},
+                     "fp64_pipe_pct_ncu": fp64_pct,
+                     "note": "not HBM-bound: ~50 fp64 flop/B; 313 CTAs = 2-3 per SM, dependent fp64 chains "
+                             "(ncu stall_wait); DRAM traffic = algorithmic bytes; see DESIGN.md 4.1 and profiles/"},
         "clocks": sampler.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
