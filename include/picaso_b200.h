@@ -326,6 +326,18 @@ typedef struct pb_climate_args {
 
 int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *args, int memspace);
 
+/* ---- rebinning onto a data grid ---------------------------------------------------------- */
+/* replaces mean_regrid, picaso/justplotit.py:31-63 = scipy.stats.binned_statistic(x, y, 'mean', bins):
+ * out[b][i] = mean of scale*y[b][start[i] .. start[i]+count[i]) (NaN for an empty bin).  The (start,
+ * count) ranges are planned once per (model grid, data grid) pair on the host (picaso_b200/regrid.py:
+ * np.digitize + scipy's right-edge rule; x must be monotonic) and kept in HBM by the plan.  `scale`
+ * folds the 1e-8 (R/d)^2 factor the retrieval driver applies (picaso/driver.py:226). */
+typedef struct pb_regrid_plan pb_regrid_plan;
+int pb_regrid_plan_create(pb_ctx *ctx, int nbins, const int *start, const int *count, pb_regrid_plan **out);
+int pb_regrid_plan_destroy(pb_ctx *ctx, pb_regrid_plan *plan);
+int pb_mean_regrid(pb_ctx *ctx, const pb_regrid_plan *plan, int nbatch, int nwno, int64_t ld, const double *y,
+                   double scale, double *out, int memspace);
+
 /* ---- self test ------------------------------------------------------------------------- */
 /* evaluates the kernels' branch-free exp() and 1/x on x[n] (host pointers); test hook */
 int pb_selftest_math(pb_ctx *ctx, const double *x, int n, double *exp_out, double *rcp_out);

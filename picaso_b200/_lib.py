@@ -147,6 +147,9 @@ SYMBOLS = {
     "pb_compute_opacity": (c_int, [c_vp, c_vp, ctypes.POINTER(OpacityArgs), c_int]),
     "pb_ck_mix": (c_int, [c_vp, ctypes.POINTER(CkMixArgs), c_int]),
     "pb_climate_get_fluxes": (c_int, [c_vp, ctypes.POINTER(ClimateArgs), c_int]),
+    "pb_regrid_plan_create": (c_int, [c_vp, c_int, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "pb_regrid_plan_destroy": (c_int, [c_vp, c_vp]),
+    "pb_mean_regrid": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_dbl, c_vp, c_int]),
 }
 
 _lib = None

@@ -48,6 +48,11 @@ struct pb_ctx {
     size_t pin_off = 0, pin_flushed = 0;
 };
 
+struct pb_regrid_plan {
+    int nbins = 0, max_index = 0;
+    int *start = nullptr, *count = nullptr;  // device, one allocation
+};
+
 int pb_fail(pb_ctx *ctx, int code, const char *fmt, ...);
 
 #define PB_CUDA(ctx, call)                                                                  \
