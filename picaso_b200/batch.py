@@ -25,8 +25,31 @@ def shard(nbatch, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def _dev(ctx, a, shape, keep):
-    from .optics import DeviceArray
+def _buf(ctx, name, nbytes):
+    """grow-only device workspace owned by the context (no cudaMalloc / cudaFree per call)"""
+    ws = ctx.__dict__.setdefault("_batch_ws", {})
+    ent = ws.get(name)
+    if ent is None or ent[1] < nbytes:
+        if ent is not None:
+            ctx.dev_free(ent[0])
+        ent = ws[name] = (ctx.dev_alloc(max(nbytes, 8)), max(nbytes, 8))
+    return ent[0]
+
+
+def _cached_vec(ctx, name, v):
+    """device copy of a small host vector, re-uploaded only when its contents change"""
+    cache = ctx.__dict__.setdefault("_batch_vec", {})
+    ent = cache.get(name)
+    if ent is None or ent[0].shape != v.shape or not np.array_equal(ent[0], v):
+        ptr = _buf(ctx, "vec_" + name, v.nbytes)
+        ctx.check(ctx.lib.pb_memcpy_h2d(ctx.h, ptr, v.ctypes.data, v.nbytes))
+        ctx.sync()
+        ent = cache[name] = (v.copy(), ptr)
+    return ent[1]
+
+
+def _dev(ctx, a, shape, name):
+    """device pointer of a [nbatch, ...] input: DeviceArray as is, numpy staged through the workspace"""
     if hasattr(a, "ptr") and hasattr(a, "ctx"):
         if tuple(a.shape) != tuple(shape):
             raise _lib.PicasoB200Error("thermal_batch: array of shape %s, expected %s" % (a.shape, shape))
@@ -34,9 +57,9 @@ def _dev(ctx, a, shape, keep):
     a = np.ascontiguousarray(a, dtype=np.float64)
     if a.shape != tuple(shape):
         raise _lib.PicasoB200Error("thermal_batch: array of shape %s, expected %s" % (a.shape, shape))
-    d = DeviceArray.from_numpy(ctx, a)
-    keep.append(d)
-    return d.ptr
+    ptr = _buf(ctx, name, a.nbytes)
+    ctx.check(ctx.lib.pb_memcpy_h2d(ctx.h, ptr, a.ctypes.data, a.nbytes))
+    return ptr
 
 
 def thermal_batch(wno, tlevel, plevel, dtau, w0, cosb, ubar1, gweight, tweight, surf_reflect=0.0, hard_surface=0,
@@ -45,7 +68,8 @@ def thermal_batch(wno, tlevel, plevel, dtau, w0, cosb, ubar1, gweight, tweight, 
 
     Per atmosphere b: compress_thermal(get_thermal_1d(...)[0]) * scale (fluxes.py:1683-1912, disco.py:152-180,
     driver.py:226), then mean_regrid onto `newx` / constant `R` (justplotit.py:31-63) if one is given.
-    Returns (x, y[nbatch, len(x)]): x = wno without rebinning, else the bin centres."""
+    Returns (x, y[nbatch, len(x)]): x = wno without rebinning, else the bin centres.  With
+    device_output=True y is a DeviceArray view of a workspace that the next call overwrites."""
     ctx = ctx or _lib.default_context()
     from .optics import DeviceArray
     tl = np.ascontiguousarray(tlevel, dtype=np.float64)
@@ -58,19 +82,20 @@ def thermal_batch(wno, tlevel, plevel, dtau, w0, cosb, ubar1, gweight, tweight, 
     ng, nt = u1.shape
     gw = np.ascontiguousarray(gweight, dtype=np.float64)
     tw = np.ascontiguousarray(tweight, dtype=np.float64)
-    keep = []
     a = ThermalArgs()
     a.nlayer, a.nwno, a.numg, a.numt, a.nbatch, a.ld = L, W, ng, nt, B, W
-    a.dtau, a.w0, a.cosb = (_dev(ctx, x, (B, L, W), keep) for x in (dtau, w0, cosb))
-    a.wno = _dev(ctx, wn, (W,), keep)
+    a.dtau, a.w0, a.cosb = (_dev(ctx, x, (B, L, W), n) for x, n in ((dtau, "dtau"), (w0, "w0"), (cosb, "cosb")))
+    a.wno = _cached_vec(ctx, "wno", wn)
     if calc_type == 1:
-        a.dwno = _dev(ctx, np.broadcast_to(np.asarray(dwno, dtype=np.float64), (W,)), (W,), keep)
+        a.dwno = _cached_vec(ctx, "dwno", np.ascontiguousarray(np.broadcast_to(np.asarray(dwno, dtype=np.float64), (W,))))
     sr = np.asarray(surf_reflect, dtype=np.float64)
-    sr = np.broadcast_to(sr, (B, W)) if sr.ndim < 2 else sr
-    a.surf_reflect = _dev(ctx, sr, (B, W), keep)
+    if sr.ndim == 0 and float(sr) == 0.0:
+        a.surf_reflect = None  # NULL = 0 (include/picaso_b200.h)
+    else:
+        a.surf_reflect = _dev(ctx, np.broadcast_to(sr, (B, W)) if sr.ndim < 2 else sr, (B, W), "surf")
     a.tlevel, a.plevel, a.ubar1, a.gweight, a.tweight = addr(tl), addr(pl), addr(u1.reshape(-1)), addr(gw), addr(tw)
     a.hard_surface, a.calc_type = int(hard_surface), int(calc_type)
-    spec = DeviceArray(ctx, (B, W))
+    spec = DeviceArray(ctx, (B, W), ptr=_buf(ctx, "spec", B * W * 8))
     a.thermal = spec.ptr
     if B and W:
         ctx.check(ctx.lib.pb_thermal_toon_1d(ctx.h, ctypes.byref(a), PB_DEVICE))
@@ -80,12 +105,8 @@ def thermal_batch(wno, tlevel, plevel, dtau, w0, cosb, ubar1, gweight, tweight, 
         x, out = wn, spec
     else:
         plan = _plan(ctx, wn, bin_edges(wn, newx, R))
-        x, out = plan.centers, plan.apply(spec, scale=scale)
-        spec.free()
-    for d in keep:
-        d.free()
+        out = DeviceArray(ctx, (B, plan.nbins), ptr=_buf(ctx, "rebinned", B * plan.nbins * 8))
+        x, out = plan.centers, plan.apply(spec, scale=scale, out=out)
     if device_output:
         return x, out
-    y = out.numpy()
-    out.free()
-    return x, y
+    return x, out.numpy()

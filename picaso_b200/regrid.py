@@ -91,15 +91,17 @@ class RegridPlan:
         ctx.check(ctx.lib.pb_regrid_plan_create(ctx.h, nbins, addr(start), addr(count), ctypes.byref(h)))
         self.h = h
 
-    def apply(self, y, scale=1.0):
-        """y: numpy [nwno] | [nbatch, nwno] -> numpy; DeviceArray [nbatch, nwno] -> DeviceArray [nbatch, nbins]"""
+    def apply(self, y, scale=1.0, out=None):
+        """y: numpy [nwno] | [nbatch, nwno] -> numpy; DeviceArray [nbatch, nwno] -> DeviceArray [nbatch, nbins]
+        (`out`: an existing DeviceArray to write into)"""
         ctx = self.ctx
         if hasattr(y, "ptr") and hasattr(y, "ctx"):
             from .optics import DeviceArray
             shp = y.shape if len(y.shape) == 2 else (1, y.shape[0])
             if shp[1] != self.nwno:
                 raise _lib.PicasoB200Error("mean_regrid: spectrum has %d points, plan %d" % (shp[1], self.nwno))
-            out = DeviceArray(ctx, (shp[0], self.nbins))
+            if out is None:
+                out = DeviceArray(ctx, (shp[0], self.nbins))
             ctx.check(ctx.lib.pb_mean_regrid(ctx.h, self.h, shp[0], self.nwno, self.nwno, y.ptr, float(scale),
                                              out.ptr, PB_DEVICE))
             return out

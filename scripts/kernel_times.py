@@ -284,10 +284,74 @@ def bench_mix(ctx, L, W, K, ngas, reps):
     ctx.dev_free(out)
 
 
+def bench_climate(ctx, L, W, K, ng, reps):
+    """picaso.climate.get_fluxes at the climate solver's shape: wall clock of the public call (host
+    tuples in, 8 host arrays out), the same call on device-resident opacities, and the CPU oracle."""
+    import time
+    from picaso_b200.optics import DeviceArray
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from oracle import climate as oclim
+    d = synth.climate_inputs(L=L, W=W, K=K, seed=77, ng=ng)
+    args = [d["Atmosphere"], d["OpacityWEd"], d["OpacityNoEd"], d["ScatteringPhase"], d["Disco"], d["Opagrid"],
+            d["F0PI"], True, True]
+    dd = list(args)
+    dd[1] = type(d["OpacityWEd"])(*[DeviceArray.from_numpy(ctx, a) for a in d["OpacityWEd"]])
+    dd[2] = type(d["OpacityNoEd"])(*[DeviceArray.from_numpy(ctx, a) for a in d["OpacityNoEd"]])
+
+    def wall(fn, n):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        return (time.perf_counter() - t0) / n * 1e3
+
+    l0 = ctx.launch_count()
+    pb.get_fluxes(*dd, ctx=ctx)
+    launches = ctx.launch_count() - l0
+    ms_host = wall(lambda: pb.get_fluxes(*args, ctx=ctx), reps)
+    ms_dev = wall(lambda: pb.get_fluxes(*dd, ctx=ctx), reps)
+    ms_cpu = wall(lambda: oclim.get_fluxes(*args, nthreads=os.cpu_count() or 1), 3)
+    ms_cpu1 = wall(lambda: oclim.get_fluxes(*args, nthreads=1), 1)
+    # algorithmic bytes: 12 opacity arrays read once + the 4 level arrays written and read back by the reductions
+    alg = (12 * L + 2) * W * K * 8 + 2 * 4 * (1 + ng) * (L + 1) * W * K * 8
+    print(json.dumps({"config": "climate.get_fluxes L=%d W=%d ngauss=%d ng=%d (reflected + thermal)" % (L, W, K, ng),
+                      "ms_per_call_host_arrays": ms_host, "ms_per_call_device_opacities": ms_dev,
+                      "kernel_launches_per_call": launches, "alg_bytes": alg,
+                      "cpu_port_ms_all_cores": ms_cpu, "cpu_port_ms_1_thread": ms_cpu1, "cores": os.cpu_count(),
+                      "rt_columns_per_s": K / (ms_dev * 1e-3)}), flush=True)
+
+
+def bench_thermal_batch(ctx, B, L, W, nbins, reps):
+    """BASELINE cfg5 per-GPU share: B atmospheres x (L x W) thermal -> disk integration -> rebin, device resident"""
+    from picaso_b200.optics import DeviceArray
+    ds = [synth.thermal_inputs(L=L, W=W, seed=900 + b) for b in range(B)]
+    d0 = ds[0]
+    kw = dict(wno=d0["wno"], tlevel=np.array([d["tlevel"] for d in ds]), plevel=np.array([d["plevel"] for d in ds]),
+              ubar1=d0["ubar1"], gweight=d0["gweight"], tweight=d0["tweight"])
+    for k in ("dtau", "w0", "cosb"):
+        kw[k] = DeviceArray.from_numpy(ctx, np.array([d[k] for d in ds]))
+    newx = np.linspace(d0["wno"][5], d0["wno"][-5], nbins)
+    fn = lambda i=0: pb.thermal_batch(**kw, newx=newx, scale=1e-8, ctx=ctx)
+    l0 = ctx.launch_count()
+    fn()
+    launches = ctx.launch_count() - l0
+    for _ in range(2):
+        fn()
+    ctx.sync()
+    import time
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    alg = ((3 * L + 3) * 8 + 8) * W * B
+    report("thermal_batch B=%d L=%d W=%d -> %d bins (cfg5 per-GPU share; wall clock of the public call, device inputs)"
+           % (B, L, W, nbins), ms, alg, W * B, "wave-points", {"launches_per_call": launches, "atmospheres/s": B / (ms * 1e-3)})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=50)
-    ap.add_argument("--only", default="refl,sh,opacity,thermal,transit,mix,batch")
+    ap.add_argument("--only", default="refl,sh,opacity,thermal,transit,mix,batch,climate,retrieval")
     a = ap.parse_args()
     only = set(a.only.split(","))
     ctx = pb.Context(0)
@@ -318,6 +382,10 @@ def main():
     if "batch" in only:
         bench_thermal(ctx, 60, 2000, 5, max(5, a.reps // 5), batch=128)
         bench_reflected(ctx, 60, 10000, 5, max(5, a.reps // 5), batch=8, tag=" (8 spectra/launch)")
+    if "climate" in only:
+        bench_climate(ctx, 90, 661, 8, 1, max(5, a.reps // 5))
+    if "retrieval" in only:
+        bench_thermal_batch(ctx, 128, 60, 2000, 300, max(5, a.reps // 5))
     ctx.close()
 
 
