@@ -23,7 +23,7 @@ __version__ = "0.1.0"
 
 _PATCHED = ("get_reflected_1d", "get_reflected_3d", "get_reflected_SH", "get_thermal_1d", "get_thermal_3d",
             "get_thermal_SH", "get_transit_1d", "compress_disco",
-            "compress_thermal", "get_fluxes")
+            "compress_thermal", "get_fluxes", "mean_regrid")
 
 
 def patch(module):
