@@ -10,6 +10,8 @@
 // of tri_diag_solve + symbolic carry of the upward flux) yields it in registers.
 // The Planck function is evaluated in the kernel from tlevel (no [nlevel, nwno]
 // blackbody matrix is ever materialised).
+#include <cstdlib>
+
 #include "pb_common.cuh"
 #include "pb_math.cuh"
 
@@ -289,6 +291,174 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
 }
 
 // ---------------------------------------------------------------------------------------
+// TOA flux, one thread per (atmosphere, wavelength) - used when the launch has enough wavelengths
+// to fill the machine without the angle axis (batched retrievals, R ~ 1e5 grids).
+//
+// In get_thermal_1d the tridiagonal system - matrix AND right-hand side - does not depend on the
+// viewing angle (fluxes.py:1812-1831: one solve per wavelength); only the upward source-function
+// recurrence does (:1864-1907).  therm_toa_kernel nevertheless repeats the elimination in every
+// angle warp (it needs the angle axis for parallelism at W = 10 000).  Here a thread eliminates
+// once per layer and carries the G linear functionals (Rp_a + Pp_a X[2l]) of all angles in
+// registers: per (layer, wavelength) the two pivots / reciprocals, sqrt, exp(lam dtau) and Planck
+// are paid once instead of G times, nothing goes through shared memory and there is no barrier.
+// ---------------------------------------------------------------------------------------
+#ifndef PB_THERM_WAVE_MINB
+#define PB_THERM_WAVE_MINB 4
+#endif
+template <int G>
+__global__ void __launch_bounds__(128, PB_THERM_WAVE_MINB) therm_toa_wave_kernel(ThermParams p)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (w >= p.W) return;
+    const int L = p.L, V = p.L + 1;
+    const int64_t ld = p.ld;
+    const int64_t ol = (int64_t)b * p.bs_layer + w;
+    const double *tl = p.tlevel + (int64_t)b * V;
+    const double *pl = p.plevel + (int64_t)b * V;
+    const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + w] : 0.0;
+    double u[G], inv_u[G], Pp[G], Rp[G];
+#pragma unroll
+    for (int a = 0; a < G; ++a) {
+        u[a] = p.ubar1[a];
+        inv_u[a] = 1.0 / u[a];
+        Pp[a] = 0.0;
+        Rp[a] = 0.0;
+    }
+    Planck planck;
+    planck.init(p.calc_type, p.wno[w], p.dwno ? p.dwno[w] : 0.0);
+    const double BL = planck(tl[L]);
+    double Bbot = BL;
+    double AS = 0.0, DS = 0.0, gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
+    const double tp = 2 * PB_PI * kMu1;
+    // software prefetch of the next layer's three inputs
+    double ndt = __ldg(p.dtau + ol + (int64_t)(L - 1) * ld), nom = __ldg(p.w0 + ol + (int64_t)(L - 1) * ld),
+           ncb = __ldg(p.cosb + ol + (int64_t)(L - 1) * ld);
+    for (int l = L - 1; l >= 0; --l) {
+        const double dt = ndt, om = nom, g = ncb;
+        if (l > 0) {
+            const int64_t il = ol + (int64_t)(l - 1) * ld;
+            ndt = __ldg(p.dtau + il);
+            nom = __ldg(p.w0 + il);
+            ncb = __ldg(p.cosb + il);
+        }
+        const double Btop = planck(tl[l]);
+        // fluxes.py:1756-1789, :1846-1847 (same arithmetic as therm_produce)
+        const double b0 = Btop;
+        const double b1 = (Bbot - Btop) * pbm::krcp(dt);
+        const double g1 = 2.0 - om * (1 + g), g2 = om * (1 - g);
+        const double lam = sqrt(g1 * g1 - g2 * g2);
+        const double gam = (g1 - lam) * pbm::krcp(g2);
+        const double qq = pbm::krcp(g1 + g2);
+        const double E = fmin(lam * dt, 35.0);
+        const double EP = pbm::kexp(E), EM = pbm::krcp(EP);
+        const double cpu = tp * (b0 + b1 * qq), cmu = tp * (b0 - b1 * qq);
+        const double cpd = tp * (b0 + b1 * dt + b1 * qq), cmd = tp * (b0 + b1 * dt - b1 * qq);
+        const double al1 = 2 * PB_PI * (b0 + b1 * (qq - kMu1)), al2 = 2 * PB_PI * b1;
+        const double e1 = EP + gam * EM, e2 = EP - gam * EM;
+        const double e3 = gam * EP + EM, e4 = gam * EP - EM;
+        // ---- angle-independent elimination step ----
+        double ASe = 0.0, DSe = 0.0;
+        const bool bottom = (l == L - 1);
+        double b_surface = 0.0;
+        if (bottom) {
+            // surface boundary, fluxes.py:1802-1806, last row :178-181
+            b_surface = p.hard_surface ? (1.0 - r) * BL * PB_PI : (BL + b1 * kMu1) * PB_PI;
+            const double a_ = e1 - r * e3, b_ = e2 - r * e4;
+            const double d_ = b_surface - cpd + r * cmd;
+            const double ib = pbm::krcp(b_);
+            AS = a_ * ib;
+            DS = d_ * ib;
+        } else {
+            const double gm1 = gam_n - 1.0;
+            const double e13 = (e1 + e3) * gm1;
+            double a_ = 2.0 * (1.0 - gam * gam);
+            double b_ = (e1 - e3) * (gam_n + 1.0);
+            double d_ = e3 * (cpu_n - cpd) + e1 * (cmd - cmu_n);
+            double xi = pbm::krcp(b_ - e13 * AS);
+            ASe = a_ * xi;
+            DSe = (d_ - e13 * DS) * xi;
+            b_ = (e2 + e4) * gm1;
+            const double c_ = 2.0 * (1.0 - gam_n * gam_n);
+            d_ = gm1 * (cpu_n - cpd) - gm1 * (cmd - cmu_n);
+            xi = pbm::krcp(b_ - c_ * ASe);
+            AS = e13 * xi;
+            DS = (d_ - c_ * DSe) * xi;
+        }
+        double EPh = 0.0, EMh = 0.0;
+        if (l == 0) {
+            EPh = pbm::kexp(0.5 * E);
+            EMh = pbm::krcp(EPh);
+        }
+        // ---- per angle: Table 3 of Toon89 (fluxes.py:1842-1849) and the flux_plus recurrence (:1897-1910) ----
+#pragma unroll
+        for (int a = 0; a < G; ++a) {
+            const double lu = lam * u[a];
+            const double inv_l = pbm::krcp(lu * lu - 1.0);
+            const double kG = (1 / kMu1 - lam) * ((lu + 1.0) * inv_l);
+            const double kH = gam * (lam + 1 / kMu1) * ((lu - 1.0) * inv_l);
+            double x, cG, cH, K;
+            if (l > 0) {
+                x = pbm::kexp(-dt * inv_u[a]);
+                cG = kG * (EP * x - 1.0);
+                cH = kH * (1.0 - EM * x);
+                K = al1 * (1. - x) + al2 * (u[a] - (dt + u[a]) * x);
+            } else {
+                x = pbm::kexp(-0.5 * dt * inv_u[a]);
+                cG = kG * (EP * x - EPh);
+                cH = -kH * (EM * x - EMh);
+                K = al1 * (1. - x) + al2 * (u[a] + 0.5 * dt - (dt + u[a]) * x);
+            }
+            double alpha, beta;
+            if (bottom) {
+                alpha = p.hard_surface ? (1.0 - r) * BL * 2 * PB_PI : (BL + b1 * u[a]) * 2 * PB_PI;
+                beta = 0.0;
+            } else {
+                alpha = Rp[a] + Pp[a] * DSe;
+                beta = -Pp[a] * ASe;
+            }
+            const double P = cG + cH;
+            const double Q = x * beta + (cG - cH);
+            const double R = x * alpha + K;
+            Pp[a] = P - Q * AS;
+            Rp[a] = R + Q * DS;
+        }
+        gam_n = gam;
+        cpu_n = cpu;
+        cmu_n = cmu;
+        Bbot = Btop;
+    }
+    // top boundary: fake isothermal overburden, fluxes.py:1797-1800; row 0 :155-158
+    const double B0 = Bbot;
+    const double tau_top = __ldg(p.dtau + ol) * pl[0] / (pl[1] - pl[0]);
+    const double b_top = (1.0 - exp(-tau_top / kMu1)) * B0 * PB_PI;
+    const double bb = gam_n + 1.0, cc = gam_n - 1.0, dd = b_top - cmu_n;
+    const double xi = pbm::krcp(bb - cc * AS);
+    const double X0 = (dd - cc * DS) * xi;
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < G; ++a) {
+        const double result = Rp[a] + Pp[a] * X0;
+        if (p.ftop) p.ftop[((int64_t)b * G + a) * p.W + w] = result;
+        if (p.fuse) {
+            const int ig = a / p.nt, it = a - ig * p.nt;
+            acc = acc + result * p.gweight[ig] * p.tweight[it];
+        }
+    }
+    if (p.fuse) {
+        const double sym = (p.nt == 1) ? 1.0 : 1 / (2 * PB_PI);
+        p.thermal[(int64_t)b * p.W + w] = acc * sym;
+    }
+}
+
+template <int G>
+static void launch_therm_wave(const ThermParams &p, int B, cudaStream_t st)
+{
+    dim3 grid((p.W + 127) / 128, B);
+    therm_toa_wave_kernel<G><<<grid, 128, 0, st>>>(p);
+}
+
+// ---------------------------------------------------------------------------------------
 // All four level arrays (fluxes.py:1864-1907).  Three sweeps per thread, with the
 // caller's output arrays doubling as O(L) scratch:
 //   1. bottom-up elimination, (AS,DS) of rows 2l | 2l+1 parked in (fm,fp) | (fmm,fpm)
@@ -532,9 +702,29 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
     dim3 block(kWavesPerCta, ay, 1);
     dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
     p.ftop = d_ftop; p.thermal = d_th;
+    // one thread per wavelength (all angles in registers) once the wavelength axis alone fills the
+    // machine: >= PB_THERM_WAVE_MIN (default 32 768) wavelengths x atmospheres.  PB_THERM_KERNEL=angle|wave forces one.
+    static const long wave_min = []() { const char *e = getenv("PB_THERM_WAVE_MIN"); return e ? atol(e) : 32768L; }();
+    const char *force = getenv("PB_THERM_KERNEL");
+    bool use_wave_kernel = !want_lvl && a->variant == 0 && G <= 8 && (!a->thermal || fuse) && (long)W * B >= wave_min;
+    if (force && force[0] == 'a') use_wave_kernel = false;
+    if (force && force[0] == 'w' && !want_lvl && a->variant == 0 && G <= 8 && (!a->thermal || fuse)) use_wave_kernel = true;
     if (want_lvl) {
         p.fm = d_lv[0]; p.fp = d_lv[1]; p.fmm = d_lv[2]; p.fpm = d_lv[3];
         therm_levels_kernel<<<grid, block, 0, ctx->stream>>>(p);
+        PB_CHECK_LAUNCH(ctx);
+    } else if (use_wave_kernel) {
+        p.fuse = fuse ? 1 : 0;
+        switch (G) {
+        case 1: launch_therm_wave<1>(p, B, ctx->stream); break;
+        case 2: launch_therm_wave<2>(p, B, ctx->stream); break;
+        case 3: launch_therm_wave<3>(p, B, ctx->stream); break;
+        case 4: launch_therm_wave<4>(p, B, ctx->stream); break;
+        case 5: launch_therm_wave<5>(p, B, ctx->stream); break;
+        case 6: launch_therm_wave<6>(p, B, ctx->stream); break;
+        case 7: launch_therm_wave<7>(p, B, ctx->stream); break;
+        default: launch_therm_wave<8>(p, B, ctx->stream); break;
+        }
         PB_CHECK_LAUNCH(ctx);
     } else {
         p.fuse = fuse ? 1 : 0;
