@@ -185,8 +185,18 @@ def main():
     gw = np.ascontiguousarray(d0["gweight"])
     tw = np.ascontiguousarray(d0["tweight"])
     d_xint = ctx.dev_alloc(G * W * 8)
-    if world > 1:
-        # double-buffered so that the all-gather of step i (stream `comm`) overlaps the kernel
+    # world == 1 with PB_BENCH_GATHER=p2p: the rank gathers to itself (diagnostic: in-kernel cost of the epilogue)
+    # p2p: own all-gather over peer memory, pushed by a side-stream copy kernel (default); p2p_fused: stores and
+    # flags in the solver kernel's epilogue; nccl: ncclAllGather on a second stream
+    gather_mode = os.environ.get("PB_BENCH_GATHER", "p2p" if world > 1 else "none")
+    if world == 1 and gather_mode == "nccl":
+        gather_mode = "none"
+    push = 1 if gather_mode == "p2p" else 0
+    if gather_mode == "p2p_fused":
+        gather_mode = "p2p"
+    NBUF = int(os.environ.get("PB_BENCH_NBUF", "3"))  # rotating gathered buffers: ranks may run NBUF - 2 steps apart
+    if gather_mode == "nccl":
+        # NCCL all-gather, double-buffered so that the gather of step i (stream `comm`) overlaps the kernel
         # of step i+1 (stream `side`)
         comm = torch.cuda.Stream()
         alb_all = [torch.empty((world, W), dtype=torch.float64, device="cuda") for _ in range(2)]
@@ -196,6 +206,46 @@ def main():
         for e in ev_gather:
             e.record(side)
         d_albs = [t.data_ptr() for t in alb_mine]
+    elif gather_mode == "p2p":
+        # all-gather fused into the kernel epilogue over peer memory (include/picaso_b200.h: pb_peer_gather):
+        # every rank maps every rank's gathered buffers [NBUF][world][W] and arrival flags [world]
+        from picaso_b200._lib import PeerGather
+        gbytes = NBUF * world * W * 8
+        d_gath = ctx.dev_alloc(gbytes)
+        d_flags = ctx.dev_alloc(256)
+        d_done = ctx.dev_alloc(256)
+        for ptr, nb in ((d_gath, gbytes), (d_flags, 256), (d_done, 256)):
+            ctx.check(ctx.lib.pb_memset(ctx.h, ptr, 0, nb))
+        ctx.sync()
+        hg, hf = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+        ctx.check(ctx.lib.pb_ipc_export(ctx.h, d_gath, hg))
+        ctx.check(ctx.lib.pb_ipc_export(ctx.h, d_flags, hf))
+        handles = [(hg.raw, hf.raw)] * world
+        if world > 1:
+            dist.all_gather_object(handles, (hg.raw, hf.raw))
+        peer_g, peer_f = [], []
+        for r, (rg, rf) in enumerate(handles):
+            if r == rank:
+                peer_g.append(d_gath)
+                peer_f.append(d_flags)
+            else:
+                pg_, pf_ = ctypes.c_void_p(), ctypes.c_void_p()
+                ctx.check(ctx.lib.pb_ipc_open(ctx.h, rg, ctypes.byref(pg_)))
+                ctx.check(ctx.lib.pb_ipc_open(ctx.h, rf, ctypes.byref(pf_)))
+                peer_g.append(pg_.value)
+                peer_f.append(pf_.value)
+        flag_ptrs = (ctypes.c_void_p * world)(*peer_f)
+        alb_ptrs = [(ctypes.c_void_p * world)(*[g + bfi * world * W * 8 for g in peer_g]) for bfi in range(NBUF)]
+        gathers = []
+        for bfi in range(NBUF):
+            pg = PeerGather()
+            pg.nranks, pg.rank = world, rank
+            pg.albedo, pg.flags = ctypes.addressof(alb_ptrs[bfi]), ctypes.addressof(flag_ptrs)
+            pg.done_counter = d_done
+            gathers.append(pg)
+        d_albs = [ctx.dev_alloc(W * 8)]
+        if world > 1:
+            dist.barrier()
     else:
         d_albs = [ctx.dev_alloc(W * 8)]
     d_alb = d_albs[0]
@@ -217,10 +267,21 @@ def main():
 
     cargs = [[make_args(dd, da) for da in d_albs] for dd in dev_sets]
     fn = ctx.lib.pb_reflected_toon_1d
+    gstep = [0]  # global step counter published through the arrival flags
 
     def step(i):
-        if world == 1:
+        if gather_mode == "none":
             ctx.check(fn(ctx.h, ctypes.byref(cargs[i % NSETS][0]), PB_DEVICE))
+            return
+        if gather_mode == "p2p":
+            gstep[0] += 1
+            s_ = gstep[0]
+            pg = gathers[s_ % NBUF]
+            pg.step, pg.wait_step = s_, max(0, s_ - (NBUF - 1))   # buffer s_ % NBUF was last written at step s_ - NBUF
+            pg.push, pg.slot = push, s_ % NBUF
+            a = cargs[i % NSETS][0]
+            a.gather = ctypes.addressof(pg)
+            ctx.check(fn(ctx.h, ctypes.byref(a), PB_DEVICE))
             return
         bf = i & 1
         side.wait_event(ev_gather[bf])  # the gather of step i-2 has consumed alb_mine[bf]
@@ -233,9 +294,11 @@ def main():
 
     def drain():
         # the launching stream waits for the outstanding gathers: the stop event covers them
-        if world > 1:
+        if gather_mode == "nccl":
             side.wait_event(ev_gather[0])
             side.wait_event(ev_gather[1])
+        elif gather_mode == "p2p" and gstep[0] > 0:
+            ctx.check(ctx.lib.pb_gather_wait(ctx.h, d_flags, world, gstep[0], d_done + 8))
 
     def barrier():
         drain()
@@ -250,7 +313,25 @@ def main():
     ctx.sync()
     drain()
     ctx.sync()
-    got = ctx.from_device(d_alb, (W,)) if world == 1 else alb_all[0][rank].cpu().numpy()
+    if gather_mode == "nccl":
+        got = alb_all[0][rank].cpu().numpy()
+    elif gather_mode == "p2p":
+        # the fused gather against NCCL's: every rank's buffer must hold every rank's slab, bit for bit
+        gath = ctx.from_device(d_gath + (gstep[0] % NBUF) * world * W * 8, (world, W))
+        mine = gath[rank].copy() if push else ctx.from_device(d_alb, (W,))
+        if world > 1:
+            ref_all = torch.empty((world, W), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(ref_all, torch.from_numpy(mine).cuda())
+            torch.cuda.synchronize()
+            ref_np = ref_all.cpu().numpy()
+        else:
+            ref_np = mine[None, :]
+        gath = ctx.from_device(d_gath + (gstep[0] % NBUF) * world * W * 8, (world, W))
+        if not np.array_equal(gath, ref_np):
+            raise SystemExit("rank %d: fused peer-memory all-gather differs from the NCCL all-gather" % rank)
+        got = gath[rank]
+    else:
+        got = ctx.from_device(d_alb, (W,))
     ox, _ = oracle.get_reflected_1d(*C.reflected_args(sets[0], KW), nthreads=os.cpu_count() or 1)
     want = oracle.compress_disco(W, d0["cos_theta"], ox, gw, tw, sets[0]["F0PI"])
     parity = float(np.max(np.abs(got - want) / np.abs(want)))
@@ -282,6 +363,11 @@ def main():
     ms = ctx.timer_stop()
     sampler.active = False
     launches = ctx.launch_count() - l0
+    if gather_mode == "p2p":
+        import struct
+        words = struct.unpack("<4I", ctx.from_device(d_done, (2,)).tobytes())
+        if words[1] or words[2]:
+            raise SystemExit("rank %d: peer all-gather timed out waiting for a flag (%r)" % (rank, words))
     barrier()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -356,7 +442,15 @@ def main():
         "spectra_per_sec": world * args.steps / (ms * 1e-3),
         "config": {"workload": WORKLOAD, "waves_per_gpu": W, "layers": L, "angles": G,
                    "l2_policy": "inputs larger than L2: %d input sets x %.1f MB rotated" % (NSETS, alg_bytes / 1e6),
-                   "collective": "ncclAllGather of the per-rank albedo [W] every step, double-buffered on a second stream so that it overlaps the next step's kernel; the timed region ends after the last gather" if world > 1 else "none",
+                   "collective": {"none": "none",
+                                  "p2p": "all-gather of the per-rank albedo [W] every step over NVLink peer memory "
+                                         "(pb_peer_gather): " + ("the solver writes its slab into the local gathered buffer, a "
+                                         "side-stream copy kernel pushes it to every peer and publishes release flags while the "
+                                         "next step computes" if push else "P2P stores + release flags in the solver kernel's "
+                                         "epilogue") + "; %d rotating buffers; checked bit-for-bit against ncclAllGather before "
+                                         "timing; the timed region ends after pb_gather_wait saw the last step of every rank" % NBUF,
+                                  "nccl": "ncclAllGather of the per-rank albedo [W] every step, double-buffered on a second "
+                                          "stream (PB_BENCH_GATHER=nccl)"}[gather_mode],
                    "parity_albedo_max_rel_err": parity},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

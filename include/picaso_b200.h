@@ -79,6 +79,30 @@ uint64_t pb_launch_count(const pb_ctx *ctx);
 /* ---- reflected light, Toon89 two-stream ------------------------------------------- */
 /* replaces get_reflected_1d, picaso/fluxes.py:1010-1413 (incl. setup_tri_diag :89-183,
  * tri_diag_solve :289-323) and, when `albedo` is given, compress_disco, disco.py:118-149 */
+/* All-gather of the per-rank result slab fused into the producing kernel (the
+ * wavelength grid shards over GPUs, one process per GPU; the only exchange is the final [nwno] vector).
+ * Every rank owns a gathered buffer [nranks][nwno] and an arrival-flag array [nranks], both cudaMalloc'ed
+ * and mapped into the peers with pb_ipc_export / pb_ipc_open.  The kernel's epilogue stores its albedo
+ * slab into row `rank` of EVERY rank's buffer (P2P stores), and the last CTA to finish publishes `step`
+ * in flags[r][rank] on every rank r (fence.sys + release store).  A consumer waits with pb_gather_wait
+ * (stream-ordered) until all of its flags reached `step`.  `wait_step` makes the kernel itself hold its
+ * peer stores until all local flags reached that value: with 3 rotating buffers and wait_step = step - 2
+ * a rank never overwrites a row a peer may still be reading, and ranks may run one step apart. */
+typedef struct pb_peer_gather {
+    int nranks, rank;                       /* nranks <= 8 */
+    double *const *albedo;                  /* host array [nranks]: rank r's gathered buffer, as mapped here */
+    unsigned long long *const *flags;       /* host array [nranks]: rank r's flag array, as mapped here */
+    unsigned long long step, wait_step;
+    unsigned int *done_counter;             /* device, this rank, 2 words, zero-initialised: CTA counter | timeout flag */
+    /* push = 0: the stores and the flag publication happen in the solver kernel's epilogue (one launch; costs
+     *   4-10 us at the kernel tail: system-scope fence + NVLink round trip before the grid can retire).
+     * push = 1: the solver kernel writes its slab into row `rank` of the LOCAL gathered buffer only; a small
+     *   copy kernel on the context's side stream (event-ordered after it) pushes that row to the peers and
+     *   publishes the flags, overlapping the next launch.  `slot` (0..7, the rotating-buffer index) names the
+     *   event that keeps a later launch from overwriting a row whose push is still in flight. */
+    int push, slot;
+} pb_peer_gather;
+
 typedef struct pb_reflected_args {
     int nlayer, nwno, numg, numt, nbatch;
     int64_t ld;
@@ -105,6 +129,10 @@ typedef struct pb_reflected_args {
      * hold one value per facet, |ubar| is used, exponents clip at 40, quadrature coefficients, 3-D
      * 'cahoy' phase function; TOA intensity only. */
     int variant;
+    /* NULL, or: also deliver the fused albedo slab of this rank to every rank's gathered buffer over
+     * peer memory (NVLink) from inside the kernel - see pb_peer_gather below.  Needs `albedo`, nbatch 1,
+     * numg*numt <= 8, PB_DEVICE. */
+    const struct pb_peer_gather *gather;
 } pb_reflected_args;
 
 int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *args, int memspace);
@@ -337,6 +365,16 @@ int pb_regrid_plan_create(pb_ctx *ctx, int nbins, const int *start, const int *c
 int pb_regrid_plan_destroy(pb_ctx *ctx, pb_regrid_plan *plan);
 int pb_mean_regrid(pb_ctx *ctx, const pb_regrid_plan *plan, int nbatch, int nwno, int64_t ld, const double *y,
                    double scale, double *out, int memspace);
+
+/* ---- peer memory for the fused all-gather ------------------------------------------------ */
+/* cudaIpcGetMemHandle / cudaIpcOpenMemHandle on pb_dev_alloc'ed blocks (handle = 64 bytes) */
+int pb_ipc_export(pb_ctx *ctx, void *dev_ptr, void *handle64);
+int pb_ipc_open(pb_ctx *ctx, const void *handle64, void **dev_ptr);
+int pb_ipc_close(pb_ctx *ctx, void *dev_ptr);
+/* stream-ordered: returns (on the stream) once flags[0..nranks) >= step; gives up after ~2 s of spinning
+ * and sets *timed_out_dev (device int, may be NULL) */
+int pb_gather_wait(pb_ctx *ctx, const unsigned long long *flags, int nranks, unsigned long long step,
+                   int *timed_out_dev);
 
 /* ---- self test ------------------------------------------------------------------------- */
 /* evaluates the kernels' branch-free exp() and 1/x on x[n] (host pointers); test hook */

@@ -32,7 +32,13 @@ class ReflectedArgs(ctypes.Structure):
         [(n, c_dbl) for n in ("frac_a", "frac_b", "frac_c", "constant_back", "constant_forward")] +
         [("get_toa_intensity", c_int), ("get_lvl_flux", c_int)] +
         [(n, c_vp) for n in ("xint_at_top", "albedo", "flux_minus", "flux_plus", "flux_minus_mdpt",
-                             "flux_plus_mdpt")] + [("variant", c_int)])
+                             "flux_plus_mdpt")] + [("variant", c_int), ("gather", c_vp)])
+
+
+class PeerGather(ctypes.Structure):
+    _fields_ = [("nranks", c_int), ("rank", c_int), ("albedo", c_vp), ("flags", c_vp),
+                ("step", ctypes.c_uint64), ("wait_step", ctypes.c_uint64), ("done_counter", c_vp),
+                ("push", c_int), ("slot", c_int)]
 
 
 class ShArgs(ctypes.Structure):
@@ -147,6 +153,10 @@ SYMBOLS = {
     "pb_compute_opacity": (c_int, [c_vp, c_vp, ctypes.POINTER(OpacityArgs), c_int]),
     "pb_ck_mix": (c_int, [c_vp, ctypes.POINTER(CkMixArgs), c_int]),
     "pb_climate_get_fluxes": (c_int, [c_vp, ctypes.POINTER(ClimateArgs), c_int]),
+    "pb_ipc_export": (c_int, [c_vp, c_vp, c_vp]),
+    "pb_ipc_open": (c_int, [c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "pb_ipc_close": (c_int, [c_vp, c_vp]),
+    "pb_gather_wait": (c_int, [c_vp, c_vp, c_int, ctypes.c_uint64, c_vp]),
     "pb_regrid_plan_create": (c_int, [c_vp, c_int, c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "pb_regrid_plan_destroy": (c_int, [c_vp, c_vp]),
     "pb_mean_regrid": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_dbl, c_vp, c_int]),

@@ -316,3 +316,60 @@ int pb_stage_in(pb_ctx *ctx, const double *src, int memspace, int64_t rows, int6
     if (ld_out) *ld_out = width;
     return PB_OK;
 }
+
+// ---- peer memory for the fused all-gather (include/picaso_b200.h: pb_peer_gather) ----
+namespace {
+__global__ void gather_wait_kernel(const unsigned long long *flags, int n, unsigned long long step, int *timed_out)
+{
+    const int r = threadIdx.x;
+    if (r >= n) return;
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+        if (v >= step) break;
+        if (clock64() - t0 > 4000000000LL) {
+            if (timed_out) *timed_out = 1;
+            break;
+        }
+    } while (true);
+}
+} // namespace
+
+int pb_ipc_export(pb_ctx *ctx, void *dev_ptr, void *handle64)
+{
+    if (!ctx || !dev_ptr || !handle64) return PB_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    PB_CUDA(ctx, cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle64, &h, sizeof(h));
+    return PB_OK;
+}
+
+int pb_ipc_open(pb_ctx *ctx, const void *handle64, void **dev_ptr)
+{
+    if (!ctx || !dev_ptr || !handle64) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    PB_CUDA(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PB_OK;
+}
+
+int pb_ipc_close(pb_ctx *ctx, void *dev_ptr)
+{
+    if (!ctx || !dev_ptr) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PB_CUDA(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    return PB_OK;
+}
+
+int pb_gather_wait(pb_ctx *ctx, const unsigned long long *flags, int nranks, unsigned long long step, int *timed_out_dev)
+{
+    if (!ctx || !flags || nranks < 1 || nranks > 32) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    gather_wait_kernel<<<1, 32, 0, ctx->stream>>>(flags, nranks, step, timed_out_dev);
+    PB_CHECK_LAUNCH(ctx);
+    return PB_OK;
+}

@@ -23,6 +23,7 @@ struct pb_ctx {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy = nullptr;
     static constexpr int kChunkEvents = 16;
     cudaEvent_t ev_chunk[kChunkEvents] = {};  // copy-stream -> compute-stream hand-off per wavelength chunk
+    bool push_pending[8] = {};               // pb_peer_gather push mode: ev_chunk[slot] has been recorded
     uint64_t launches = 0;
     char err[512] = {0};
     // grow-only device arena used to stage PB_HOST calls and small geometry vectors

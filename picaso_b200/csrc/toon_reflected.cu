@@ -41,7 +41,69 @@ struct ReflParams {
     int fuse_albedo;
     int variant;   // 1: per-facet get_reflected_3d semantics (geometry indexed by batch entry)
     double clip;   // exponent clip: 35 (1-D, fluxes.py:1174) or 40 (3-D, fluxes.py:516)
+    // fused all-gather of the albedo slab over peer memory (pb_peer_gather); g_n == 0: off
+    int g_n, g_rank;
+    double *g_alb[8];
+    unsigned long long *g_flag[8];
+    unsigned long long g_step, g_wait;
+    unsigned int *g_done;
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr long long kSpinLimit = 4000000000LL;  // ~2 s of SM clocks: never hang the GPU on a dead peer
+
+struct PushParams {
+    int n, rank, W;
+    double *alb[8];
+    unsigned long long *flag[8];
+    unsigned long long step, wait;
+    unsigned int *done;
+};
+
+// push = 1 of pb_peer_gather: CTA r copies row `rank` of the local gathered buffer to rank r and publishes
+// the step there (its own CTA only publishes: the solver kernel wrote the local row).  Runs on the side
+// stream while the next solver kernel computes.
+__global__ void __launch_bounds__(256) peer_push_kernel(PushParams p)
+{
+    const int r = blockIdx.x;
+    if (p.wait && threadIdx.x == 0) {
+        const unsigned long long *mine = p.flag[p.rank];
+        const long long t0 = clock64();
+        for (int rk = 0; rk < p.n; ++rk)
+            while (ld_acquire_sys(mine + rk) < p.wait)
+                if (clock64() - t0 > kSpinLimit) { atomicExch(p.done + 1, 1u); break; }
+    }
+    __syncthreads();
+    if (r != p.rank) {
+        const double2 *src = reinterpret_cast<const double2 *>(p.alb[p.rank] + (int64_t)p.rank * p.W);
+        double2 *dst = reinterpret_cast<double2 *>(p.alb[r] + (int64_t)p.rank * p.W);
+        const int n2 = p.W / 2;
+        if ((((int64_t)p.rank * p.W) & 1) == 0) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = src[i];
+            if ((p.W & 1) && threadIdx.x == 0)
+                p.alb[r][(int64_t)p.rank * p.W + p.W - 1] = p.alb[p.rank][(int64_t)p.rank * p.W + p.W - 1];
+        } else {
+            for (int i = threadIdx.x; i < p.W; i += blockDim.x)
+                p.alb[r][(int64_t)p.rank * p.W + i] = p.alb[p.rank][(int64_t)p.rank * p.W + i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys(p.flag[r] + p.rank, p.step);
+    }
+}
 
 constexpr int kWavesPerCta = 32;
 
@@ -514,6 +576,15 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
     if (want_lvl && (!a->flux_minus || !a->flux_plus || !a->flux_minus_mdpt || !a->flux_plus_mdpt))
         return pb_fail(ctx, PB_ERR_ARG, "reflected: get_lvl_flux without the four level arrays");
     const bool want_toa = a->get_toa_intensity != 0 && (a->xint_at_top || a->albedo);
+    if (a->gather) {
+        const pb_peer_gather *gt = a->gather;
+        if (memspace != PB_DEVICE || !a->albedo || B != 1 || G > 8 || !want_toa || a->variant != 0 || gt->nranks < 1 ||
+            gt->nranks > 8 || gt->rank < 0 || gt->rank >= gt->nranks || !gt->albedo || !gt->flags || !gt->done_counter ||
+            gt->slot < 0 || gt->slot > 7)
+            return pb_fail(ctx, PB_ERR_ARG, "reflected: peer gather needs PB_DEVICE, a fused albedo (numg*numt <= 8), nbatch 1, 1 <= nranks <= 8");
+        static const int kv = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 4; }();
+        if (kv != 4) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "reflected: peer gather is implemented in refl_toa_kernel4 only");
+    }
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
 
     const int V = L + 1;
@@ -616,6 +687,15 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
         if (q.f0pi) q.f0pi += w0;
         if (q.btop) q.btop += w0;
         q.xint = xo; q.albedo = ao; q.fuse_albedo = fuse ? 1 : 0;
+        if (a->gather && a->gather->push) {
+            // the solver writes its slab straight into row `rank` of the local gathered buffer
+            q.albedo = a->gather->albedo[a->gather->rank] + (int64_t)a->gather->rank * W;
+        } else if (a->gather) {
+            const pb_peer_gather *gt = a->gather;
+            q.g_n = gt->nranks; q.g_rank = gt->rank;
+            for (int r = 0; r < gt->nranks; ++r) { q.g_alb[r] = gt->albedo[r]; q.g_flag[r] = gt->flags[r]; }
+            q.g_step = gt->step; q.g_wait = gt->wait_step; q.g_done = gt->done_counter;
+        }
         dim3 grid((wc + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
         // PB_REFL_KERNEL=2|3 select the previous generations (bottom-up sweeps) for A/B runs
         static const int variant = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 4; }();
@@ -700,7 +780,24 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
 
     if (host) PB_TRY(copy_in(0, W, ctx->stream));
     dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
-    if (want_toa) {
+    if (want_toa && a->gather && a->gather->push) {
+        const pb_peer_gather *gt = a->gather;
+        cudaEvent_t ev_row = ctx->ev_chunk[gt->slot], ev_kernel = ctx->ev_chunk[8 + gt->slot];
+        // the push that last read this slot's local row must have finished before the row is overwritten
+        if (ctx->push_pending[gt->slot]) PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_row, 0));
+        PB_TRY(launch_toa(0, W, d_xint, d_alb));
+        PB_CUDA(ctx, cudaEventRecord(ev_kernel, ctx->stream));
+        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev_kernel, 0));
+        PushParams pp;
+        memset(&pp, 0, sizeof(pp));
+        pp.n = gt->nranks; pp.rank = gt->rank; pp.W = W;
+        for (int r = 0; r < gt->nranks; ++r) { pp.alb[r] = gt->albedo[r]; pp.flag[r] = gt->flags[r]; }
+        pp.step = gt->step; pp.wait = gt->wait_step; pp.done = gt->done_counter;
+        peer_push_kernel<<<gt->nranks, 256, 0, ctx->copy_stream>>>(pp);
+        PB_CHECK_LAUNCH(ctx);
+        PB_CUDA(ctx, cudaEventRecord(ev_row, ctx->copy_stream));
+        ctx->push_pending[gt->slot] = true;
+    } else if (want_toa) {
         PB_TRY(launch_toa(0, W, d_xint, d_alb));
     } else if (a->xint_at_top && memspace == PB_DEVICE) {
         PB_CUDA(ctx, cudaMemsetAsync(a->xint_at_top, 0, (size_t)B * G * nW, ctx->stream));

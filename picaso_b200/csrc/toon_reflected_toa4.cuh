@@ -340,6 +340,14 @@ __global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
     const bool active = (w < p.W) && (a < p.G);
     if (active && p.xint) p.xint[((int64_t)b * p.G + a) * p.W + w] = result;
     if (p.fuse_albedo) {
+        if (p.g_n > 0 && p.g_wait && wy == 0 && lane == 0) {
+            // hold the peer stores until every rank has published wait_step (buffer rotation, see pb_peer_gather)
+            const unsigned long long *mine = p.g_flag[p.g_rank];
+            const long long t0 = clock64();
+            for (int rk = 0; rk < p.g_n; ++rk)
+                while (ld_acquire_sys(mine + rk) < p.g_wait)
+                    if (clock64() - t0 > kSpinLimit) { atomicExch(p.g_done + 1, 1u); break; }
+        }
         // compress_disco (disco.py:138-149): sequential sum over (ig, it) in index order
         smem[wy * kWavesPerCta + lane] = result;
         __syncthreads();
@@ -350,7 +358,28 @@ __global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
                 acc = acc + smem[aa * kWavesPerCta + lane] * p.gweight[ig] * p.tweight[it];
             }
             const double sym = (p.nt == 1) ? 2.0 * PB_PI : 1.0;
-            p.albedo[(int64_t)b * p.W + w] = sym * 0.5 * acc / g.f0 * (p.cos_theta + 1.0);
+            const double alb = sym * 0.5 * acc / g.f0 * (p.cos_theta + 1.0);
+            p.albedo[(int64_t)b * p.W + w] = alb;
+            // fused all-gather: this rank's slab goes to row g_rank of every rank's buffer (NVLink P2P stores)
+            for (int rk = 0; rk < p.g_n; ++rk) p.g_alb[rk][(int64_t)p.g_rank * p.W + w] = alb;
+        }
+        if (p.g_n > 0) {
+            // last CTA to finish publishes the step on every rank.  The CTA barrier orders the writers' peer
+            // stores before thread 0; its gpu-scope fence + counter increment order them before the last
+            // CTA's observation of the full count, and that CTA's (cumulative) system-scope fence orders
+            // everything it has observed before the release stores of the flags (PTX causality order is
+            // transitive over morally strong edges of different scopes).  A system-scope fence in every
+            // CTA costs 8-10 us per launch (measured, self-gather on one GPU).
+            __syncthreads();
+            if (wy == 0 && lane == 0) {
+                __threadfence();
+                const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+                if (atomicAdd(p.g_done, 1u) == total - 1) {
+                    atomicExch(p.g_done, 0u);
+                    __threadfence_system();
+                    for (int rk = 0; rk < p.g_n; ++rk) st_release_sys(p.g_flag[rk] + p.g_rank, p.g_step);
+                }
+            }
         }
     }
 }

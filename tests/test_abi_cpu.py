@@ -39,9 +39,28 @@ def test_version(lib):
 
 def test_struct_sizes_match_header():
     # 5 ints + pad, i64, 18 pointers, double, 3 ints (+pad), 5 doubles, 2 ints, 6 pointers
-    assert ctypes.sizeof(_lib.ReflectedArgs) == 24 + 8 + 18 * 8 + 8 + 16 + 40 + 8 + 48 + 8
+    # ... variant (+pad), gather pointer
+    assert ctypes.sizeof(_lib.ReflectedArgs) == 24 + 8 + 18 * 8 + 8 + 16 + 40 + 8 + 48 + 8 + 8
     assert ctypes.sizeof(_lib.ThermalArgs) == 24 + 8 + 11 * 8 + 8 + 6 * 8 + 8
     assert ctypes.sizeof(_lib.TransitArgs) == 16 + 8 + 7 * 8 + 24 + 8
+
+
+def test_ctypes_structs_match_the_compiled_header(tmp_path):
+    """sizeof of every argument struct as gcc lays out include/picaso_b200.h == the ctypes mirror"""
+    import subprocess
+    pairs = {"pb_reflected_args": _lib.ReflectedArgs, "pb_thermal_args": _lib.ThermalArgs,
+             "pb_transit_args": _lib.TransitArgs, "pb_sh_args": _lib.ShArgs, "pb_thermal_sh_args": _lib.ThermalShArgs,
+             "pb_opacity_args": _lib.OpacityArgs, "pb_ck_mix_args": _lib.CkMixArgs, "pb_climate_args": _lib.ClimateArgs,
+             "pb_peer_gather": _lib.PeerGather}
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "picaso_b200.h"\nint main(void){\n' +
+                   "".join('printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in pairs) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    sizes = dict(zip(out[0::2], map(int, out[1::2])))
+    for n, cls in pairs.items():
+        assert sizes[n] == ctypes.sizeof(cls), (n, sizes[n], ctypes.sizeof(cls))
 
 
 def test_no_cpu_fallback(lib):
