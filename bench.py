@@ -209,40 +209,8 @@ def main():
     elif gather_mode == "p2p":
         # all-gather fused into the kernel epilogue over peer memory (include/picaso_b200.h: pb_peer_gather):
         # every rank maps every rank's gathered buffers [NBUF][world][W] and arrival flags [world]
-        from picaso_b200._lib import PeerGather
-        gbytes = NBUF * world * W * 8
-        d_gath = ctx.dev_alloc(gbytes)
-        d_flags = ctx.dev_alloc(256)
-        d_done = ctx.dev_alloc(256)
-        for ptr, nb in ((d_gath, gbytes), (d_flags, 256), (d_done, 256)):
-            ctx.check(ctx.lib.pb_memset(ctx.h, ptr, 0, nb))
-        ctx.sync()
-        hg, hf = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
-        ctx.check(ctx.lib.pb_ipc_export(ctx.h, d_gath, hg))
-        ctx.check(ctx.lib.pb_ipc_export(ctx.h, d_flags, hf))
-        handles = [(hg.raw, hf.raw)] * world
-        if world > 1:
-            dist.all_gather_object(handles, (hg.raw, hf.raw))
-        peer_g, peer_f = [], []
-        for r, (rg, rf) in enumerate(handles):
-            if r == rank:
-                peer_g.append(d_gath)
-                peer_f.append(d_flags)
-            else:
-                pg_, pf_ = ctypes.c_void_p(), ctypes.c_void_p()
-                ctx.check(ctx.lib.pb_ipc_open(ctx.h, rg, ctypes.byref(pg_)))
-                ctx.check(ctx.lib.pb_ipc_open(ctx.h, rf, ctypes.byref(pf_)))
-                peer_g.append(pg_.value)
-                peer_f.append(pf_.value)
-        flag_ptrs = (ctypes.c_void_p * world)(*peer_f)
-        alb_ptrs = [(ctypes.c_void_p * world)(*[g + bfi * world * W * 8 for g in peer_g]) for bfi in range(NBUF)]
-        gathers = []
-        for bfi in range(NBUF):
-            pg = PeerGather()
-            pg.nranks, pg.rank = world, rank
-            pg.albedo, pg.flags = ctypes.addressof(alb_ptrs[bfi]), ctypes.addressof(flag_ptrs)
-            pg.done_counter = d_done
-            gathers.append(pg)
+        from picaso_b200.sharded import PeerAllGather
+        pag = PeerAllGather(ctx, rank, world, W, nbuf=NBUF, push=bool(push))
         d_albs = [ctx.dev_alloc(W * 8)]
         if world > 1:
             dist.barrier()
@@ -267,20 +235,14 @@ def main():
 
     cargs = [[make_args(dd, da) for da in d_albs] for dd in dev_sets]
     fn = ctx.lib.pb_reflected_toon_1d
-    gstep = [0]  # global step counter published through the arrival flags
 
     def step(i):
         if gather_mode == "none":
             ctx.check(fn(ctx.h, ctypes.byref(cargs[i % NSETS][0]), PB_DEVICE))
             return
         if gather_mode == "p2p":
-            gstep[0] += 1
-            s_ = gstep[0]
-            pg = gathers[s_ % NBUF]
-            pg.step, pg.wait_step = s_, max(0, s_ - (NBUF - 1))   # buffer s_ % NBUF was last written at step s_ - NBUF
-            pg.push, pg.slot = push, s_ % NBUF
             a = cargs[i % NSETS][0]
-            a.gather = ctypes.addressof(pg)
+            a.gather = pag.next()   # step counter, rotating buffer, wait_step = step - (NBUF - 1)
             ctx.check(fn(ctx.h, ctypes.byref(a), PB_DEVICE))
             return
         bf = i & 1
@@ -297,8 +259,8 @@ def main():
         if gather_mode == "nccl":
             side.wait_event(ev_gather[0])
             side.wait_event(ev_gather[1])
-        elif gather_mode == "p2p" and gstep[0] > 0:
-            ctx.check(ctx.lib.pb_gather_wait(ctx.h, d_flags, world, gstep[0], d_done + 8))
+        elif gather_mode == "p2p":
+            pag.wait()
 
     def barrier():
         drain()
@@ -317,7 +279,7 @@ def main():
         got = alb_all[0][rank].cpu().numpy()
     elif gather_mode == "p2p":
         # the fused gather against NCCL's: every rank's buffer must hold every rank's slab, bit for bit
-        gath = ctx.from_device(d_gath + (gstep[0] % NBUF) * world * W * 8, (world, W))
+        gath = pag.gathered()
         mine = gath[rank].copy() if push else ctx.from_device(d_alb, (W,))
         if world > 1:
             ref_all = torch.empty((world, W), dtype=torch.float64, device="cuda")
@@ -326,7 +288,6 @@ def main():
             ref_np = ref_all.cpu().numpy()
         else:
             ref_np = mine[None, :]
-        gath = ctx.from_device(d_gath + (gstep[0] % NBUF) * world * W * 8, (world, W))
         if not np.array_equal(gath, ref_np):
             raise SystemExit("rank %d: fused peer-memory all-gather differs from the NCCL all-gather" % rank)
         got = gath[rank]
@@ -364,10 +325,8 @@ def main():
     sampler.active = False
     launches = ctx.launch_count() - l0
     if gather_mode == "p2p":
-        import struct
-        words = struct.unpack("<4I", ctx.from_device(d_done, (2,)).tobytes())
-        if words[1] or words[2]:
-            raise SystemExit("rank %d: peer all-gather timed out waiting for a flag (%r)" % (rank, words))
+        if pag.timed_out():
+            raise SystemExit("rank %d: peer all-gather timed out waiting for a flag" % rank)
     barrier()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")

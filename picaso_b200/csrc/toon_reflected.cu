@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PushParams p)
         const double2 *src = reinterpret_cast<const double2 *>(p.alb[p.rank] + (int64_t)p.rank * p.W);
         double2 *dst = reinterpret_cast<double2 *>(p.alb[r] + (int64_t)p.rank * p.W);
         const int n2 = p.W / 2;
-        if ((((int64_t)p.rank * p.W) & 1) == 0) {
+        if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
             for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = src[i];
             if ((p.W & 1) && threadIdx.x == 0)
                 p.alb[r][(int64_t)p.rank * p.W + p.W - 1] = p.alb[p.rank][(int64_t)p.rank * p.W + p.W - 1];

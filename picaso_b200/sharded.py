@@ -5,10 +5,12 @@ reference loop is elementwise over wavelengths or recurrent over layers.  So the
 scheme is: contiguous wave slabs per rank, no data-path collective, and one all-gather of
 the final [nwno] vector(s) (albedo / thermal flux / transit depth).  torch.distributed is
 used for the plumbing only (NCCL on GPUs, gloo in the CPU tests) and imported lazily.
+`PeerAllGather` is the device-side collective: the producing kernel (or a side-stream copy kernel)
+stores each rank's slab into every rank's buffer over NVLink peer memory.
 """
 import numpy as np
 
-__all__ = ["partition", "wave_slice", "shard_inputs", "allgather_waves", "run_sharded"]
+__all__ = ["partition", "wave_slice", "shard_inputs", "allgather_waves", "run_sharded", "PeerAllGather"]
 
 
 def partition(nwno, world):
@@ -74,3 +76,113 @@ def run_sharded(compute, inputs, nwno, group=None, wave_keys=None):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     local = compute(shard_inputs(inputs, nwno, rank, world, wave_keys))
     return allgather_waves(np.asarray(local), nwno, group)
+
+
+class PeerAllGather:
+    """The all-gather of the final [nwno] slab over NVLink peer memory (include/picaso_b200.h: pb_peer_gather).
+
+    One instance per rank (one process per GPU).  Every rank owns `nbuf` rotating gathered buffers
+    [world][nwno] and an arrival-flag array [world]; `exchange(obj)` must return the list of every rank's
+    `obj` (default: torch.distributed.all_gather_object) and is used once, to swap the CUDA IPC handles.
+    Per step: ``a.gather = g.next()`` on the ReflectedArgs of a PB_DEVICE `pb_reflected_toon_1d` call; the
+    slab of step s lands in row `rank` of buffer s % nbuf on every rank.  ``g.wait()`` enqueues a
+    stream-ordered wait for the last step of every rank; ``g.gathered()`` reads the local buffer.
+    push=True (default): a side-stream copy kernel pushes the slab while the next launch computes;
+    push=False: the solver kernel's epilogue stores to the peers itself."""
+
+    def __init__(self, ctx, rank, world, nwno, nbuf=3, push=True, exchange=None, _peers=None):
+        import ctypes
+        from ._lib import PeerGather
+        if not 1 <= world <= 8:
+            raise ValueError("PeerAllGather: 1 <= world <= 8")
+        self.ctx, self.rank, self.world, self.nwno, self.nbuf, self.push = ctx, rank, world, nwno, max(3, nbuf), push
+        self.step = 0
+        gbytes = self.nbuf * world * nwno * 8
+        self.d_gath, self.d_flags, self.d_done = ctx.dev_alloc(gbytes), ctx.dev_alloc(256), ctx.dev_alloc(256)
+        for ptr, nb in ((self.d_gath, gbytes), (self.d_flags, 256), (self.d_done, 256)):
+            ctx.check(ctx.lib.pb_memset(ctx.h, ptr, 0, nb))
+        ctx.sync()
+        self._opened = []
+        if _peers is not None:            # ranks living in one process (tests): plain device pointers
+            self._setup = lambda: self._bind([p.d_gath for p in _peers], [p.d_flags for p in _peers])
+            return
+        hg, hf = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+        ctx.check(ctx.lib.pb_ipc_export(ctx.h, self.d_gath, hg))
+        ctx.check(ctx.lib.pb_ipc_export(ctx.h, self.d_flags, hf))
+        if world == 1:
+            handles = [(hg.raw, hf.raw)]
+        elif exchange is not None:
+            handles = exchange((hg.raw, hf.raw))
+        else:
+            import torch.distributed as dist
+            handles = [None] * world
+            dist.all_gather_object(handles, (hg.raw, hf.raw))
+        pg, pf = [], []
+        for r, (rg, rf) in enumerate(handles):
+            if r == rank:
+                pg.append(self.d_gath)
+                pf.append(self.d_flags)
+            else:
+                a, b = ctypes.c_void_p(), ctypes.c_void_p()
+                ctx.check(ctx.lib.pb_ipc_open(ctx.h, rg, ctypes.byref(a)))
+                ctx.check(ctx.lib.pb_ipc_open(ctx.h, rf, ctypes.byref(b)))
+                pg.append(a.value)
+                pf.append(b.value)
+                self._opened += [a.value, b.value]
+        self._bind(pg, pf)
+
+    def _bind(self, peer_g, peer_f):
+        import ctypes
+        from ._lib import PeerGather
+        world, W = self.world, self.nwno
+        self._flag_ptrs = (ctypes.c_void_p * world)(*peer_f)
+        self._alb_ptrs = [(ctypes.c_void_p * world)(*[g + b * world * W * 8 for g in peer_g]) for b in range(self.nbuf)]
+        self._structs = []
+        for b in range(self.nbuf):
+            s = PeerGather()
+            s.nranks, s.rank = world, self.rank
+            s.albedo, s.flags = ctypes.addressof(self._alb_ptrs[b]), ctypes.addressof(self._flag_ptrs)
+            s.done_counter = self.d_done
+            self._structs.append(s)
+
+    @classmethod
+    def local_group(cls, ctxs, nwno, nbuf=3, push=True):
+        """`len(ctxs)` ranks inside one process (one Context = one stream each), e.g. on a single GPU"""
+        world = len(ctxs)
+        group = []
+        for r, c in enumerate(ctxs):
+            group.append(cls(c, r, world, nwno, nbuf=nbuf, push=push, _peers=group))
+        for g in group:
+            g._setup()
+        return group
+
+    def next(self):
+        """address of the pb_peer_gather struct of the next step (valid until the call after next)"""
+        import ctypes
+        self.step += 1
+        s = self._structs[self.step % self.nbuf]
+        s.step, s.wait_step = self.step, max(0, self.step - (self.nbuf - 1))
+        s.push, s.slot = int(self.push), self.step % self.nbuf
+        return ctypes.addressof(s)
+
+    def wait(self):
+        if self.step > 0:
+            self.ctx.check(self.ctx.lib.pb_gather_wait(self.ctx.h, self.d_flags, self.world, self.step, self.d_done + 8))
+
+    def gathered(self, step=None):
+        step = self.step if step is None else step
+        return self.ctx.from_device(self.d_gath + (step % self.nbuf) * self.world * self.nwno * 8, (self.world, self.nwno))
+
+    def timed_out(self):
+        import struct
+        w = struct.unpack("<4I", self.ctx.from_device(self.d_done, (2,)).tobytes())
+        return bool(w[1] or w[2])
+
+    def close(self):
+        for p in self._opened:
+            self.ctx.lib.pb_ipc_close(self.ctx.h, p)
+        self._opened = []
+        for p in (self.d_gath, self.d_flags, self.d_done):
+            if p is not None:
+                self.ctx.dev_free(p)
+        self.d_gath = self.d_flags = self.d_done = None
