@@ -313,6 +313,21 @@ def main():
             step(i)
             i += 1
         ctx.sync()
+    # ---- diagnostic (multi-GPU): every rank alone, same kernel, no exchange - the slowest GPU bounds the
+    # coupled rate, so weak-scaling loss can be attributed to GPU-to-GPU variation vs the collective ----
+    uncoupled = None
+    if world > 1:
+        barrier()
+        for a_ in (c[0] for c in cargs):
+            a_.gather = None
+        ctx.timer_start()
+        for i in range(100):
+            ctx.check(fn(ctx.h, ctypes.byref(cargs[i % NSETS][0]), PB_DEVICE))
+        own = ctx.timer_stop() / 100 * 1e3
+        t = torch.tensor([own], dtype=torch.float64, device="cuda")
+        allt = torch.empty((world,), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allt, t)
+        uncoupled = [round(float(x), 2) for x in allt.cpu()]
     # ---- timed region: exactly K steps, CUDA events on the launching stream ----
     barrier()
     l0 = ctx.launch_count()
@@ -410,7 +425,8 @@ def main():
                                          "timing; the timed region ends after pb_gather_wait saw the last step of every rank" % NBUF,
                                   "nccl": "ncclAllGather of the per-rank albedo [W] every step, double-buffered on a second "
                                           "stream (PB_BENCH_GATHER=nccl)"}[gather_mode],
-                   "parity_albedo_max_rel_err": parity},
+                   "parity_albedo_max_rel_err": parity,
+                   "kernel_us_per_rank_without_exchange": uncoupled},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": ke, "ms_per_step": 1e3 * e2e_dt / ke,
