@@ -320,6 +320,18 @@ __global__ void __launch_bounds__(128) sh_reflected_kernel(ShParams p)
         double Tn[S][S], Zdn[S];
         double *fdm_out = (p.fdm_out && a == p.G - 1) ? p.fdm_out : nullptr;
         for (int l = L - 1; l >= 0; --l) {
+#ifndef PB_SH_NO_PREFETCH
+            // ncu (profiles/r1_sh4.summary.json): the sweep stalls on its own global loads (long_scoreboard
+            // 3.8 of 7.4 cycles per instruction at 10 % occupancy, no registers left for a software pipeline):
+            // pull the next layer's rows towards the SM while this layer is eliminated
+            if (l > 0) {
+                const int64_t il = ol + (int64_t)(l - 1) * ld, iv = ov + (int64_t)(l - 1) * ld;
+                const double *rows[10] = {p.w0 + il, p.dtau + il, p.fcld + il, p.fray + il, p.cosb_og + il, p.fdm + il,
+                                          p.dtau_og + il, p.w0_og + il, p.tau + iv, p.tau_og + iv};
+#pragma unroll
+                for (int i = 0; i < 10; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(rows[i]));
+            }
+#endif
             Layer<S> y;
             double et;
             sh_layer<S>(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, u0, u1, f0, Pu0, Pu1, mus, a, et, eb, y,

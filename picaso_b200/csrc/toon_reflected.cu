@@ -42,6 +42,7 @@ struct ReflParams {
     int variant;   // 1: per-facet get_reflected_3d semantics (geometry indexed by batch entry)
     double clip;   // exponent clip: 35 (1-D, fluxes.py:1174) or 40 (3-D, fluxes.py:516)
     // fused all-gather of the albedo slab over peer memory (pb_peer_gather); g_n == 0: off
+    int wt, ay;    // refl_toa_kernel4<GEN = true>: wavelengths / angles per CTA
     int g_n, g_rank;
     double *g_alb[8];
     unsigned long long *g_flag[8];
@@ -716,13 +717,42 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             if (q.mp == 0) refl_toa_kernel3<0><<<grid, block, smem, ctx->stream>>>(q);
             else refl_toa_kernel3<1><<<grid, block, smem, ctx->stream>>>(q);
         } else {
-            const size_t smem = (size_t)2 * (2 * ay) * NR * 32 * sizeof(double);
-            if (smem > 48 * 1024) {
-                PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // Tile width.  32-wide tiles when they fill the machine evenly; otherwise (single residency wave,
+            // uneven CTA count per SM) a narrower tile that makes the grid just under a multiple of the SM count.
+            const char *wte = getenv("PB_REFL_WT");
+            int wt = wte ? atoi(wte) : 0;
+            if (wt <= 0 || wt > 32) {
+                wt = 32;
+                const int nsm = ctx->sm_count > 0 ? ctx->sm_count : 148;
+                const int std_ctas = (wc + 31) / 32;
+                const int per_sm = (std_ctas + nsm - 1) / nsm;              // CTAs on the busiest SM
+                const int cap = 16 / ay;                                      // resident CTAs per SM (127 registers)
+                if (B == 1 && G <= 8 && per_sm >= 2 && per_sm <= cap &&
+                    (double)per_sm * nsm > 1.15 * std_ctas) {
+                    const int cand = (wc + nsm * per_sm - 1) / (nsm * per_sm);
+                    if (cand >= 16 && cand < 32) wt = cand;
+                }
             }
-            if (q.mp == 0) refl_toa_kernel4<0><<<grid, block, smem, ctx->stream>>>(q);
-            else refl_toa_kernel4<1><<<grid, block, smem, ctx->stream>>>(q);
+            if (wt == 32) {
+                const size_t smem = (size_t)2 * (2 * ay) * NR * 32 * sizeof(double);
+                if (smem > 48 * 1024) {
+                    PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                }
+                if (q.mp == 0) refl_toa_kernel4<0, false><<<grid, block, smem, ctx->stream>>>(q);
+                else refl_toa_kernel4<1, false><<<grid, block, smem, ctx->stream>>>(q);
+            } else {
+                q.wt = wt; q.ay = ay;
+                const int nthreads = (wt * ay + 31) / 32 * 32, nwarp = nthreads / 32;
+                const size_t smem = (size_t)2 * (2 * nwarp) * NR * 32 * sizeof(double);
+                dim3 ggrid((wc + wt - 1) / wt, (G + ay - 1) / ay, B);
+                if (smem > 48 * 1024) {
+                    PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                }
+                if (q.mp == 0) refl_toa_kernel4<0, true><<<ggrid, nthreads, smem, ctx->stream>>>(q);
+                else refl_toa_kernel4<1, true><<<ggrid, nthreads, smem, ctx->stream>>>(q);
+            }
         }
         PB_CHECK_LAUNCH(ctx);
         if (ao && !fuse) {

@@ -231,22 +231,37 @@ __device__ __forceinline__ void refl4_carry(const Refl4Rec &c, Refl4State &s)
     s.e1p = c.e1; s.e3p = c.e3; s.s13p = c.e1 + c.e3; s.s24p = c.e2 + c.e4;
 }
 
-template <int MP /*multi_phase*/>
+// GEN = false: CTA = 32 wavelengths (threadIdx.x) x blockDim.y angle warps.
+// GEN = true : CTA = p.wt (< 32) wavelengths x p.ay angles flattened over a 1-D block, thread t ->
+//   (wave t % wt, angle t / wt).  Used when 32-wide tiles would leave the SMs unevenly loaded in a
+//   single residency wave (W = 10 000: 313 CTAs = 2 or 3 per SM, the 3-CTA SMs set the duration);
+//   the launcher then picks wt so that the grid is (just under) a multiple of the SM count - 23
+//   wavelengths, 435 CTAs of 4 warps, 12 warps on every SM.  As a producer a thread is still lane
+//   `t % 32` of warp `t / 32` and fills column `lane` of its warp's layer rows.
+template <int MP /*multi_phase*/, bool GEN>
 __global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
 {
     extern __shared__ double smem[];  // [2][2*NW][NR][32]
-    const int lane = threadIdx.x, wy = threadIdx.y, NW = blockDim.y;
+    const int tid = GEN ? (int)threadIdx.x : (int)(threadIdx.y * 32 + threadIdx.x);
+    const int lane = tid & 31, wy = tid >> 5;                   // producer identity
+    const int NW = GEN ? (int)(blockDim.x >> 5) : (int)blockDim.y;
+    const int WT = GEN ? p.wt : kWavesPerCta, AY = GEN ? p.ay : NW;
+    const int cw = GEN ? tid % WT : lane, ca = GEN ? tid / WT : wy;  // consumer identity
     const int CH = 2 * NW;  // layers per chunk
-    const int w = blockIdx.x * kWavesPerCta + lane;
-    const int wc = w < p.W ? w : p.W - 1;  // clamp: every lane takes part in the tile protocol
-    const int a = blockIdx.y * NW + wy;
+    const int w = blockIdx.x * WT + cw;
+    const int wc = w < p.W ? w : p.W - 1;  // clamp: every thread takes part in the tile protocol
+    const int wp = blockIdx.x * WT + lane;
+    const int wpc = wp < p.W ? wp : p.W - 1;
+    const int a = blockIdx.y * AY + ca;
     const int ac = a < p.G ? a : p.G - 1;
     const int b = blockIdx.z;
     const int L = p.L;
     const int64_t ld = p.ld;
-    const int64_t ol = (int64_t)b * p.bs_layer + wc;
-    const int64_t ov = (int64_t)b * p.bs_level + wc;
+    const int64_t ol = (int64_t)b * p.bs_layer + wpc;   // producer column
+    const int64_t ov = (int64_t)b * p.bs_level + wpc;
+    const int64_t ovc = (int64_t)b * p.bs_level + wc;   // consumer column
     const int64_t ow = (int64_t)b * p.bs_wave + wc;
+    const double f0p = p.f0pi ? p.f0pi[(int64_t)b * p.bs_wave + wpc] : 1.0;
     ReflAngle g;
     g.u0 = p.variant ? fabs(p.ubar0[b]) : p.ubar0[ac];  // 3-D facets: geometry per batch entry, |ubar|
     g.u1 = p.variant ? fabs(p.ubar1[b]) : p.ubar1[ac];
@@ -272,7 +287,7 @@ __global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
             if (l < L) {
                 Refl4Inputs x;
                 refl4_load(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, ld, x);
-                refl4_produce(p, x, g.f0, smem + (c & 1) * tile + pos * NR * 32 + lane);
+                refl4_produce(p, x, f0p, smem + (c & 1) * tile + pos * NR * 32 + lane);
             }
         }
     };
@@ -280,15 +295,15 @@ __global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
     Refl4State s;
     s.CS = s.DS = s.P = s.R = 0.0;
     s.T1 = 1.0;
-    s.T0 = pbm::kexp(-__ldg(p.tau + ov) * g.inv_u0);  // exp(-tau[0]/u0): 1 for tau[0] = 0
-    s.TO = g.og_alias ? s.T0 : pbm::kexp(-__ldg(p.tau_og + ov) * g.inv_u0);
+    s.T0 = pbm::kexp(-__ldg(p.tau + ovc) * g.inv_u0);  // exp(-tau[0]/u0): 1 for tau[0] = 0
+    s.TO = g.og_alias ? s.T0 : pbm::kexp(-__ldg(p.tau_og + ovc) * g.inv_u0);
     s.f1p = s.gam_p = s.cpd_p = s.cmd_p = s.e1p = s.e3p = s.s13p = s.s24p = 0.0;
     double e2L = 0.0, e4L = 0.0;  // e2, e4 of the last processed layer (surface row)
     produce(0);
     __syncthreads();
     for (int c = 0; c < nchunks; ++c) {
         if (c + 1 < nchunks) produce(c + 1);
-        const double *buf = smem + (c & 1) * tile + lane;
+        const double *buf = smem + (c & 1) * tile + cw;
         const int lbase = c * CH;
         const int nk = L - lbase < CH ? L - lbase : CH;
         int k = 0;
@@ -337,7 +352,7 @@ __global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
         const double x = pbm::krcp(B_ - A_ * s.CS);
         result = R + P * ((D_ - A_ * s.DS) * x);
     }
-    const bool active = (w < p.W) && (a < p.G);
+    const bool active = (w < p.W) && (a < p.G) && (ca < AY);
     if (active && p.xint) p.xint[((int64_t)b * p.G + a) * p.W + w] = result;
     if (p.fuse_albedo) {
         if (p.g_n > 0 && p.g_wait && wy == 0 && lane == 0) {
@@ -349,13 +364,13 @@ __global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
                     if (clock64() - t0 > kSpinLimit) { atomicExch(p.g_done + 1, 1u); break; }
         }
         // compress_disco (disco.py:138-149): sequential sum over (ig, it) in index order
-        smem[wy * kWavesPerCta + lane] = result;
+        if (ca < AY) smem[ca * kWavesPerCta + cw] = result;
         __syncthreads();
-        if (wy == 0 && w < p.W) {
+        if (ca == 0 && w < p.W) {
             double acc = 0.0;
             for (int aa = 0; aa < p.G; ++aa) {
                 const int ig = aa / p.nt, it = aa - ig * p.nt;
-                acc = acc + smem[aa * kWavesPerCta + lane] * p.gweight[ig] * p.tweight[it];
+                acc = acc + smem[aa * kWavesPerCta + cw] * p.gweight[ig] * p.tweight[it];
             }
             const double sym = (p.nt == 1) ? 2.0 * PB_PI : 1.0;
             const double alb = sym * 0.5 * acc / g.f0 * (p.cos_theta + 1.0);
