@@ -29,6 +29,7 @@ struct ThermParams {
     double *fm, *fp, *fmm, *fpm;
     int fuse;
     int variant;  // 1: get_thermal_3d per-facet semantics (fluxes.py:2148-2352)
+    int wt, ay;   // therm_toa_kernel<GEN = true>: wavelengths / angles per CTA
 };
 
 constexpr int kWavesPerCta = 32;
@@ -134,13 +135,22 @@ __device__ __forceinline__ void therm_produce(double dt, double om, double g, do
     q[T_B1 * 32] = b1;
 }
 
+// GEN: wt (< 32) wavelengths x ay angles flattened over a 1-D block (thread t -> wave t % wt, angle t / wt)
+// so that the grid can be sized to the SM count - see refl_toa_kernel4 in toon_reflected_toa4.cuh.
+template <bool GEN>
 __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
 {
     extern __shared__ double smem[];  // [V][32] Planck | [2][NW][TNQ][32] tiles
-    const int lane = threadIdx.x, wy = threadIdx.y, NW = blockDim.y;
-    const int w = blockIdx.x * kWavesPerCta + lane;
-    const int wc = w < p.W ? w : p.W - 1;
-    const int a = blockIdx.y * NW + wy;
+    const int tid = GEN ? (int)threadIdx.x : (int)(threadIdx.y * 32 + threadIdx.x);
+    const int lane = tid & 31, wy = tid >> 5;  // producer identity
+    const int NW = GEN ? (int)(blockDim.x >> 5) : (int)blockDim.y;
+    const int WT = GEN ? p.wt : kWavesPerCta, AY = GEN ? p.ay : NW;
+    const int cw = GEN ? tid % WT : lane, ca = GEN ? tid / WT : wy;  // consumer identity
+    const int w = blockIdx.x * WT + cw;
+    const int wp = blockIdx.x * WT + lane;
+    const int wc = wp < p.W ? wp : p.W - 1;          // producer column (clamped)
+    const int wcc = w < p.W ? w : p.W - 1;           // consumer column (clamped)
+    const int a = blockIdx.y * AY + ca;
     const int ac = a < p.G ? a : p.G - 1;
     const int b = blockIdx.z;
     const int L = p.L, V = p.L + 1;
@@ -150,7 +160,7 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
     const double *pl = p.plevel + (int64_t)b * V;
     const double u = p.variant ? p.ubar1[b] : p.ubar1[ac];
     const double inv_u = 1.0 / u;
-    const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + wc] : 0.0;
+    const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + wcc] : 0.0;
     double *sB = smem;
     double *tiles = smem + (size_t)V * 32;
     const int tile = NW * TNQ * 32;
@@ -162,7 +172,7 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
         for (int v = wy; v < V; v += NW) sB[v * 32 + lane] = planck(tl[v]);
     }
     __syncthreads();
-    const double BL = sB[L * 32 + lane], B0 = sB[lane];
+    const double BL = sB[L * 32 + cw], B0 = sB[cw];
     {
         const int l = L - 1 - wy;
         if (l >= 0) {
@@ -184,7 +194,7 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
             nom = __ldg(p.w0 + il);
             ncb = __ldg(p.cosb + il);
         }
-        const double *buf = tiles + (c & 1) * tile + lane;
+        const double *buf = tiles + (c & 1) * tile + cw;
         const int lbase = L - 1 - c * NW;
         const int nk = lbase + 1 < NW ? lbase + 1 : NW;
         for (int k = 0; k < nk; ++k) {
@@ -265,24 +275,24 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
     double result;
     {
         // top boundary: fake isothermal overburden, fluxes.py:1797-1800; row 0 :155-158
-        const double tau_top = __ldg(p.dtau + ol) * pl[0] / (pl[1] - pl[0]);
+        const double tau_top = __ldg(p.dtau + (int64_t)b * p.bs_layer + wcc) * pl[0] / (pl[1] - pl[0]);
         const double b_top = (1.0 - exp(-tau_top / kMu1)) * B0 * PB_PI;
         const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = b_top - cmu_n;
         const double xi = pbm::krcp(b_ - c_ * AS);
         const double X0 = (d_ - c_ * DS) * xi;
         result = Rp + Pp * X0;
     }
-    const bool active = (w < p.W) && (a < p.G);
+    const bool active = (w < p.W) && (a < p.G) && (ca < AY);
     if (active && p.ftop) p.ftop[((int64_t)b * p.G + a) * p.W + w] = result;
     if (p.fuse) {
         double *s_f = tiles;
-        s_f[wy * kWavesPerCta + lane] = result;
+        if (ca < AY) s_f[ca * kWavesPerCta + cw] = result;
         __syncthreads();
-        if (wy == 0 && w < p.W) {
+        if (ca == 0 && w < p.W) {
             double acc = 0.0;
             for (int aa = 0; aa < p.G; ++aa) {
                 const int ig = aa / p.nt, it = aa - ig * p.nt;
-                acc = acc + s_f[aa * kWavesPerCta + lane] * p.gweight[ig] * p.tweight[it];
+                acc = acc + s_f[aa * kWavesPerCta + cw] * p.gweight[ig] * p.tweight[it];
             }
             const double sym = (p.nt == 1) ? 1.0 : 1 / (2 * PB_PI);
             p.thermal[(int64_t)b * p.W + w] = acc * sym;
@@ -728,11 +738,36 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
         PB_CHECK_LAUNCH(ctx);
     } else {
         p.fuse = fuse ? 1 : 0;
-        const size_t smem = ((size_t)V * 32 + (size_t)2 * ay * TNQ * 32) * sizeof(double);
-        if (smem > 200 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "thermal: nlevel=%d exceeds the shared-memory Planck tile", V);
-        if (smem > 48 * 1024)
-            PB_CUDA(ctx, cudaFuncSetAttribute(therm_toa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        therm_toa_kernel<<<grid, block, smem, ctx->stream>>>(p);
+        // tile width from the SM count when 32-wide tiles give an uneven single residency wave (see toon_reflected.cu)
+        const char *wte = getenv("PB_THERM_WT");
+        int wt = wte ? atoi(wte) : 0;
+        if (wt <= 0 || wt > 32) {
+            wt = 32;
+            const int nsm = ctx->sm_count > 0 ? ctx->sm_count : 148;
+            const int std_ctas = (W + 31) / 32;
+            const int per_sm = (std_ctas + nsm - 1) / nsm;
+            const int cap = 16 / ay;
+            if (B == 1 && G <= 8 && a->variant == 0 && per_sm >= 2 && per_sm <= cap && (double)per_sm * nsm > 1.15 * std_ctas) {
+                const int cand = (W + nsm * per_sm - 1) / (nsm * per_sm);
+                if (cand >= 16 && cand < 32) wt = cand;
+            }
+        }
+        if (wt == 32) {
+            const size_t smem = ((size_t)V * 32 + (size_t)2 * ay * TNQ * 32) * sizeof(double);
+            if (smem > 200 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "thermal: nlevel=%d exceeds the shared-memory Planck tile", V);
+            if (smem > 48 * 1024)
+                PB_CUDA(ctx, cudaFuncSetAttribute(therm_toa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            therm_toa_kernel<false><<<grid, block, smem, ctx->stream>>>(p);
+        } else {
+            p.wt = wt; p.ay = ay;
+            const int nthreads = (wt * ay + 31) / 32 * 32, nwarp = nthreads / 32;
+            const size_t smem = ((size_t)V * 32 + (size_t)2 * nwarp * TNQ * 32) * sizeof(double);
+            if (smem > 200 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "thermal: nlevel=%d exceeds the shared-memory Planck tile", V);
+            if (smem > 48 * 1024)
+                PB_CUDA(ctx, cudaFuncSetAttribute(therm_toa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 ggrid((W + wt - 1) / wt, (G + ay - 1) / ay, B);
+            therm_toa_kernel<true><<<ggrid, nthreads, smem, ctx->stream>>>(p);
+        }
         PB_CHECK_LAUNCH(ctx);
     }
     if (a->thermal && !(fuse && !want_lvl)) {
