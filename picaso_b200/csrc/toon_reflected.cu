@@ -746,12 +746,21 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
                 const int nthreads = (wt * ay + 31) / 32 * 32, nwarp = nthreads / 32;
                 const size_t smem = (size_t)2 * (2 * nwarp) * NR * 32 * sizeof(double);
                 dim3 ggrid((wc + wt - 1) / wt, (G + ay - 1) / ay, B);
+                // more than 4 warps per CTA (wide angle sets) cannot use the larger register budget
+                const bool wide = nwarp <= 4;
                 if (smem > 48 * 1024) {
+                    PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4_gen<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4_gen<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel4<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 }
-                if (q.mp == 0) refl_toa_kernel4<0, true><<<ggrid, nthreads, smem, ctx->stream>>>(q);
-                else refl_toa_kernel4<1, true><<<ggrid, nthreads, smem, ctx->stream>>>(q);
+                if (wide) {
+                    if (q.mp == 0) refl_toa_kernel4_gen<0><<<ggrid, nthreads, smem, ctx->stream>>>(q);
+                    else refl_toa_kernel4_gen<1><<<ggrid, nthreads, smem, ctx->stream>>>(q);
+                } else {
+                    if (q.mp == 0) refl_toa_kernel4<0, true><<<ggrid, nthreads, smem, ctx->stream>>>(q);
+                    else refl_toa_kernel4<1, true><<<ggrid, nthreads, smem, ctx->stream>>>(q);
+                }
             }
         }
         PB_CHECK_LAUNCH(ctx);

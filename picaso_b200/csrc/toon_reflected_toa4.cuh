@@ -33,6 +33,8 @@
 // elimination step of layer k (102 us, spills), branch-free pbm::exp (92 us), 136 registers (2 CTAs
 // per SM: 127 us), prefetch.global.L2 of the next-but-one chunk (91 us), both layers' 26 loads in
 // flight before the first use (93 us, spills).
+// With SM-count-sized tiles (GEN, 4 warps per CTA) the register budget is 168 instead of 128: 82.2 -> 77.3 us
+// (no spills); the software-pipelined consume loop is still slower there (80.7 us).
 
 #ifndef PB_REFL4_REGS
 #define PB_REFL4_REGS 128
@@ -239,7 +241,7 @@ __device__ __forceinline__ void refl4_carry(const Refl4Rec &c, Refl4State &s)
 //   wavelengths, 435 CTAs of 4 warps, 12 warps on every SM.  As a producer a thread is still lane
 //   `t % 32` of warp `t / 32` and fills column `lane` of its warp's layer rows.
 template <int MP /*multi_phase*/, bool GEN>
-__global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
+__device__ __forceinline__ void refl4_body(const ReflParams &p)
 {
     extern __shared__ double smem[];  // [2][2*NW][NR][32]
     const int tid = GEN ? (int)threadIdx.x : (int)(threadIdx.y * 32 + threadIdx.x);
@@ -306,6 +308,7 @@ __global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
         const double *buf = smem + (c & 1) * tile + cw;
         const int lbase = c * CH;
         const int nk = L - lbase < CH ? L - lbase : CH;
+        {
         int k = 0;
         for (; k + 1 < nk; k += 2) {
             const double *q0 = buf + k * NR * 32, *q1 = q0 + NR * 32;
@@ -333,6 +336,7 @@ __global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
             else refl4_step(c0, s);
             refl4_carry(c0, s);
             e2L = c0.e2; e4L = c0.e4;
+        }
         }
         __syncthreads();
     }
@@ -397,4 +401,20 @@ __global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
             }
         }
     }
+}
+
+// 32-wide tiles: 5 angle warps per CTA, 3 CTAs per SM -> 128 registers.  SM-count-sized tiles: 4 warps per
+// CTA, 3 CTAs per SM -> up to 168 registers (no spills).
+#ifndef PB_REFL4_GEN_REGS
+#define PB_REFL4_GEN_REGS 168
+#endif
+template <int MP, bool GEN>
+__global__ void __maxnreg__(PB_REFL4_REGS) refl_toa_kernel4(ReflParams p)
+{
+    refl4_body<MP, GEN>(p);
+}
+template <int MP>
+__global__ void __maxnreg__(PB_REFL4_GEN_REGS) refl_toa_kernel4_gen(ReflParams p)
+{
+    refl4_body<MP, true>(p);
 }
