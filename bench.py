@@ -401,7 +401,7 @@ def main():
             traffic = json.load(open(tpath)).get("refl_toa_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    fpath = os.path.join(ROOT, "profiles", "r1_refl_toa_v4.summary.json")
+    fpath = os.path.join(ROOT, "profiles", "r1_refl_toa_v4gen.summary.json")
     fp64_pct = None
     if os.path.isfile(fpath):
         try:
@@ -432,11 +432,11 @@ def main():
                 "steps": ke, "ms_per_step": 1e3 * e2e_dt / ke,
                 "api": "picaso_b200.get_reflected_1d(..., return_albedo=True), pinned host inputs"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel": "refl_toa_kernel4",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": "refl_toa_kernel4_gen",
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "fp64_pipe_pct_ncu": fp64_pct,
-                     "note": "not HBM-bound: ~50 fp64 flop/B; 313 CTAs = 2-3 per SM, dependent fp64 chains "
-                             "(ncu stall_wait); DRAM traffic = algorithmic bytes; see DESIGN.md 4.1 and profiles/"},
+                     "note": "not HBM-bound: ~50 fp64 flop/B; 435 CTAs of 4 warps = 12 warps per SM, dependent fp64 "
+                             "chains (ncu stall_wait); DRAM traffic = algorithmic bytes; see DESIGN.md 4.1 and profiles/"},
         "clocks": sampler.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
