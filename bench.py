@@ -101,6 +101,100 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Spectrum-level end to end (extra key `e2e_spectrum`): what picaso() does per spectrum - opacityclass.
+# get_opacities(atm) + compute_opacity(atm, opa) + get_reflected_1d + compress_disco (justdoit.py:236-310) -
+# with the cross-section tables resident (HBM here, host memory in the CPU arm), a fresh atmosphere profile per
+# step.  Only O(nlayer) scalars go to the device and the [nwno] albedo (+ xint) comes back.
+# ---------------------------------------------------------------------------------------------------------
+NMOL_SPEC, NPROF = 12, 4
+
+
+def _spectrum_setup():
+    import types
+    from picaso_b200 import synth
+    db = synth.opacity_database(W=W, nmol=NMOL_SPEC, seed=4001, nT=20, nP=18, ragged=True)
+    # the synthetic tables are rescaled to a planet-like regime (Rayleigh tau ~ 10, total tau ~ 1e3-1e4 at 80 bar,
+    # single-scattering albedo from ~1 at the top to ~0 at depth): values only, the arithmetic is the same
+    for k in db["continuum"]:
+        db["continuum"][k] = db["continuum"][k] * 1e-6
+    for m in db["tables"]:
+        db["tables"][m] = db["tables"][m] * 1e-1
+    ray = {m: 6e-4 * (db["wno"] / 1e4) ** 4 * (1.0 + 0.3 * i) for i, m in enumerate(db["rayleigh_molecules"])}
+    atms, ducks = [], []
+    for i in range(NPROF):
+        atm = synth.atmosphere_profile(db, L=L, seed=4100 + i, cloudy=False)
+        a = types.SimpleNamespace()
+        a.c = types.SimpleNamespace(nlayer=atm["nlayer"], pconv=atm["pconv"], rgas=atm["rgas"], amu=atm["amu"], k_b=atm["k_b"])
+        a.level = {"temperature": atm["tlevel"], "pressure": atm["plevel"]}
+        a.layer = {"temperature": atm["tlayer"], "pressure": atm["player"], "colden": atm["colden"], "mmw": atm["mmw"],
+                   "mixingratios": atm["mixingratios"], "electrons": atm["electrons"], "cloud": None}
+        a.planet = types.SimpleNamespace(gravity=atm["gravity"])
+        a.molecules = list(db["molecules"])
+        a.continuum_molecules = [list(x) for x in db["continuum_molecules"]]
+        a.rayleigh_molecules = list(db["rayleigh_molecules"])
+        atm["cia_pairs"] = {x + y: (x, y) for x, y in db["continuum_molecules"]}
+        atms.append(atm)
+        ducks.append(a)
+    return db, ray, atms, ducks
+
+
+def _spectrum_geometry():
+    from picaso_b200 import synth
+    gangle, gweight, tangle, tweight, ubar0, ubar1, cos_theta = synth.geometry_1d(NG, 0.0)
+    tail = (0, ubar0, ubar1, cos_theta, np.ones(W), KW["single_phase"], KW["multi_phase"], 1.0, -1.0, 2.0, -0.5, 1.0)
+    return gweight, tweight, cos_theta, tail
+
+
+def spectrum_cpu(db, ray, atm, nthreads):
+    """CPU port of the same chain: oracle/optics.py (numpy) + the C oracle (OpenMP)."""
+    import oracle
+    from oracle import optics as oo
+    pbar = atm["player"] / atm["pconv"]
+    ti, pi, ill, ihl, ilh, ihh = oo.find_needed_pts(db["temps"], db["pressures"], db["nc_p"], atm["tlayer"], pbar)
+    mol = {m: oo.interp_molecular(db["tables"][m], ti, pi, ill, ihl, ilh, ihh) for m in db["molecules"]}
+    ic = oo.nearest_cia_temp(db["cia_temps"], atm["tlayer"])
+    cont = {k: db["continuum"][k][ic] for k in db["continuum"]}
+    o = oo.compute_opacity(atm, mol, cont, ray, None, stream=2, delta_eddington=True)
+    DTAU, TAU, W0, COSB, fcld, fray, GCOS2, DTAU_OG, TAU_OG, W0_OG, COSB_OG = o[:11]
+    gweight, tweight, cos_theta, tail = _spectrum_geometry()
+    x, _ = oracle.get_reflected_1d(L + 1, db["wno"], W, NG, 1, DTAU, TAU, W0, COSB, GCOS2, fcld, fray, DTAU_OG, TAU_OG,
+                                   W0_OG, COSB_OG, *tail, nthreads=nthreads)
+    return oracle.compress_disco(W, cos_theta, x, gweight, tweight, np.ones(W))
+
+
+def spectrum_gpu_factory(pb, ctx, db, ray, ducks):
+    opa = pb.DeviceOpacities(db["wno"], db["pt_pairs"], db["tables"], db["cia_temps"], db["continuum"], ray,
+                             query_method="linear", ctx=ctx)
+    gweight, tweight, cos_theta, tail = _spectrum_geometry()
+
+    def one(i):
+        a = ducks[i % NPROF]
+        opa.get_opacities(a)
+        dev = pb.compute_opacity(a, opa, ngauss=1, stream=2, delta_eddington=True, test_mode=None, raman=2,
+                                 device_outputs=True)
+        DTAU, TAU, W0, COSB, fcld, fray, GCOS2, DTAU_OG, TAU_OG, W0_OG, COSB_OG = dev[:11]
+        sl = lambda d: d[:, :, 0]
+        _, _, alb = pb.get_reflected_1d(L + 1, db["wno"], W, NG, 1, sl(DTAU), sl(TAU), sl(W0), sl(COSB), sl(GCOS2),
+                                        sl(fcld), sl(fray), sl(DTAU_OG), sl(TAU_OG), sl(W0_OG), sl(COSB_OG), *tail,
+                                        gweight=gweight, tweight=tweight, return_albedo=True, ctx=ctx)
+        return alb
+    return opa, one
+
+
+def time_spectrum_cpu(db, ray, atms, nthreads, budget_s=8.0):
+    spectrum_cpu(db, ray, atms[0], nthreads)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        spectrum_cpu(db, ray, atms[n % NPROF], nthreads)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 40:
+            break
+    return W * n / el, n, el
+
+
 def make_sets(rank):
     from picaso_b200 import synth
     return [synth.reflected_inputs(L=L, W=W, seed=1000 + 97 * rank + i) for i in range(NSETS)]
@@ -125,6 +219,8 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     val = W * args.steps / dt
     sample = "%d full spectra (60x10000x5) per run, C port of the reference algorithm, OpenMP over wavelengths" % args.steps
+    db, ray, atms, _ = _spectrum_setup()
+    sv, sn, sel = time_spectrum_cpu(db, ray, atms, nthreads)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -133,6 +229,9 @@ def run_reference(args, rank, world):
         "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e_spectrum": {"value": sv, "unit": UNIT, "steps": sn,
+                         "api": "numpy port of get_opacities(linear) + compute_opacity (%d molecules, clear, no Raman) + C port of "
+                                "get_reflected_1d + compress_disco, %d threads" % (NMOL_SPEC, nthreads)},
     }))
 
 
@@ -458,6 +557,35 @@ def main():
         out["cpu_baseline"] = {"value": W * n / el, "unit": UNIT, "cores": nthreads, "kind": "port",
                                "sample": "%d full 60x10000x5 spectra in %.1f s; C port of the reference algorithm (oracle/), OpenMP over wavelengths" % (n, el),
                                "single_thread_value": W / one, "host_cpus": os.cpu_count()}
+    if rank == 0 and world == 1:
+        # ---- spectrum-level end to end: profile in, albedo out, opacity tables resident in HBM ----
+        db, ray, atms, ducks = _spectrum_setup()
+        opa, one = spectrum_gpu_factory(pb, ctx, db, ray, ducks)
+        got = one(0)
+        want = spectrum_cpu(db, ray, atms[0], os.cpu_count() or 1)
+        sp_par = float(np.max(np.abs(got - want) / np.abs(want)))
+        if not sp_par < 1e-6:
+            raise SystemExit("spectrum-level parity gate failed: %.3e" % sp_par)
+        for i in range(3):
+            one(i)
+        ns = max(ke, 40)
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        for i in range(ns):
+            one(i)
+        sdt = time.perf_counter() - t0
+        sp = {"value": W * ns / sdt, "unit": UNIT, "steps": ns, "ms_per_step": 1e3 * sdt / ns,
+              "gpu_launches_per_step": (ctx.launch_count() - l0) / ns,
+              "h2d_bytes_per_step": int(L * (NMOL_SPEC + len(db["continuum"]) + len(ray) + 12) * 8),
+              "d2h_bytes_per_step": int((NG + 1) * W * 8), "parity_albedo_max_rel_err": sp_par,
+              "api": "DeviceOpacities.get_opacities(linear) + compute_opacity(device_outputs=True, %d molecules, clear, "
+                     "no Raman) + get_reflected_1d(DeviceArray..., return_albedo=True); tables resident in HBM" % NMOL_SPEC}
+        if not args.no_cpu_baseline:
+            cv, cn, cel = time_spectrum_cpu(db, ray, atms, os.cpu_count() or 1)
+            sp["cpu_port_value"] = cv
+            sp["cpu_port_sample"] = "%d spectra in %.1f s on %d threads" % (cn, cel, os.cpu_count() or 1)
+        out["e2e_spectrum"] = sp
+        opa.close()
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -250,6 +250,18 @@ class Context:
     def dev_free(self, ptr):
         self.check(self.lib.pb_dev_free(self.h, ptr))
 
+    def workspace(self, name, nbytes):
+        """grow-only device buffer owned by the context and reused by the next call that asks for `name`
+        (no cudaMalloc / cudaFree on the per-call path)"""
+        ws = self.__dict__.setdefault("_ws", {})
+        ent = ws.get(name)
+        if ent is None or ent[1] < nbytes:
+            if ent is not None:
+                self.dev_free(ent[0])
+            cap = max(int(nbytes), 8)
+            ent = ws[name] = (self.dev_alloc(cap), cap)
+        return ent[0]
+
     def to_device(self, arr):
         """copy a numpy float64 array to a fresh device buffer; returns the device address."""
         a = np.ascontiguousarray(arr, dtype=np.float64)

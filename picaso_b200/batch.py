@@ -26,14 +26,7 @@ def shard(nbatch, rank, world):
 
 
 def _buf(ctx, name, nbytes):
-    """grow-only device workspace owned by the context (no cudaMalloc / cudaFree per call)"""
-    ws = ctx.__dict__.setdefault("_batch_ws", {})
-    ent = ws.get(name)
-    if ent is None or ent[1] < nbytes:
-        if ent is not None:
-            ctx.dev_free(ent[0])
-        ent = ws[name] = (ctx.dev_alloc(max(nbytes, 8)), max(nbytes, 8))
-    return ent[0]
+    return ctx.workspace("batch_" + name, nbytes)
 
 
 def _cached_vec(ctx, name, v):

@@ -166,8 +166,11 @@ def _reflected_device(ctx, nlevel, nwno, numg, numt, lay, lev, surf_reflect, uba
     if return_albedo:
         gw = np.ascontiguousarray(gweight, dtype=np.float64)
         tw = np.ascontiguousarray(tweight, dtype=np.float64)
-    d_x = DeviceArray(ctx, (numg, numt, nwno))
-    d_a = DeviceArray(ctx, (nwno,)) if return_albedo else None
+    # TOA outputs share one context-owned workspace block ([G + 1][nwno]: xint rows, then the albedo) so that a
+    # call costs no cudaMalloc and one device-to-host copy
+    ws = ctx.workspace("refl_toa_out", (G + 1) * nwno * 8)
+    d_x = DeviceArray(ctx, (numg, numt, nwno), ptr=ws)
+    d_a = DeviceArray(ctx, (nwno,), ptr=ws + G * nwno * 8) if return_albedo else None
     d_lv = [DeviceArray(ctx, (numg, numt, nlevel, nwno)) for _ in range(4)] if get_lvl_flux else None
     a = ReflectedArgs()
     a.nlayer, a.nwno, a.numg, a.numt, a.nbatch, a.ld = nlayer, nwno, numg, numt, 1, ld
@@ -183,14 +186,15 @@ def _reflected_device(ctx, nlevel, nwno, numg, numt, lay, lev, surf_reflect, uba
     if d_lv:
         a.flux_minus, a.flux_plus, a.flux_minus_mdpt, a.flux_plus_mdpt = [x.ptr for x in d_lv]
     ctx.check(ctx.lib.pb_reflected_toon_1d(ctx.h, ctypes.byref(a), memspace))
-    xint = d_x.numpy()
+    both = ctx.from_device(ws, ((G + 1) if return_albedo else G, nwno))
+    xint = both[:G].reshape(numg, numt, nwno)
     if d_lv:
         lv = [x.numpy() for x in d_lv]
     else:
         z = np.broadcast_to(_ZERO, (numg, numt, nlevel, nwno))
         lv = [z, z, z, z]
     if return_albedo:
-        return xint, tuple(lv), d_a.numpy()
+        return xint, tuple(lv), both[G]
     return xint, tuple(lv)
 
 

@@ -203,16 +203,17 @@ class DeviceOpacities:
         t_inv = 1 / np.asarray(tlayer, dtype=np.float64)
         p_log = np.log10(np.asarray(player, dtype=np.float64))
         nT = self.t_inv_grid.size
-        # last grid temperature strictly below T (t_inv_grid is descending): count of entries > t_inv
-        cnt = np.array([np.count_nonzero(self.t_inv_grid > x) for x in t_inv])
-        t_low = np.where(cnt == 0, 0, cnt - 1)
-        if np.any(np.diff(self.t_inv_grid) > 0):  # non-monotonic grid: fall back to the literal rule
-            t_low = np.array([(np.where(self.t_inv_grid > x)[0][-1] if np.any(self.t_inv_grid > x) else 0)
-                              for x in t_inv])
+
+        def last_true(mask):
+            """per row: index of the last True (np.where(row)[0][-1]), 0 if none - any grid ordering"""
+            n = mask.shape[1]
+            return np.where(mask.any(axis=1), n - 1 - np.argmax(mask[:, ::-1], axis=1), 0)
+
+        # last grid temperature strictly below T, last grid pressure <= P (all layers at once)
+        t_low = last_true(self.t_inv_grid[None, :] > t_inv[:, None])
         t_low = np.where(t_low == nT - 1, nT - 2, t_low)
         t_hi = t_low + 1
-        p_low = np.array([(np.where(self.p_log_grid <= x)[0][-1] if np.any(self.p_log_grid <= x) else 0)
-                          for x in p_log])
+        p_low = last_true(self.p_log_grid[None, :] <= p_log[:, None])
         p_low = np.minimum(p_low, self.nc_p[t_hi] - 3)
         p_hi = p_low + 1
         off = np.concatenate([[0], np.cumsum(self.nc_p)])
@@ -236,11 +237,10 @@ class DeviceOpacities:
             wts[:, 0], wts[:, 1], wts[:, 2], wts[:, 3] = (1 - t) * (1 - p), t * (1 - p), t * p, (1 - t) * p
             atmosphere.layer["pt_opa_index"] = 1 + np.unique(np.concatenate([ill, ihl, ilh, ihh]))
         else:
-            rows = np.array([int(np.argmin(np.hypot(self._lnP - np.log(p), self._T - t)))
-                             for p, t in zip(pbar, tlayer)])
+            rows = np.argmin(np.hypot(self._lnP[None, :] - np.log(pbar)[:, None], self._T[None, :] - tlayer[:, None]), axis=1)
             idx[:, 0] = rows
             atmosphere.layer["pt_opa_index"] = [int(self._ptid[r]) for r in rows]
-        cia = np.array([int(np.abs(self._cia_unique - t).argmin()) for t in tlayer], dtype=np.int32)
+        cia = np.abs(self._cia_unique[None, :] - tlayer[:, None]).argmin(axis=1).astype(np.int32)
         fac = {}
         for m in atmosphere.molecules:
             fac[m] = 1 if (np.isscalar(exclude_mol) and exclude_mol == 1) else exclude_mol[m]
