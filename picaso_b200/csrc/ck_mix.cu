@@ -76,27 +76,38 @@ __global__ void __launch_bounds__(kWarps * 32) ck_mix_kernel(MixParams p)
             // deq_chem.py:575-578
             const double a0 = __shfl_sync(0xffffffffu, k1, i0 < K ? i0 : 0), b0 = __shfl_sync(0xffffffffu, k2, j0);
             const double a1 = __shfl_sync(0xffffffffu, k1, i1 < K ? i1 : 0), b1 = __shfl_sync(0xffffffffu, k2, j1);
-            key[e0] = e0 < n ? (mix_t * a0 + m2 * b0) / mt : CUDART_INF;
-            key[e1] = e1 < n ? (mix_t * a1 + m2 * b1) / mt : CUDART_INF;
-            idx[e0] = (unsigned char)e0;
-            idx[e1] = (unsigned char)e1;
-            __syncwarp();
-            // deq_chem.py:582 (stable argsort) as a bitonic network on (key, index)
+            // two elements per lane, in registers: sorted position 2*lane + s after the network
+            double q0 = e0 < n ? (mix_t * a0 + m2 * b0) / mt : CUDART_INF;
+            double q1 = e1 < n ? (mix_t * a1 + m2 * b1) / mt : CUDART_INF;
+            int x0 = e0, x1 = e1;
+            // deq_chem.py:582 (stable argsort) as a 64-element bitonic network on (key, flat index): partner
+            // distance 1 is the lane's own pair, larger distances are lane-xor shuffles - no shared memory,
+            // no warp barriers (the index makes the order strict, so min/max selection is unambiguous)
 #pragma unroll
             for (int k = 2; k <= kElems; k <<= 1) {
 #pragma unroll
                 for (int j = k >> 1; j > 0; j >>= 1) {
-                    const int lo = 2 * j * (lane / j) + (lane % j), hi = lo + j;
-                    const double ka = key[lo], kb = key[hi];
-                    const int ia = idx[lo], ib = idx[hi];
-                    const bool up = (lo & k) == 0;
-                    if (key_less(kb, ib, ka, ia) == up) {
-                        key[lo] = kb; key[hi] = ka;
-                        idx[lo] = (unsigned char)ib; idx[hi] = (unsigned char)ia;
+                    const bool up = ((2 * lane) & k) == 0;
+                    if (j == 1) {
+                        const bool swap = key_less(q1, x1, q0, x0) == up;
+                        const double tq = swap ? q1 : q0;
+                        const int tx = swap ? x1 : x0;
+                        q1 = swap ? q0 : q1; x1 = swap ? x0 : x1;
+                        q0 = tq; x0 = tx;
+                    } else {
+                        const int m = j >> 1;
+                        const double oq0 = __shfl_xor_sync(0xffffffffu, q0, m), oq1 = __shfl_xor_sync(0xffffffffu, q1, m);
+                        const int ox0 = __shfl_xor_sync(0xffffffffu, x0, m), ox1 = __shfl_xor_sync(0xffffffffu, x1, m);
+                        const bool keep_min = ((lane & m) == 0) == up;
+                        const bool l0 = key_less(oq0, ox0, q0, x0), l1 = key_less(oq1, ox1, q1, x1);  // other < mine
+                        const bool t0 = (l0 == keep_min), t1 = (l1 == keep_min);                      // take the other
+                        q0 = t0 ? oq0 : q0; x0 = t0 ? ox0 : x0;
+                        q1 = t1 ? oq1 : q1; x1 = t1 ? ox1 : x1;
                     }
-                    __syncwarp();
                 }
             }
+            key[e0] = q0; key[e1] = q1;
+            idx[e0] = (unsigned char)x0; idx[e1] = (unsigned char)x1;
             // deq_chem.py:585-590: cumulative weights -> x in (0, 1]
             const int s0 = idx[e0], s1 = idx[e1];
             const double w0 = e0 < n ? s_gw[s0 / K] * s_gw[s0 % K] : 0.0;
