@@ -193,7 +193,7 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
     need += (size_t)n_lay * pb_align(K * nLW) + (size_t)n_lev * pb_align(K * nVW);
     if (host) need += pb_align(K * nVW);                        // raw [rows][W][K] staging
     need += 2 * pb_align(K * nW) + 2 * pb_align(nW);             // surf, F0PI replicated; wno, dwno
-    need += 4 * pb_align((size_t)K * Gmax * nVW);                // level arrays
+    need += ((a->reflected && a->thermal) ? 8 : 4) * pb_align((size_t)K * Gmax * nVW);  // level arrays
     need += 4 * pb_align(nVW) + 8 * pb_align((size_t)V * 8);     // reduced outputs
     need += pb_align((size_t)(K + G + 16) * 8 * 4);
     PB_TRY(aux_reserve(ctx, need));
@@ -263,12 +263,16 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
         replicate_kernel<<<(W + 255) / 256, 256, 0, ctx->stream>>>(W, K, d_f1, 1.0, d_f0);
         PB_CHECK_LAUNCH(ctx);
     }
-    double *lv[4];
+    // level arrays: the visible half needs [K][1][V][W], the IR half [K][G][V][W]; separate blocks when both run
+    // (they run concurrently)
+    double *lv[4], *lvi[4];
     for (int i = 0; i < 4; ++i) lv[i] = take((size_t)K * Gmax * nVW);
+    for (int i = 0; i < 4; ++i) lvi[i] = (a->reflected && a->thermal) ? take((size_t)K * Gmax * nVW) : lv[i];
     double *o_plus = take(nVW), *o_minus = take(nVW), *o_lay = take((size_t)V * 8), *o_net = take((size_t)V * 8);
     double *o_plus_ir = take(nVW), *o_minus_ir = take(nVW), *o_lay_ir = take((size_t)V * 8), *o_net_ir = take((size_t)V * 8);
     if (off > ctx->aux_cap) return pb_fail(ctx, PB_ERR_NOMEM, "climate: scratch layout overflow (%zu > %zu)", off, ctx->aux_cap);
 
+    if (a->reflected && a->thermal) PB_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));  // staging done
     if (a->reflected) {
         // climate.py:1803-1816: one stream at mu0 = mu1 = 0.5, fluxes only
         pb_reflected_args r;
@@ -289,12 +293,22 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
         climate_visible_reduce<<<V, kRedThreads, 0, ctx->stream>>>(V, W, K, lv[0], lv[1], lv[2], lv[3], d_gw, o_plus,
                                                                    o_minus, o_lay, o_net);
         PB_CHECK_LAUNCH(ctx);
-        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_v, o_plus, nVW, cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_v, o_minus, nVW, cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_v_layer, o_lay, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_v, o_net, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        // the copies back to (pageable) host arrays block the host until the stream gets there: they are issued
+        // further down, after the IR half has been enqueued on the side stream
     }
-    if (a->thermal) {
+    // The visible and the IR halves are independent and each is a handful of small, latency-bound launches
+    // (the level kernels walk nlayer layers three times with ~20 CTAs per gauss point): run the IR half on the
+    // context's side stream, concurrently with the visible half.
+    cudaStream_t main_stream = ctx->stream;
+    const bool overlap = a->reflected && a->thermal;
+    if (overlap) {
+        // everything staged so far (inputs, weights) was enqueued on the main stream before the visible half;
+        // the side stream must see it, so fork from an event recorded BEFORE the visible launches.  The event
+        // was recorded below, right after staging.
+        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+        ctx->stream = ctx->copy_stream;
+    }
+    auto run_thermal = [&]() -> int {
         // climate.py:1887-1892: OG optical depths, W0_no_raman, hard_surface = 0, calc_type = 1
         std::vector<double> tl((size_t)K * V), pl((size_t)K * V);
         for (int k = 0; k < K; ++k)
@@ -315,9 +329,9 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
         t.tlevel = tl.data(); t.plevel = pl.data();
         t.ubar1 = a->ubar1; t.gweight = a->gweight; t.tweight = a->tweight;
         t.hard_surface = 0; t.calc_type = 1;
-        t.flux_minus = lv[0]; t.flux_plus = lv[1]; t.flux_minus_mdpt = lv[2]; t.flux_plus_mdpt = lv[3];
+        t.flux_minus = lvi[0]; t.flux_plus = lvi[1]; t.flux_minus_mdpt = lvi[2]; t.flux_plus_mdpt = lvi[3];
         PB_TRY(pb_thermal_toon_1d(ctx, &t, PB_DEVICE));
-        climate_ir_reduce<<<V, kRedThreads, 0, ctx->stream>>>(V, W, K, G, a->numt, lv[0], lv[1], lv[2], lv[3], d_gw,
+        climate_ir_reduce<<<V, kRedThreads, 0, ctx->stream>>>(V, W, K, G, a->numt, lvi[0], lvi[1], lvi[2], lvi[3], d_gw,
                                                               d_gweight, d_tweight, d_dwno, o_plus_ir, o_minus_ir,
                                                               o_lay_ir, o_net_ir);
         PB_CHECK_LAUNCH(ctx);
@@ -326,7 +340,21 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
         PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_ir_layer, o_lay_ir, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_ir, o_net_ir, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
         // tl / pl are consumed by pb_thermal_toon_1d's packed pinned upload before it returns
+        return PB_OK;
+    };
+    int rc_thermal = PB_OK;
+    if (a->thermal) rc_thermal = run_thermal();
+    if (overlap) ctx->stream = main_stream;  // restored on every path before any return below
+    if (a->reflected) {
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_v, o_plus, nVW, cudaMemcpyDeviceToHost, main_stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_v, o_minus, nVW, cudaMemcpyDeviceToHost, main_stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_v_layer, o_lay, (size_t)V * 8, cudaMemcpyDeviceToHost, main_stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_v, o_net, (size_t)V * 8, cudaMemcpyDeviceToHost, main_stream));
+    }
+    if (overlap) {
+        if (rc_thermal == PB_OK) PB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        else cudaStreamSynchronize(ctx->copy_stream);
     }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return PB_OK;
+    return rc_thermal;
 }
