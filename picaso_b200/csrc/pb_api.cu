@@ -72,6 +72,7 @@ void pb_destroy(pb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->aux) cudaFree(ctx->aux);
     for (auto &sl : ctx->pin) {
@@ -247,20 +248,28 @@ int pb_arena_alloc(pb_ctx *ctx, size_t bytes, void **out)
 
 int pb_pinned_reserve(pb_ctx *ctx, size_t bytes)
 {
-    pb_ctx::PinSlot &sl = ctx->pin[ctx->pin_cur];
-    if (!sl.ev) PB_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
-    if (bytes <= sl.cap) return PB_OK;
-    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // kernels may still read the old device block
-    if (sl.host) PB_CUDA(ctx, cudaFreeHost(sl.host));
-    if (sl.dev) PB_CUDA(ctx, cudaFree(sl.dev));
-    sl.host = sl.dev = nullptr;
-    sl.cap = 0;
+    pb_ctx::PinSlot &cur = ctx->pin[ctx->pin_cur];
+    if (!cur.ev) PB_CUDA(ctx, cudaEventCreateWithFlags(&cur.ev, cudaEventDisableTiming));
+    if (bytes <= cur.cap) return PB_OK;
+    // Grow EVERY slot of the ring now: a caller that needs this much will need it on its next calls too, and
+    // paying cudaHostAlloc once per slot over the first kPinSlots calls made those calls 3-4x slower
+    // (128-atmosphere batches: 3.8 ms instead of 0.65 ms per launch until the ring had turned once).
+    PB_CUDA(ctx, cudaDeviceSynchronize());  // kernels / copies on any stream may still use the old blocks
     const size_t cap = pb_align(bytes * 2, 1 << 16);
-    cudaError_t e = cudaHostAlloc((void **)&sl.host, cap, cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&sl.dev, cap);
-    if (e != cudaSuccess)
-        return pb_fail(ctx, PB_ERR_NOMEM, "pinned slot allocation (%zu bytes) -> %s", cap, cudaGetErrorString(e));
-    sl.cap = cap;
+    for (auto &sl : ctx->pin) {
+        if (sl.cap >= cap) continue;
+        if (!sl.ev) PB_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+        sl.pending = false;
+        if (sl.host) PB_CUDA(ctx, cudaFreeHost(sl.host));
+        if (sl.dev) PB_CUDA(ctx, cudaFree(sl.dev));
+        sl.host = sl.dev = nullptr;
+        sl.cap = 0;
+        cudaError_t e = cudaHostAlloc((void **)&sl.host, cap, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&sl.dev, cap);
+        if (e != cudaSuccess)
+            return pb_fail(ctx, PB_ERR_NOMEM, "pinned slot allocation (%zu bytes) -> %s", cap, cudaGetErrorString(e));
+        sl.cap = cap;
+    }
     return PB_OK;
 }
 
