@@ -14,6 +14,7 @@ from .fluxes_sh_thermal import get_thermal_SH  # noqa: F401
 from .fluxes_3d import get_reflected_3d, get_thermal_3d  # noqa: F401
 from .optics import DeviceArray, DeviceOpacities, compute_opacity  # noqa: F401
 from .optics_ck import DeviceCKs, DeviceGasCKs  # noqa: F401
+from .opacity_db import opannection, read_opacity_db  # noqa: F401
 from .climate import get_fluxes  # noqa: F401
 from .regrid import mean_regrid, RegridPlan  # noqa: F401
 from .batch import thermal_batch  # noqa: F401
