@@ -75,6 +75,7 @@ void pb_destroy(pb_ctx *ctx)
     cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->aux) cudaFree(ctx->aux);
+    if (ctx->rec) cudaFree(ctx->rec);
     for (auto &sl : ctx->pin) {
         if (sl.host) cudaFreeHost(sl.host);
         if (sl.dev) cudaFree(sl.dev);

@@ -32,6 +32,9 @@ struct pb_ctx {
     // second grow-only block for entry points that call other entry points (climate.cu): survives arena resets
     char *aux = nullptr;
     size_t aux_cap = 0;
+    // per-layer records of the level-flux kernels (toon_thermal.cu: therm_layer_records_kernel)
+    char *rec = nullptr;
+    size_t rec_cap = 0;
     // grow-only pinned bounce buffer for small host vectors (geometry) so that their
     // H2D copies are truly asynchronous
     // H2D copies are truly asynchronous and ONE copy per API call carries all of them.  A ring

@@ -620,6 +620,177 @@ __global__ void __launch_bounds__(256) therm_levels_kernel(ThermParams p)
     if (p.ftop) p.ftop[((int64_t)b * p.G + a) * p.W + w] = p.fpm[oo];
 }
 
+// ---------------------------------------------------------------------------------------
+// Level fluxes with precomputed layer records.  therm_levels_kernel is pure single-warp latency when the
+// wavelength axis is short (climate solver: 661 waves x 8 gauss points = 166 warps on 148 SMs, 270 serial
+// layer steps of ~300 dependent instructions: sqrt, 6 exponentials, 6 divisions, Planck).  Everything that
+// does not depend on the solution is therefore evaluated first by a fully parallel kernel (one thread per
+// (atmosphere, layer, wavelength[, angle])) into a record array in HBM, with exactly the expressions of the
+// one-kernel version (bit-identical results); the three serial sweeps then only load, multiply and add.
+// ---------------------------------------------------------------------------------------
+enum { LR_LAM = 0, LR_GAM, LR_Q, LR_B0, LR_B1, LR_EP, LR_EM, LR_EPH, LR_EMH, LR_DT, LR_N };
+
+__global__ void __launch_bounds__(128) therm_layer_records_kernel(ThermParams p, double *rec /* [B][L][LR_N][W] */,
+                                                                  double *xrec /* [B][G][L][2][W] */)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y, b = blockIdx.z;
+    if (w >= p.W) return;
+    const int L = p.L, V = L + 1;
+    const double *tl = p.tlevel + (int64_t)b * V;
+    Planck planck;
+    planck.init(p.calc_type, p.wno[w], p.dwno ? p.dwno[w] : 0.0);
+    const int64_t il = (int64_t)b * p.bs_layer + (int64_t)l * p.ld + w;
+    const double dt = p.dtau[il];
+    TLayer t;
+    thermal_layer(dt, p.w0[il], p.cosb[il], planck(tl[l]), planck(tl[l + 1]), t);
+    double *r = rec + (((int64_t)b * L + l) * LR_N) * p.W + w;
+    r[LR_LAM * (int64_t)p.W] = t.lam; r[LR_GAM * (int64_t)p.W] = t.gam; r[LR_Q * (int64_t)p.W] = t.q;
+    r[LR_B0 * (int64_t)p.W] = t.b0; r[LR_B1 * (int64_t)p.W] = t.b1;
+    r[LR_EP * (int64_t)p.W] = t.EP; r[LR_EM * (int64_t)p.W] = t.EM;
+    const double EPh = exp(0.5 * t.E);
+    r[LR_EPH * (int64_t)p.W] = EPh; r[LR_EMH * (int64_t)p.W] = 1 / EPh;
+    r[LR_DT * (int64_t)p.W] = dt;
+    for (int a = 0; a < p.G; ++a) {
+        const double u = p.ubar1[a];
+        double *x = xrec + ((((int64_t)b * p.G + a) * L + l) * 2) * p.W + w;
+        x[0] = exp(-dt / u);
+        x[p.W] = exp(-0.5 * dt / u);
+    }
+}
+
+// same three sweeps as therm_levels_kernel, fed from the records
+__global__ void __launch_bounds__(256) therm_levels_rec_kernel(ThermParams p, const double *__restrict__ rec,
+                                                               const double *__restrict__ xrec)
+{
+    const int lane = threadIdx.x;
+    const int w = blockIdx.x * kWavesPerCta + lane;
+    const int a = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    if (w >= p.W || a >= p.G) return;
+    const int L = p.L, V = p.L + 1;
+    const int64_t W = p.W;
+    const int64_t oo = (((int64_t)b * p.G + a) * V) * W + w;
+    const double *tl = p.tlevel + (int64_t)b * V;
+    const double *pl = p.plevel + (int64_t)b * V;
+    const double u = p.ubar1[a];
+    const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + w] : 0.0;
+    const double *R = rec + ((int64_t)b * L * LR_N) * W + w;           // + (l * LR_N + field) * W
+    const double *X = xrec + ((((int64_t)b * p.G + a) * L) * 2) * W + w;  // + (l * 2 + {0,1}) * W
+    Planck planck;
+    planck.init(p.calc_type, p.wno[w], p.dwno ? p.dwno[w] : 0.0);
+    const double tp = 2 * PB_PI * kMu1;
+
+    // ---- sweep 1: bottom-up elimination ----
+    double AS = 0.0, DS = 0.0, gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
+    const double BL = planck(tl[L]);
+    double b1_last = 0.0;
+    for (int l = L - 1; l >= 0; --l) {
+        const double *q = R + (int64_t)l * LR_N * W;
+        const double gam = q[LR_GAM * W], qq = q[LR_Q * W], b0 = q[LR_B0 * W], b1 = q[LR_B1 * W];
+        const double EP = q[LR_EP * W], EM = q[LR_EM * W], dt = q[LR_DT * W];
+        // thermal_layer(): fluxes.py:1772-1789
+        const double cpu = tp * (b0 + b1 * qq), cmu = tp * (b0 - b1 * qq);
+        const double cpd = tp * (b0 + b1 * dt + b1 * qq), cmd = tp * (b0 + b1 * dt - b1 * qq);
+        const double e1 = EP + gam * EM, e2 = EP - gam * EM, e3 = gam * EP + EM, e4 = gam * EP - EM;
+        if (l == L - 1) {
+            b1_last = b1;
+            const double b_surface = p.hard_surface ? (1.0 - r) * BL * PB_PI : (BL + b1 * kMu1) * PB_PI;
+            const double a_ = e1 - r * e3, b_ = e2 - r * e4;
+            const double d_ = b_surface - cpd + r * cmd;
+            AS = a_ / b_;
+            DS = d_ / b_;
+        } else {
+            double a_ = 2.0 * (1.0 - gam * gam);
+            double b_ = (e1 - e3) * (gam_n + 1.0);
+            double c_ = (e1 + e3) * (gam_n - 1.0);
+            double d_ = e3 * (cpu_n - cpd) + e1 * (cmd - cmu_n);
+            double xi = 1.0 / (b_ - c_ * AS);
+            const double ASe = a_ * xi, DSe = (d_ - c_ * DS) * xi;
+            const int64_t o1 = oo + (int64_t)(l + 1) * W;
+            p.fm[o1] = ASe;
+            p.fp[o1] = DSe;
+            a_ = (e1 + e3) * (gam_n - 1.0);
+            b_ = (e2 + e4) * (gam_n - 1.0);
+            c_ = 2.0 * (1.0 - gam_n * gam_n);
+            d_ = (gam_n - 1.0) * (cpu_n - cpd) + (1.0 - gam_n) * (cmd - cmu_n);
+            xi = 1.0 / (b_ - c_ * ASe);
+            AS = a_ * xi;
+            DS = (d_ - c_ * DSe) * xi;
+        }
+        const int64_t o0 = oo + (int64_t)l * W;
+        p.fmm[o0] = AS;
+        p.fpm[o0] = DS;
+        gam_n = gam;
+        cpu_n = cpu;
+        cmu_n = cmu;
+    }
+    const double B0 = R[LR_B0 * W];  // b0 of layer 0 = Planck at level 0
+    const double tau_top = R[LR_DT * W] * pl[0] / (pl[1] - pl[0]);
+    {
+        const double b_top = (1.0 - exp(-tau_top / kMu1)) * B0 * PB_PI;
+        const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = b_top - cmu_n;
+        const double xi = 1.0 / (b_ - c_ * AS);
+        p.fm[oo] = 0.0;
+        p.fp[oo] = (d_ - c_ * DS) * xi;
+    }
+    // ---- sweep 2: top-down substitution + downward recurrence (fluxes.py:1875-1893) ----
+    double Xprev = 0.0;
+    double fminus = (1 - exp(-tau_top / u)) * B0 * 2 * PB_PI;
+    for (int l = 0; l < L; ++l) {
+        const double *q = R + (int64_t)l * LR_N * W;
+        const int64_t o0 = oo + (int64_t)l * W;
+        const double X0 = p.fp[o0] - p.fm[o0] * Xprev;
+        const double X1 = p.fpm[o0] - p.fmm[o0] * X0;
+        Xprev = X1;
+        const double pos = X0 + X1, neg = X0 - X1;
+        const double lam = q[LR_LAM * W], gam = q[LR_GAM * W], qq = q[LR_Q * W], b0 = q[LR_B0 * W], b1 = q[LR_B1 * W];
+        const double EP = q[LR_EP * W], EM = q[LR_EM * W], EPh = q[LR_EPH * W], EMh = q[LR_EMH * W], dt = q[LR_DT * W];
+        const double xa = X[(int64_t)l * 2 * W], xh = X[((int64_t)l * 2 + 1) * W];
+        const double J = gam * (lam + 1 / kMu1) * pos;
+        const double K = (1 / kMu1 - lam) * neg;
+        const double si1 = 2 * PB_PI * (b0 - b1 * (qq - kMu1));
+        const double si2 = 2 * PB_PI * b1;
+        const double lu = lam * u;
+        const double fnext = fminus * xa + (J / (lu + 1.0)) * (EP - xa) + (K / (lu - 1.0)) * (xa - EM) + si1 * (1. - xa) +
+                             si2 * (u * xa + dt - u);
+        const double fmid = fminus * xh + (J / (lu + 1.0)) * (EPh - xh) + (K / (-lu + 1.0)) * (EMh - xh) + si1 * (1. - xh) +
+                            si2 * (u * xh + 0.5 * dt - u);
+        p.fm[o0] = fminus;
+        p.fmm[o0] = fmid;
+        p.fp[o0] = pos;   // parked for sweep 3
+        p.fpm[o0] = neg;
+        fminus = fnext;
+    }
+    const int64_t oL = oo + (int64_t)L * W;
+    p.fm[oL] = fminus;
+    p.fmm[oL] = 0.0;
+    // ---- sweep 3: bottom-up upward recurrence (fluxes.py:1897-1907) ----
+    double fplus = p.hard_surface ? (1.0 - r) * BL * 2 * PB_PI : (BL + b1_last * u) * 2 * PB_PI;
+    p.fp[oL] = fplus;
+    p.fpm[oL] = 0.0;
+    for (int l = L - 1; l >= 0; --l) {
+        const double *q = R + (int64_t)l * LR_N * W;
+        const int64_t o0 = oo + (int64_t)l * W;
+        const double pos = p.fp[o0], neg = p.fpm[o0];
+        const double lam = q[LR_LAM * W], gam = q[LR_GAM * W], qq = q[LR_Q * W], b0 = q[LR_B0 * W], b1 = q[LR_B1 * W];
+        const double EP = q[LR_EP * W], EM = q[LR_EM * W], EPh = q[LR_EPH * W], EMh = q[LR_EMH * W], dt = q[LR_DT * W];
+        const double xa = X[(int64_t)l * 2 * W], xh = X[((int64_t)l * 2 + 1) * W];
+        const double Gt = (1 / kMu1 - lam) * pos;
+        const double Ht = gam * (lam + 1 / kMu1) * neg;
+        const double al1 = 2 * PB_PI * (b0 + b1 * (qq - kMu1));
+        const double al2 = 2 * PB_PI * b1;
+        const double lu = lam * u;
+        const double fmid = fplus * xh + (Gt / (lu - 1.0)) * (EP * xh - EPh) - (Ht / (lu + 1.0)) * (EM * xh - EMh) +
+                            al1 * (1. - xh) + al2 * (u + 0.5 * dt - (dt + u) * xh);
+        fplus = fplus * xa + (Gt / (lu - 1.0)) * (EP * xa - 1.0) + (Ht / (lu + 1.0)) * (1.0 - EM * xa) + al1 * (1. - xa) +
+                al2 * (u - (dt + u) * xa);
+        p.fp[o0] = fplus;
+        p.fpm[o0] = fmid;
+    }
+    if (p.ftop) p.ftop[((int64_t)b * p.G + a) * W + w] = p.fpm[oo];
+}
+
 __global__ void compress_thermal_kernel(int64_t n, int G, int nt, const double *flux,
                                         const double *gweight, const double *tweight, double *out)
 {
@@ -721,8 +892,33 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
     if (force && force[0] == 'w' && !want_lvl && a->variant == 0 && G <= 8 && (!a->thermal || fuse)) use_wave_kernel = true;
     if (want_lvl) {
         p.fm = d_lv[0]; p.fp = d_lv[1]; p.fmm = d_lv[2]; p.fpm = d_lv[3];
-        therm_levels_kernel<<<grid, block, 0, ctx->stream>>>(p);
-        PB_CHECK_LAUNCH(ctx);
+        // Short wavelength axes (the climate solver) are serial-latency bound: precompute the layer records with
+        // a fully parallel kernel when the launch cannot fill the machine anyway.  PB_THERM_LEVELS=rec|fused forces.
+        const size_t rec_bytes = ((size_t)B * L * LR_N + (size_t)B * G * L * 2) * nW;
+        const char *lf = getenv("PB_THERM_LEVELS");
+        bool use_rec = (long)W * B * G <= 64L * 1024 && rec_bytes <= ((size_t)1 << 31);
+        if (lf && lf[0] == 'r' && rec_bytes <= ((size_t)1 << 31)) use_rec = true;
+        if (lf && lf[0] == 'f') use_rec = false;
+        if (use_rec) {
+            if (rec_bytes > ctx->rec_cap) {
+                PB_CUDA(ctx, cudaDeviceSynchronize());
+                if (ctx->rec) PB_CUDA(ctx, cudaFree(ctx->rec));
+                ctx->rec = nullptr; ctx->rec_cap = 0;
+                const size_t cap = pb_align(rec_bytes + rec_bytes / 8, 1 << 20);
+                cudaError_t e = cudaMalloc((void **)&ctx->rec, cap);
+                if (e != cudaSuccess) return pb_fail(ctx, PB_ERR_NOMEM, "thermal: layer-record cudaMalloc(%zu) -> %s", cap, cudaGetErrorString(e));
+                ctx->rec_cap = cap;
+            }
+            double *rec = (double *)ctx->rec, *xrec = rec + (size_t)B * L * LR_N * W;
+            dim3 g1((W + 127) / 128, L, B);
+            therm_layer_records_kernel<<<g1, 128, 0, ctx->stream>>>(p, rec, xrec);
+            PB_CHECK_LAUNCH(ctx);
+            therm_levels_rec_kernel<<<grid, block, 0, ctx->stream>>>(p, rec, xrec);
+            PB_CHECK_LAUNCH(ctx);
+        } else {
+            therm_levels_kernel<<<grid, block, 0, ctx->stream>>>(p);
+            PB_CHECK_LAUNCH(ctx);
+        }
     } else if (use_wave_kernel) {
         p.fuse = fuse ? 1 : 0;
         switch (G) {
