@@ -347,9 +347,9 @@ typedef struct pb_climate_args {
     double frac_a, frac_b, frac_c, constant_back, constant_forward;
     /* outputs; the reference broadcasts the visible ones over (ng, nt): here one copy */
     double *flux_net_v_layer, *flux_net_v;   /* [nlevel] */
-    double *flux_plus_v, *flux_minus_v;      /* [nlevel][nwno] */
+    double *flux_plus_v, *flux_minus_v;      /* [nlevel][nwno], or NULL: not copied back */
     double *flux_net_ir_layer, *flux_net_ir; /* [nlevel] */
-    double *flux_plus_ir, *flux_minus_ir;    /* [nlevel][nwno] */
+    double *flux_plus_ir, *flux_minus_ir;    /* [nlevel][nwno], or NULL: not copied back */
 } pb_climate_args;
 
 int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *args, int memspace);

@@ -41,7 +41,7 @@ def _as3(a):
     return np.ascontiguousarray(a)
 
 
-def _one_column(ctx, Atmosphere, wed, noed, ScatteringPhase, Disco, Opagrid, F0PI, reflected, thermal):
+def _one_column(ctx, Atmosphere, wed, noed, ScatteringPhase, Disco, Opagrid, F0PI, reflected, thermal, full_arrays=True):
     nlevel = int(Atmosphere.nlevel)
     nlayer = nlevel - 1
     nwno = int(Opagrid.nwno)
@@ -98,10 +98,9 @@ def _one_column(ctx, Atmosphere, wed, noed, ScatteringPhase, Disco, Opagrid, F0P
     a.frac_a, a.frac_b, a.frac_c = (float(ScatteringPhase.frac_a), float(ScatteringPhase.frac_b),
                                     float(ScatteringPhase.frac_c))
     a.constant_back, a.constant_forward = float(ScatteringPhase.constant_back), float(ScatteringPhase.constant_forward)
-    out = dict(flux_net_v_layer=np.zeros(nlevel), flux_net_v=np.zeros(nlevel),
-               flux_plus_v=np.zeros((nlevel, nwno)), flux_minus_v=np.zeros((nlevel, nwno)),
-               flux_net_ir_layer=np.zeros(nlevel), flux_net_ir=np.zeros(nlevel),
-               flux_plus_ir=np.zeros((nlevel, nwno)), flux_minus_ir=np.zeros((nlevel, nwno)))
+    big = (lambda: np.zeros((nlevel, nwno))) if full_arrays else (lambda: None)
+    out = dict(flux_net_v_layer=np.zeros(nlevel), flux_net_v=np.zeros(nlevel), flux_plus_v=big(), flux_minus_v=big(),
+               flux_net_ir_layer=np.zeros(nlevel), flux_net_ir=np.zeros(nlevel), flux_plus_ir=big(), flux_minus_ir=big())
     for k, v in out.items():
         setattr(a, k, addr(v))
     ctx.check(ctx.lib.pb_climate_get_fluxes(ctx.h, ctypes.byref(a), memspace))
@@ -110,22 +109,30 @@ def _one_column(ctx, Atmosphere, wed, noed, ScatteringPhase, Disco, Opagrid, F0P
 
 
 def get_fluxes(Atmosphere, OpacityWEd, OpacityNoEd, ScatteringPhase, Disco, Opagrid, F0PI, reflected, thermal,
-               do_holes=False, fhole=0.0, hole_OpacityWEd=None, hole_OpacityNoEd=None, *, ctx=None):
-    """picaso.climate.get_fluxes (climate.py:1686-1952) on the device.  Same arguments, same 8-tuple."""
+               do_holes=False, fhole=0.0, hole_OpacityWEd=None, hole_OpacityNoEd=None, *, ctx=None, full_arrays=True):
+    """picaso.climate.get_fluxes (climate.py:1686-1952) on the device.  Same arguments, same 8-tuple.
+    full_arrays=False (extension): the four [.., nlevel, nwno] arrays are not copied back (None in the tuple) -
+    the solver's Newton / Jacobian iterations only consume the four net-flux vectors."""
     ctx = ctx or _lib.default_context()
     out = _one_column(ctx, Atmosphere, OpacityWEd, OpacityNoEd, ScatteringPhase, Disco, Opagrid, F0PI,
-                      reflected, thermal)
+                      reflected, thermal, full_arrays)
     if do_holes:
         # climate.py:1822-1837, :1894-1909: the level arrays of the clear column are mixed in with weight
         # fhole before every (linear) reduction, i.e. the outputs mix with the same weights
         clr = _one_column(ctx, Atmosphere, hole_OpacityWEd, hole_OpacityNoEd, ScatteringPhase, Disco, Opagrid,
-                          F0PI, reflected, thermal)
+                          F0PI, reflected, thermal, full_arrays)
         for k in out:
-            out[k] = (1.0 - fhole) * out[k] + fhole * clr[k]
+            if out[k] is not None:
+                out[k] = (1.0 - fhole) * out[k] + fhole * clr[k]
     ng, nt = int(Disco.ng), int(Disco.nt)
     nlevel, nwno = int(Atmosphere.nlevel), int(Opagrid.nwno)
     # the visible arrays are [ng, nt, ...] in the reference; the single mu = 0.5 stream is broadcast (climate.py:1757-1761)
-    bc = lambda x, shape: np.ascontiguousarray(np.broadcast_to(x, shape))
+    def bc(x, shape):
+        if x is None:
+            return None
+        if ng * nt == 1:
+            return x.reshape(shape)  # no copy
+        return np.ascontiguousarray(np.broadcast_to(x, shape))
     return (bc(out["flux_net_v_layer"], (ng, nt, nlevel)), bc(out["flux_net_v"], (ng, nt, nlevel)),
             bc(out["flux_plus_v"], (ng, nt, nlevel, nwno)), bc(out["flux_minus_v"], (ng, nt, nlevel, nwno)),
             out["flux_net_ir_layer"], out["flux_net_ir"], out["flux_plus_ir"], out["flux_minus_ir"])

@@ -169,14 +169,14 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
         if (!a->DTAU || !a->TAU || !a->W0 || !a->COSB || !a->GCOS2 || !a->ftau_cld || !a->ftau_ray ||
             !a->DTAU_OG || !a->TAU_OG || !a->W0_OG || !a->COSB_OG)
             return pb_fail(ctx, PB_ERR_ARG, "climate: reflected needs the 11 opacity arrays");
-        if (!a->flux_net_v_layer || !a->flux_net_v || !a->flux_plus_v || !a->flux_minus_v)
+        if (!a->flux_net_v_layer || !a->flux_net_v)
             return pb_fail(ctx, PB_ERR_ARG, "climate: reflected outputs missing");
     }
     if (a->thermal) {
         if (!a->DTAU_OG || !a->W0_no_raman || !a->COSB_OG || !a->tlevel || !a->plevel || !a->wno || !a->dwno ||
             !a->ubar1 || !a->gweight || !a->tweight)
             return pb_fail(ctx, PB_ERR_ARG, "climate: thermal needs DTAU_OG, W0_no_raman, COSB_OG, tlevel, plevel, wno, dwno, ubar1, gweight, tweight");
-        if (!a->flux_net_ir_layer || !a->flux_net_ir || !a->flux_plus_ir || !a->flux_minus_ir)
+        if (!a->flux_net_ir_layer || !a->flux_net_ir)
             return pb_fail(ctx, PB_ERR_ARG, "climate: thermal outputs missing");
     }
     if (!a->reflected && !a->thermal) return PB_OK;
@@ -223,15 +223,13 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
         *dst = d;
         return PB_OK;
     };
+    // O(K), O(G), O(W) vectors are host pointers in both memory spaces: they travel in ONE packed asynchronous
+    // copy through the context's pinned ring (pageable cudaMemcpyAsync calls would each block the host)
+    pb_arena_reset(ctx);  // next pinned slot
+    PB_TRY(pb_pinned_reserve(ctx, (size_t)(K + 4 * (size_t)W + a->numg + a->numt + 64) * sizeof(double) + 16 * 64));
     auto small_to_dev = [&](const double *src, size_t n, const double **dst) -> int {
-        // O(K), O(G), O(W) vectors: host pointers in both memory spaces (pageable copy is synchronous
-        // with respect to the host buffer)
-        double *d = take(n * sizeof(double));
-        PB_CUDA(ctx, cudaMemcpyAsync(d, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        *dst = d;
-        return PB_OK;
+        return pb_upload_small(ctx, src, n, dst);
     };
-
     const double *d_dtau = nullptr, *d_tau = nullptr, *d_w0 = nullptr, *d_cosb = nullptr, *d_gcos2 = nullptr,
                  *d_fcld = nullptr, *d_fray = nullptr, *d_dtau_og = nullptr, *d_tau_og = nullptr, *d_w0_og = nullptr,
                  *d_cosb_og = nullptr, *d_w0nr = nullptr;
@@ -250,14 +248,21 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
     PB_TRY(stage(a->COSB_OG, L, &d_cosb_og));
     if (a->thermal) PB_TRY(stage(a->W0_no_raman, L, &d_w0nr));
 
-    const double *d_gw = nullptr;
+    const double *d_gw = nullptr, *d_wno = nullptr, *d_dwno = nullptr, *d_gweight = nullptr, *d_tweight = nullptr;
     PB_TRY(small_to_dev(a->gauss_wts, K, &d_gw));
+    if (a->thermal) {
+        PB_TRY(small_to_dev(a->wno, W, &d_wno));
+        PB_TRY(small_to_dev(a->dwno, W, &d_dwno));
+        PB_TRY(small_to_dev(a->gweight, a->numg, &d_gweight));
+        PB_TRY(small_to_dev(a->tweight, a->numt, &d_tweight));
+    }
     double *d_surf = take(K * nW), *d_f0 = take(K * nW);
     {
         // per-wave vectors are host pointers (they come from the solver's tuples), shared by all gauss points
         const double *d_s1 = nullptr, *d_f1 = nullptr;
         if (a->surf_reflect) PB_TRY(small_to_dev(a->surf_reflect, W, &d_s1));
         if (a->F0PI) PB_TRY(small_to_dev(a->F0PI, W, &d_f1));
+        PB_TRY(pb_upload_flush(ctx));
         replicate_kernel<<<(W + 255) / 256, 256, 0, ctx->stream>>>(W, K, d_s1, 0.0, d_surf);
         PB_CHECK_LAUNCH(ctx);
         replicate_kernel<<<(W + 255) / 256, 256, 0, ctx->stream>>>(W, K, d_f1, 1.0, d_f0);
@@ -316,11 +321,6 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
                 tl[(size_t)k * V + v] = a->tlevel[v];
                 pl[(size_t)k * V + v] = a->plevel[v];
             }
-        const double *d_wno = nullptr, *d_dwno = nullptr, *d_gweight = nullptr, *d_tweight = nullptr;
-        PB_TRY(small_to_dev(a->wno, W, &d_wno));
-        PB_TRY(small_to_dev(a->dwno, W, &d_dwno));
-        PB_TRY(small_to_dev(a->gweight, a->numg, &d_gweight));
-        PB_TRY(small_to_dev(a->tweight, a->numt, &d_tweight));
         pb_thermal_args t;
         memset(&t, 0, sizeof(t));
         t.nlayer = L; t.nwno = W; t.numg = a->numg; t.numt = a->numt; t.nbatch = K; t.ld = W;
@@ -335,8 +335,8 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
                                                               d_gweight, d_tweight, d_dwno, o_plus_ir, o_minus_ir,
                                                               o_lay_ir, o_net_ir);
         PB_CHECK_LAUNCH(ctx);
-        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_ir, o_plus_ir, nVW, cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_ir, o_minus_ir, nVW, cudaMemcpyDeviceToHost, ctx->stream));
+        if (a->flux_plus_ir) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_ir, o_plus_ir, nVW, cudaMemcpyDeviceToHost, ctx->stream));
+        if (a->flux_minus_ir) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_ir, o_minus_ir, nVW, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_ir_layer, o_lay_ir, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_ir, o_net_ir, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
         // tl / pl are consumed by pb_thermal_toon_1d's packed pinned upload before it returns
@@ -346,8 +346,8 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
     if (a->thermal) rc_thermal = run_thermal();
     if (overlap) ctx->stream = main_stream;  // restored on every path before any return below
     if (a->reflected) {
-        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_v, o_plus, nVW, cudaMemcpyDeviceToHost, main_stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_v, o_minus, nVW, cudaMemcpyDeviceToHost, main_stream));
+        if (a->flux_plus_v) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_v, o_plus, nVW, cudaMemcpyDeviceToHost, main_stream));
+        if (a->flux_minus_v) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_v, o_minus, nVW, cudaMemcpyDeviceToHost, main_stream));
         PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_v_layer, o_lay, (size_t)V * 8, cudaMemcpyDeviceToHost, main_stream));
         PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_v, o_net, (size_t)V * 8, cudaMemcpyDeviceToHost, main_stream));
     }

@@ -76,6 +76,7 @@ void pb_destroy(pb_ctx *ctx)
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->rec) cudaFree(ctx->rec);
+    if (ctx->rec2) cudaFree(ctx->rec2);
     for (auto &sl : ctx->pin) {
         if (sl.host) cudaFreeHost(sl.host);
         if (sl.dev) cudaFree(sl.dev);

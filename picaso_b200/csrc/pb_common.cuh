@@ -35,6 +35,8 @@ struct pb_ctx {
     // per-layer records of the level-flux kernels (toon_thermal.cu: therm_layer_records_kernel)
     char *rec = nullptr;
     size_t rec_cap = 0;
+    char *rec2 = nullptr;   // toon_reflected.cu: refl_layer_records_kernel
+    size_t rec2_cap = 0;
     // grow-only pinned bounce buffer for small host vectors (geometry) so that their
     // H2D copies are truly asynchronous
     // H2D copies are truly asynchronous and ONE copy per API call carries all of them.  A ring

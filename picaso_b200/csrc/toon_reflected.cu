@@ -534,6 +534,155 @@ __global__ void __launch_bounds__(256) refl_levels_kernel(ReflParams p)
     p.fpm[oL] = 0.0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Level fluxes with precomputed layer records (same idea as therm_levels_rec_kernel in toon_thermal.cu):
+// for short wavelength axes refl_levels_kernel is serial-latency bound (sqrt, 5 exponentials and 6 divisions
+// per layer step in each of its two sweeps).  A fully parallel kernel evaluates everything that does not
+// depend on the solution - with the expressions of the one-kernel version - into a record array; the serial
+// sweeps then only load, multiply and add (the top-down sweep's true dependency is two FMAs per layer).
+// ---------------------------------------------------------------------------------------
+enum { RR_GAM = 0, RR_AM, RR_AP, RR_XU, RR_EP, RR_EM, RR_EPM, RR_EMM, RR_XM, RR_N };
+
+__global__ void __launch_bounds__(128) refl_layer_records_kernel(ReflParams p, double *rec /* [B][G][L][RR_N][W] */)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    const int ba = blockIdx.z, b = ba / p.G, a = ba - b * p.G;
+    if (w >= p.W) return;
+    const int64_t ld = p.ld;
+    const int64_t il = (int64_t)b * p.bs_layer + (int64_t)l * ld + w;
+    const int64_t iv = (int64_t)b * p.bs_level + (int64_t)l * ld + w;
+    const double u0 = p.ubar0[a];
+    const double f0 = p.f0pi ? p.f0pi[(int64_t)b * p.bs_wave + w] : 1.0;
+    const double inv_u0 = 1.0 / u0;
+    const double om = p.w0[il];
+    const double g = p.fcld[il] * p.cosb[il];
+    const double dt = p.dtau[il];
+    double g1, g2;
+    toon_g(p.tc, om, g, g1, g2);
+    const double lam = sqrt(g1 * g1 - g2 * g2);
+    const double gam = (g1 - lam) / g2;
+    const double g3 = toon_g3(p.tc, g, u0), g4 = 1.0 - g3;
+    const double den = lam * lam - 1.0 / (u0 * u0);
+    const double am = f0 * om * (g4 * (g1 + inv_u0) + g2 * g3) / den;
+    const double ap = f0 * om * (g3 * (g1 - inv_u0) + g2 * g4) / den;
+    const double tl = p.tau[iv];
+    const double xu = exp(-tl / u0);
+    const double E = fmin(lam * dt, 35.0);
+    const double EP = exp(E), EM = 1.0 / EP;
+    const double EPm = exp(0.5 * E), EMm = 1.0 / EPm;
+    const double taumid = tl + 0.5 * dt;
+    const double xm = exp(-taumid / u0);
+    const int64_t W = p.W;
+    double *r = rec + (((int64_t)ba * p.L + l) * RR_N) * W + w;
+    r[RR_GAM * W] = gam; r[RR_AM * W] = am; r[RR_AP * W] = ap; r[RR_XU * W] = xu;
+    r[RR_EP * W] = EP; r[RR_EM * W] = EM; r[RR_EPM * W] = EPm; r[RR_EMM * W] = EMm; r[RR_XM * W] = xm;
+}
+
+__global__ void __launch_bounds__(256) refl_levels_rec_kernel(ReflParams p, const double *__restrict__ rec)
+{
+    const int lane = threadIdx.x;
+    const int w = blockIdx.x * kWavesPerCta + lane;
+    const int a = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    if (w >= p.W || a >= p.G) return;
+    const int L = p.L, V = p.L + 1;
+    const int64_t W = p.W, ld = p.ld;
+    const int64_t ov = (int64_t)b * p.bs_level + w;
+    const int64_t ow = (int64_t)b * p.bs_wave + w;
+    const int64_t oo = (((int64_t)b * p.G + a) * V) * W + w;  // output offset of level 0
+    const double u0 = p.ubar0[a];
+    const double f0 = p.f0pi ? p.f0pi[ow] : 1.0;
+    const double r = p.surf ? p.surf[ow] : 0.0;
+    const double btop = p.btop ? p.btop[ow] : 0.0;
+    const double *R = rec + (((int64_t)b * p.G + a) * L * RR_N) * W + w;  // + (l * RR_N + field) * W
+
+    double AS = 0.0, DS = 0.0, gam_n = 0.0, cpu_n = 0.0, cmu_n = 0.0;
+    const double xdn = exp(-p.tau[ov + (int64_t)L * ld] / u0);
+    double xd = xdn;
+    const double b_surface = 0.0 + r * u0 * f0 * xd;
+    for (int l = L - 1; l >= 0; --l) {
+        const double *q = R + (int64_t)l * RR_N * W;
+        const double gam = q[RR_GAM * W], am = q[RR_AM * W], ap = q[RR_AP * W], xu = q[RR_XU * W];
+        const double EP = q[RR_EP * W], EM = q[RR_EM * W];
+        const double cmu = am * xu, cpu = ap * xu, cmd = am * xd, cpd = ap * xd;
+        const double e1 = EP + gam * EM, e2 = EP - gam * EM;
+        const double e3 = gam * EP + EM, e4 = gam * EP - EM;
+        double ASe = 0.0, DSe = 0.0;
+        if (l == L - 1) {
+            const double a_ = e1 - r * e3, b_ = e2 - r * e4;
+            const double d_ = b_surface - cpd + r * cmd;
+            AS = a_ / b_;
+            DS = d_ / b_;
+        } else {
+            double a_ = 2.0 * (1.0 - gam * gam);
+            double b_ = (e1 - e3) * (gam_n + 1.0);
+            double c_ = (e1 + e3) * (gam_n - 1.0);
+            double d_ = e3 * (cpu_n - cpd) + e1 * (cmd - cmu_n);
+            double x = 1.0 / (b_ - c_ * AS);
+            ASe = a_ * x;
+            DSe = (d_ - c_ * DS) * x;
+            const int64_t o1 = oo + (int64_t)(l + 1) * W;
+            p.fm[o1] = ASe;
+            p.fp[o1] = DSe;
+            a_ = (e1 + e3) * (gam_n - 1.0);
+            b_ = (e2 + e4) * (gam_n - 1.0);
+            c_ = 2.0 * (1.0 - gam_n * gam_n);
+            d_ = (gam_n - 1.0) * (cpu_n - cpd) + (1.0 - gam_n) * (cmd - cmu_n);
+            x = 1.0 / (b_ - c_ * ASe);
+            AS = a_ * x;
+            DS = (d_ - c_ * DSe) * x;
+        }
+        const int64_t o0 = oo + (int64_t)l * W;
+        p.fmm[o0] = AS;
+        p.fpm[o0] = DS;
+        gam_n = gam;
+        cpu_n = cpu;
+        cmu_n = cmu;
+        xd = xu;
+    }
+    {
+        const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = btop - cmu_n;
+        const double x = 1.0 / (b_ - c_ * AS);
+        p.fm[oo] = 0.0;
+        p.fp[oo] = (d_ - c_ * DS) * x;
+    }
+    double Xprev = 0.0;
+    double fm_last = 0.0, fp_last = 0.0;
+    for (int l = 0; l < L; ++l) {
+        const double *q = R + (int64_t)l * RR_N * W;
+        const int64_t o0 = oo + (int64_t)l * W;
+        const double X0 = p.fp[o0] - p.fm[o0] * Xprev;
+        const double X1 = p.fpm[o0] - p.fmm[o0] * X0;
+        Xprev = X1;
+        const double pos = X0 + X1, neg = X0 - X1;
+        const double gam = q[RR_GAM * W], am = q[RR_AM * W], ap = q[RR_AP * W], xu = q[RR_XU * W];
+        const double EPm = q[RR_EPM * W], EMm = q[RR_EMM * W], xm = q[RR_XM * W];
+        // level l, fluxes.py:1227-1236
+        double fm = pos * gam + neg + am * xu;
+        const double fp = pos + gam * neg + ap * xu;
+        fm = fm + u0 * f0 * xu;
+        // midpoint, fluxes.py:1239-1251
+        double fmm = gam * pos * EPm + neg * EMm + am * xm;
+        const double fpm = pos * EPm + gam * neg * EMm + ap * xm;
+        fmm = fmm + u0 * f0 * xm;
+        if (l == L - 1) {
+            const double EP = q[RR_EP * W], EM = q[RR_EM * W];
+            fm_last = gam * pos * EP + neg * EM + am * xdn + u0 * f0 * xdn;
+            fp_last = pos * EP + gam * neg * EM + ap * xdn;
+        }
+        p.fm[o0] = fm;
+        p.fp[o0] = fp;
+        p.fmm[o0] = fmm;
+        p.fpm[o0] = fpm;
+    }
+    const int64_t oL = oo + (int64_t)L * W;
+    p.fm[oL] = fm_last;
+    p.fp[oL] = fp_last;
+    p.fmm[oL] = 0.0;
+    p.fpm[oL] = 0.0;
+}
+
 __global__ void compress_disco_kernel(int W, int G, int nt, double cos_theta, const double *xint,
                                       const double *gweight, const double *tweight,
                                       const double *f0pi, int64_t bs_wave, double *albedo)
@@ -843,8 +992,34 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
     }
     if (want_lvl) {
         p.fm = d_lv[0]; p.fp = d_lv[1]; p.fmm = d_lv[2]; p.fpm = d_lv[3];
-        refl_levels_kernel<<<grid, block, 0, ctx->stream>>>(p);
-        PB_CHECK_LAUNCH(ctx);
+        // short wavelength axes (the climate solver) are serial-latency bound: precompute the layer records
+        // with a fully parallel kernel.  PB_REFL_LEVELS=rec|fused forces one path.  (Own record block, not the
+        // thermal one: the climate call runs the two level kernels concurrently on two streams.)
+        const size_t rec_bytes = (size_t)B * G * L * RR_N * nW;
+        const char *lf = getenv("PB_REFL_LEVELS");
+        bool use_rec = (long)W * B * G <= 64L * 1024 && rec_bytes <= ((size_t)1 << 31) && (int64_t)B * G <= 65535;
+        if (lf && lf[0] == 'r' && rec_bytes <= ((size_t)1 << 31) && (int64_t)B * G <= 65535) use_rec = true;
+        if (lf && lf[0] == 'f') use_rec = false;
+        if (use_rec) {
+            if (rec_bytes > ctx->rec2_cap) {
+                PB_CUDA(ctx, cudaDeviceSynchronize());
+                if (ctx->rec2) PB_CUDA(ctx, cudaFree(ctx->rec2));
+                ctx->rec2 = nullptr; ctx->rec2_cap = 0;
+                const size_t cap = pb_align(rec_bytes + rec_bytes / 8, 1 << 20);
+                cudaError_t e = cudaMalloc((void **)&ctx->rec2, cap);
+                if (e != cudaSuccess) return pb_fail(ctx, PB_ERR_NOMEM, "reflected: layer-record cudaMalloc(%zu) -> %s", cap, cudaGetErrorString(e));
+                ctx->rec2_cap = cap;
+            }
+            double *rec = (double *)ctx->rec2;
+            dim3 g1((W + 127) / 128, L, B * G);
+            refl_layer_records_kernel<<<g1, 128, 0, ctx->stream>>>(p, rec);
+            PB_CHECK_LAUNCH(ctx);
+            refl_levels_rec_kernel<<<grid, block, 0, ctx->stream>>>(p, rec);
+            PB_CHECK_LAUNCH(ctx);
+        } else {
+            refl_levels_kernel<<<grid, block, 0, ctx->stream>>>(p);
+            PB_CHECK_LAUNCH(ctx);
+        }
     }
     if (host) {
         if (want_toa && a->xint_at_top)

@@ -310,12 +310,14 @@ def bench_climate(ctx, L, W, K, ng, reps):
     launches = ctx.launch_count() - l0
     ms_host = wall(lambda: pb.get_fluxes(*args, ctx=ctx), reps)
     ms_dev = wall(lambda: pb.get_fluxes(*dd, ctx=ctx), reps)
+    ms_net = wall(lambda: pb.get_fluxes(*dd, ctx=ctx, full_arrays=False), reps)
     ms_cpu = wall(lambda: oclim.get_fluxes(*args, nthreads=os.cpu_count() or 1), 3)
     ms_cpu1 = wall(lambda: oclim.get_fluxes(*args, nthreads=1), 1)
     # algorithmic bytes: 12 opacity arrays read once + the 4 level arrays written and read back by the reductions
     alg = (12 * L + 2) * W * K * 8 + 2 * 4 * (1 + ng) * (L + 1) * W * K * 8
     print(json.dumps({"config": "climate.get_fluxes L=%d W=%d ngauss=%d ng=%d (reflected + thermal)" % (L, W, K, ng),
                       "ms_per_call_host_arrays": ms_host, "ms_per_call_device_opacities": ms_dev,
+                      "ms_per_call_device_opacities_net_fluxes_only": ms_net,
                       "kernel_launches_per_call": launches, "alg_bytes": alg,
                       "cpu_port_ms_all_cores": ms_cpu, "cpu_port_ms_1_thread": ms_cpu1, "cores": os.cpu_count(),
                       "rt_columns_per_s": K / (ms_dev * 1e-3)}), flush=True)

@@ -79,3 +79,18 @@ def test_gpu_device_resident_opacities():
     got = pb.get_fluxes(*C.climate_args(dd, case))
     for k, a, b in zip(C.CLIMATE_OUT, got, ref):
         assert np.array_equal(a, b), k
+
+
+@pytest.mark.gpu
+def test_gpu_net_fluxes_only():
+    """full_arrays=False: the [nlevel, nwno] arrays are not copied back; the net-flux vectors are the same bits"""
+    import picaso_b200 as pb
+    case = C.climate_cases()["clim_k8_disk5"]
+    d = C.build_climate(case)
+    full = pb.get_fluxes(*C.climate_args(d, case))
+    net = pb.get_fluxes(*C.climate_args(d, case), full_arrays=False)
+    for i, k in enumerate(C.CLIMATE_OUT):
+        if k.startswith("flux_net"):
+            assert np.array_equal(net[i], full[i]), k
+        else:
+            assert net[i] is None
