@@ -16,7 +16,14 @@
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kBlk = 8;
+#ifndef PB_TRANSIT_BLK
+#define PB_TRANSIT_BLK 16
+#endif
+#ifndef PB_TRANSIT_UNROLL
+#define PB_TRANSIT_UNROLL 4
+#endif
+constexpr int kBlk = PB_TRANSIT_BLK;  // tangent levels per pass (accumulators per thread)
+constexpr int kUnroll = PB_TRANSIT_UNROLL;
 
 __global__ void transit_path_kernel(int V, int Vp, const double *z, const double *dz, const double *player,
                                     const double *tlayer, double k_b, double *MT, double *zdz)
@@ -48,26 +55,29 @@ __global__ void __launch_bounds__(kThreads) transit_kernel(int V, int Vp, int W,
                                                          const double *MT, const double *zdz,
                                                          const double *zmin, double rstar, double *F)
 {
-    extern __shared__ double s_mt[];  // [L][Vp] then zdz[Vp]
+    extern __shared__ double s_mt[];  // [L][Vp], zdz[Vp], scale[L]
     const int L = V - 1;
     const int b = blockIdx.y;
     const double *mt = MT + (int64_t)b * V * Vp;
     for (int i = threadIdx.x; i < L * Vp; i += kThreads) s_mt[i] = mt[i];
     double *s_zdz = s_mt + L * Vp;
     for (int i = threadIdx.x; i < Vp; i += kThreads) s_zdz[i] = zdz[(int64_t)b * Vp + i];
+    double *s_sc = s_zdz + Vp;
+    for (int i = threadIdx.x; i < L; i += kThreads) s_sc[i] = scale[(int64_t)b * L + i];
     __syncthreads();
     const int w = blockIdx.x * kThreads + threadIdx.x;
     if (w >= W) return;
     const double *col = DTAU + (int64_t)b * bs_layer + w;
-    const double *sc = scale + (int64_t)b * L;
     double acc = 0.0;
     for (int i0 = 0; i0 < V; i0 += kBlk) {
         double t[kBlk];
 #pragma unroll
         for (int u = 0; u < kBlk; ++u) t[u] = 0.0;
-        const int kend = (i0 + kBlk - 1 < L) ? i0 + kBlk - 1 : L;  // rows k < i <= i0+7
+        const int kend = (i0 + kBlk - 1 < L) ? i0 + kBlk - 1 : L;  // rows k < i <= i0 + kBlk - 1
+        // four sigma loads in flight per trip: the loop is otherwise one load -> kBlk dependent-free DFMAs
+#pragma unroll kUnroll
         for (int k = 0; k < kend; ++k) {
-            const double s = __ldg(col + (int64_t)k * ld) * sc[k];
+            const double s = __ldg(col + (int64_t)k * ld) * s_sc[k];
             const double *m = s_mt + k * Vp + i0;
 #pragma unroll
             for (int u = 0; u < kBlk; ++u) t[u] = fma(s, m[u], t[u]);
@@ -92,7 +102,7 @@ extern "C" int pb_transit_1d(pb_ctx *ctx, const pb_transit_args *a, int memspace
     if (!a->DTAU || !a->z || !a->dz || !a->player || !a->tlayer || !a->mmw || !a->colden || !a->F)
         return pb_fail(ctx, PB_ERR_ARG, "transit: NULL argument");
     const int Vp = (V + kBlk - 1) / kBlk * kBlk;
-    const size_t smem = ((size_t)L * Vp + Vp) * sizeof(double);
+    const size_t smem = ((size_t)L * Vp + Vp + L) * sizeof(double);
     if (smem > 220 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "transit: nlevel=%d exceeds the shared-memory chord matrix (max ~165 levels)", V);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool host = memspace == PB_HOST;
