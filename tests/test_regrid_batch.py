@@ -40,6 +40,35 @@ def test_plan_matches_scipy_bin_numbers(name):
             assert idx[0] == start[i] and idx[-1] == start[i] + count[i] - 1
 
 
+def test_plan_matches_scipy_on_random_grids():
+    """property test: random monotone model grids (both directions, duplicates allowed) against random data
+    grids - bin membership identical to scipy's for every bin"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(5, 400), st.integers(2, 40), st.booleans())
+    def check(seed, n, nb, descending):
+        rng = np.random.default_rng(seed)
+        x = np.sort(np.round(rng.uniform(0.0, 100.0, size=n), rng.integers(0, 4)))
+        if descending:
+            x = x[::-1].copy()
+        lo, hi = sorted(rng.uniform(-10.0, 110.0, size=2))
+        if hi - lo < 1e-3:
+            hi = lo + 1.0
+        edges = np.unique(np.concatenate([[lo, hi], rng.uniform(lo, hi, size=nb - 1)]))
+        if edges.size < 2:
+            return
+        start, count = plan_ranges(x, edges)
+        _, _, binnum = binned_statistic(x, x, bins=edges)
+        for i in range(edges.size - 1):
+            idx = np.nonzero(binnum == i + 1)[0]
+            assert idx.size == count[i]
+            if idx.size:
+                assert idx[0] == start[i] and idx[-1] == start[i] + count[i] - 1
+
+    check()
+
+
 def test_plan_rejects_non_monotonic_x():
     from picaso_b200 import PicasoB200Error
     x = np.array([1.0, 5.0, 2.0, 6.0, 3.0])
