@@ -29,6 +29,32 @@ OUTPUT_NAMES = ("DTAU", "TAU", "W0", "COSB", "ftau_cld", "ftau_ray", "GCOS2", "D
 _LEVEL = {"TAU", "TAU_OG"}
 
 
+def find_needed_pts_grid(t_inv_grid, p_log_grid, nc_p, tlayer, player):
+    """RetrieveOpacities.find_needed_pts (picaso/optics.py:2048-2123) for all layers at once: the bilinear
+    neighbours in (1/T, log10 P) of every layer on a (T-major, P-minor, possibly ragged) table grid.
+    Returns t_interp[:, None], p_interp[:, None] and the four 0-based row indices (ll, hl, lh, hh)."""
+    t_inv = 1 / np.asarray(tlayer, dtype=np.float64)
+    p_log = np.log10(np.asarray(player, dtype=np.float64))
+    nT = t_inv_grid.size
+
+    def last_true(mask):
+        """per row: index of the last True (np.where(row)[0][-1]), 0 if none - any grid ordering"""
+        n = mask.shape[1]
+        return np.where(mask.any(axis=1), n - 1 - np.argmax(mask[:, ::-1], axis=1), 0)
+
+    # last grid temperature strictly below T, last grid pressure <= P
+    t_low = last_true(t_inv_grid[None, :] > t_inv[:, None])
+    t_low = np.where(t_low == nT - 1, nT - 2, t_low)
+    t_hi = t_low + 1
+    p_low = last_true(p_log_grid[None, :] <= p_log[:, None])
+    p_low = np.minimum(p_low, nc_p[t_hi] - 3)
+    p_hi = p_low + 1
+    off = np.concatenate([[0], np.cumsum(nc_p)])
+    t_interp = ((t_inv - t_inv_grid[t_low]) / (t_inv_grid[t_hi] - t_inv_grid[t_low]))[:, np.newaxis]
+    p_interp = ((p_log - p_log_grid[p_low]) / (p_log_grid[p_hi] - p_log_grid[p_low]))[:, np.newaxis]
+    return (t_interp, p_interp, off[t_low] + p_low, off[t_hi] + p_low, off[t_low] + p_hi, off[t_hi] + p_hi)
+
+
 class DeviceArray:
     """A float64 C-order array living in HBM (owned unless `owner` is given)."""
 
@@ -200,27 +226,7 @@ class DeviceOpacities:
     def find_needed_pts(self, tlayer, player):
         """bilinear neighbours in (1/T, log10 P); same return convention as the reference:
         t_interp[:,None], p_interp[:,None], and the four 0-based row indices."""
-        t_inv = 1 / np.asarray(tlayer, dtype=np.float64)
-        p_log = np.log10(np.asarray(player, dtype=np.float64))
-        nT = self.t_inv_grid.size
-
-        def last_true(mask):
-            """per row: index of the last True (np.where(row)[0][-1]), 0 if none - any grid ordering"""
-            n = mask.shape[1]
-            return np.where(mask.any(axis=1), n - 1 - np.argmax(mask[:, ::-1], axis=1), 0)
-
-        # last grid temperature strictly below T, last grid pressure <= P (all layers at once)
-        t_low = last_true(self.t_inv_grid[None, :] > t_inv[:, None])
-        t_low = np.where(t_low == nT - 1, nT - 2, t_low)
-        t_hi = t_low + 1
-        p_low = last_true(self.p_log_grid[None, :] <= p_log[:, None])
-        p_low = np.minimum(p_low, self.nc_p[t_hi] - 3)
-        p_hi = p_low + 1
-        off = np.concatenate([[0], np.cumsum(self.nc_p)])
-        t_interp = ((t_inv - self.t_inv_grid[t_low]) / (self.t_inv_grid[t_hi] - self.t_inv_grid[t_low]))[:, np.newaxis]
-        p_interp = ((p_log - self.p_log_grid[p_low]) / (self.p_log_grid[p_hi] - self.p_log_grid[p_low]))[:, np.newaxis]
-        return (t_interp, p_interp, off[t_low] + p_low, off[t_hi] + p_low, off[t_low] + p_hi,
-                off[t_hi] + p_hi)
+        return find_needed_pts_grid(self.t_inv_grid, self.p_log_grid, self.nc_p, tlayer, player)
 
     def get_opacities(self, atmosphere, exclude_mol=1):
         """Record the table rows / weights for this atmosphere; nothing is fetched or copied.

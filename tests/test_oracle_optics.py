@@ -38,3 +38,19 @@ def test_opacity_path(name):
                              delta_eddington=case["dedd"])
     for n, arr in zip(OUT_NAMES, res):
         assert_close(arr, g[f"{name}/out/{n}"], 1e-11, name + " " + n)
+
+
+def test_product_bin_search_matches_oracle():
+    """the vectorised (all layers at once) find_needed_pts of the product's host mirror against the oracle's
+    restatement of RetrieveOpacities.find_needed_pts, on ragged grids and profiles that leave the grid"""
+    from picaso_b200.optics import find_needed_pts_grid
+    from picaso_b200 import synth
+    rng = np.random.default_rng(12)
+    for seed, ragged in ((1, True), (2, False), (3, True)):
+        db = synth.opacity_database(W=8, nmol=1, seed=seed, nT=14, nP=11, ragged=ragged)
+        tlayer = np.concatenate([rng.uniform(40.0, 5000.0, size=60), db["temps"][:3], [db["temps"][-1]]])
+        pbar = np.concatenate([10.0 ** rng.uniform(-7.5, 4.0, size=60), db["pressures"][:3], [db["pressures"][-1]]])
+        want = oo.find_needed_pts(db["temps"], db["pressures"], db["nc_p"], tlayer, pbar)
+        got = find_needed_pts_grid(1 / db["temps"], np.log10(db["pressures"]), db["nc_p"], tlayer, pbar)
+        for a, b in zip(got, want):
+            assert np.array_equal(np.asarray(a).ravel(), np.asarray(b).ravel())   # reference shape [:, None] vs flat
