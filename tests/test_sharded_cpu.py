@@ -67,3 +67,54 @@ def test_gloo_sharded_equals_unsharded(world, W):
     for rank, full, xs in res:
         assert np.array_equal(full, alb), "rank %d albedo" % rank
         assert np.array_equal(xs, x), "rank %d xint" % rank
+
+
+# ---- atmosphere sharding of the batched retrieval model (BASELINE cfg5; picaso_b200/batch.py: shard) ----
+def _batch_inputs(B, L, W):
+    ds = [synth.thermal_inputs(L=L, W=W, seed=700 + b, t_range=(300.0 + 15 * b, 1400.0 + 30 * b)) for b in range(B)]
+    d0 = ds[0]
+    return dict(wno=d0["wno"], tlevel=np.array([d["tlevel"] for d in ds]), plevel=np.array([d["plevel"] for d in ds]),
+                dtau=np.array([d["dtau"] for d in ds]), w0=np.array([d["w0"] for d in ds]),
+                cosb=np.array([d["cosb"] for d in ds]), ubar1=d0["ubar1"], gweight=d0["gweight"], tweight=d0["tweight"])
+
+
+def _batch_worker(rank, world, port, B, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import regrid as oreg
+    from picaso_b200.batch import shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kw = _batch_inputs(B, 9, 120)
+    newx = np.linspace(500.0, 9000.0, 17)
+    lo, hi = shard(B, rank, world)
+    sub = dict(kw, **{k: kw[k][lo:hi] for k in ("tlevel", "plevel", "dtau", "w0", "cosb")})
+    _, y = (oreg.thermal_batch(**sub, newx=newx, scale=2.0) if hi > lo else (None, np.zeros((0, 17))))
+    # no exchange on the data path; gathering the per-rank rows (ragged) only assembles the result
+    parts = [None] * world
+    dist.all_gather_object(parts, (lo, hi, y))
+    full = np.zeros((B, 17))
+    for a, b, rows in parts:
+        full[a:b] = rows
+    q.put((rank, full))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,B", [(2, 5), (3, 2)])  # (3, 2): the last rank owns no atmosphere
+def test_gloo_atmosphere_shards_equal_whole_batch(world, B):
+    import torch.multiprocessing as mp
+    from oracle import regrid as oreg
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, B, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _, want = oreg.thermal_batch(**_batch_inputs(B, 9, 120), newx=np.linspace(500.0, 9000.0, 17), scale=2.0)
+    for rank, full in res:
+        assert np.array_equal(full, want, equal_nan=True), "rank %d" % rank
