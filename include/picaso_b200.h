@@ -350,6 +350,12 @@ typedef struct pb_climate_args {
     double *flux_plus_v, *flux_minus_v;      /* [nlevel][nwno], or NULL: not copied back */
     double *flux_net_ir_layer, *flux_net_ir; /* [nlevel] */
     double *flux_plus_ir, *flux_minus_ir;    /* [nlevel][nwno], or NULL: not copied back */
+    /* Alternative to the eight pointers above (which are then ignored): ONE host block, one device-to-host copy.
+     * Layout: [4][nlevel] = flux_net_v_layer, flux_net_v, flux_net_ir_layer, flux_net_ir; if packed_full != 0
+     * followed by [4][nlevel][nwno] = flux_plus_v, flux_minus_v, flux_plus_ir, flux_minus_ir.  The half that
+     * is not computed (reflected = 0 or thermal = 0) reads as zeros. */
+    double *packed;
+    int packed_full;
 } pb_climate_args;
 
 int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *args, int memspace);

@@ -102,7 +102,8 @@ class ClimateArgs(ctypes.Structure):
         [("cos_theta", c_dbl), ("single_phase", c_int), ("multi_phase", c_int)] +
         [(n, c_dbl) for n in ("frac_a", "frac_b", "frac_c", "constant_back", "constant_forward")] +
         [(n, c_vp) for n in ("flux_net_v_layer", "flux_net_v", "flux_plus_v", "flux_minus_v",
-                             "flux_net_ir_layer", "flux_net_ir", "flux_plus_ir", "flux_minus_ir")])
+                             "flux_net_ir_layer", "flux_net_ir", "flux_plus_ir", "flux_minus_ir", "packed")] +
+        [("packed_full", c_int)])
 
 
 class TransitArgs(ctypes.Structure):

@@ -98,11 +98,16 @@ def _one_column(ctx, Atmosphere, wed, noed, ScatteringPhase, Disco, Opagrid, F0P
     a.frac_a, a.frac_b, a.frac_c = (float(ScatteringPhase.frac_a), float(ScatteringPhase.frac_b),
                                     float(ScatteringPhase.frac_c))
     a.constant_back, a.constant_forward = float(ScatteringPhase.constant_back), float(ScatteringPhase.constant_forward)
-    big = (lambda: np.zeros((nlevel, nwno))) if full_arrays else (lambda: None)
-    out = dict(flux_net_v_layer=np.zeros(nlevel), flux_net_v=np.zeros(nlevel), flux_plus_v=big(), flux_minus_v=big(),
-               flux_net_ir_layer=np.zeros(nlevel), flux_net_ir=np.zeros(nlevel), flux_plus_ir=big(), flux_minus_ir=big())
-    for k, v in out.items():
-        setattr(a, k, addr(v))
+    # all outputs arrive in one host block with one device-to-host copy (pb_climate_args.packed); the arrays
+    # handed back are non-overlapping views of it
+    nvw = nlevel * nwno
+    blk = np.empty(4 * nlevel + (4 * nvw if full_arrays else 0))
+    a.packed, a.packed_full = addr(blk), int(bool(full_arrays))
+    big = (lambda i: blk[4 * nlevel + i * nvw:4 * nlevel + (i + 1) * nvw].reshape(nlevel, nwno)) if full_arrays \
+        else (lambda i: None)
+    vecn = lambda i: blk[i * nlevel:(i + 1) * nlevel]
+    out = dict(flux_net_v_layer=vecn(0), flux_net_v=vecn(1), flux_plus_v=big(0), flux_minus_v=big(1),
+               flux_net_ir_layer=vecn(2), flux_net_ir=vecn(3), flux_plus_ir=big(2), flux_minus_ir=big(3))
     ctx.check(ctx.lib.pb_climate_get_fluxes(ctx.h, ctypes.byref(a), memspace))
     del keep
     return out

@@ -169,14 +169,14 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
         if (!a->DTAU || !a->TAU || !a->W0 || !a->COSB || !a->GCOS2 || !a->ftau_cld || !a->ftau_ray ||
             !a->DTAU_OG || !a->TAU_OG || !a->W0_OG || !a->COSB_OG)
             return pb_fail(ctx, PB_ERR_ARG, "climate: reflected needs the 11 opacity arrays");
-        if (!a->flux_net_v_layer || !a->flux_net_v)
+        if (!a->packed && (!a->flux_net_v_layer || !a->flux_net_v))
             return pb_fail(ctx, PB_ERR_ARG, "climate: reflected outputs missing");
     }
     if (a->thermal) {
         if (!a->DTAU_OG || !a->W0_no_raman || !a->COSB_OG || !a->tlevel || !a->plevel || !a->wno || !a->dwno ||
             !a->ubar1 || !a->gweight || !a->tweight)
             return pb_fail(ctx, PB_ERR_ARG, "climate: thermal needs DTAU_OG, W0_no_raman, COSB_OG, tlevel, plevel, wno, dwno, ubar1, gweight, tweight");
-        if (!a->flux_net_ir_layer || !a->flux_net_ir)
+        if (!a->packed && (!a->flux_net_ir_layer || !a->flux_net_ir))
             return pb_fail(ctx, PB_ERR_ARG, "climate: thermal outputs missing");
     }
     if (!a->reflected && !a->thermal) return PB_OK;
@@ -194,7 +194,7 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
     if (host) need += pb_align(K * nVW);                        // raw [rows][W][K] staging
     need += 2 * pb_align(K * nW) + 2 * pb_align(nW);             // surf, F0PI replicated; wno, dwno
     need += ((a->reflected && a->thermal) ? 8 : 4) * pb_align((size_t)K * Gmax * nVW);  // level arrays
-    need += 4 * pb_align(nVW) + 8 * pb_align((size_t)V * 8);     // reduced outputs
+    need += pb_align(4 * nVW + 4 * (size_t)V * 8) + 256;           // reduced outputs (one block)
     need += pb_align((size_t)(K + G + 16) * 8 * 4);
     PB_TRY(aux_reserve(ctx, need));
     size_t off = 0;
@@ -273,9 +273,16 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
     double *lv[4], *lvi[4];
     for (int i = 0; i < 4; ++i) lv[i] = take((size_t)K * Gmax * nVW);
     for (int i = 0; i < 4; ++i) lvi[i] = (a->reflected && a->thermal) ? take((size_t)K * Gmax * nVW) : lv[i];
-    double *o_plus = take(nVW), *o_minus = take(nVW), *o_lay = take((size_t)V * 8), *o_net = take((size_t)V * 8);
-    double *o_plus_ir = take(nVW), *o_minus_ir = take(nVW), *o_lay_ir = take((size_t)V * 8), *o_net_ir = take((size_t)V * 8);
+    // reduced outputs in ONE contiguous block - [4][V] net fluxes (visible layer, visible level, IR layer, IR
+    // level), then [4][V][W] (plus_v, minus_v, plus_ir, minus_ir) - so that `packed` callers get them with a
+    // single device-to-host copy instead of eight host-blocking ones
+    double *blk = take(4 * (size_t)V * 8 + 4 * nVW);
+    double *o_lay = blk, *o_net = blk + V, *o_lay_ir = blk + 2 * V, *o_net_ir = blk + 3 * V;
+    double *o_plus = blk + 4 * V, *o_minus = o_plus + (size_t)V * W, *o_plus_ir = o_minus + (size_t)V * W,
+           *o_minus_ir = o_plus_ir + (size_t)V * W;
     if (off > ctx->aux_cap) return pb_fail(ctx, PB_ERR_NOMEM, "climate: scratch layout overflow (%zu > %zu)", off, ctx->aux_cap);
+    if (a->packed && !(a->reflected && a->thermal))  // the half that does not run reads as zeros (climate.py:1757-1786)
+        PB_CUDA(ctx, cudaMemsetAsync(blk, 0, 4 * (size_t)V * 8 + 4 * nVW, ctx->stream));
 
     if (a->reflected && a->thermal) PB_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));  // staging done
     if (a->reflected) {
@@ -335,17 +342,25 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
                                                               d_gweight, d_tweight, d_dwno, o_plus_ir, o_minus_ir,
                                                               o_lay_ir, o_net_ir);
         PB_CHECK_LAUNCH(ctx);
-        if (a->flux_plus_ir) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_ir, o_plus_ir, nVW, cudaMemcpyDeviceToHost, ctx->stream));
-        if (a->flux_minus_ir) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_ir, o_minus_ir, nVW, cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_ir_layer, o_lay_ir, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_ir, o_net_ir, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!a->packed) {
+            if (a->flux_plus_ir) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_ir, o_plus_ir, nVW, cudaMemcpyDeviceToHost, ctx->stream));
+            if (a->flux_minus_ir) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_ir, o_minus_ir, nVW, cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_ir_layer, o_lay_ir, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_ir, o_net_ir, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        } else if (overlap) {
+            PB_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[15], ctx->stream));  // IR half done (side stream)
+        }
         // tl / pl are consumed by pb_thermal_toon_1d's packed pinned upload before it returns
         return PB_OK;
     };
     int rc_thermal = PB_OK;
     if (a->thermal) rc_thermal = run_thermal();
     if (overlap) ctx->stream = main_stream;  // restored on every path before any return below
-    if (a->reflected) {
+    if (a->packed) {
+        if (overlap && rc_thermal == PB_OK) PB_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_chunk[15], 0));
+        const size_t nb = 4 * (size_t)V * 8 + (a->packed_full ? 4 * nVW : 0);
+        if (rc_thermal == PB_OK) PB_CUDA(ctx, cudaMemcpyAsync(a->packed, blk, nb, cudaMemcpyDeviceToHost, main_stream));
+    } else if (a->reflected) {
         if (a->flux_plus_v) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_plus_v, o_plus, nVW, cudaMemcpyDeviceToHost, main_stream));
         if (a->flux_minus_v) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_minus_v, o_minus, nVW, cudaMemcpyDeviceToHost, main_stream));
         PB_CUDA(ctx, cudaMemcpyAsync(a->flux_net_v_layer, o_lay, (size_t)V * 8, cudaMemcpyDeviceToHost, main_stream));
