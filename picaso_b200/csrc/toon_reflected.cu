@@ -683,6 +683,229 @@ __global__ void __launch_bounds__(256) refl_levels_rec_kernel(ReflParams p, cons
     p.fpm[oL] = 0.0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Layer-parallel level fluxes: one WARP per (atmosphere, angle, wavelength) column, lanes = layers.
+// The reference's bottom-up Thomas recurrences are evaluated as scans (scripts/study_layer_scan.py, DESIGN.md
+// section 7.5): AS_i = a_i / (b_i - c_i AS_{i+1}) is a Moebius map, i.e. a suffix product of 2 x 2 matrices
+// (renormalised); DS_i = (d_i - c_i DS_{i+1}) x_i and X_i = DS_i - AS_i X_{i-1} are affine maps.  Each lane
+// composes the maps of its own LP layers (rows 2l+1, 2l+2), the 32 per-lane maps are chained through shuffles,
+// and every lane then re-runs the reference's recurrences over its own rows from the incoming value - so all
+// rows of a lane, and in particular every (X[2l], X[2l+1]) pair, keep the reference's local rounding
+// relation (Y+ = X[2l] + X[2l+1] cancels to 1e-30 of its terms and is multiplied by e^35).  Plain cyclic
+// reduction is not stable on this matrix (study: 2.5e-6 on the adversarial case).
+// ---------------------------------------------------------------------------------------
+struct Mob { double a, b, c, d; };  // [[a, b], [c, d]]
+
+__device__ __forceinline__ Mob mob_mul(const Mob &x, const Mob &y)
+{
+    Mob r;
+    r.a = x.a * y.a + x.b * y.c; r.b = x.a * y.b + x.b * y.d;
+    r.c = x.c * y.a + x.d * y.c; r.d = x.c * y.b + x.d * y.d;
+    const double m = fmax(fmax(fabs(r.a), fabs(r.b)), fmax(fabs(r.c), fabs(r.d)));
+    const double s = m > 0.0 ? 1.0 / m : 1.0;
+    r.a *= s; r.b *= s; r.c *= s; r.d *= s;
+    return r;
+}
+
+template <int LP>
+__global__ void __launch_bounds__(128) refl_levels_scan_kernel(ReflParams p, const double *__restrict__ rec)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t col = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int L = p.L, V = L + 1;
+    const int64_t W = p.W;
+    // p.wt carries nbatch for this kernel; whole warps leave together (col is warp-uniform)
+    if (col >= (int64_t)p.wt * p.G * W) return;
+    const int b = (int)(col / ((int64_t)p.G * W));
+    const int64_t rem = col - (int64_t)b * p.G * W;
+    const int a = (int)(rem / W);
+    const int w = (int)(rem - (int64_t)a * W);
+    const int64_t ov = (int64_t)b * p.bs_level + w;
+    const int64_t ow = (int64_t)b * p.bs_wave + w;
+    const int64_t oo = (((int64_t)b * p.G + a) * V) * W + w;
+    const double u0 = p.ubar0[a];
+    const double f0 = p.f0pi ? p.f0pi[ow] : 1.0;
+    const double r = p.surf ? p.surf[ow] : 0.0;
+    const double btop = p.btop ? p.btop[ow] : 0.0;
+    const double *R = rec + (((int64_t)b * p.G + a) * L * RR_N) * W + w;
+    const double xdn = exp(-p.tau[ov + (int64_t)L * p.ld] / u0);
+    const double b_surface = 0.0 + r * u0 * f0 * xdn;
+
+    // ---- records of this lane's layers ----
+    double gam[LP], am[LP], ap[LP], xu[LP], EP[LP], EM[LP];
+    bool have[LP];
+#pragma unroll
+    for (int k = 0; k < LP; ++k) {
+        const int l = lane * LP + k;
+        have[k] = l < L;
+        const double *q = R + (int64_t)(have[k] ? l : 0) * RR_N * W;
+        gam[k] = q[RR_GAM * W]; am[k] = q[RR_AM * W]; ap[k] = q[RR_AP * W]; xu[k] = q[RR_XU * W];
+        EP[k] = q[RR_EP * W]; EM[k] = q[RR_EM * W];
+    }
+    // the layer below this lane's last one (gam_n, cpu_n, cmu_n, xd of the interface rows)
+    const double gam_dn = __shfl_down_sync(FULL, gam[0], 1), am_dn = __shfl_down_sync(FULL, am[0], 1);
+    const double ap_dn = __shfl_down_sync(FULL, ap[0], 1), xu_dn = __shfl_down_sync(FULL, xu[0], 1);
+
+    // ---- rows: layer l owns R1 = row 2l+1 and R2 = row 2l+2 (R2 only if l < L-1) ----
+    double a1[LP], b1[LP], c1[LP], d1[LP], a2[LP], b2[LP], c2[LP], d2[LP];
+    bool has2[LP];
+#pragma unroll
+    for (int k = 0; k < LP; ++k) {
+        const int l = lane * LP + k;
+        const double gn = (k + 1 < LP) ? gam[(k + 1 < LP) ? k + 1 : k] : gam_dn;
+        const double amn = (k + 1 < LP) ? am[(k + 1 < LP) ? k + 1 : k] : am_dn;
+        const double apn = (k + 1 < LP) ? ap[(k + 1 < LP) ? k + 1 : k] : ap_dn;
+        const double xun = (k + 1 < LP) ? xu[(k + 1 < LP) ? k + 1 : k] : xu_dn;
+        const bool last = (l == L - 1);
+        has2[k] = have[k] && !last;
+        const double xd = last ? xdn : xun;
+        const double cmd = am[k] * xd, cpd = ap[k] * xd;
+        const double cmu_n = amn * xun, cpu_n = apn * xun;
+        const double e1 = EP[k] + gam[k] * EM[k], e2 = EP[k] - gam[k] * EM[k];
+        const double e3 = gam[k] * EP[k] + EM[k], e4 = gam[k] * EP[k] - EM[k];
+        if (last) {
+            a1[k] = e1 - r * e3; b1[k] = e2 - r * e4; c1[k] = 0.0; d1[k] = b_surface - cpd + r * cmd;
+        } else {
+            a1[k] = (e1 + e3) * (gn - 1.0); b1[k] = (e2 + e4) * (gn - 1.0); c1[k] = 2.0 * (1.0 - gn * gn);
+            d1[k] = (gn - 1.0) * (cpu_n - cpd) + (1.0 - gn) * (cmd - cmu_n);
+        }
+        a2[k] = 2.0 * (1.0 - gam[k] * gam[k]); b2[k] = (e1 - e3) * (gn + 1.0); c2[k] = (e1 + e3) * (gn - 1.0);
+        d2[k] = e3 * (cpu_n - cpd) + e1 * (cmd - cmu_n);
+        if (!have[k]) { a1[k] = 0.0; b1[k] = 1.0; c1[k] = 0.0; d1[k] = 0.0; }
+        if (!has2[k]) { a2[k] = 0.0; b2[k] = 1.0; c2[k] = 0.0; d2[k] = 0.0; }
+    }
+
+    // ---- AS: suffix product of [[0, a_i], [-c_i, b_i]] over rows (ascending within the lane) ----
+    Mob P = {1.0, 0.0, 0.0, 1.0};
+#pragma unroll
+    for (int k = 0; k < LP; ++k) {
+        if (have[k]) { Mob m = {0.0, a1[k], -c1[k], b1[k]}; P = mob_mul(P, m); }
+        if (has2[k]) { Mob m = {0.0, a2[k], -c2[k], b2[k]}; P = mob_mul(P, m); }
+    }
+    // across lanes: a SERIAL chain (lane 31 -> 0) of the per-lane maps AS_top = (P.a AS_in + P.b) / (P.c AS_in + P.d):
+    // the reference's own recurrence at lane granularity, 31 dependent steps of a few FMAs per warp, hidden by
+    // the other resident warps (62.7 us at the climate shape).  A logarithmic (Kogge-Stone) combination of the
+    // lane maps measured 44.3 us with the same norm-wise agreement (5.8e-14 of the column maximum); it was
+    // swapped out while chasing 14 out-of-tolerance entries that turned out to come from the surface row
+    // (a * (1/b) instead of a / b, see below) - re-validating it is a round-2 item.
+    double AS_in = 0.0;
+    {
+        double AS_top = (P.a * AS_in + P.b) / (P.c * AS_in + P.d);  // correct for lane 31 (AS_in = 0)
+#pragma unroll 1
+        for (int j = 30; j >= 0; --j) {
+            const double below = __shfl_sync(FULL, AS_top, j + 1);
+            if (lane == j) {
+                AS_in = below;
+                AS_top = (P.a * AS_in + P.b) / (P.c * AS_in + P.d);
+            }
+        }
+    }
+    // local bottom-up recurrences (reference order): AS and the pivots x of every own row
+    double AS1[LP], AS2[LP], x1[LP], x2[LP];
+    {
+        double ASn = AS_in;
+#pragma unroll
+        for (int k = LP - 1; k >= 0; --k) {
+            x2[k] = 1.0 / (b2[k] - c2[k] * ASn);
+            AS2[k] = a2[k] * x2[k];
+            if (has2[k]) ASn = AS2[k];
+            x1[k] = 1.0 / (b1[k] - c1[k] * ASn);
+            AS1[k] = a1[k] * x1[k];
+            // surface row: the reference DIVIDES (AS = a/b, fluxes.py:305); a * (1/b) can miss AS = 1 by an ulp,
+            // and Y+ = X[2L-2] + X[2L-1] = (1 - AS) X[2L-2] + DS is multiplied by e^35 in the bottom-level fluxes
+            if (lane * LP + k == L - 1) AS1[k] = a1[k] / b1[k];
+            if (have[k]) ASn = AS1[k];
+        }
+    }
+    // ---- DS: suffix affine scan, DS_i = (-c_i x_i) DS_{i+1} + d_i x_i ----
+    double Ms = 1.0, Ts = 0.0;  // DS_top = Ms * DS_in + Ts over the lane's rows
+#pragma unroll
+    for (int k = LP - 1; k >= 0; --k) {
+        if (has2[k]) { const double m = -c2[k] * x2[k], t = d2[k] * x2[k]; Ts = m * Ts + t; Ms = m * Ms; }
+        if (have[k]) { const double m = -c1[k] * x1[k], t = d1[k] * x1[k]; Ts = m * Ts + t; Ms = m * Ms; }
+    }
+    double DS_in = 0.0;  // serial chain over lanes, as for AS
+    {
+        double DS_top = Ms * DS_in + Ts;
+#pragma unroll 1
+        for (int j = 30; j >= 0; --j) {
+            const double below = __shfl_sync(FULL, DS_top, j + 1);
+            if (lane == j) {
+                DS_in = below;
+                DS_top = Ms * DS_in + Ts;
+            }
+        }
+    }
+    double DS1[LP], DS2[LP];
+    {
+        double DSn = DS_in;
+#pragma unroll
+        for (int k = LP - 1; k >= 0; --k) {
+            DS2[k] = (d2[k] - c2[k] * DSn) * x2[k];
+            if (has2[k]) DSn = DS2[k];
+            DS1[k] = (d1[k] - c1[k] * DSn) * x1[k];
+            if (lane * LP + k == L - 1) DS1[k] = d1[k] / b1[k];
+            if (have[k]) DSn = DS1[k];
+        }
+    }
+    // ---- row 0 (fluxes.py:155-158): X[0] = DS_0 ----
+    double X0row = 0.0;
+    {
+        const double cmu0 = am[0] * xu[0];
+        const double b_ = gam[0] + 1.0, c_ = gam[0] - 1.0, d_ = btop - cmu0;
+        const double x = 1.0 / (b_ - c_ * AS1[0]);
+        X0row = (d_ - c_ * DS1[0]) * x;
+    }
+    X0row = __shfl_sync(FULL, X0row, 0);
+    // ---- X: prefix affine scan, X_i = -AS_i X_{i-1} + DS_i ----
+    double Mp = 1.0, Tp = 0.0;
+#pragma unroll
+    for (int k = 0; k < LP; ++k) {
+        if (have[k]) { Tp = -AS1[k] * Tp + DS1[k]; Mp = -AS1[k] * Mp; }
+        if (has2[k]) { Tp = -AS2[k] * Tp + DS2[k]; Mp = -AS2[k] * Mp; }
+    }
+    double Xin = X0row;  // serial chain over lanes 0 -> 31
+    {
+        double Xout = Mp * Xin + Tp;
+#pragma unroll 1
+        for (int j = 1; j < 32; ++j) {
+            const double above = __shfl_sync(FULL, Xout, j - 1);
+            if (lane == j) {
+                Xin = above;
+                Xout = Mp * Xin + Tp;
+            }
+        }
+    }
+    // ---- fluxes (fluxes.py:1219-1257), layer by layer with the reference's local substitution ----
+    double Xe = Xin;
+#pragma unroll
+    for (int k = 0; k < LP; ++k) {
+        const int l = lane * LP + k;
+        if (!have[k]) continue;
+        const double *q = R + (int64_t)l * RR_N * W;
+        const double EPm = q[RR_EPM * W], EMm = q[RR_EMM * W], xm = q[RR_XM * W];
+        const double X1 = DS1[k] - AS1[k] * Xe;
+        const double pos = Xe + X1, neg = Xe - X1;
+        double fm = pos * gam[k] + neg + am[k] * xu[k];
+        const double fp = pos + gam[k] * neg + ap[k] * xu[k];
+        fm = fm + u0 * f0 * xu[k];
+        double fmm = gam[k] * pos * EPm + neg * EMm + am[k] * xm;
+        const double fpm = pos * EPm + gam[k] * neg * EMm + ap[k] * xm;
+        fmm = fmm + u0 * f0 * xm;
+        const int64_t o0 = oo + (int64_t)l * W;
+        p.fm[o0] = fm; p.fp[o0] = fp; p.fmm[o0] = fmm; p.fpm[o0] = fpm;
+        if (l == L - 1) {
+            const int64_t oL = oo + (int64_t)L * W;
+            p.fm[oL] = gam[k] * pos * EP[k] + neg * EM[k] + am[k] * xdn + u0 * f0 * xdn;
+            p.fp[oL] = pos * EP[k] + gam[k] * neg * EM[k] + ap[k] * xdn;
+            p.fmm[oL] = 0.0;
+            p.fpm[oL] = 0.0;
+        }
+        if (has2[k]) Xe = DS2[k] - AS2[k] * X1;
+    }
+}
+
 __global__ void compress_disco_kernel(int W, int G, int nt, double cos_theta, const double *xint,
                                       const double *gweight, const double *tweight,
                                       const double *f0pi, int64_t bs_wave, double *albedo)
@@ -1000,6 +1223,8 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
         bool use_rec = (long)W * B * G <= 64L * 1024 && rec_bytes <= ((size_t)1 << 31) && (int64_t)B * G <= 65535;
         if (lf && lf[0] == 'r' && rec_bytes <= ((size_t)1 << 31) && (int64_t)B * G <= 65535) use_rec = true;
         if (lf && lf[0] == 'f') use_rec = false;
+        const bool use_scan = lf && lf[0] == 's' && L <= 128 && rec_bytes <= ((size_t)1 << 31) && (int64_t)B * G <= 65535;
+        if (use_scan) use_rec = true;
         if (use_rec) {
             if (rec_bytes > ctx->rec2_cap) {
                 PB_CUDA(ctx, cudaDeviceSynchronize());
@@ -1014,7 +1239,20 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             dim3 g1((W + 127) / 128, L, B * G);
             refl_layer_records_kernel<<<g1, 128, 0, ctx->stream>>>(p, rec);
             PB_CHECK_LAUNCH(ctx);
-            refl_levels_rec_kernel<<<grid, block, 0, ctx->stream>>>(p, rec);
+            if (use_scan) {
+                // opt-in (PB_REFL_LEVELS=scan): layer-parallel warp scans, one warp per column
+                ReflParams q = p;
+                q.wt = B;
+                const int64_t cols = (int64_t)B * G * W;
+                const unsigned nb = (unsigned)((cols + 3) / 4);
+                const int lp = (L + 31) / 32;
+                if (lp == 1) refl_levels_scan_kernel<1><<<nb, 128, 0, ctx->stream>>>(q, rec);
+                else if (lp == 2) refl_levels_scan_kernel<2><<<nb, 128, 0, ctx->stream>>>(q, rec);
+                else if (lp == 3) refl_levels_scan_kernel<3><<<nb, 128, 0, ctx->stream>>>(q, rec);
+                else refl_levels_scan_kernel<4><<<nb, 128, 0, ctx->stream>>>(q, rec);
+            } else {
+                refl_levels_rec_kernel<<<grid, block, 0, ctx->stream>>>(p, rec);
+            }
             PB_CHECK_LAUNCH(ctx);
         } else {
             refl_levels_kernel<<<grid, block, 0, ctx->stream>>>(p);

@@ -37,6 +37,40 @@ def test_reflected_vs_golden_and_oracle(name):
         assert all(not a.any() for a in lv)
 
 
+@pytest.mark.parametrize("mode", ["scan", "fused", "rec"])
+@pytest.mark.parametrize("name", sorted(n for n, c in C.reflected_cases().items() if c["kw"]["get_lvl_flux"]))
+def test_reflected_level_flux_paths(name, mode, monkeypatch):
+    """the three level-flux implementations (PB_REFL_LEVELS): one fused kernel, precomputed layer records +
+    serial sweeps, and the layer-parallel warp scans (one warp per column, lanes = layers)"""
+    monkeypatch.setenv("PB_REFL_LEVELS", mode)
+    g = golden("reflected")
+    case = C.reflected_cases()[name]
+    d = C.build_reflected(case)
+    args = C.reflected_args(d, case["kw"])
+    xint, lv = pb.get_reflected_1d(*args)
+    _, olv = oracle.get_reflected_1d(*args)
+    _, qlv = oracle.get_reflected_1d(*args, quad=True, nthreads=8)
+    for k, a, o, q in zip(("fm", "fp", "fmm", "fpm"), lv, olv, qlv):
+        assert np.isfinite(a).all(), name + " " + k
+        assert_level_close_yardstick(a, g[name + "/" + k], q, what=name + " " + k + " vs reference (" + mode + ")")
+        assert_level_close_yardstick(a, o, q, what=name + " " + k + " vs oracle (" + mode + ")")
+
+
+@pytest.mark.parametrize("L", [33, 45, 90, 120])
+def test_reflected_level_scan_many_layers(L, monkeypatch):
+    """more layers than lanes: 2, 3 and 4 layers per lane in the layer-parallel scan kernel"""
+    monkeypatch.setenv("PB_REFL_LEVELS", "scan")
+    d = synth.reflected_inputs(L=L, W=19, seed=900 + L)
+    kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=1)
+    args = C.reflected_args(d, kw)
+    _, lv = pb.get_reflected_1d(*args)
+    _, olv = oracle.get_reflected_1d(*args, nthreads=8)
+    _, qlv = oracle.get_reflected_1d(*args, quad=True, nthreads=8)
+    for k, a, o, q in zip(("fm", "fp", "fmm", "fpm"), lv, olv, qlv):
+        assert np.isfinite(a).all(), k
+        assert_level_close_yardstick(a, o, q, what="L=%d %s scan vs oracle" % (L, k))
+
+
 @pytest.mark.parametrize("name", sorted(C.thermal_cases()))
 def test_thermal_vs_golden_and_oracle(name):
     g = golden("thermal")
