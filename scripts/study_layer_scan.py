@@ -95,7 +95,7 @@ def _affine_scan(m, t, reverse=False):
     return t
 
 
-def scan_solve(A, B, Cc, D, split=True):
+def scan_solve(A, B, Cc, D, split=True, surface_divide=False):
     """The reference's bottom-up Thomas recurrences evaluated as tree-ordered scans.
     split=False: one 3 x 3 homogeneous (Moebius + affine) suffix product for (AS, DS) - DS loses RELATIVE
     accuracy where it is tiny against AS (deep layers), which the e^{35}-scaled level fluxes cannot tolerate.
@@ -127,6 +127,9 @@ def scan_solve(A, B, Cc, D, split=True):
         ASn = np.vstack([AS[1:], np.zeros((1, W))])
         x = 1.0 / (B - Cc * ASn)          # the Thomas pivots, all rows at once
         DS = _affine_scan(-Cc * x, D * x, reverse=True)   # DS_i = (d_i - c_i DS_{i+1}) x_i
+        if surface_divide:                # the reference DIVIDES in the surface row (fluxes.py:305): AS = a / b
+            AS[-1] = A[-1] / B[-1]
+            DS[-1] = D[-1] / B[-1]
     X = _affine_scan(-AS, DS)             # X_i = DS_i - AS_i X_{i-1}
     if split:
         # Y+ = X[2l] + X[2l+1] cancels to ~1e-30 of its terms in optically thick layers and is multiplied by
@@ -232,5 +235,102 @@ def main():
         print("%-28s level arrays from the scan pass the level-flux (yardstick) criterion of tests/util.py" % name)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--thermal" not in sys.argv:
     main()
+
+
+# ------------------------------------------------------------------------------------------------------
+# Thermal (get_thermal_1d, fluxes.py:1746-1912): the same split scan for X, then the downward / upward
+# source-function recurrences (:1875-1907) as affine scans over layers.
+# ------------------------------------------------------------------------------------------------------
+def thermal_levels_from_scan(d, ia=0):
+    h, c, k = 6.62607004e-27, 2.99792458e+10, 1.38064852e-16
+    L = d["nlevel"] - 1
+    W = d["nwno"]
+    dt, om, g = d["dtau"], d["w0"], d["cosb"]
+    wl = 1.0 / d["wno"]
+    B = ((2.0 * h * c * c) / wl ** 5.0)[None, :] * (1.0 / (np.exp((h * c) / (wl[None, :] * k) / d["tlevel"][:, None]) - 1.0))
+    mu1 = 0.5
+    u = d["ubar1"].reshape(-1)[ia]
+    surf = d["surf_reflect"]
+    b0 = B[:-1]
+    b1 = (B[1:] - B[:-1]) / dt
+    g1 = 2.0 - om * (1 + g)
+    g2 = om * (1 - g)
+    lam = np.sqrt(g1 * g1 - g2 * g2)
+    gam = (g1 - lam) / g2
+    q = 1.0 / (g1 + g2)
+    tp = 2 * np.pi * mu1
+    cpu, cmu = tp * (b0 + b1 * q), tp * (b0 - b1 * q)
+    cpd, cmd = tp * (b0 + b1 * dt + b1 * q), tp * (b0 + b1 * dt - b1 * q)
+    E = np.minimum(lam * dt, 35.0)
+    EP = np.exp(E); EM = 1 / EP
+    e1, e2, e3, e4 = EP + gam * EM, EP - gam * EM, gam * EP + EM, gam * EP - EM
+    pl = d["plevel"]
+    tau_top = dt[0] * pl[0] / (pl[1] - pl[0])
+    b_top = (1.0 - np.exp(-tau_top / mu1)) * B[0] * np.pi
+    if d["hard_surface"]:
+        b_surface = (1.0 - surf) * B[-1] * np.pi
+    else:
+        b_surface = (B[-1] + b1[-1] * mu1) * np.pi
+    A = np.zeros((2 * L, W)); Bm = np.zeros((2 * L, W)); Cc = np.zeros((2 * L, W)); D = np.zeros((2 * L, W))
+    Bm[0] = gam[0] + 1; Cc[0] = gam[0] - 1; D[0] = b_top - cmu[0]
+    A[1::2][:-1] = (e1[:-1] + e3[:-1]) * (gam[1:] - 1); Bm[1::2][:-1] = (e2[:-1] + e4[:-1]) * (gam[1:] - 1)
+    Cc[1::2][:-1] = 2 * (1 - gam[1:] ** 2)
+    D[1::2][:-1] = (gam[1:] - 1) * (cpu[1:] - cpd[:-1]) + (1 - gam[1:]) * (cmd[:-1] - cmu[1:])
+    A[::2][1:] = 2 * (1 - gam[:-1] ** 2); Bm[::2][1:] = (e1[:-1] - e3[:-1]) * (gam[1:] + 1)
+    Cc[::2][1:] = (e1[:-1] + e3[:-1]) * (gam[1:] - 1)
+    D[::2][1:] = e3[:-1] * (cpu[1:] - cpd[:-1]) + e1[:-1] * (cmd[:-1] - cmu[1:])
+    A[-1] = e1[-1] - surf * e3[-1]; Bm[-1] = e2[-1] - surf * e4[-1]; D[-1] = b_surface - cpd[-1] + surf * cmd[-1]
+    X = scan_solve(A, Bm, Cc, D, surface_divide=True)
+    pos, neg = X[::2] + X[1::2], X[::2] - X[1::2]
+    xa, xh = np.exp(-dt / u), np.exp(-0.5 * dt / u)
+    EPh = np.exp(0.5 * E); EMh = 1 / EPh
+    lu = lam * u
+    # downward: f_{l+1} = xa f_l + src_l  (fluxes.py:1883-1888), prefix scan
+    J = gam * (lam + 1 / mu1) * pos
+    K = (1 / mu1 - lam) * neg
+    si1 = 2 * np.pi * (b0 - b1 * (q - mu1)); si2 = 2 * np.pi * b1
+    src_dn = (J / (lu + 1.0)) * (EP - xa) + (K / (lu - 1.0)) * (xa - EM) + si1 * (1. - xa) + si2 * (u * xa + dt - u)
+    f0 = (1 - np.exp(-tau_top / u)) * B[0] * 2 * np.pi
+    t = src_dn.copy(); t[0] = xa[0] * f0 + src_dn[0]
+    fnext = _affine_scan(xa, t)                              # f at levels 1..L
+    fm = np.vstack([f0[None, :], fnext])
+    fmm = np.zeros_like(fm)
+    fmm[:-1] = fm[:-1] * xh + (J / (lu + 1.0)) * (EPh - xh) + (K / (-lu + 1.0)) * (EMh - xh) + si1 * (1. - xh) + \
+        si2 * (u * xh + 0.5 * dt - u)
+    # upward: f_l = xa f_{l+1} + src_l  (fluxes.py:1897-1901), suffix scan
+    Gt = (1 / mu1 - lam) * pos
+    Ht = gam * (lam + 1 / mu1) * neg
+    al1 = 2 * np.pi * (b0 + b1 * (q - mu1)); al2 = 2 * np.pi * b1
+    src_up = (Gt / (lu - 1.0)) * (EP * xa - 1.0) + (Ht / (lu + 1.0)) * (1.0 - EM * xa) + al1 * (1. - xa) + al2 * (u - (dt + u) * xa)
+    fL = (1.0 - surf) * B[-1] * 2 * np.pi if d["hard_surface"] else (B[-1] + b1[-1] * u) * 2 * np.pi
+    t = src_up.copy(); t[-1] = xa[-1] * fL + src_up[-1]
+    fup = _affine_scan(xa, t, reverse=True)                  # f at levels 0..L-1
+    fp = np.vstack([fup, fL[None, :]])
+    fpm = np.zeros_like(fp)
+    fpm[:-1] = fp[1:] * xh + (Gt / (lu - 1.0)) * (EP * xh - EPh) - (Ht / (lu + 1.0)) * (EM * xh - EMh) + al1 * (1. - xh) + \
+        al2 * (u + 0.5 * dt - (dt + u) * xh)
+    return fm, fp, fmm, fpm
+
+
+def thermal_main():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from util import assert_level_close_yardstick, golden
+    g = golden("thermal")
+    for name in ("therm_ct0_hs0", "therm_ct0_hs1", "therm_cfg2_small", "therm_cold"):
+        case = C.thermal_cases()[name]
+        d = C.build_thermal(case)
+        args = C.thermal_args(d)
+        _, o64 = oracle.get_thermal_1d(*args, nthreads=8)
+        _, q = oracle.get_thermal_1d(*args, quad=True, nthreads=8)
+        for ia in range(d["numg"]):
+            lv = thermal_levels_from_scan(d, ia)
+            for k, a, o, x in zip(("fm", "fp", "fmm", "fpm"), lv, o64, q):
+                assert_level_close_yardstick(a, o[ia, 0], x[ia, 0], what=name + " " + k + " angle %d" % ia)
+        print("%-28s thermal level arrays from the scans pass the level-flux (yardstick) criterion" % name)
+
+
+if __name__ == "__main__" and "--thermal" in sys.argv:
+    thermal_main()
