@@ -80,3 +80,21 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and \
                     "picaso_oracle" not in src, f
+
+
+def test_patch_rebinds_and_restores_names():
+    """picaso_b200.patch(module): the drop-in seam of INTEGRATION.md - names the module has are rebound to the
+    CUDA mirrors, names it does not have are left alone, unpatch restores the originals"""
+    import types
+    mod = types.ModuleType("fake_justdoit")
+    sentinel = object()
+    for n in ("get_reflected_1d", "get_thermal_1d", "compress_disco", "get_fluxes", "mean_regrid"):
+        setattr(mod, n, sentinel)
+    mod.unrelated = 7
+    old = picaso_b200.patch(mod)
+    assert set(old) == {"get_reflected_1d", "get_thermal_1d", "compress_disco", "get_fluxes", "mean_regrid"}
+    assert mod.get_reflected_1d is picaso_b200.get_reflected_1d and mod.get_fluxes is picaso_b200.get_fluxes
+    assert mod.mean_regrid is picaso_b200.mean_regrid and mod.unrelated == 7
+    assert not hasattr(mod, "get_transit_1d")
+    picaso_b200.unpatch(mod, old)
+    assert mod.get_reflected_1d is sentinel and mod.get_fluxes is sentinel
