@@ -143,6 +143,7 @@ SYMBOLS = {
                                   c_int]),
     "pb_compress_thermal": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int]),
     "pb_selftest_math": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
+    "pb_microbench": (c_int, [c_vp, c_int, c_int, c_vp]),
     "pb_optab_create": (c_int, [c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
     "pb_optab_destroy": (c_int, [c_vp, c_vp]),
     "pb_optab_set_molecular": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int]),
@@ -212,8 +213,22 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None) is not None and self._pid == os.getpid():
+            for ent in self.__dict__.pop("_ws", {}).values():  # context-owned workspaces
+                self.lib.pb_dev_free(self.h, ent[0])
             self.lib.pb_destroy(self.h)
         self.h = None
+
+    def microbench(self, which, iters=4096):
+        """machine numbers of the fp64 pipe (pb_microbench): dict with ms, ops, Gop/s, cycles per iteration"""
+        out = (ctypes.c_double * 4)()
+        self.check(self.lib.pb_microbench(self.h, int(which), int(iters), out))
+        ms, per_thread, threads, cyc = out[0], out[1], out[2], out[3]
+        return {"ms": ms, "ops": per_thread * threads, "gops": per_thread * threads / (ms * 1e-3) / 1e9,
+                "cycles_per_iter": cyc}
+
+    def fp64_peak_tflops(self):
+        """measured DFMA peak of this GPU (2 flop per FMA), TFLOP/s"""
+        return 2.0 * self.microbench(0, 8192)["gops"] / 1e3
 
     # ---- helpers used by bench/tests ----
     def device_name(self):

@@ -220,6 +220,7 @@ __device__ __forceinline__ void refl_produce(const ReflParams &p, const ReflInpu
 
 #include "toon_reflected_toa3.cuh"
 #include "toon_reflected_toa4.cuh"
+#include "toon_reflected_toa5.cuh"
 
 template <int MP /*multi_phase*/>
 __global__ void __launch_bounds__(256) refl_toa_kernel(ReflParams p)
@@ -955,8 +956,8 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             gt->nranks > 8 || gt->rank < 0 || gt->rank >= gt->nranks || !gt->albedo || !gt->flags || !gt->done_counter ||
             gt->slot < 0 || gt->slot > 7)
             return pb_fail(ctx, PB_ERR_ARG, "reflected: peer gather needs PB_DEVICE, a fused albedo (numg*numt <= 8), nbatch 1, 1 <= nranks <= 8");
-        static const int kv = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 4; }();
-        if (kv != 4) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "reflected: peer gather is implemented in refl_toa_kernel4 only");
+        static const int kv = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 5; }();
+        if (kv < 4) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "reflected: peer gather is implemented in refl_toa_kernel4/5 only");
     }
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
 
@@ -1071,8 +1072,36 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
         }
         dim3 grid((wc + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
         // PB_REFL_KERNEL=2|3 select the previous generations (bottom-up sweeps) for A/B runs
-        static const int variant = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 4; }();
-        if (variant == 2) {
+        static const int variant = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 5; }();
+        if (variant == 5) {
+            // v5 (toon_reflected_toa5.cuh): angle-shared pivot chain on one extra warp, table exp.
+            // Tile width as for v4: 32 wavelengths unless that leaves the SMs unevenly loaded in one residency wave.
+            const int nsm = ctx->sm_count > 0 ? ctx->sm_count : 148;
+            const char *wte = getenv("PB_REFL_WT");
+            int wt = wte ? atoi(wte) : 0;
+            if (wt <= 0 || wt > 32) {
+                wt = 32;
+                const int std_ctas = (wc + 31) / 32;
+                const int per_sm = (std_ctas + nsm - 1) / nsm;
+                if (B == 1 && G <= 8 && per_sm >= 2 && per_sm <= 3 && (double)per_sm * nsm > 1.15 * std_ctas) {
+                    const int cand = (wc + nsm * per_sm - 1) / (nsm * per_sm);
+                    if (cand >= 16 && cand < 32) wt = cand;
+                }
+            }
+            q.wt = wt; q.ay = ay;
+            const int nwc = (wt * ay + 31) / 32, nw = nwc + 1;
+            const size_t smem = ((size_t)kExpTabDoubles + (size_t)2 * nw * (NP5 + NC5) * 32) * sizeof(double) + 16;
+            bool same = true;
+            for (int i = 0; i < (a->variant ? B : G); ++i) same = same && (fabs(a->ubar0[i]) == fabs(a->ubar1[i]));
+            dim3 ggrid((wc + wt - 1) / wt, (G + ay - 1) / ay, B);
+            auto go = [&](auto kern) -> int {
+                PB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<ggrid, nw * 32, smem, ctx->stream>>>(q);
+                return PB_OK;
+            };
+            if (q.mp == 0) PB_TRY(same ? go(refl_toa_kernel5<0, true>) : go(refl_toa_kernel5<0, false>));
+            else PB_TRY(same ? go(refl_toa_kernel5<1, true>) : go(refl_toa_kernel5<1, false>));
+        } else if (variant == 2) {
             const size_t smem = (size_t)2 * ay * NQ * 32 * sizeof(double);
             if (smem > 48 * 1024) {
                 PB_CUDA(ctx, cudaFuncSetAttribute(refl_toa_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
