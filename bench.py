@@ -49,6 +49,30 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_for(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu captures (profiles/traffic.json), or None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None
+    key = "".join(ch if ch.isalnum() else "_" for ch in kernel).strip("_") + "_dram_bytes_per_launch"
+    return t.get(key)
+
+
+def numba_reference():
+    """The UNMODIFIED reference functions (picaso/fluxes.py, picaso/disco.py loaded by file path, oracle/ref_loader.py)
+    when the reference tree and numba are on this box - they are in the build container, not on the GPU box - else
+    None."""
+    try:
+        from oracle import ref_loader
+        if not ref_loader.available():
+            return None
+        import numba  # noqa: F401
+        return ref_loader.load("fluxes"), ref_loader.load("disco")
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed regions run."""
 
@@ -201,7 +225,11 @@ def make_sets(rank):
 
 
 def run_reference(args, rank, world):
-    """The reference arm: the CPU port of the reference algorithm (oracle/) on all host cores."""
+    """The reference arm.  The reference is single-threaded numba (no parallel=True / prange / nogil anywhere,
+    SURVEY.md section 1), so the line's `value` is a 1-core figure: the reference's own get_reflected_1d +
+    compress_disco (JIT excluded) where /root/reference and numba exist (`kind: reference`); on the GPU box the
+    reference tree cannot travel, so the C port of the same algorithm (oracle/) on ONE thread stands in
+    (`kind: port`), with its all-threads OpenMP figure beside it (`all_threads_value`)."""
     if rank != 0:
         return
     import cases as C
@@ -209,16 +237,40 @@ def run_reference(args, rank, world):
     nthreads = os.cpu_count() or 1
     d = make_sets(0)[0]
     a = C.reflected_args(d, KW)
-    for _ in range(max(args.warmup, 1)):
-        x, _ = oracle.get_reflected_1d(*a, nthreads=nthreads)
-        oracle.compress_disco(W, d["cos_theta"], x, d["gweight"], d["tweight"], d["F0PI"])
+
+    def port(n):
+        x, _ = oracle.get_reflected_1d(*a, nthreads=n)
+        return oracle.compress_disco(W, d["cos_theta"], x, d["gweight"], d["tweight"], d["F0PI"])
+
+    ref = numba_reference()
+    if ref is not None:
+        rf, rd = ref
+
+        def one():
+            x, _ = rf.get_reflected_1d(*a)
+            return rd.compress_disco(W, d["cos_theta"], x, d["gweight"], d["tweight"], d["F0PI"])
+        kind, cores = "reference", 1
+        sample = "%d full spectra (60x10000x5) per run: the unmodified picaso.fluxes.get_reflected_1d + disco.compress_disco (numba, JIT excluded), 1 core of %d" % (args.steps, nthreads)
+    else:
+        one = lambda: port(1)
+        kind, cores = "port", 1
+        sample = ("%d full spectra (60x10000x5) per run: C port of the reference algorithm (oracle/) on 1 thread - the reference "
+                  "itself is single-threaded numba and /root/reference does not exist on this box; all-threads OpenMP figure in "
+                  "all_threads_value" % args.steps)
+    for _ in range(max(min(args.warmup, 2), 1)):
+        one()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        x, _ = oracle.get_reflected_1d(*a, nthreads=nthreads)
-        oracle.compress_disco(W, d["cos_theta"], x, d["gweight"], d["tweight"], d["F0PI"])
+        one()
     dt = time.perf_counter() - t0
     val = W * args.steps / dt
-    sample = "%d full spectra (60x10000x5) per run, C port of the reference algorithm, OpenMP over wavelengths" % args.steps
+    port(nthreads)
+    t0 = time.perf_counter()
+    n = 0
+    while n < 50 and (n < 3 or time.perf_counter() - t0 < 5.0):
+        port(nthreads)
+        n += 1
+    allv = W * n / (time.perf_counter() - t0)
     db, ray, atms, _ = _spectrum_setup()
     sv, sn, sel = time_spectrum_cpu(db, ray, atms, nthreads)
     print(json.dumps({
@@ -227,7 +279,9 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "spectra_per_sec": args.steps / dt,
         "config": {"workload": WORKLOAD},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "all_threads_value": allv, "all_threads_cores": nthreads, "all_threads_kind": "port (OpenMP over wavelengths)",
+                         "host_cpus": os.cpu_count()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "e2e_spectrum": {"value": sv, "unit": UNIT, "steps": sn,
                          "api": "numpy port of get_opacities(linear) + compute_opacity (%d molecules, clear, no Raman) + C port of "
@@ -243,10 +297,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 40)")
+    ap.add_argument("--config", default="headline", choices=["headline", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configuration; headline = 60 x 10 000 x 5 reflected Toon (the metric's own config)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config != "headline":
+        import bench_configs
+        return bench_configs.run(args, rank, local_rank, world)
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -493,21 +552,21 @@ def main():
     peak, peak_src = peaks()
     alg_bytes = ALG_BYTES_PER_WAVE * W
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("refl_toa_kernel_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    fpath = os.path.join(ROOT, "profiles", "r1_refl_toa_v4gen.summary.json")
+    kernel = "refl_toa_kernel5"
+    traffic = traffic_for(kernel)
     fp64_pct = None
-    if os.path.isfile(fpath):
+    for fpath in ("r2_refl_toa_v5.summary.json", "r1_refl_toa_v4gen.summary.json"):
         try:
-            fp64_pct = json.load(open(fpath))["launches"][0][
+            fp64_pct = json.load(open(os.path.join(ROOT, "profiles", fpath)))["launches"][0][
                 "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]["value"]
+            break
         except Exception:
-            fp64_pct = None
+            continue
+    # second roof: the fp64 pipe (there is no fp64 figure in MEASURED_PEAKS.json; measured here with a DFMA loop)
+    try:
+        fp64_peak = ctx.fp64_peak_tflops()
+    except Exception:
+        fp64_peak = None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -531,10 +590,12 @@ def main():
                 "steps": ke, "ms_per_step": 1e3 * e2e_dt / ke,
                 "api": "picaso_b200.get_reflected_1d(..., return_albedo=True), pinned host inputs"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel": "refl_toa_kernel4_gen",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": kernel,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                     "fp64_pipe_pct_ncu": fp64_pct,
-                     "note": "not HBM-bound: ~50 fp64 flop/B; 435 CTAs of 4 warps = 12 warps per SM, dependent fp64 "
+                     "fp64_pipe_pct_ncu": fp64_pct, "fp64_peak_tflops_measured": fp64_peak,
+                     "fp64_roof_note": "second roof: DFMA loop measured in this run (pb_microbench); the kernel issues ~14 M fp64 "
+                                       "warp-instructions per launch = 24 us at that rate, against 8.2 us of HBM time",
+                     "note": "not HBM-bound: ~45 fp64 flop/B; 435 CTAs of 5 warps = 15 warps per SM, dependent fp64 "
                              "chains (ncu stall_wait); DRAM traffic = algorithmic bytes; see DESIGN.md 4.1 and profiles/"},
         "clocks": sampler.summary(),
     }
@@ -554,9 +615,10 @@ def main():
         t1 = time.perf_counter()
         oracle.get_reflected_1d(*a, nthreads=1)
         one = time.perf_counter() - t1
-        out["cpu_baseline"] = {"value": W * n / el, "unit": UNIT, "cores": nthreads, "kind": "port",
-                               "sample": "%d full 60x10000x5 spectra in %.1f s; C port of the reference algorithm (oracle/), OpenMP over wavelengths" % (n, el),
-                               "single_thread_value": W / one, "host_cpus": os.cpu_count()}
+        out["cpu_baseline"] = {"value": W / one, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": "one full 60x10000x5 spectrum on 1 thread (the reference is single-threaded numba); C port of the "
+                                         "reference algorithm (oracle/); all-threads OpenMP figure: %d spectra in %.1f s" % (n, el),
+                               "all_threads_value": W * n / el, "all_threads_cores": nthreads, "host_cpus": os.cpu_count()}
     if rank == 0 and world == 1:
         # ---- spectrum-level end to end: profile in, albedo out, opacity tables resident in HBM ----
         db, ray, atms, ducks = _spectrum_setup()

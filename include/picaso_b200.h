@@ -385,6 +385,8 @@ int pb_gather_wait(pb_ctx *ctx, const unsigned long long *flags, int nranks, uns
 /* ---- self test ------------------------------------------------------------------------- */
 /* evaluates the kernels' branch-free exp() and 1/x on x[n] (host pointers); test hook */
 int pb_selftest_math(pb_ctx *ctx, const double *x, int n, double *exp_out, double *rcp_out);
+/* evaluates the flux kernels' shared-memory table exp() on x[n] (host pointers, x <= 709); test hook */
+int pb_selftest_exp_tab(pb_ctx *ctx, const double *x, int n, double *exp_out);
 /* machine numbers of the fp64 pipe (the second roof in bench.py's roofline block; no reference counterpart).
  * which: 0 DFMA throughput, 1 DFMA latency, 2 DFMA throughput with half-active warps, 3 LDS.64 throughput,
  * 4 reciprocal latency, 5 DFMA throughput at 3 warps per SM sub-partition.

@@ -73,16 +73,60 @@ __device__ __forceinline__ double rcp(double x)
 {
     double y0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    double e = fma(-x, y0, 1.0);
+    // y0 (1 + e)(1 + e^2) = y0 (1 - e^4) / (1 - e): the second step reuses e (e^2 in parallel with the first update)
+    // instead of a second residual - dependent depth 3 instead of 4, x y = 1 - e^4 with |e| < 2^-20
+    const double e = fma(-x, y0, 1.0);
     double y = fma(y0, e, y0);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
+    y = fma(y, e * e, y);
     const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;  // biased exponent
     const bool regular = (ex - 1u) < 0x7feu;                           // 1 .. 0x7fe
     return regular ? y : y0;
 }
 
 __device__ __forceinline__ double div(double a, double b) { return a * rcp(b); }
+
+// ---- table exp (toon_reflected_toa5.cuh, toon_thermal.cu) ----------------------------------------------
+// A CTA keeps 2^(j/64), j = 0..63, in shared memory, 16 interleaved copies (entry j of copy c at [16 j + c]): a
+// thread reads copy (lane & 15), so the 16 lanes of each half-warp phase of an LDS.64 hit 16 different bank
+// pairs whatever their j - conflict-free for any argument pattern.  8 KB.
+constexpr int kExpTabDoubles = 64 * 16;
+__device__ __forceinline__ void exp_tab_fill(double *tabw, int tid, int nthreads)
+{
+    for (int i = tid; i < kExpTabDoubles; i += nthreads) tabw[i] = ::exp2((double)(i >> 4) * (1.0 / 64.0));
+}
+
+// exp(x) for x <= 709 (every argument in this kernel is -dtau/u <= 0 or the clipped lambda dtau <= 40).
+// tab = shared table base + (lane & 15); entry j at tab[16 j] holds 2^(j/64).
+// 9 fp64 instructions, no branch, dependent depth 8: x = (64 k + j) ln2/64 + r, exp(x) = 2^k 2^(j/64) exp(r); the power of two goes
+// into the exponent field of the table entry.  x <= -1024 (optically very thick layers, -inf) is clamped to -1024
+// on the integer pipe and k to the normal range, so such results come out as ~1e-308 instead of 0 - every one of
+// them multiplies an O(1) quantity; NaN propagates.  Relative error <= 1.2e-16 |x| + 1 ulp.
+__constant__ double kExpTabC[5] = {92.33248261689366 /* 64/ln2 */, -0.010830424696249145 /* -ln2/64 */,
+                                 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+__device__ __forceinline__ double exp_tab(double x, const double *tab)
+{
+    const double kMagic = 6755399441055744.0;               // 1.5 * 2^52
+    {
+        const unsigned hx = (unsigned)__double2hiint(x);    // -inf <= x <= -1024  <=>  0xC0900000 <= hx <= 0xFFF00000
+        const bool big = (hx - 0xC0900000u) <= (0xFFF00000u - 0xC0900000u);
+        x = __hiloint2double(big ? (int)0xC0900000u : (int)hx, big ? 0 : __double2loint(x));
+    }
+    const double t = fma(x, kExpTabC[0], kMagic);
+    const int n = __double2loint(t);
+    const double nf = t - kMagic;
+    const double r = fma(nf, kExpTabC[1], x);                 // |r| <= 5.42e-3
+    // exp(r) - 1 = r + r^2 (1/2 + r/6 + r^2 (1/24 + r/120)), Estrin: dependent depth 4 instead of Horner's 6
+    const double r2 = r * r;
+    const double a = fma(r, kExpTabC[4], 0.5);
+    const double b = fma(r, kExpTabC[2], kExpTabC[3]);
+    const double c = fma(r2, b, a);
+    const double pm1 = fma(r2, c, r);
+    const double T = tab[(n & 63) << 4];
+    const int k = max(min(n >> 6, 1023), -1022);
+    const double Ts = __hiloint2double(__double2hiint(T) + (k << 20), __double2loint(T));
+    return fma(Ts, pm1, Ts);
+}
+
 
 // What the kernels call.  Measured on B200 (r1 A/B, reflected 60x10000x5, us per launch):
 // libdevice exp + pbm::rcp 104.2 | libdevice both 108.4 | pbm::exp + libdevice div 110.7 |

@@ -11,7 +11,35 @@ __global__ void math_kernel(int n, const double *x, double *e, double *r)
     e[i] = pbm::exp(x[i]);
     r[i] = pbm::rcp(x[i]);
 }
+__global__ void exp_tab_kernel(int n, const double *x, double *e)
+{
+    __shared__ double tab[pbm::kExpTabDoubles];
+    pbm::exp_tab_fill(tab, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) e[i] = pbm::exp_tab(x[i], tab + (threadIdx.x & 15));
+}
 } // namespace
+
+extern "C" int pb_selftest_exp_tab(pb_ctx *ctx, const double *x, int n, double *exp_out)
+{
+    if (!ctx || !x || !exp_out || n < 0) return pb_fail(ctx, PB_ERR_ARG, "selftest_exp_tab: bad arguments");
+    if (n == 0) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)n * sizeof(double);
+    pb_arena_reset(ctx);
+    PB_TRY(pb_arena_reserve(ctx, 2 * pb_align(nb) + 1024));
+    const double *dx;
+    int64_t ldo;
+    PB_TRY(pb_stage_in(ctx, x, PB_HOST, 1, n, n, &dx, &ldo));
+    double *de;
+    PB_TRY(pb_arena_alloc(ctx, nb, (void **)&de));
+    exp_tab_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, dx, de);
+    PB_CHECK_LAUNCH(ctx);
+    PB_CUDA(ctx, cudaMemcpyAsync(exp_out, de, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
 
 extern "C" int pb_selftest_math(pb_ctx *ctx, const double *x, int n, double *exp_out, double *rcp_out)
 {

@@ -22,6 +22,7 @@
 //    stores the elimination coefficients in the caller's four output arrays (they are
 //    exactly 4 doubles per level) and overwrites them with fluxes on the way down.
 #include <cstdlib>
+#include <type_traits>
 
 #include "pb_common.cuh"
 #include "pb_math.cuh"
@@ -42,7 +43,8 @@ struct ReflParams {
     int variant;   // 1: per-facet get_reflected_3d semantics (geometry indexed by batch entry)
     double clip;   // exponent clip: 35 (1-D, fluxes.py:1174) or 40 (3-D, fluxes.py:516)
     // fused all-gather of the albedo slab over peer memory (pb_peer_gather); g_n == 0: off
-    int wt, ay;    // refl_toa_kernel4<GEN = true>: wavelengths / angles per CTA
+    int wt, ay;    // refl_toa_kernel4<GEN = true>, refl_toa_kernel5: wavelengths / angles per CTA
+    int ch;        // refl_toa_kernel5: layers per chunk (= producing warps)
     int g_n, g_rank;
     double *g_alb[8];
     unsigned long long *g_flag[8];
@@ -1080,17 +1082,24 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             const char *wte = getenv("PB_REFL_WT");
             int wt = wte ? atoi(wte) : 0;
             if (wt <= 0 || wt > 32) {
-                wt = 32;
-                const int std_ctas = (wc + 31) / 32;
+                // 128 registers x 3 CTAs per SM leave room for 5 warps per CTA (4 consumer warps + the chain warp):
+                // the widest tile whose wt * ay consumer threads fit 4 warps (ay = 5: 25 wavelengths) ...
+                const int cap = ay <= 4 ? 32 : (128 / ay);
+                wt = cap;
+                // ... narrowed, when the whole launch is a single residency wave, so that every SM gets the same
+                // number of CTAs (W = 10 000: 3 x 148 CTAs of 23 wavelengths instead of 400 of 25)
+                const int std_ctas = (wc + cap - 1) / cap;
                 const int per_sm = (std_ctas + nsm - 1) / nsm;
-                if (B == 1 && G <= 8 && per_sm >= 2 && per_sm <= 3 && (double)per_sm * nsm > 1.15 * std_ctas) {
+                if (B == 1 && per_sm <= 3 && (double)per_sm * nsm > 1.05 * std_ctas) {
                     const int cand = (wc + nsm * per_sm - 1) / (nsm * per_sm);
-                    if (cand >= 16 && cand < 32) wt = cand;
+                    if (cand >= 12 && cand < cap) wt = cand;
                 }
             }
             q.wt = wt; q.ay = ay;
             const int nwc = (wt * ay + 31) / 32, nw = nwc + 1;
-            const size_t smem = ((size_t)kExpTabDoubles + (size_t)2 * nw * (NP5 + NC5) * 32) * sizeof(double) + 16;
+            // 5 producing warps keep the tiles at 76 KB: three CTAs per SM (a sixth warp, if any, only consumes)
+            q.ch = nw < 5 ? nw : 5;
+            const size_t smem = ((size_t)pbm::kExpTabDoubles + (size_t)q.ch * (3 * NP5 + 2 * NC5) * 32) * sizeof(double) + 16;
             bool same = true;
             for (int i = 0; i < (a->variant ? B : G); ++i) same = same && (fabs(a->ubar0[i]) == fabs(a->ubar1[i]));
             dim3 ggrid((wc + wt - 1) / wt, (G + ay - 1) / ay, B);

@@ -32,38 +32,14 @@
 // layer from global memory and re-base their running products with a true exponential.
 
 #ifndef PB_REFL5_UNROLL
-#define PB_REFL5_UNROLL 1
+#define PB_REFL5_UNROLL 2
+#endif
+#ifndef PB_REFL5_PREFETCH
+#define PB_REFL5_PREFETCH 1
 #endif
 enum { P5_DT = 0, P5_DTO, P5_LAM, P5_B0, P5_A1, P5_FW, P5_OMC, P5_OGC, P5_OG, P5_GAM, P5_EP, P5_EM, P5_S0, NP5 };
 enum { C5_QO = 0, C5_S13, C5_CSO, C5_R1, C5_R2, C5_R3, C5_CS, NC5 };
-constexpr int kExpTabDoubles = 64 * 16;
 constexpr int kRefl5Unroll = PB_REFL5_UNROLL;
-
-// exp(x), tab = shared table base + (lane & 15); entry j at tab[16 j] holds 2^(j/64)
-__device__ __forceinline__ double exp5(double x, const double *tab)
-{
-    const double kMagic = 6755399441055744.0;               // 1.5 * 2^52
-    const double t = fma(x, 92.33248261689366, kMagic);     // 64 / ln 2
-    const int n = __double2loint(t);
-    const double nf = t - kMagic;
-    const double r = fma(nf, -0.010830424696249145, x);     // ln 2 / 64, |r| <= 5.42e-3
-    double q = fma(1.0 / 120.0, r, 1.0 / 24.0);
-    q = fma(q, r, 1.0 / 6.0);
-    q = fma(q, r, 0.5);
-    q = fma(q, r, 1.0);
-    q = fma(q, r, 1.0);
-    const double y = tab[(n & 63) << 4] * q;                 // in [0.994, 1.99)
-    const int hx = __double2hiint(x);
-    const int ax = hx & 0x7fffffff;
-    const bool in_range = ax < (hx < 0 ? 0x40861800 /* 707 */ : 0x40862800 /* 709 */);
-    const bool is_nan = ax > 0x7ff00000 || (ax == 0x7ff00000 && __double2loint(x) != 0);
-    const int sat = hx < 0 ? 0 : 0x7ff00000;                 // underflow -> 0, overflow -> +inf
-    int hi = in_range ? __double2hiint(y) + ((n >> 6) << 20) : sat;
-    int lo = in_range ? __double2loint(y) : 0;
-    hi = is_nan ? (hx | 0x00080000) : hi;
-    lo = is_nan ? __double2loint(x) : lo;
-    return __hiloint2double(hi, lo);
-}
 
 struct Refl5Angle {  // per-thread constants of one viewing geometry
     double u0, u1, inv_u0, inv_u1, c, hm, t2c, wgt, f0;
@@ -81,7 +57,7 @@ __device__ __forceinline__ void refl5_produce(const ReflParams &p, const Refl4In
     const double lam = sqrt(g1 * g1 - g2 * g2);
     const double gam = (g1 - lam) * pbm::krcp(g2);
     const double E = fmin(lam * x.dt, p.clip);  // slice_gt(exptrm, 35 | 40), fluxes.py:1174, :516
-    const double EP = exp5(E, tab);
+    const double EP = pbm::exp_tab(E, tab);
     const double ps = p_single(p, x.cbo, x.gc2, x.fc, x.fr);
     const double omc = x.om * c2pi;
     q[P5_DT * 32] = x.dt;
@@ -102,17 +78,36 @@ __device__ __forceinline__ void refl5_produce(const ReflParams &p, const Refl4In
     if (!ok) *bad = 1;
 }
 
+// The caller's tau / tau_og are not cumsum(dtau) somewhere in this CTA's tile: re-check level l + 1 of one column and
+// return exp(-tau[l+1]/u0), exp(-tau_og[l+1]/u0) where the running product must be re-based (marker NaN otherwise).
+// Out of line: it is never taken for compute_opacity's arrays and must not cost the main loop registers.
+__device__ __noinline__ double2 refl5_exact_tau(const double *tau, const double *tau_og, const double *dtau_og,
+                                                int64_t iv, int64_t il, int64_t ld, double dt, double inv_u0,
+                                                bool og_alias)
+{
+    double2 out;
+    const double td = refl4_tau_slot(__ldg(tau + iv), dt, __ldg(tau + iv + ld));
+    out.x = __double2hiint(td) != kConsistentHi ? ::exp(-td * inv_u0) : td;
+    if (og_alias) {
+        out.y = out.x;
+    } else {
+        const double sd = refl4_tau_slot(__ldg(tau_og + iv), __ldg(dtau_og + il), __ldg(tau_og + iv + ld));
+        out.y = __double2hiint(sd) != kConsistentHi ? ::exp(-sd * inv_u0) : sd;
+    }
+    return out;
+}
+
 // SAME: every angle of the launch has u0 == u1 (zero phase).
 template <int MP /*multi_phase*/, bool SAME>
 __device__ __forceinline__ void refl5_body(const ReflParams &p)
 {
     extern __shared__ double smem[];
-    // layout: exp table [64][16] | P tiles [2][CH][NP5][32] | C tiles [2][CH][NC5][32] | flag
+    // layout: exp table [64][16] | P tiles [3][CH][NP5][32] | C tiles [2][CH][NC5][32] | flag
     const int tid = threadIdx.x;
     const int lane = tid & 31, wy = tid >> 5;
-    const int NW = (int)(blockDim.x >> 5);   // all warps produce; the last one is the chain warp
+    const int NW = (int)(blockDim.x >> 5);   // the last warp is the chain warp
     const int NWC = NW - 1;
-    const int CH = NW;                       // layers per chunk (one per producing warp)
+    const int CH = p.ch;                     // layers per chunk = producing warps (wy < CH), CH <= NW
     const int WT = p.wt, AY = p.ay;
     const bool is_chain = wy == NWC;
     const bool is_cons = tid < WT * AY;
@@ -132,11 +127,11 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
     const int64_t ovc = (int64_t)b * p.bs_level + wc;
     const int64_t ow = (int64_t)b * p.bs_wave + wc;
     double *tabw = smem;
-    double *ptile = smem + kExpTabDoubles;
+    double *ptile = smem + pbm::kExpTabDoubles;
     const int psz = CH * NP5 * 32, csz = CH * NC5 * 32;
-    double *ctile = ptile + 2 * psz;
+    double *ctile = ptile + 3 * psz;
     int *bad = (int *)(ctile + 2 * csz);
-    for (int i = tid; i < kExpTabDoubles; i += blockDim.x) tabw[i] = exp2((double)(i >> 4) * (1.0 / 64.0));
+    pbm::exp_tab_fill(tabw, tid, blockDim.x);
     if (tid == 0) *bad = 0;
     const double *tab = tabw + (lane & 15);
     const double f0p = p.f0pi ? p.f0pi[(int64_t)b * p.bs_wave + wpc] : 1.0;
@@ -155,22 +150,45 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
     const double ubar2 = 0.767;  // fluxes.py:1280
     g.t2c = (3.0 * ubar2 * ubar2 * g.u1 * g.u1 - 1.0) / 2.0;
     g.og_alias = (p.dtau_og == p.dtau) && (p.tau_og == p.tau);
+    // opaque to the optimiser: otherwise ptxas re-derives these per-angle constants inside the layer loop
+    // (6 fp64 instructions per layer) instead of keeping three registers
+    asm volatile("" : "+d"(g.c), "+d"(g.hm), "+d"(g.t2c));
     const int nchunks = (L + CH - 1) / CH;
 
-    Refl4Inputs pre;  // inputs of the layer this warp produces next
+    // Inputs of the layer this warp produces next.  PB_REFL5_PREFETCH 0: loaded into registers one iteration ahead
+    // (26 registers live across the consume phase); 1: pulled into L2 one iteration ahead, loaded when produced.
+    Refl4Inputs pre;
     auto prefetch = [&](int c) {
         const int l = c * CH + wy;
-        if (l < L) refl4_load(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, ld, pre);
+        if (wy < CH && l < L) {
+#if PB_REFL5_PREFETCH == 0
+            refl4_load(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, ld, pre);
+#else
+            const int64_t il = ol + (int64_t)l * ld, iv = ov + (int64_t)l * ld;
+            if (lane == 0 || lane == 16) {  // one prefetch per 128-byte line of the 256-byte row segment
+                const double *rows[12] = {p.w0 + il, p.fcld + il, p.cosb + il, p.dtau + il, p.gcos2 + il, p.fray + il,
+                                          p.dtau_og + il, p.w0_og + il, p.cosb_og + il, p.tau + iv + ld, p.tau_og + iv + ld,
+                                          p.tau + iv};
+#pragma unroll
+                for (int i = 0; i < 12; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(rows[i]));
+            }
+#endif
+        }
     };
     auto produce = [&](int c) {
         const int l = c * CH + wy;
-        if (l < L) refl5_produce(p, pre, f0p, kappa, tab, ptile + (c & 1) * psz + wy * NP5 * 32 + lane, bad);
+        if (wy < CH && l < L) {
+#if PB_REFL5_PREFETCH != 0
+            refl4_load(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, ld, pre);
+#endif
+            refl5_produce(p, pre, f0p, kappa, tab, ptile + (c % 3) * psz + wy * NP5 * 32 + lane, bad);
+        }
     };
 
     // chain-warp state: relation X[2l] = DS - CS X[2l+1] of the last even row, previous layer's e-terms
     double ch_CS = 0.0, ch_e1p = 0.0, ch_e3p = 0.0, ch_s13p = 0.0, ch_s24p = 0.0, ch_gamp = 0.0;
     auto chain = [&](int c) {
-        const double *pt = ptile + (c & 1) * psz + lane;
+        const double *pt = ptile + (c % 3) * psz + lane;
         double *ct = ctile + (c & 1) * csz + lane;
         const int lbase = c * CH;
         const int nk = L - lbase < CH ? L - lbase : CH;
@@ -211,47 +229,41 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
     double T1 = 1.0, T0 = 1.0, TO = 1.0, f1p = 0.0, am_p = 0.0, ap_p = 0.0;
     __syncthreads();  // table
     if (is_cons) {
-        T0 = exp5(-__ldg(p.tau + ovc) * g.inv_u0, tab);  // exp(-tau[0]/u0): 1 for tau[0] = 0
-        TO = g.og_alias ? T0 : exp5(-__ldg(p.tau_og + ovc) * g.inv_u0, tab);
+        T0 = pbm::exp_tab(-__ldg(p.tau + ovc) * g.inv_u0, tab);  // exp(-tau[0]/u0): 1 for tau[0] = 0
+        TO = g.og_alias ? T0 : pbm::exp_tab(-__ldg(p.tau_og + ovc) * g.inv_u0, tab);
     }
 
-    auto consume = [&](int c) {
-        const double *pt = ptile + (c & 1) * psz + cw;
+    // SLOW (std::true_type): some level of this CTA's tile has tau[l+1] != tau[l] + dtau[l] - re-check every level
+    auto consume = [&](int c, auto slow_tag) {
+        constexpr bool slow = decltype(slow_tag)::value;
+        const double *pt = ptile + (c % 3) * psz + cw;
         const double *ct = ctile + (c & 1) * csz + cw;
         const int lbase = c * CH;
         const int nk = L - lbase < CH ? L - lbase : CH;
-        const bool slow = *(volatile int *)bad != 0;
+        const double *q = pt, *o = ct;
 #pragma unroll kRefl5Unroll
-        for (int k = 0; k < nk; ++k) {
-            const double *q = pt + k * NP5 * 32;
-            const double *o = ct + k * NC5 * 32;
+        for (int k = 0; k < nk; ++k, q += NP5 * 32, o += NC5 * 32) {
             const double dt = q[P5_DT * 32];
-            const double xa = exp5(-dt * g.inv_u1, tab);
-            const double xa0 = SAME ? xa : exp5(-dt * g.inv_u0, tab);
+            const double xa = pbm::exp_tab(-dt * g.inv_u1, tab);
+            const double xa0 = SAME ? xa : pbm::exp_tab(-dt * g.inv_u0, tab);
             double xoa0, xoa1;
             if (g.og_alias) {
                 xoa0 = xa0; xoa1 = xa;
             } else {
                 const double dto = q[P5_DTO * 32];
-                xoa0 = exp5(-dto * g.inv_u0, tab);
-                xoa1 = SAME ? xoa0 : exp5(-dto * g.inv_u1, tab);
+                xoa0 = pbm::exp_tab(-dto * g.inv_u0, tab);
+                xoa1 = SAME ? xoa0 : pbm::exp_tab(-dto * g.inv_u1, tab);
             }
             const double xu = T0, xo = TO;
             double xd = xu * xa0;
             double xod = g.og_alias ? xd : xo * xoa0;
             if (slow) {
-                // the caller's tau is not cumsum(dtau) somewhere in this tile: re-check this level, exact exponentials
                 const int l = lbase + k;
-                const double t0 = __ldg(p.tau + ovc + (int64_t)l * ld), t1 = __ldg(p.tau + ovc + (int64_t)(l + 1) * ld);
-                const double td = refl4_tau_slot(t0, dt, t1);
-                if (__double2hiint(td) != kConsistentHi) xd = pbm::kexp(-td * g.inv_u0);
-                if (g.og_alias) {
-                    xod = xd;
-                } else {
-                    const double s0 = __ldg(p.tau_og + ovc + (int64_t)l * ld), s1 = __ldg(p.tau_og + ovc + (int64_t)(l + 1) * ld);
-                    const double sd = refl4_tau_slot(s0, __ldg(p.dtau_og + olc + (int64_t)l * ld), s1);
-                    if (__double2hiint(sd) != kConsistentHi) xod = pbm::kexp(-sd * g.inv_u0);
-                }
+                const double2 ex = refl5_exact_tau(p.tau, p.tau_og, p.dtau_og, ovc + (int64_t)l * ld, olc + (int64_t)l * ld,
+                                                   ld, dt, g.inv_u0, g.og_alias);
+                if (__double2hiint(ex.x) != kConsistentHi) xd = ex.x;
+                if (g.og_alias) xod = xd;
+                else if (__double2hiint(ex.y) != kConsistentHi) xod = ex.y;
             }
             // a-, a+ (fluxes.py:1161-1166) as B0 +- v.  lambda^2 - 1/u0^2 is formed as (lambda - 1/u0)(lambda + 1/u0):
             // near lambda u0 = 1 the rounded squares would lose ~9 digits, and at zero phase 1/(lambda u1 + 1) below is
@@ -311,31 +323,38 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
         }
     };
 
+    // Pipeline, one barrier per chunk: in iteration c the consumers integrate chunk c (P[c % 3], C[c & 1]), the chain warp
+    // eliminates chunk c + 1 (P[(c+1) % 3] -> C[(c+1) & 1]) and every producing warp writes its layer of chunk c + 2
+    // (P[(c+2) % 3]) from registers loaded one iteration earlier, then loads its layer of chunk c + 3.
     prefetch(0);
     produce(0);
     prefetch(1);
     __syncthreads();
+    if (is_chain) chain(0);
+    produce(1);
+    prefetch(2);
+    __syncthreads();
     // warp-specialised main loops (same barrier sequence in both): the chain warp's state and the consumers'
     // state never live in the same registers
     if (is_chain) {
-        chain(0);
         for (int c = 0; c < nchunks; ++c) {
-            if (c + 1 < nchunks) {
-                produce(c + 1);
-                prefetch(c + 2);
-            }
-            __syncthreads();
             if (c + 1 < nchunks) chain(c + 1);
+            if (c + 2 < nchunks) {
+                produce(c + 2);
+                prefetch(c + 3);
+            }
             __syncthreads();
         }
     } else {
         for (int c = 0; c < nchunks; ++c) {
-            if (c + 1 < nchunks) {
-                produce(c + 1);
-                prefetch(c + 2);
+            if (c + 2 < nchunks) {
+                produce(c + 2);
+                prefetch(c + 3);
             }
-            __syncthreads();
-            if (is_cons) consume(c);
+            if (is_cons) {
+                if (*(volatile int *)bad != 0) consume(c, std::true_type());
+                else consume(c, std::false_type());
+            }
             __syncthreads();
         }
     }
@@ -344,7 +363,7 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
         // I_L = flux_zero/pi (fluxes.py:1266-1270) enters with weight T_L; fold X[2L-2], then the
         // surface row 2L-1 (fluxes.py:178-181) closes the chain
         const int kl = (L - 1) - (nchunks - 1) * CH;
-        const double *q = ptile + ((nchunks - 1) & 1) * psz + kl * NP5 * 32 + cw;
+        const double *q = ptile + ((nchunks - 1) % 3) * psz + kl * NP5 * 32 + cw;
         const double gam = q[P5_GAM * 32], EP = q[P5_EP * 32], EM = q[P5_EM * 32];
         const double e1 = EP + gam * EM, e2 = EP - gam * EM, e3 = gam * EP + EM, e4 = gam * EP - EM;
         const double cpd = ap_p * T0, cmd = am_p * T0;
@@ -404,7 +423,7 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
 }
 
 #ifndef PB_REFL5_UNROLL
-#define PB_REFL5_UNROLL 1
+#define PB_REFL5_UNROLL 2
 #endif
 #ifndef PB_REFL5_REGS
 #define PB_REFL5_REGS 128

@@ -243,6 +243,31 @@ def test_chunked_host_pipeline_ragged_padded(monkeypatch):
     assert np.array_equal(x_only, xint)
 
 
+def test_table_exp():
+    """shared-memory table exp of the v5 reflected kernel (pb_math.cuh: exp_tab) vs libm on its domain x <= 709:
+    relative error <= 1.2e-16 |x| + 1 ulp; x <= -708 comes out <= 2.3e-308 (never inf / NaN); NaN propagates."""
+    from picaso_b200 import _lib
+    ctx = _lib.default_context()
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-707, 700, 300000), rng.uniform(-40, 40, 300000), rng.normal(0, 1e-3, 1000),
+                        -10.0 ** rng.uniform(-300, 300, 50000), 10.0 ** rng.uniform(-300, 2, 20000),
+                        [0.0, -0.0, -np.inf, np.nan, 35.0, -35.0, 709.0, -745.1, -1023.9, -1024.0, -1e6, -2.4e7, -1e15,
+                         -1e100, -1e300, -1e-310, 1e-310]])
+    x = x[np.isnan(x) | (x <= 709.0)]
+    e = np.empty_like(x)
+    ctx.check(ctx.lib.pb_selftest_exp_tab(ctx.h, x.ctypes.data, x.size, e.ctypes.data))
+    with np.errstate(all="ignore"):
+        we = np.exp(x)
+    assert np.array_equal(np.isnan(e), np.isnan(x))
+    reg = (x > -707.0) & ~np.isnan(x)
+    err = np.abs(e[reg] - we[reg]) / we[reg]
+    assert np.all(err <= 1.2e-16 * np.abs(x[reg]) + 2.3e-16), err.max()
+    assert np.max(err[np.abs(x[reg]) <= 40]) < 4e-15
+    low = (x <= -707.0)
+    assert np.all((e[low] >= 0.0) & (e[low] < 1e-306))
+    assert e[np.flatnonzero(x == 0.0)[0]] == 1.0
+
+
 def test_kernel_math_primitives():
     """branch-free exp / reciprocal used inside the kernels vs numpy (libm)."""
     from picaso_b200 import _lib
