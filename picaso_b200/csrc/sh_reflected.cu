@@ -22,6 +22,8 @@
 //    constant term IS xint_at_top.  No LU factors, no back-substitution, no O(L) storage.
 // The reference's cumulative in-place scaling of f_deltaM across angles (fluxes.py:2823,
 // SURVEY.md Appendix A1) is reproduced: angle k uses f_deltaM * factor^(k+1).
+#include <cstdlib>
+
 #include "pb_common.cuh"
 #include "pb_math.cuh"
 
@@ -424,6 +426,8 @@ __global__ void __launch_bounds__(128) sh_reflected_kernel(ShParams p)
     }
 }
 
+#include "sh_reflected_tile.cuh"
+
 // ---------------------------------------------------------------------------------------
 // Thermal SH (get_thermal_SH, fluxes.py:2979-3186): same block structure with the linear-in-tau
 // Planck particular solution (calculation == 1 branches, :3266-3270 / :3451-3459); the upward
@@ -716,7 +720,13 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool host = memspace == PB_HOST;
     const size_t nW = (size_t)W * sizeof(double);
-    const bool fuse = a->albedo && G <= 4;
+    // SH4 with drift-free (OTHG) moment forms and the explicit single-scattering phase function: the matrix work is
+    // angle-independent -> sh4_tile_kernel (sh_reflected_tile.cuh); PB_SH_TILE=0 forces the per-angle kernel
+    const char *tile_e = getenv("PB_SH_TILE");
+    const int tile_env = tile_e ? atoi(tile_e) : 1;
+    const bool tile = tile_env != 0 && a->stream == 4 && a->w_single_form == 1 && a->w_multi_form == 1 &&
+                      a->single_form == 0 && !a->f_deltaM_out;
+    const bool fuse = a->albedo && G <= (tile ? 8 : 4);
     const bool need_xint = a->xint_at_top || (a->albedo && !fuse);
     size_t need = 16 * 256 + 4 * pb_align((size_t)G * 8);
     if (host) {
@@ -774,7 +784,13 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
     dim3 block(kWaves, ay, 1);
     dim3 grid((W + kWaves - 1) / kWaves, (G + ay - 1) / ay, B);
     const size_t smem = fuse ? (size_t)ay * kWaves * sizeof(double) : 0;
-    if (a->stream == 2) sh_reflected_kernel<2><<<grid, block, smem, ctx->stream>>>(p);
+    if (tile) {
+        const int nwa = G < 8 ? G : 8;
+        const size_t tsmem = ((size_t)pbm::kExpTabDoubles + (size_t)2 * TS_N * 32) * sizeof(double);
+        dim3 tgrid((W + 31) / 32, (G + nwa - 1) / nwa, B);
+        PB_CUDA(ctx, cudaFuncSetAttribute(sh4_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        sh4_tile_kernel<<<tgrid, (nwa + 1) * 32, tsmem, ctx->stream>>>(p);
+    } else if (a->stream == 2) sh_reflected_kernel<2><<<grid, block, smem, ctx->stream>>>(p);
     else sh_reflected_kernel<4><<<grid, block, smem, ctx->stream>>>(p);
     PB_CHECK_LAUNCH(ctx);
     if (a->albedo && !fuse) {
