@@ -63,6 +63,8 @@ def numba_reference():
     """The UNMODIFIED reference functions (picaso/fluxes.py, picaso/disco.py loaded by file path, oracle/ref_loader.py)
     when the reference tree and numba are on this box - they are in the build container, not on the GPU box - else
     None."""
+    if os.environ.get("PB_BENCH_REFERENCE") == "port":
+        return None
     try:
         from oracle import ref_loader
         if not ref_loader.available():

@@ -226,7 +226,19 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
     // O(K), O(G), O(W) vectors are host pointers in both memory spaces: they travel in ONE packed asynchronous
     // copy through the context's pinned ring (pageable cudaMemcpyAsync calls would each block the host)
     pb_arena_reset(ctx);  // next pinned slot
-    PB_TRY(pb_pinned_reserve(ctx, (size_t)(K + 4 * (size_t)W + a->numg + a->numt + 64) * sizeof(double) + 16 * 64));
+    {
+        // The flux entry points called below reserve pinned space themselves, and a reserve that has to grow the ring
+        // frees EVERY slot - including the one holding this call's vectors.  Reserve the largest of the three needs
+        // here (pb_pinned_reserve grows all slots to twice the request), so the inner reserves never reallocate.
+        const size_t Gc = (size_t)a->numg * a->numt;
+        const size_t outer = (size_t)(K + 4 * (size_t)W + a->numg + a->numt + 64) * sizeof(double) + 16 * 64;
+        const size_t inner_refl = 4 * (Gc + (size_t)K + 16) * sizeof(double);
+        const size_t inner_therm = (2 * (size_t)K * V + 3 * Gc + (size_t)K + 64) * sizeof(double);
+        size_t need_pin = outer;
+        if (inner_refl > need_pin) need_pin = inner_refl;
+        if (inner_therm > need_pin) need_pin = inner_therm;
+        PB_TRY(pb_pinned_reserve(ctx, need_pin));
+    }
     auto small_to_dev = [&](const double *src, size_t n, const double **dst) -> int {
         return pb_upload_small(ctx, src, n, dst);
     };

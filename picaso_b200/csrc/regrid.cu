@@ -74,6 +74,7 @@ extern "C" int pb_mean_regrid(pb_ctx *ctx, const pb_regrid_plan *plan, int nbatc
     if (!ctx || !plan || !y || !out || nbatch < 0 || nwno < 0 || ld < nwno)
         return pb_fail(ctx, PB_ERR_ARG, "mean_regrid: bad arguments");
     if (plan->max_index > nwno) return pb_fail(ctx, PB_ERR_ARG, "mean_regrid: plan reaches index %d, spectrum has %d points", plan->max_index, nwno);
+    if (nbatch > 65535) return pb_fail(ctx, PB_ERR_ARG, "mean_regrid: nbatch = %d exceeds 65535 (spectra map to gridDim.y); split the batch", nbatch);
     if (nbatch == 0 || plan->nbins == 0) return PB_OK;
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool host = memspace == PB_HOST;

@@ -934,6 +934,7 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
     const int L = a->nlayer, W = a->nwno, G = a->numg * a->numt;
     const int B = a->nbatch > 0 ? a->nbatch : 1;
     if (L < 1 || W < 0 || G < 1) return pb_fail(ctx, PB_ERR_ARG, "reflected: bad sizes L=%d W=%d G=%d", L, W, G);
+    if (B > 65535) return pb_fail(ctx, PB_ERR_ARG, "reflected: nbatch = %d exceeds 65535 (batch entries map to gridDim.z); split the batch", B);
     if (W == 0) return PB_OK;
     if (a->ld < W) return pb_fail(ctx, PB_ERR_ARG, "reflected: ld (%lld) < nwno (%d)", (long long)a->ld, W);
     if (!a->dtau || !a->tau || !a->w0 || !a->cosb || !a->gcos2 || !a->ftau_cld || !a->ftau_ray ||
@@ -1235,6 +1236,11 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
         // the push that last read this slot's local row must have finished before the row is overwritten
         if (ctx->push_pending[gt->slot]) PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_row, 0));
         PB_TRY(launch_toa(0, W, d_xint, d_alb));
+        // push mode: the solver wrote its slab into row `rank` of the local gathered buffer; the caller's albedo vector
+        // (required by the header) gets the same values
+        if (d_alb && d_alb != gt->albedo[gt->rank] + (int64_t)gt->rank * W)
+            PB_CUDA(ctx, cudaMemcpyAsync(d_alb, gt->albedo[gt->rank] + (int64_t)gt->rank * W, (size_t)W * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
         PB_CUDA(ctx, cudaEventRecord(ev_kernel, ctx->stream));
         PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev_kernel, 0));
         PushParams pp;

@@ -815,6 +815,7 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
     const int B = a->nbatch > 0 ? a->nbatch : 1;
     const int V = L + 1;
     if (L < 1 || W < 0 || G < 1) return pb_fail(ctx, PB_ERR_ARG, "thermal: bad sizes L=%d W=%d G=%d", L, W, G);
+    if (B > 65535) return pb_fail(ctx, PB_ERR_ARG, "thermal: nbatch = %d exceeds 65535 (batch entries map to gridDim.y/z); split the batch", B);
     if (W == 0) return PB_OK;
     if (a->ld < W) return pb_fail(ctx, PB_ERR_ARG, "thermal: ld < nwno");
     if (!a->dtau || !a->w0 || !a->cosb || !a->wno || !a->tlevel || !a->plevel || !a->ubar1)

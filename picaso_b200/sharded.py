@@ -95,7 +95,9 @@ class PeerAllGather:
         from ._lib import PeerGather
         if not 1 <= world <= 8:
             raise ValueError("PeerAllGather: 1 <= world <= 8")
-        self.ctx, self.rank, self.world, self.nwno, self.nbuf, self.push = ctx, rank, world, nwno, max(3, nbuf), push
+        if not 3 <= int(nbuf) <= 8:
+            raise ValueError("PeerAllGather: nbuf must be 3..8 (ranks may run nbuf - 2 steps apart; pb_peer_gather has 8 slots)")
+        self.ctx, self.rank, self.world, self.nwno, self.nbuf, self.push = ctx, rank, world, nwno, int(nbuf), push
         self.step = 0
         gbytes = self.nbuf * world * nwno * 8
         self.d_gath, self.d_flags, self.d_done = ctx.dev_alloc(gbytes), ctx.dev_alloc(256), ctx.dev_alloc(256)
