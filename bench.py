@@ -75,6 +75,35 @@ def numba_reference():
         return None
 
 
+def pin_to_gpu_numa(index):
+    """Bind this process (and so its first-touch / pinned allocations) to the CPUs of the NUMA node GPU `index`
+    hangs off.  With 8 ranks each staging ~50 MB per step through pinned host memory, un-pinned ranks pull half of
+    their traffic across the socket interconnect (round 1: e2e 1.29 ms per rank at N = 1, 2.39 ms at N = 8).
+    Returns a short description for the JSON line, or None when the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:          # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed regions run."""
 
@@ -324,6 +353,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    numa = pin_to_gpu_numa(local_rank) if world > 1 else None
     ctx = pb.Context(local_rank)
     if world > 1:
         # run our kernels on the stream NCCL's collectives are enqueued on: no host sync needed
@@ -351,8 +381,12 @@ def main():
     gather_mode = os.environ.get("PB_BENCH_GATHER", "p2p" if world > 1 else "none")
     if world == 1 and gather_mode == "nccl":
         gather_mode = "none"
-    push = 1 if gather_mode == "p2p" else 0
-    if gather_mode == "p2p_fused":
+    # p2p_lazy (default): stores in the solver's epilogue, flags published by the next launch; p2p: side-stream push
+    # kernel; p2p_fused: stores + fence + flags in the solver's epilogue
+    if world > 1 and "PB_BENCH_GATHER" not in os.environ:
+        gather_mode = "p2p_lazy"
+    push = {"p2p": True, "p2p_fused": False, "p2p_lazy": "lazy"}.get(gather_mode, True)
+    if gather_mode in ("p2p_fused", "p2p_lazy"):
         gather_mode = "p2p"
     NBUF = int(os.environ.get("PB_BENCH_NBUF", "3"))  # rotating gathered buffers: ranks may run NBUF - 2 steps apart
     if gather_mode == "nccl":
@@ -370,7 +404,11 @@ def main():
         # all-gather fused into the kernel epilogue over peer memory (include/picaso_b200.h: pb_peer_gather):
         # every rank maps every rank's gathered buffers [NBUF][world][W] and arrival flags [world]
         from picaso_b200.sharded import PeerAllGather
-        pag = PeerAllGather(ctx, rank, world, W, nbuf=NBUF, push=bool(push))
+        def exchange(obj):   # bench plumbing: the IPC handles travel over the process group that exists anyway
+            parts = [None] * world
+            dist.all_gather_object(parts, obj)
+            return parts
+        pag = PeerAllGather(ctx, rank, world, W, nbuf=NBUF, push=push, exchange=exchange if world > 1 else None)
         d_albs = [ctx.dev_alloc(W * 8)]
         if world > 1:
             dist.barrier()
@@ -440,7 +478,7 @@ def main():
     elif gather_mode == "p2p":
         # the fused gather against NCCL's: every rank's buffer must hold every rank's slab, bit for bit
         gath = pag.gathered()
-        mine = gath[rank].copy() if push else ctx.from_device(d_alb, (W,))
+        mine = gath[rank].copy() if push is True else ctx.from_device(d_alb, (W,))
         if world > 1:
             ref_all = torch.empty((world, W), dtype=torch.float64, device="cuda")
             dist.all_gather_into_tensor(ref_all, torch.from_numpy(mine).cuda())
@@ -490,6 +528,10 @@ def main():
         uncoupled = [round(float(x), 2) for x in allt.cpu()]
     # ---- timed region: exactly K steps, CUDA events on the launching stream ----
     barrier()
+    if gather_mode == "p2p" and world > 1:
+        # device-side start barrier over the peer mappings: the ranks' GPUs leave it within a microsecond of each
+        # other, so host-side skew after the NCCL barrier is not billed to the first coupled steps
+        pag.barrier()
     l0 = ctx.launch_count()
     sampler.active = True
     ctx.timer_start()
@@ -580,8 +622,10 @@ def main():
                                   "p2p": "all-gather of the per-rank albedo [W] every step over NVLink peer memory "
                                          "(pb_peer_gather): " + ("the solver writes its slab into the local gathered buffer, a "
                                          "side-stream copy kernel pushes it to every peer and publishes release flags while the "
-                                         "next step computes" if push else "P2P stores + release flags in the solver kernel's "
-                                         "epilogue") + "; %d rotating buffers; checked bit-for-bit against ncclAllGather before "
+                                         "next step computes" if push is True else ("P2P stores in the solver kernel's epilogue, the flags "
+                                         "of step s published by the first CTA of launch s + 1 (no fence on any launch's critical path)"
+                                         if push == "lazy" else "P2P stores + release flags in the solver kernel's "
+                                         "epilogue")) + "; device-side start barrier; %d rotating buffers; checked bit-for-bit against ncclAllGather before "
                                          "timing; the timed region ends after pb_gather_wait saw the last step of every rank" % NBUF,
                                   "nccl": "ncclAllGather of the per-rank albedo [W] every step, double-buffered on a second "
                                           "stream (PB_BENCH_GATHER=nccl)"}[gather_mode],
@@ -590,7 +634,8 @@ def main():
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": ke, "ms_per_step": 1e3 * e2e_dt / ke,
-                "api": "picaso_b200.get_reflected_1d(..., return_albedo=True), pinned host inputs"},
+                "api": "picaso_b200.get_reflected_1d(..., return_albedo=True), pinned host inputs",
+                "host_affinity": numa},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "kernel": kernel,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,

@@ -566,6 +566,7 @@ def run(args, rank, local_rank, world):
     import picaso_b200 as pb
     if args.impl == "reference":
         return run_reference(args, rank)
+    numa = bench.pin_to_gpu_numa(local_rank) if world > 1 else None
     torch, dist = _dist(world, local_rank)
     ctx = pb.Context(local_rank)
     if world > 1:
@@ -639,7 +640,8 @@ def run(args, rank, local_rank, world):
                    "collective": cfg.collective, "parity_max_rel_err": parity},
         "gpu_launches": int(launches),
         "e2e": {"value": cfg.units_per_step * ke / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(cfg.h2d),
-                "d2h_bytes_per_step": int(cfg.d2h), "steps": ke, "ms_per_step": 1e3 * e2e_dt / ke, "api": cfg.e2e_api},
+                "d2h_bytes_per_step": int(cfg.d2h), "steps": ke, "ms_per_step": 1e3 * e2e_dt / ke, "api": cfg.e2e_api,
+                "host_affinity": numa},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": bench.traffic_for(cfg.kernel), "kernel": cfg.kernel,
                      "algorithmic_bytes_per_launch": int(cfg.alg_bytes), "peak_source": peak_src,

@@ -99,7 +99,10 @@ typedef struct pb_peer_gather {
      * push = 1: the solver kernel writes its slab into row `rank` of the LOCAL gathered buffer only; a small
      *   copy kernel on the context's side stream (event-ordered after it) pushes that row to the peers and
      *   publishes the flags, overlapping the next launch.  `slot` (0..7, the rotating-buffer index) names the
-     *   event that keeps a later launch from overwriting a row whose push is still in flight. */
+     *   event that keeps a later launch from overwriting a row whose push is still in flight.
+     * push = 2 ("lazy"): as push = 0, but the epilogue only stores; the flags of step s are published by the first
+     *   CTA of the launch of step s + 1 (a finished grid's stores are performed system-wide), the last step's by
+     *   pb_peer_signal.  No fence, counter or NVLink round trip on any launch's critical path. */
     int push, slot;
 } pb_peer_gather;
 
@@ -381,6 +384,11 @@ int pb_ipc_close(pb_ctx *ctx, void *dev_ptr);
  * and sets *timed_out_dev (device int, may be NULL) */
 int pb_gather_wait(pb_ctx *ctx, const unsigned long long *flags, int nranks, unsigned long long step,
                    int *timed_out_dev);
+/* stream-ordered: after everything queued before it, store `value` into word `offset + rank` of every rank's flag
+ * array (flags: host array [nranks] of device pointers as mapped here; release at system scope).  Publishes the last
+ * step of a push = 2 ("lazy") gather, and - with pb_gather_wait on flags + offset - makes a device-side barrier. */
+int pb_peer_signal(pb_ctx *ctx, unsigned long long *const *flags, int nranks, int rank, int offset,
+                   unsigned long long value);
 
 /* ---- self test ------------------------------------------------------------------------- */
 /* evaluates the kernels' branch-free exp() and 1/x on x[n] (host pointers); test hook */

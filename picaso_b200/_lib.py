@@ -144,6 +144,7 @@ SYMBOLS = {
     "pb_compress_thermal": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int]),
     "pb_selftest_math": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
     "pb_microbench": (c_int, [c_vp, c_int, c_int, c_vp]),
+    "pb_peer_signal": (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.c_ulonglong]),
     "pb_selftest_exp_tab": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "pb_optab_create": (c_int, [c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
     "pb_optab_destroy": (c_int, [c_vp, c_vp]),

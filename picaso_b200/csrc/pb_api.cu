@@ -345,6 +345,15 @@ __global__ void gather_wait_kernel(const unsigned long long *flags, int n, unsig
         }
     } while (true);
 }
+// rank `rank` stores `value` into word offset + rank of every rank's flag array (release, system scope); the
+// preceding system-scope fence makes everything this GPU wrote before (earlier kernels of the stream) visible first
+struct PeerFlagTab { unsigned long long *p[32]; };
+__global__ void peer_signal_kernel(PeerFlagTab tab, int n, int rank, int offset, unsigned long long value)
+{
+    if (threadIdx.x >= n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(tab.p[threadIdx.x] + offset + rank), "l"(value) : "memory");
+}
 } // namespace
 
 int pb_ipc_export(pb_ctx *ctx, void *dev_ptr, void *handle64)
@@ -381,6 +390,19 @@ int pb_gather_wait(pb_ctx *ctx, const unsigned long long *flags, int nranks, uns
     if (!ctx || !flags || nranks < 1 || nranks > 32) return PB_ERR_ARG;
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     gather_wait_kernel<<<1, 32, 0, ctx->stream>>>(flags, nranks, step, timed_out_dev);
+    PB_CHECK_LAUNCH(ctx);
+    return PB_OK;
+}
+
+extern "C" int pb_peer_signal(pb_ctx *ctx, unsigned long long *const *flags, int nranks, int rank, int offset,
+                              unsigned long long value)
+{
+    if (!ctx || !flags || nranks < 1 || nranks > 32 || rank < 0 || rank >= nranks || offset < 0)
+        return pb_fail(ctx, PB_ERR_ARG, "peer_signal: bad arguments");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PeerFlagTab tab;  // the pointer table is a host array: it travels in the launch parameters
+    for (int r = 0; r < 32; ++r) tab.p[r] = r < nranks ? flags[r] : nullptr;
+    peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(tab, nranks, rank, offset, value);
     PB_CHECK_LAUNCH(ctx);
     return PB_OK;
 }

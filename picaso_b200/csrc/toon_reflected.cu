@@ -46,6 +46,7 @@ struct ReflParams {
     int wt, ay;    // refl_toa_kernel4<GEN = true>, refl_toa_kernel5: wavelengths / angles per CTA
     int ch;        // refl_toa_kernel5: layers per chunk (= producing warps)
     int g_n, g_rank;
+    int g_lazy;    // push = 2: flags of step g_step - 1 are published by the first CTA of this launch, none at its end
     double *g_alb[8];
     unsigned long long *g_flag[8];
     unsigned long long g_step, g_wait;
@@ -957,7 +958,7 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
         const pb_peer_gather *gt = a->gather;
         if (memspace != PB_DEVICE || !a->albedo || B != 1 || G > 8 || !want_toa || a->variant != 0 || gt->nranks < 1 ||
             gt->nranks > 8 || gt->rank < 0 || gt->rank >= gt->nranks || !gt->albedo || !gt->flags || !gt->done_counter ||
-            gt->slot < 0 || gt->slot > 7)
+            gt->slot < 0 || gt->slot > 7 || gt->push < 0 || gt->push > 2)
             return pb_fail(ctx, PB_ERR_ARG, "reflected: peer gather needs PB_DEVICE, a fused albedo (numg*numt <= 8), nbatch 1, 1 <= nranks <= 8");
         static const int kv = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 5; }();
         if (kv < 4) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "reflected: peer gather is implemented in refl_toa_kernel4/5 only");
@@ -1064,7 +1065,7 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
         if (q.f0pi) q.f0pi += w0;
         if (q.btop) q.btop += w0;
         q.xint = xo; q.albedo = ao; q.fuse_albedo = fuse ? 1 : 0;
-        if (a->gather && a->gather->push) {
+        if (a->gather && a->gather->push == 1) {
             // the solver writes its slab straight into row `rank` of the local gathered buffer
             q.albedo = a->gather->albedo[a->gather->rank] + (int64_t)a->gather->rank * W;
         } else if (a->gather) {
@@ -1072,6 +1073,7 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             q.g_n = gt->nranks; q.g_rank = gt->rank;
             for (int r = 0; r < gt->nranks; ++r) { q.g_alb[r] = gt->albedo[r]; q.g_flag[r] = gt->flags[r]; }
             q.g_step = gt->step; q.g_wait = gt->wait_step; q.g_done = gt->done_counter;
+            q.g_lazy = gt->push == 2;
         }
         dim3 grid((wc + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
         // PB_REFL_KERNEL=2|3 select the previous generations (bottom-up sweeps) for A/B runs
@@ -1230,7 +1232,7 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
 
     if (host) PB_TRY(copy_in(0, W, ctx->stream));
     dim3 grid((W + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
-    if (want_toa && a->gather && a->gather->push) {
+    if (want_toa && a->gather && a->gather->push == 1) {
         const pb_peer_gather *gt = a->gather;
         cudaEvent_t ev_row = ctx->ev_chunk[gt->slot], ev_kernel = ctx->ev_chunk[8 + gt->slot];
         // the push that last read this slot's local row must have finished before the row is overwritten

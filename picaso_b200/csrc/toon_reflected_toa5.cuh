@@ -326,6 +326,11 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
     // Pipeline, one barrier per chunk: in iteration c the consumers integrate chunk c (P[c % 3], C[c & 1]), the chain warp
     // eliminates chunk c + 1 (P[(c+1) % 3] -> C[(c+1) & 1]) and every producing warp writes its layer of chunk c + 2
     // (P[(c+2) % 3]) from registers loaded one iteration earlier, then loads its layer of chunk c + 3.
+    if (p.g_n > 0 && p.g_lazy && p.g_step > 1 && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        // lazy flags: the previous launch's peer stores are performed (its grid has retired): publish its step
+        __threadfence_system();
+        for (int rk = 0; rk < p.g_n; ++rk) st_release_sys(p.g_flag[rk] + p.g_rank, p.g_step - 1);
+    }
     prefetch(0);
     produce(0);
     prefetch(1);
@@ -406,7 +411,7 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
             // fused all-gather: this rank's slab goes to row g_rank of every rank's buffer (NVLink P2P stores)
             for (int rk = 0; rk < p.g_n; ++rk) p.g_alb[rk][(int64_t)p.g_rank * p.W + w] = alb;
         }
-        if (p.g_n > 0) {
+        if (p.g_n > 0 && !p.g_lazy) {
             // last CTA to finish publishes the step on every rank (ordering argument: toon_reflected_toa4.cuh)
             __syncthreads();
             if (tid == 0) {

@@ -3,14 +3,98 @@
 Wavelength bins are independent through the whole hot path: every
 reference loop is elementwise over wavelengths or recurrent over layers.  So the multi-GPU
 scheme is: contiguous wave slabs per rank, no data-path collective, and one all-gather of
-the final [nwno] vector(s) (albedo / thermal flux / transit depth).  torch.distributed is
-used for the plumbing only (NCCL on GPUs, gloo in the CPU tests) and imported lazily.
+the final [nwno] vector(s) (albedo / thermal flux / transit depth).
+
+No PyTorch in here.  The host-side helpers take an `exchange` callable - exchange(obj) returns the list of
+every rank's obj - which is all the plumbing they need: `TcpExchange` (plain sockets, below) for
+stand-alone use, or a one-line wrapper around whatever the caller already runs (torch.distributed
+all_gather_object in bench.py and in the gloo tests, mpi4py allgather under the retrieval driver).
 `PeerAllGather` is the device-side collective: the producing kernel (or a side-stream copy kernel)
-stores each rank's slab into every rank's buffer over NVLink peer memory.
+stores each rank's slab into every rank's buffer over NVLink peer memory; `exchange` is used once, to
+swap the CUDA IPC handles.
 """
+import pickle
+import socket
+import struct
+import time
+
 import numpy as np
 
-__all__ = ["partition", "wave_slice", "shard_inputs", "allgather_waves", "run_sharded", "PeerAllGather"]
+__all__ = ["partition", "wave_slice", "shard_inputs", "allgather_waves", "run_sharded", "PeerAllGather", "TcpExchange"]
+
+
+class TcpExchange:
+    """exchange(obj) -> [obj of rank 0, ..., obj of rank world-1] over plain TCP (rank 0 listens on addr:port;
+    the connections stay open between calls).  Host-side rendezvous only - nothing on the data path."""
+
+    def __init__(self, rank, world, addr="127.0.0.1", port=29533, timeout=120.0):
+        self.rank, self.world = int(rank), int(world)
+        self.peers, self.sock = [], None
+        if self.world == 1:
+            return
+        if self.rank == 0:
+            srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind((addr, port))
+            srv.listen(self.world)
+            srv.settimeout(timeout)
+            conns = {}
+            while len(conns) < self.world - 1:
+                c, _ = srv.accept()
+                c.settimeout(timeout)
+                conns[struct.unpack("<i", self._recvn(c, 4))[0]] = c
+            srv.close()
+            self.peers = [conns[r] for r in range(1, self.world)]
+        else:
+            t0 = time.time()
+            while True:
+                try:
+                    self.sock = socket.create_connection((addr, port), timeout=timeout)
+                    break
+                except OSError:
+                    if time.time() - t0 > timeout:
+                        raise
+                    time.sleep(0.05)
+            self.sock.sendall(struct.pack("<i", self.rank))
+
+    @staticmethod
+    def _recvn(c, n):
+        buf = b""
+        while len(buf) < n:
+            chunk = c.recv(n - len(buf))
+            if not chunk:
+                raise ConnectionError("peer closed the exchange socket")
+            buf += chunk
+        return buf
+
+    @classmethod
+    def _send(cls, c, obj):
+        data = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+        c.sendall(struct.pack("<q", len(data)) + data)
+
+    @classmethod
+    def _recv(cls, c):
+        n = struct.unpack("<q", cls._recvn(c, 8))[0]
+        return pickle.loads(cls._recvn(c, n))
+
+    def __call__(self, obj):
+        if self.world == 1:
+            return [obj]
+        if self.rank == 0:
+            parts = [obj] + [self._recv(c) for c in self.peers]
+            for c in self.peers:
+                self._send(c, parts)
+            return parts
+        self._send(self.sock, obj)
+        return self._recv(self.sock)
+
+    def close(self):
+        for c in self.peers + ([self.sock] if self.sock else []):
+            try:
+                c.close()
+            except OSError:
+                pass
+        self.peers, self.sock = [], None
 
 
 def partition(nwno, world):
@@ -49,33 +133,28 @@ def shard_inputs(inputs, nwno, rank, world, wave_keys=None):
     return out
 
 
-def allgather_waves(local, nwno, group=None):
-    """All-gather per-rank results along the wavelength (last) axis -> full [..., nwno] array on
-    every rank.  `local` is this rank's numpy slab (or a torch tensor on the rank's device)."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
+def allgather_waves(local, nwno, rank, world, exchange):
+    """All-gather per-rank results along the wavelength (last) axis -> full [..., nwno] numpy array on every
+    rank.  `local` is this rank's slab (ragged slabs are fine, a rank may own no wavelength at all);
+    exchange(obj) returns every rank's obj."""
     parts = partition(nwno, world)
-    nmax = max(e - s for s, e in parts)
-    is_np = isinstance(local, np.ndarray)
-    t = torch.from_numpy(np.ascontiguousarray(local)) if is_np else local
-    if dist.get_backend(group) == "nccl" and not t.is_cuda:
-        t = t.cuda()
-    lead = tuple(t.shape[:-1])
-    pad = torch.zeros(lead + (nmax,), dtype=t.dtype, device=t.device)
-    pad[..., : t.shape[-1]] = t
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    full = torch.cat([b[..., : e - s] for b, (s, e) in zip(bufs, parts)], dim=-1)
-    return full.cpu().numpy() if is_np else full
+    mine = np.ascontiguousarray(local)
+    s, e = parts[rank]
+    if mine.shape[-1] != e - s:
+        raise ValueError("rank %d holds %d wavelengths, its slab has %d" % (rank, mine.shape[-1], e - s))
+    slabs = exchange(mine)
+    return np.concatenate([np.asarray(x) for x in slabs], axis=-1)
 
 
-def run_sharded(compute, inputs, nwno, group=None, wave_keys=None):
+def run_sharded(compute, inputs, nwno, rank, world, exchange, wave_keys=None):
     """compute(shard_dict) -> ndarray [..., n_local]; returns the gathered [..., nwno] result."""
-    import torch.distributed as dist
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
     local = compute(shard_inputs(inputs, nwno, rank, world, wave_keys))
-    return allgather_waves(np.asarray(local), nwno, group)
+    return allgather_waves(np.asarray(local), nwno, rank, world, exchange)
+
+
+def ctypes_addr(obj):
+    import ctypes
+    return ctypes.addressof(obj)
 
 
 class PeerAllGather:
@@ -83,12 +162,16 @@ class PeerAllGather:
 
     One instance per rank (one process per GPU).  Every rank owns `nbuf` rotating gathered buffers
     [world][nwno] and an arrival-flag array [world]; `exchange(obj)` must return the list of every rank's
-    `obj` (default: torch.distributed.all_gather_object) and is used once, to swap the CUDA IPC handles.
+    `obj` (TcpExchange, or a wrapper of the caller's own collective) and is used once, to swap the CUDA IPC handles.
     Per step: ``a.gather = g.next()`` on the ReflectedArgs of a PB_DEVICE `pb_reflected_toon_1d` call; the
     slab of step s lands in row `rank` of buffer s % nbuf on every rank.  ``g.wait()`` enqueues a
     stream-ordered wait for the last step of every rank; ``g.gathered()`` reads the local buffer.
     push=True (default): a side-stream copy kernel pushes the slab while the next launch computes;
-    push=False: the solver kernel's epilogue stores to the peers itself."""
+    push=False: the solver kernel's epilogue stores to the peers itself and publishes the flags before it retires;
+    push="lazy": the epilogue only stores - the flags of step s are published by the FIRST CTA of launch s + 1
+    (stores of a finished grid are performed system-wide, so no fence / NVLink round trip sits on any launch's
+    critical path); `wait()` publishes the last step.  `barrier()` is a device-side barrier over the same peer
+    mappings (stream-ordered): ranks leave it within a microsecond of each other whatever the host skew."""
 
     def __init__(self, ctx, rank, world, nwno, nbuf=3, push=True, exchange=None, _peers=None):
         import ctypes
@@ -97,8 +180,9 @@ class PeerAllGather:
             raise ValueError("PeerAllGather: 1 <= world <= 8")
         if not 3 <= int(nbuf) <= 8:
             raise ValueError("PeerAllGather: nbuf must be 3..8 (ranks may run nbuf - 2 steps apart; pb_peer_gather has 8 slots)")
-        self.ctx, self.rank, self.world, self.nwno, self.nbuf, self.push = ctx, rank, world, nwno, int(nbuf), push
-        self.step = 0
+        self.ctx, self.rank, self.world, self.nwno, self.nbuf = ctx, rank, world, nwno, int(nbuf)
+        self.push = 2 if push == "lazy" else int(bool(push))
+        self.step, self.epoch = 0, 0
         gbytes = self.nbuf * world * nwno * 8
         self.d_gath, self.d_flags, self.d_done = ctx.dev_alloc(gbytes), ctx.dev_alloc(256), ctx.dev_alloc(256)
         for ptr, nb in ((self.d_gath, gbytes), (self.d_flags, 256), (self.d_done, 256)):
@@ -116,9 +200,8 @@ class PeerAllGather:
         elif exchange is not None:
             handles = exchange((hg.raw, hf.raw))
         else:
-            import torch.distributed as dist
-            handles = [None] * world
-            dist.all_gather_object(handles, (hg.raw, hf.raw))
+            raise ValueError("PeerAllGather over several processes needs an `exchange` callable (sharded.TcpExchange "
+                             "or a wrapper of the caller's all-gather) to swap the CUDA IPC handles")
         pg, pf = [], []
         for r, (rg, rf) in enumerate(handles):
             if r == rank:
@@ -164,12 +247,24 @@ class PeerAllGather:
         self.step += 1
         s = self._structs[self.step % self.nbuf]
         s.step, s.wait_step = self.step, max(0, self.step - (self.nbuf - 1))
-        s.push, s.slot = int(self.push), self.step % self.nbuf
+        s.push, s.slot = self.push, self.step % self.nbuf
         return ctypes.addressof(s)
 
     def wait(self):
         if self.step > 0:
+            if self.push == 2:  # lazy flags: nobody has published the last step yet
+                self.ctx.check(self.ctx.lib.pb_peer_signal(self.ctx.h, ctypes_addr(self._flag_ptrs), self.world, self.rank, 0, self.step))
             self.ctx.check(self.ctx.lib.pb_gather_wait(self.ctx.h, self.d_flags, self.world, self.step, self.d_done + 8))
+
+    BARRIER_OFFSET = 16   # flag words 16 .. 16 + world of the 256-byte flag block count barrier epochs
+
+    def barrier(self):
+        """device-side barrier on the context's stream: signal this rank's arrival on every rank, wait for all"""
+        self.epoch += 1
+        self.ctx.check(self.ctx.lib.pb_peer_signal(self.ctx.h, ctypes_addr(self._flag_ptrs), self.world, self.rank,
+                                                   self.BARRIER_OFFSET, self.epoch))
+        self.ctx.check(self.ctx.lib.pb_gather_wait(self.ctx.h, self.d_flags + 8 * self.BARRIER_OFFSET, self.world, self.epoch,
+                                                   self.d_done + 8))
 
     def gathered(self, step=None):
         step = self.step if step is None else step

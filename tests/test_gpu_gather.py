@@ -1,6 +1,7 @@
 """The all-gather over peer memory (pb_peer_gather, sharded.PeerAllGather) with the ranks simulated inside
 one process on one GPU (one Context = one stream per rank; plain device pointers instead of IPC mappings).
-Both delivery modes: in the solver kernel's epilogue, and pushed by the side-stream copy kernel.  The
+All delivery modes: in the solver kernel's epilogue (flags published at its end, or lazily by the next launch), and
+pushed by the side-stream copy kernel.  The
 multi-process / multi-GPU path (CUDA IPC over NVLink) is exercised by bench.py, which checks the gathered
 buffers bit-for-bit against ncclAllGather before timing."""
 import ctypes
@@ -38,7 +39,7 @@ def _args(ctx, d, keep):
     return a
 
 
-@pytest.mark.parametrize("push", [False, True])
+@pytest.mark.parametrize("push", [False, True, "lazy"])
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_peer_all_gather_in_process(world, push):
     W, nsteps = 333, 7
@@ -63,6 +64,12 @@ def test_peer_all_gather_in_process(world, push):
                 got = group[r].gathered()
                 for q in range(world):
                     assert np.array_equal(got[q], want[q][s]), (world, push, s, r, q)
+    # device-side barrier over the same peer mappings: every rank signals, every rank waits (stream-ordered)
+    for _ in range(2):
+        for r in range(world):
+            group[r].barrier()
+    for r in range(world):
+        ctxs[r].sync()
     for g in group:
         assert not g.timed_out()
         g.close()

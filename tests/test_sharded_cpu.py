@@ -31,30 +31,48 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, W, q):
-    import torch.distributed as dist
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _gloo_exchange(dist, world):
+    """exchange(obj) -> every rank's obj, over the test's own gloo group (the product takes any such callable)"""
+    def exchange(obj):
+        parts = [None] * world
+        dist.all_gather_object(parts, obj)
+        return parts
+    return exchange
+
+
+def _worker(rank, world, port, W, q, transport="gloo"):
+    if transport == "gloo":
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        exchange = _gloo_exchange(dist, world)
+    else:
+        exchange = sharded.TcpExchange(rank, world, port=port)
     d = synth.reflected_inputs(L=12, W=W, seed=42)
 
     def compute(sd):
         x, _ = oracle.get_reflected_1d(*C.reflected_args(sd, KW))
         return oracle.compress_disco(sd["nwno"], sd["cos_theta"], x, sd["gweight"], sd["tweight"], sd["F0PI"])
 
-    full = sharded.run_sharded(compute, d, W)
-    xs = sharded.run_sharded(lambda sd: oracle.get_reflected_1d(*C.reflected_args(sd, KW))[0], d, W)
+    full = sharded.run_sharded(compute, d, W, rank, world, exchange)
+    xs = sharded.run_sharded(lambda sd: oracle.get_reflected_1d(*C.reflected_args(sd, KW))[0], d, W, rank, world, exchange)
     q.put((rank, full, xs))
-    dist.destroy_process_group()
+    if transport == "gloo":
+        dist.destroy_process_group()
+    else:
+        exchange.close()
 
 
+@pytest.mark.parametrize("transport", ["gloo", "tcp"])
 @pytest.mark.parametrize("world,W", [(2, 37), (3, 2)])  # (3, 2): the last rank owns no wavelength
-def test_gloo_sharded_equals_unsharded(world, W):
+def test_gloo_sharded_equals_unsharded(world, W, transport):
+    """world_size 2 / 3 over torch.distributed gloo, and over the package's own socket rendezvous (TcpExchange)"""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, W, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, W, q, transport)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
@@ -118,3 +136,13 @@ def test_gloo_atmosphere_shards_equal_whole_batch(world, B):
     _, want = oreg.thermal_batch(**_batch_inputs(B, 9, 120), newx=np.linspace(500.0, 9000.0, 17), scale=2.0)
     for rank, full in res:
         assert np.array_equal(full, want, equal_nan=True), "rank %d" % rank
+
+
+def test_product_has_no_torch_import():
+    """north_star: Python host code over ctypes, no PyTorch - the package never imports torch"""
+    import re
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "picaso_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(import torch|from torch)", src, flags=re.M), fn
