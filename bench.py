@@ -84,6 +84,15 @@ def pin_to_gpu_numa(index):
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        try:
+            # NVML knows the CPUs closest to the GPU: binds the calling (main, allocating) thread to them
+            before = len(os.sched_getaffinity(0))
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            after = len(os.sched_getaffinity(0))
+            if 0 < after < before or after == before:
+                return "nvmlDeviceSetCpuAffinity: %d of %d cpus" % (after, before)
+        except Exception:
+            pass
         bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
         bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
         if len(bdf.split(":")[0]) == 8:          # NVML prints an 8-digit PCI domain, sysfs a 4-digit one

@@ -597,7 +597,8 @@ def run(args, rank, local_rank, world):
     ctx.timer_start()
     for i in range(3):
         cfg.step(i)
-    probe_ms = max(ctx.timer_stop() / 3, 1e-3)
+    # the ramp length must be the SAME on every rank (steps may contain collectives): agree on the slowest probe
+    probe_ms = _max_over_ranks(torch, dist, max(ctx.timer_stop() / 3, 1e-3))
     for i in range(int(min(300.0 / probe_ms, 3000))):
         cfg.step(i)
     barrier()

@@ -326,10 +326,24 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
     // Pipeline, one barrier per chunk: in iteration c the consumers integrate chunk c (P[c % 3], C[c & 1]), the chain warp
     // eliminates chunk c + 1 (P[(c+1) % 3] -> C[(c+1) & 1]) and every producing warp writes its layer of chunk c + 2
     // (P[(c+2) % 3]) from registers loaded one iteration earlier, then loads its layer of chunk c + 3.
-    if (p.g_n > 0 && p.g_lazy && p.g_step > 1 && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-        // lazy flags: the previous launch's peer stores are performed (its grid has retired): publish its step
-        __threadfence_system();
-        for (int rk = 0; rk < p.g_n; ++rk) st_release_sys(p.g_flag[rk] + p.g_rank, p.g_step - 1);
+    if (p.g_n > 0 && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        if (p.g_lazy && p.g_step > 1) {
+            // lazy flags: the previous launch's peer stores are performed (its grid has retired): publish its step
+            __threadfence_system();
+            for (int rk = 0; rk < p.g_n; ++rk) st_release_sys(p.g_flag[rk] + p.g_rank, p.g_step - 1);
+        }
+        // buffer-rotation guard (pb_peer_gather.wait_step), ONCE per launch and under the layer sweep: this thread
+        // polls the system-scope flags, every CTA's epilogue then needs a single gpu-scope load of the go word
+        // (polling 8 system-scope flags in each of the 435 CTA tails cost ~15 us per step at 8 GPUs)
+        if (p.g_wait) {
+            const unsigned long long *mine = p.g_flag[p.g_rank];
+            const long long t0 = clock64();
+            for (int rk = 0; rk < p.g_n; ++rk)
+                while (ld_acquire_sys(mine + rk) < p.g_wait)
+                    if (clock64() - t0 > kSpinLimit) { atomicExch(p.g_done + 1, 1u); break; }
+        }
+        __threadfence();
+        atomicExch(p.g_done + 4, (unsigned)p.g_step);
     }
     prefetch(0);
     produce(0);
@@ -387,13 +401,12 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
     const bool active = is_cons && (w < p.W) && (a < p.G);
     if (active && p.xint) p.xint[((int64_t)b * p.G + a) * p.W + w] = result;
     if (p.fuse_albedo) {
-        if (p.g_n > 0 && p.g_wait && tid == 0) {
-            // hold the peer stores until every rank has published wait_step (buffer rotation, see pb_peer_gather)
-            const unsigned long long *mine = p.g_flag[p.g_rank];
+        if (p.g_n > 0 && tid == 0) {
+            // hold the peer stores until CTA 0 has seen every rank publish wait_step (go word = this launch's step)
             const long long t0 = clock64();
-            for (int rk = 0; rk < p.g_n; ++rk)
-                while (ld_acquire_sys(mine + rk) < p.g_wait)
-                    if (clock64() - t0 > kSpinLimit) { atomicExch(p.g_done + 1, 1u); break; }
+            while (*(volatile unsigned *)(p.g_done + 4) != (unsigned)p.g_step)
+                if (clock64() - t0 > kSpinLimit) { atomicExch(p.g_done + 1, 1u); break; }
+            __threadfence();
         }
         // compress_disco (disco.py:138-149): sequential sum over (ig, it) in index order
         double *red = ctile;  // the chain tiles are dead (the closing step above still reads ptile)

@@ -58,8 +58,9 @@ def test_peer_all_gather_in_process(world, push):
             a.gather = group[r].next()
             ctxs[r].check(fn(ctxs[r].h, ctypes.byref(a), PB_DEVICE))
         if s in (2, nsteps - 1):
-            for r in range(world):
+            for r in range(world):      # every rank enqueues its wait (lazy mode: publishes its last step) ...
                 group[r].wait()
+            for r in range(world):      # ... before any rank blocks the host (the ranks share this process)
                 ctxs[r].sync()
                 got = group[r].gathered()
                 for q in range(world):
