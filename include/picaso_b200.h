@@ -303,6 +303,9 @@ typedef struct pb_opacity_args {
     /* resort-rebin path: molecular_opa [nlayer][nwno][ngauss] written by pb_ck_mix with PB_DEVICE
      * (ALWAYS a device pointer), used instead of the pre-mixed table; needs ck_scale */
     const double *ck_direct;
+    /* full_output (optics.py:322-325, atmosphere.taugas / tauray / taucld): the three per-layer optical depths the
+     * totals are built from, [nlayer][nwno(*ngauss)]; NULL = not wanted */
+    double *TAUGAS, *TAURAY, *TAUCLD;
 } pb_opacity_args;
 
 int pb_compute_opacity(pb_ctx *ctx, pb_optab *tab, const pb_opacity_args *args, int memspace);

@@ -112,13 +112,20 @@ def compute_raman(nwno, nlayer, wno, stellar_shifts, tlayer, cross_sections, j_i
 
 
 # ---- a9: assembling the layer optical properties --------------------------------------------------
+def raman_pollack(wno, table_w, table_f, nlayer):
+    """optics.py:652-660: np.interp of the raman_fortran.txt table onto 1e4 / wno, one identical row per layer"""
+    row = np.interp(1e4 / np.asarray(wno, dtype=np.float64), table_w, table_f)
+    return np.array([row] * nlayer)
+
+
 def compute_opacity(atm, molecular_opa, continuum_opa, rayleigh_opa, raman_factor, stream=2,
-                    delta_eddington=True, fthin_cld=None, do_holes=False):
+                    delta_eddington=True, fthin_cld=None, do_holes=False, full=None):
     """optics.py:147-431 for ngauss = 1 and test_mode = None.
 
     atm: dict from picaso_b200.synth.atmosphere_profile; molecular_opa {mol: [L, W]} (already x N_A),
     continuum_opa {pair: [L, W]}, rayleigh_opa {mol: [W]}, raman_factor [L, W] BEFORE the 0.99999
-    cap, or None for raman = 2 ("none").  Returns the reference's 13-tuple of [L|V, W] arrays."""
+    cap, or None for raman = 2 ("none").  Returns the reference's 13-tuple of [L|V, W] arrays; a dict passed as
+    `full` receives taugas / tauray / taucld (full_output)."""
     L = atm["nlayer"]
     W = next(iter(rayleigh_opa.values())).shape[0]
     mix = atm["mixingratios"]
@@ -163,6 +170,8 @@ def compute_opacity(atm, molecular_opa, continuum_opa, rayleigh_opa, raman_facto
     w0c = atm["cloud_w0"]
     if do_holes:
         TAUCLD = fthin_cld * TAUCLD
+    if full is not None:   # full_output (optics.py:322-325): atmosphere.taugas / tauray / taucld
+        full.update(taugas=TAUGAS.copy(), tauray=TAURAY.copy(), taucld=TAUCLD.copy())
     with np.errstate(all="ignore"):
         DTAU = TAUGAS + TAURAY + TAUCLD
         ftau_cld = (w0c * TAUCLD) / (w0c * TAUCLD + TAURAY)

@@ -80,6 +80,7 @@ struct OpaParams {
     double fthin;
     int do_holes, stream, dedd;
     double *o[13];
+    double *x[3];              // full_output: TAUGAS, TAURAY, TAUCLD
     int64_t bs_out;
 };
 
@@ -346,6 +347,14 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
         }
     }
     const int64_t io = (int64_t)l * C + j;
+    if (p.x[0] || p.x[1] || p.x[2]) {
+        Vec<VEC> xg, xr;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { xg.v[v] = taugas[v]; xr.v[v] = tauray[v]; }
+        if (p.x[0]) xg.store(p.x[0] + io);
+        if (p.x[1]) xr.store(p.x[1] + io);
+        if (p.x[2]) opd.store(p.x[2] + io);
+    }
     if (p.o[0]) o0.store(p.o[0] + io);
     if (p.o[2]) o2.store(p.o[2] + io);
     if (p.o[3]) o3.store(p.o[3] + io);
@@ -607,6 +616,7 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
         if (a->raman == 1) need += pb_align(nW);
         for (int k = 0; k < 13; ++k)
             if (outs[k]) need += pb_align((size_t)(L + (is_level[k] ? 1 : 0)) * nC);
+        need += 3 * pb_align((size_t)L * nC);  // full_output arrays
     }
     pb_arena_reset(ctx);
     PB_TRY(pb_arena_reserve(ctx, need));
@@ -672,6 +682,13 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
         if (host) PB_TRY(pb_arena_alloc(ctx, (size_t)(L + (is_level[k] ? 1 : 0)) * nC, (void **)&p.o[k]));
         else p.o[k] = outs[k];
     }
+    double *const xouts[3] = {a->TAUGAS, a->TAURAY, a->TAUCLD};
+    for (int k = 0; k < 3; ++k) {
+        p.x[k] = nullptr;
+        if (!xouts[k]) continue;
+        if (host) PB_TRY(pb_arena_alloc(ctx, (size_t)L * nC, (void **)&p.x[k]));
+        else p.x[k] = xouts[k];
+    }
     PB_TRY(pb_upload_flush(ctx));
     // the running optical depths need the per-layer values even if the caller did not ask for them
     double *dtau_d = p.o[0], *dtau_og = p.o[7];
@@ -686,6 +703,7 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
         const int C = W * K;
         bool vec2 = (W % 2 == 0) && K == 1;
         for (int k = 0; k < 13; ++k) if (p.o[k] && ((uintptr_t)p.o[k] & 15)) vec2 = false;
+        for (int k = 0; k < 3; ++k) if (p.x[k] && ((uintptr_t)p.x[k] & 15)) vec2 = false;
         if (p.pollack && ((uintptr_t)p.pollack & 15)) vec2 = false;
         if (p.cld_opd && (((uintptr_t)p.cld_opd | (uintptr_t)p.cld_w0 | (uintptr_t)p.cld_g0) & 15)) vec2 = false;
         if (vec2) {
@@ -710,6 +728,8 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
             if (outs[k])
                 PB_CUDA(ctx, cudaMemcpyAsync(outs[k], p.o[k], (size_t)(L + (is_level[k] ? 1 : 0)) * nC,
                                              cudaMemcpyDeviceToHost, ctx->stream));
+        for (int k = 0; k < 3; ++k)
+            if (xouts[k]) PB_CUDA(ctx, cudaMemcpyAsync(xouts[k], p.x[k], (size_t)L * nC, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return PB_OK;

@@ -315,6 +315,27 @@ def _layer_scalars(atm, opa):
     return mol, cont, ray
 
 
+def pollack_factor(opa):
+    """raman_pollack(nlayer, 1e4 / wno)[0] of the reference (optics.py:652-660): np.interp of the two-column
+    table raman_fortran.txt (wavelength, factor) onto the connection's wavelength grid; cached on `opa`."""
+    cached = getattr(opa, "_pollack", None)
+    if cached is not None:
+        return cached
+    tab = getattr(opa, "raman_pollack_table", None)
+    if tab is None:
+        import os
+        root = os.environ.get("picaso_refdata")
+        path = os.path.join(root, "opacities", "raman_fortran.txt") if root else None
+        if not path or not os.path.isfile(path):
+            raise FileNotFoundError("raman='pollack' reads $picaso_refdata/opacities/raman_fortran.txt (as the reference does, "
+                                    "optics.py:652); set picaso_refdata or opacityclass.raman_pollack_table = (w, f)")
+        dat = np.loadtxt(path)
+        tab = (dat[:, 0], dat[:, 1])
+    w, f = (np.asarray(x, dtype=np.float64) for x in tab)
+    opa._pollack = np.ascontiguousarray(np.interp(1e4 / np.asarray(opa.wno, dtype=np.float64), w, f))
+    return opa._pollack
+
+
 def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddington=True, test_mode=False,
                     raman=0, plot_opacity=False, full_output=False, return_mode=False, fthin_cld=None,
                     do_holes=False, *, device_outputs=False, outputs=None):
@@ -326,9 +347,14 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
     overwritten by the next compute_opacity call on the same ``DeviceOpacities``; ``outputs``
     restricts the computed set to the given names (others are returned as None).
 
-    Not supported on this path: ngauss > 1 (correlated-k), test_mode strings, plot_opacity,
-    return_mode, full_output.  ``test_mode`` None/False both mean "normal run": the reference's
-    own default False would enter its test branch (optics.py:372), real callers pass None."""
+    ``raman=1`` ('pollack', the reference's config default): the per-wavelength factor is the reference's
+    np.interp(1e4 / wno, w, f) of ``$picaso_refdata/opacities/raman_fortran.txt`` (optics.py:584-660), read once
+    per connection, or of ``opacityclass.raman_pollack_table = (w, f)`` if that is set.
+    ``full_output=True`` sets ``atmosphere.taugas / tauray / taucld`` ([nlayer, nwno, 1] numpy arrays) like the
+    reference (optics.py:322-325).
+    Not supported on this path: test_mode strings, plot_opacity, return_mode (host-side diagnostics).
+    ``test_mode`` None/False both mean "normal run": the reference's own default False would enter its test
+    branch (optics.py:372), real callers pass None."""
     from .optics_ck import DeviceCKs, compute_opacity_ck
     if not isinstance(opacityclass, (DeviceOpacities, DeviceCKs)):
         raise TypeError("picaso_b200.compute_opacity needs a DeviceOpacities or DeviceCKs connection")
@@ -338,8 +364,8 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
         raise ValueError("ngauss must equal the number of gauss points of the DeviceCKs table")
     if test_mode not in (None, False):
         raise NotImplementedError("compute_opacity test modes are not implemented on the GPU path")
-    if plot_opacity or return_mode or full_output:
-        raise NotImplementedError("plot_opacity / return_mode / full_output are host-side diagnostics")
+    if plot_opacity or return_mode:
+        raise NotImplementedError("plot_opacity / return_mode are host-side diagnostics")
     opa, atm = opacityclass, atmosphere
     if isinstance(opa, DeviceCKs):
         import copy
@@ -367,7 +393,9 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
         a.jfrac = addr(jf)
         keep.append(jf)
     elif raman == 1:
-        raise NotImplementedError("raman='pollack' needs the reference's raman_fortran.txt table; pass raman=0 or 2")
+        pol = pollack_factor(opa)
+        a.raman_pollack = addr(pol)
+        keep.append(pol)
     cloud = atm.layer.get("cloud") if isinstance(atm.layer, dict) else atm.layer["cloud"]
     memspace = PB_DEVICE if device_outputs else PB_HOST
     tmp_dev = []
@@ -401,8 +429,21 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
         else:
             res[n] = np.zeros(shape)
             setattr(a, n, addr(res[n]))
+    extra = None
+    if full_output:
+        # atmosphere.taugas / tauray / taucld (optics.py:322-325): three more [nlayer, nwno] outputs of the same launch
+        if device_outputs:
+            extra = [opa._buffer(n, (L, W)) for n in ("TAUGAS", "TAURAY", "TAUCLD")]
+            a.TAUGAS, a.TAURAY, a.TAUCLD = [x.ptr for x in extra]
+        else:
+            extra = [np.zeros((L, W)) for _ in range(3)]
+            a.TAUGAS, a.TAURAY, a.TAUCLD = [addr(x) for x in extra]
     ctx.check(ctx.lib.pb_compute_opacity(ctx.h, opa._tab, ctypes.byref(a), memspace))
     if device_outputs:
         ctx.sync()   # the host staging arrays in `keep` may be released after this point
+    if extra is not None:
+        host3 = [x.numpy() if device_outputs else x for x in extra]
+        atm.taugas, atm.tauray, atm.taucld = [x[:, :, np.newaxis] for x in host3]
+    if device_outputs:
         return tuple(res[n] for n in OUTPUT_NAMES)
     return tuple(None if res[n] is None else res[n][:, :, np.newaxis] for n in OUTPUT_NAMES)

@@ -73,3 +73,40 @@ def test_device_resident_chain_matches_oracle():
     F = pb.get_transit_1d(*tr_args, DTAU_OG)
     assert_close(F, oracle.get_transit_1d(*tr_args, ref["DTAU_OG"]), RTOL, "chain transit")
     opa.close()
+
+
+def test_pollack_raman_and_full_output(tmp_path, monkeypatch):
+    """raman=1 ('pollack', the reference's config default) and full_output=True through the public mirror: the table
+    comes from $picaso_refdata/opacities/raman_fortran.txt like the reference's (optics.py:652); golden vectors from
+    the unmodified reference (tests/golden/make_golden_pollack.py)"""
+    from util import golden
+    g = golden("pollack")
+    case, _, db, atm, ins = load_case(str(g["case"]))
+    (tmp_path / "opacities").mkdir()
+    np.savetxt(tmp_path / "opacities" / "raman_fortran.txt", np.column_stack([g["table_w"], g["table_f"]]))
+    monkeypatch.setenv("picaso_refdata", str(tmp_path))
+    for dev in (False, True):
+        opa = device_opacities(pb, dict(case, raman=2), db, ins)
+        a = duck_atmosphere(db, atm)
+        opa.get_opacities(a)
+        res = pb.compute_opacity(a, opa, ngauss=1, stream=case["stream"], delta_eddington=case["dedd"], test_mode=None,
+                                 raman=1, full_output=True, device_outputs=dev)
+        for n, arr in zip(OUT_NAMES, res):
+            got = arr.numpy() if dev else arr[:, :, 0]
+            assert_close(got, g["out/" + n], 1e-10, "pollack %s (device_outputs=%s)" % (n, dev))
+        for n in ("taugas", "tauray", "taucld"):
+            got = getattr(a, n)
+            assert got.shape == g["full/" + n].shape + (1,)
+            assert_close(got[:, :, 0], g["full/" + n], 1e-10, "full_output " + n)
+        opa.close()
+    # without the file: the reference's own failure mode
+    monkeypatch.setenv("picaso_refdata", str(tmp_path / "nowhere"))
+    opa = device_opacities(pb, dict(case, raman=2), db, ins)
+    a = duck_atmosphere(db, atm)
+    opa.get_opacities(a)
+    with pytest.raises(FileNotFoundError):
+        pb.compute_opacity(a, opa, stream=2, delta_eddington=True, test_mode=None, raman=1)
+    opa.raman_pollack_table = (g["table_w"], g["table_f"])      # or hand the table over directly
+    res = pb.compute_opacity(a, opa, ngauss=1, stream=case["stream"], delta_eddington=case["dedd"], test_mode=None, raman=1)
+    assert_close(res[2][:, :, 0], g["out/W0"], 1e-10, "pollack via raman_pollack_table")
+    opa.close()

@@ -54,3 +54,25 @@ def test_product_bin_search_matches_oracle():
         got = find_needed_pts_grid(1 / db["temps"], np.log10(db["pressures"]), db["nc_p"], tlayer, pbar)
         for a, b in zip(got, want):
             assert np.array_equal(np.asarray(a).ravel(), np.asarray(b).ravel())   # reference shape [:, None] vs flat
+
+
+def test_pollack_raman_and_full_output():
+    """compute_opacity(raman=1 'pollack', full_output=True): oracle against the unmodified reference run on a synthetic
+    raman_fortran.txt (tests/golden/make_golden_pollack.py)"""
+    from util import golden
+    g = golden("pollack")
+    case, _, db, atm, ins = load_case(str(g["case"]))
+    pbar = atm["player"] / atm["pconv"]
+    ti, pi, ill, ihl, ilh, ihh = oo.find_needed_pts(db["temps"], db["pressures"], db["nc_p"], atm["tlayer"], pbar)
+    mol = {m: oo.interp_molecular(db["tables"][m], ti, pi, ill, ihl, ilh, ihh) for m in db["molecules"]}
+    ic = oo.nearest_cia_temp(db["cia_temps"], atm["tlayer"])
+    cont = {k: db["continuum"][k][ic] for k in db["continuum"]}
+    rf = oo.raman_pollack(db["wno"], g["table_w"], g["table_f"], atm["nlayer"])
+    assert (rf > 0.99999).any() and (rf < 0.99999).any()      # the cap is exercised
+    full = {}
+    res = oo.compute_opacity(atm, mol, cont, ins["rayleigh"], rf, stream=case["stream"], delta_eddington=case["dedd"],
+                             full=full)
+    for n, arr in zip(OUT_NAMES, res):
+        assert_close(arr, g["out/" + n], 1e-11, "pollack " + n)
+    for n in ("taugas", "tauray", "taucld"):
+        assert_close(full[n], g["full/" + n], 1e-11, "full_output " + n)
