@@ -208,6 +208,10 @@ typedef struct pb_thermal_args {
      * tlevel/plevel/opacities, numg = numt = 1, ubar1 one value per facet, pi-based boundary terms,
      * calc_type 0, TOA only. */
     int variant;
+    /* > 0: the nbatch entries share `opacity_period` blocks of dtau / w0 / cosb / surf_reflect - entry b reads block
+     * b % opacity_period - while tlevel / plevel / outputs stay per entry (Jacobian batching of the climate solver:
+     * many temperature profiles over one set of opacities) */
+    int opacity_period;
 } pb_thermal_args;
 
 int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *args, int memspace);
@@ -363,9 +367,27 @@ typedef struct pb_climate_args {
      * is not computed (reflected = 0 or thermal = 0) reads as zeros. */
     double *packed;
     int packed_full;
+    /* Jacobian batching (climate.py:1108-1180: t_start perturbs one level temperature per get_fluxes call, thermal
+     * only - the opacities stay fixed, only the Planck terms change).  nprofiles > 0: the thermal half is run for
+     * `nprofiles` temperature profiles tlevels[nprofiles][nlevel] (host) in ONE launch sequence over the shared
+     * opacity arrays (batch = nprofiles x ngauss), `reflected` is ignored, and jac_out (host) receives
+     * [nprofiles][2][nlevel] = flux_net_ir_layer, flux_net_ir of every profile with one device-to-host copy.
+     * tlevel / the eight pointers / packed above are not used in this mode. */
+    int nprofiles;
+    const double *tlevels;
+    double *jac_out;
 } pb_climate_args;
 
 int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *args, int memspace);
+
+/* A climate call bound once and re-run with two integers - callable from numba nopython code through ctypes
+ * (the reference's solver loop t_start and get_fluxes are jitted, climate.py:804, :1686, so Python rebinding cannot
+ * reach them).  pb_climate_bind copies the argument struct (the arrays it points to stay owned by the caller and
+ * must outlive the binding; the solver writes new temperatures into the bound tlevel / tlevels array in place);
+ * pb_climate_run_bound(ctx address, handle) runs it and returns the status code. */
+int pb_climate_bind(pb_ctx *ctx, const pb_climate_args *args, int memspace, int *handle_out);
+int pb_climate_run_bound(unsigned long long ctx_address, int handle);
+int pb_climate_unbind(pb_ctx *ctx, int handle);
 
 /* ---- rebinning onto a data grid ---------------------------------------------------------- */
 /* replaces mean_regrid, picaso/justplotit.py:31-63 = scipy.stats.binned_statistic(x, y, 'mean', bins):

@@ -15,7 +15,7 @@ from .fluxes_3d import get_reflected_3d, get_thermal_3d  # noqa: F401
 from .optics import DeviceArray, DeviceOpacities, compute_opacity  # noqa: F401
 from .optics_ck import DeviceCKs, DeviceGasCKs  # noqa: F401
 from .opacity_db import opannection, read_opacity_db  # noqa: F401
-from .climate import get_fluxes  # noqa: F401
+from .climate import get_fluxes, get_fluxes_jacobian, BoundFluxes  # noqa: F401
 from .regrid import mean_regrid, RegridPlan  # noqa: F401
 from .batch import thermal_batch  # noqa: F401
 from .disco import compress_disco, compress_thermal, get_angles_1d, get_angles_3d, compute_disco  # noqa: F401

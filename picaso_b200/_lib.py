@@ -91,7 +91,7 @@ class ThermalArgs(ctypes.Structure):
                              "plevel", "ubar1", "gweight", "tweight")] +
         [("hard_surface", c_int), ("calc_type", c_int)] +
         [(n, c_vp) for n in ("flux_at_top", "thermal", "flux_minus", "flux_plus",
-                             "flux_minus_mdpt", "flux_plus_mdpt")] + [("variant", c_int)])
+                             "flux_minus_mdpt", "flux_plus_mdpt")] + [("variant", c_int), ("opacity_period", c_int)])
 
 
 class ClimateArgs(ctypes.Structure):
@@ -104,7 +104,7 @@ class ClimateArgs(ctypes.Structure):
         [(n, c_dbl) for n in ("frac_a", "frac_b", "frac_c", "constant_back", "constant_forward")] +
         [(n, c_vp) for n in ("flux_net_v_layer", "flux_net_v", "flux_plus_v", "flux_minus_v",
                              "flux_net_ir_layer", "flux_net_ir", "flux_plus_ir", "flux_minus_ir", "packed")] +
-        [("packed_full", c_int)])
+        [("packed_full", c_int), ("nprofiles", c_int), ("tlevels", c_vp), ("jac_out", c_vp)])
 
 
 class TransitArgs(ctypes.Structure):
@@ -145,6 +145,9 @@ SYMBOLS = {
     "pb_compress_thermal": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int]),
     "pb_selftest_math": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
     "pb_microbench": (c_int, [c_vp, c_int, c_int, c_vp]),
+    "pb_climate_bind": (c_int, [c_vp, c_vp, c_int, ctypes.POINTER(c_int)]),
+    "pb_climate_run_bound": (c_int, [ctypes.c_ulonglong, c_int]),
+    "pb_climate_unbind": (c_int, [c_vp, c_int]),
     "pb_peer_signal": (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.c_ulonglong]),
     "pb_selftest_exp_tab": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "pb_optab_create": (c_int, [c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),

@@ -24,7 +24,7 @@ import numpy as np
 from . import _lib
 from ._lib import PB_DEVICE, PB_HOST, ClimateArgs, addr
 
-__all__ = ["get_fluxes"]
+__all__ = ["get_fluxes", "get_fluxes_jacobian", "BoundFluxes"]
 
 _WED = ("DTAU", "TAU", "W0", "COSB", "ftau_cld", "ftau_ray", "GCOS2", "W0_no_raman")
 _NOED = ("DTAU", "TAU", "W0", "COSB")
@@ -41,7 +41,10 @@ def _as3(a):
     return np.ascontiguousarray(a)
 
 
-def _one_column(ctx, Atmosphere, wed, noed, ScatteringPhase, Disco, Opagrid, F0PI, reflected, thermal, full_arrays=True):
+def _build_args(ctx, Atmosphere, wed, noed, ScatteringPhase, Disco, Opagrid, F0PI, reflected, thermal, full_arrays=True,
+                tlevels=None):
+    """fill a pb_climate_args; returns (args, memspace, outputs dict, keep-alive list).  tlevels [P, nlevel] selects
+    the Jacobian-batch mode (thermal half for P temperature profiles over one set of opacities)."""
     nlevel = int(Atmosphere.nlevel)
     nlayer = nlevel - 1
     nwno = int(Opagrid.nwno)
@@ -108,9 +111,86 @@ def _one_column(ctx, Atmosphere, wed, noed, ScatteringPhase, Disco, Opagrid, F0P
     vecn = lambda i: blk[i * nlevel:(i + 1) * nlevel]
     out = dict(flux_net_v_layer=vecn(0), flux_net_v=vecn(1), flux_plus_v=big(0), flux_minus_v=big(1),
                flux_net_ir_layer=vecn(2), flux_net_ir=vecn(3), flux_plus_ir=big(2), flux_minus_ir=big(3))
+    if tlevels is not None:
+        tl = np.ascontiguousarray(tlevels, dtype=np.float64)
+        if tl.ndim != 2 or tl.shape[1] != nlevel:
+            raise _lib.PicasoB200Error("tlevels must be [nprofiles, nlevel]")
+        jac = np.empty((tl.shape[0], 2, nlevel))
+        keep += [tl, jac]
+        a.nprofiles, a.tlevels, a.jac_out = tl.shape[0], addr(tl), addr(jac)
+        out = dict(tlevels=tl, jac=jac)
+    keep.append(blk)
+    return a, memspace, out, keep
+
+
+def _one_column(ctx, Atmosphere, wed, noed, ScatteringPhase, Disco, Opagrid, F0PI, reflected, thermal, full_arrays=True):
+    a, memspace, out, keep = _build_args(ctx, Atmosphere, wed, noed, ScatteringPhase, Disco, Opagrid, F0PI, reflected,
+                                         thermal, full_arrays)
     ctx.check(ctx.lib.pb_climate_get_fluxes(ctx.h, ctypes.byref(a), memspace))
     del keep
     return out
+
+
+def get_fluxes_jacobian(Atmosphere, OpacityWEd, OpacityNoEd, ScatteringPhase, Disco, Opagrid, tlevels, *, ctx=None):
+    """The thermal half of get_fluxes for every row of tlevels [nprofiles, nlevel] in ONE device call - what the
+    Jacobian loop of t_start asks for one perturbed level at a time (climate.py:1108-1180: temp[jm] += deltaT,
+    get_fluxes(thermal only), restore).  The opacities (which do not change inside that loop) are staged once;
+    only the Planck terms differ between profiles.  Returns (flux_net_ir_layer, flux_net_ir), each
+    [nprofiles, nlevel]; row p equals get_fluxes(..., reflected=False, thermal=True)[4:6] with t_level = tlevels[p]."""
+    ctx = ctx or _lib.default_context()
+    a, memspace, out, keep = _build_args(ctx, Atmosphere, OpacityWEd, OpacityNoEd, ScatteringPhase, Disco, Opagrid, None,
+                                         False, True, False, tlevels=tlevels)
+    ctx.check(ctx.lib.pb_climate_get_fluxes(ctx.h, ctypes.byref(a), memspace))
+    jac = out["jac"]
+    del keep
+    return jac[:, 0, :].copy(), jac[:, 1, :].copy()
+
+
+class BoundFluxes:
+    """A get_fluxes call bound once and re-run from numba nopython code (the reference's t_start / get_fluxes are jitted,
+    so rebinding Python names cannot reach them - SURVEY.md section 8b).
+
+        bf = BoundFluxes(Atmosphere, OpacityWEd, ..., reflected=False, thermal=True)      # or tlevels=[P, nlevel]
+        run, addr, h = bf.run, bf.ctx_address, bf.handle        # ctypes function + two integers
+        @numba.njit
+        def solver_step(t_level, net_ir):                       # t_level, net_ir: bf.t_level, bf.flux_net_ir
+            t_level[3] += 1.0                                    # the solver writes temperatures in place ...
+            rc = run(addr, h)                                    # ... and calls the device
+            return net_ir[0]
+
+    `run` takes two integers, so numba's ctypes support can call it; inputs are read from / outputs written to the
+    numpy arrays exposed as attributes (t_level or tlevels, flux_net_v_layer, flux_net_v, flux_net_ir_layer,
+    flux_net_ir, jac)."""
+
+    def __init__(self, Atmosphere, OpacityWEd, OpacityNoEd, ScatteringPhase, Disco, Opagrid, F0PI=None, reflected=False,
+                 thermal=True, tlevels=None, *, ctx=None):
+        self.ctx = ctx or _lib.default_context()
+        nlevel = int(Atmosphere.nlevel)
+        self.t_level = np.ascontiguousarray(Atmosphere.t_level, dtype=np.float64).copy()
+        atm = type("Atm", (), dict(nlevel=nlevel, t_level=self.t_level, p_level=Atmosphere.p_level))()
+        a, memspace, out, keep = _build_args(self.ctx, atm, OpacityWEd, OpacityNoEd, ScatteringPhase, Disco, Opagrid, F0PI,
+                                             reflected, thermal, False, tlevels=tlevels)
+        if tlevels is None:
+            # _build_args copied t_level into a fresh vector: point the struct at OUR array so in-place writes count
+            a.tlevel = addr(self.t_level)
+            self.flux_net_v_layer, self.flux_net_v = out["flux_net_v_layer"], out["flux_net_v"]
+            self.flux_net_ir_layer, self.flux_net_ir = out["flux_net_ir_layer"], out["flux_net_ir"]
+        else:
+            self.tlevels, self.jac = out["tlevels"], out["jac"]
+        self._keep, self._args = keep, a
+        h = ctypes.c_int(-1)
+        self.ctx.check(self.ctx.lib.pb_climate_bind(self.ctx.h, ctypes.byref(a), memspace, ctypes.byref(h)))
+        self.handle = int(h.value)
+        self.ctx_address = int(self.ctx.h.value)
+        self.run = self.ctx.lib.pb_climate_run_bound
+
+    def __call__(self):
+        self.ctx.check(self.run(self.ctx_address, self.handle))
+
+    def close(self):
+        if self.handle >= 0:
+            self.ctx.lib.pb_climate_unbind(self.ctx.h, self.handle)
+            self.handle = -1
 
 
 def get_fluxes(Atmosphere, OpacityWEd, OpacityNoEd, ScatteringPhase, Disco, Opagrid, F0PI, reflected, thermal,

@@ -100,14 +100,18 @@ __global__ void __launch_bounds__(kRedThreads) climate_visible_reduce(
 // IR part (climate.py:1916-1942): gauss-weighted accumulation, compress_thermal (disco.py:152-180)
 // over the G = ng*nt disk angles, dwni-weighted wavelength sums.  Level arrays [K][G][V][W].
 __global__ void __launch_bounds__(kRedThreads) climate_ir_reduce(
-    int V, int W, int K, int G, int nt, const double *__restrict__ fm, const double *__restrict__ fp,
-    const double *__restrict__ fmm, const double *__restrict__ fpm, const double *__restrict__ gw,
+    int V, int W, int K, int G, int nt, const double *fm, const double *fp,
+    const double *fmm, const double *fpm, const double *__restrict__ gw,
     const double *__restrict__ gweight, const double *__restrict__ tweight, const double *__restrict__ dwni,
-    double *__restrict__ plus_ir, double *__restrict__ minus_ir, double *__restrict__ net_layer,
-    double *__restrict__ net)
+    double *plus_ir, double *minus_ir, double *net_layer, double *net)
 {
     __shared__ double sh[kRedThreads / 32];
     const int v = blockIdx.x;
+    // blockIdx.y: temperature profile of a Jacobian batch (level arrays [P][K][G][V][W], net fluxes [P][V]); the
+    // [V][W] arrays are only written for a single profile
+    const int64_t pofs = (int64_t)blockIdx.y * K * G * V * W;
+    fm += pofs; fp += pofs; fmm += pofs; fpm += pofs;
+    net_layer += (int64_t)blockIdx.y * V; net += (int64_t)blockIdx.y * V;
     const double sym = (nt == 1) ? 1.0 : 1.0 / (2.0 * PB_PI);
     double s_net = 0.0, s_lay = 0.0;
     for (int w = threadIdx.x; w < W; w += kRedThreads) {
@@ -132,8 +136,8 @@ __global__ void __launch_bounds__(kRedThreads) climate_ir_reduce(
         const double dw = dwni[w];
         s_lay += (c_fpm - c_fmm) * dw;
         s_net += (c_fp - c_fm) * dw;
-        plus_ir[(int64_t)v * W + w] = c_fp * dw;
-        minus_ir[(int64_t)v * W + w] = c_fm * dw;
+        if (plus_ir) plus_ir[(int64_t)v * W + w] = c_fp * dw;
+        if (minus_ir) minus_ir[(int64_t)v * W + w] = c_fm * dw;
     }
     const double t_lay = block_sum(s_lay, sh), t_net = block_sum(s_net, sh);
     if (threadIdx.x == 0) {
@@ -158,6 +162,116 @@ int aux_reserve(pb_ctx *ctx, size_t bytes)
 
 } // namespace
 
+// Jacobian batching (pb_climate_args.nprofiles > 0): the thermal half of get_fluxes for P temperature profiles over one
+// set of opacities.  The three opacity arrays are staged (de-interleaved) once; pb_thermal_toon_1d runs with
+// nbatch = P x K and opacity_period = K, in chunks of profiles whose level arrays fit the scratch budget; one
+// climate_ir_reduce launch per chunk folds gauss weights, disk weights, dwni and the wavelength sums per profile.
+static int climate_jacobian(pb_ctx *ctx, const pb_climate_args *a, int memspace)
+{
+    const int L = a->nlayer, W = a->nwno, K = a->ngauss, G = a->numg * a->numt, V = L + 1, P = a->nprofiles;
+    if (!a->DTAU_OG || !a->W0_no_raman || !a->COSB_OG || !a->tlevels || !a->plevel || !a->wno || !a->dwno ||
+        !a->ubar1 || !a->gweight || !a->tweight || !a->jac_out)
+        return pb_fail(ctx, PB_ERR_ARG, "climate jacobian: needs DTAU_OG, W0_no_raman, COSB_OG, tlevels, plevel, wno, dwno, ubar1, gweight, tweight, jac_out");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool host = memspace == PB_HOST;
+    const size_t nLW = (size_t)L * W * sizeof(double), nVW = (size_t)V * W * sizeof(double), nW = (size_t)W * sizeof(double);
+    const bool restage = host || K > 1;
+    // profiles per chunk: four level arrays of Pc x K x G x V x W doubles within ~3 GB
+    const size_t per_profile = 4 * (size_t)K * G * nVW;
+    int Pc = (int)(((size_t)3 << 30) / per_profile);
+    if (Pc < 1) Pc = 1;
+    if (Pc > P) Pc = P;
+    if ((int64_t)Pc * K > 65535) Pc = 65535 / K;
+    size_t need = 64 * 256 + (restage ? 3 * pb_align(K * nLW) : 0) + (host ? pb_align(K * nLW) : 0) + pb_align(K * nW) +
+                  4 * pb_align((size_t)Pc * K * G * nVW) + pb_align(2 * (size_t)P * V * 8) + pb_align((size_t)(K + G + 16) * 8 * 4);
+    PB_TRY(aux_reserve(ctx, need));
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> double * {
+        double *ptr = (double *)(ctx->aux + off);
+        off += pb_align(bytes);
+        return ptr;
+    };
+    double *raw = host ? take(K * nLW) : nullptr;
+    auto stage = [&](const double *src, const double **dst) -> int {
+        if (!restage) { *dst = src; return PB_OK; }
+        const int64_t n = (int64_t)L * W;
+        double *d = take((size_t)K * n * sizeof(double));
+        const double *in = src;
+        if (host) {
+            PB_CUDA(ctx, cudaMemcpyAsync(raw, src, (size_t)K * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            in = raw;
+        }
+        if (K == 1) PB_CUDA(ctx, cudaMemcpyAsync(d, in, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        else {
+            deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, K, in, d);
+            PB_CHECK_LAUNCH(ctx);
+        }
+        *dst = d;
+        return PB_OK;
+    };
+    pb_arena_reset(ctx);
+    {
+        const size_t Gc = (size_t)G;
+        const size_t outer = (size_t)(K + 4 * (size_t)W + a->numg + a->numt + 64) * sizeof(double) + 16 * 64;
+        const size_t inner = (2 * (size_t)Pc * K * V + 3 * Gc + (size_t)Pc * K + 64) * sizeof(double);
+        PB_TRY(pb_pinned_reserve(ctx, outer > inner ? outer : inner));
+    }
+    const double *d_dtau = nullptr, *d_w0 = nullptr, *d_cosb = nullptr;
+    PB_TRY(stage(a->DTAU_OG, &d_dtau));
+    PB_TRY(stage(a->W0_no_raman, &d_w0));
+    PB_TRY(stage(a->COSB_OG, &d_cosb));
+    const double *d_gw = nullptr, *d_wno = nullptr, *d_dwno = nullptr, *d_gweight = nullptr, *d_tweight = nullptr, *d_s1 = nullptr;
+    PB_TRY(pb_upload_small(ctx, a->gauss_wts, K, &d_gw));
+    PB_TRY(pb_upload_small(ctx, a->wno, W, &d_wno));
+    PB_TRY(pb_upload_small(ctx, a->dwno, W, &d_dwno));
+    PB_TRY(pb_upload_small(ctx, a->gweight, a->numg, &d_gweight));
+    PB_TRY(pb_upload_small(ctx, a->tweight, a->numt, &d_tweight));
+    if (a->surf_reflect) PB_TRY(pb_upload_small(ctx, a->surf_reflect, W, &d_s1));
+    double *d_surf = take(K * nW);
+    PB_TRY(pb_upload_flush(ctx));
+    replicate_kernel<<<(W + 255) / 256, 256, 0, ctx->stream>>>(W, K, d_s1, 0.0, d_surf);
+    PB_CHECK_LAUNCH(ctx);
+    double *lv[4];
+    for (int i = 0; i < 4; ++i) lv[i] = take((size_t)Pc * K * G * nVW);
+    double *o_net = take(2 * (size_t)P * V * 8);   // [2][P][V]: layer, level
+    if (off > ctx->aux_cap) return pb_fail(ctx, PB_ERR_NOMEM, "climate jacobian: scratch layout overflow (%zu > %zu)", off, ctx->aux_cap);
+    std::vector<double> tl, pl;
+    for (int p0 = 0; p0 < P; p0 += Pc) {
+        const int pc = P - p0 < Pc ? P - p0 : Pc;
+        tl.assign((size_t)pc * K * V, 0.0);
+        pl.assign((size_t)pc * K * V, 0.0);
+        for (int pr = 0; pr < pc; ++pr)
+            for (int k = 0; k < K; ++k)
+                for (int v = 0; v < V; ++v) {
+                    tl[((size_t)pr * K + k) * V + v] = a->tlevels[(size_t)(p0 + pr) * V + v];
+                    pl[((size_t)pr * K + k) * V + v] = a->plevel[v];
+                }
+        pb_thermal_args t;
+        memset(&t, 0, sizeof(t));
+        t.nlayer = L; t.nwno = W; t.numg = a->numg; t.numt = a->numt; t.nbatch = pc * K; t.ld = W;
+        t.dtau = d_dtau; t.w0 = d_w0; t.cosb = d_cosb;
+        t.wno = d_wno; t.dwno = d_dwno; t.surf_reflect = d_surf;
+        t.tlevel = tl.data(); t.plevel = pl.data();
+        t.ubar1 = a->ubar1; t.gweight = a->gweight; t.tweight = a->tweight;
+        t.hard_surface = 0; t.calc_type = 1;
+        t.opacity_period = K;
+        t.flux_minus = lv[0]; t.flux_plus = lv[1]; t.flux_minus_mdpt = lv[2]; t.flux_plus_mdpt = lv[3];
+        PB_TRY(pb_thermal_toon_1d(ctx, &t, PB_DEVICE));
+        dim3 grid(V, pc);
+        climate_ir_reduce<<<grid, kRedThreads, 0, ctx->stream>>>(V, W, K, G, a->numt, lv[0], lv[1], lv[2], lv[3], d_gw,
+                                                                 d_gweight, d_tweight, d_dwno, nullptr, nullptr,
+                                                                 o_net + (size_t)p0 * V, o_net + (size_t)(P + p0) * V);
+        PB_CHECK_LAUNCH(ctx);
+    }
+    // jac_out [P][2][V] <- o_net [2][P][V]: two strided copies
+    PB_CUDA(ctx, cudaMemcpy2DAsync(a->jac_out, 2 * (size_t)V * 8, o_net, (size_t)V * 8, (size_t)V * 8, P,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpy2DAsync(a->jac_out + V, 2 * (size_t)V * 8, o_net + (size_t)P * V, (size_t)V * 8, (size_t)V * 8, P,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
 extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int memspace)
 {
     if (!ctx || !a) return PB_ERR_ARG;
@@ -165,6 +279,7 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
     const int V = L + 1;
     if (L < 1 || W < 1 || K < 1 || G < 1) return pb_fail(ctx, PB_ERR_ARG, "climate: bad sizes L=%d W=%d K=%d G=%d", L, W, K, G);
     if (!a->gauss_wts) return pb_fail(ctx, PB_ERR_ARG, "climate: gauss_wts missing");
+    if (a->nprofiles > 0) return climate_jacobian(ctx, a, memspace);
     if (a->reflected) {
         if (!a->DTAU || !a->TAU || !a->W0 || !a->COSB || !a->GCOS2 || !a->ftau_cld || !a->ftau_ray ||
             !a->DTAU_OG || !a->TAU_OG || !a->W0_OG || !a->COSB_OG)
@@ -384,4 +499,47 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
     }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return rc_thermal;
+}
+
+// ---- bound calls (numba nopython -> ctypes) -------------------------------------------------------------
+namespace {
+struct BoundCall { pb_ctx *ctx; pb_climate_args args; int memspace; bool live; };
+std::vector<BoundCall> &bound_calls()
+{
+    static std::vector<BoundCall> v;
+    return v;
+}
+} // namespace
+
+extern "C" int pb_climate_bind(pb_ctx *ctx, const pb_climate_args *args, int memspace, int *handle_out)
+{
+    if (!ctx || !args || !handle_out) return pb_fail(ctx, PB_ERR_ARG, "climate_bind: bad arguments");
+    auto &v = bound_calls();
+    for (size_t i = 0; i < v.size(); ++i)
+        if (!v[i].live) {
+            v[i] = BoundCall{ctx, *args, memspace, true};
+            *handle_out = (int)i;
+            return PB_OK;
+        }
+    v.push_back(BoundCall{ctx, *args, memspace, true});
+    *handle_out = (int)v.size() - 1;
+    return PB_OK;
+}
+
+extern "C" int pb_climate_run_bound(unsigned long long ctx_address, int handle)
+{
+    auto &v = bound_calls();
+    if (handle < 0 || (size_t)handle >= v.size() || !v[handle].live) return PB_ERR_ARG;
+    BoundCall &b = v[handle];
+    if ((unsigned long long)(uintptr_t)b.ctx != ctx_address) return PB_ERR_ARG;
+    return pb_climate_get_fluxes(b.ctx, &b.args, b.memspace);
+}
+
+extern "C" int pb_climate_unbind(pb_ctx *ctx, int handle)
+{
+    auto &v = bound_calls();
+    if (handle < 0 || (size_t)handle >= v.size() || !v[handle].live || v[handle].ctx != ctx)
+        return pb_fail(ctx, PB_ERR_ARG, "climate_unbind: no such binding");
+    v[handle].live = false;
+    return PB_OK;
 }

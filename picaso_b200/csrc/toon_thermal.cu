@@ -30,6 +30,7 @@ struct ThermParams {
     int fuse;
     int variant;  // 1: get_thermal_3d per-facet semantics (fluxes.py:2148-2352)
     int wt, ay;   // therm_toa_kernel<GEN = true>: wavelengths / angles per CTA
+    int ob_period; // > 0: batch entry b reads opacity / surf block b % ob_period (pb_thermal_args.opacity_period)
 };
 
 constexpr int kWavesPerCta = 32;
@@ -155,12 +156,12 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
     const int b = blockIdx.z;
     const int L = p.L, V = p.L + 1;
     const int64_t ld = p.ld;
-    const int64_t ol = (int64_t)b * p.bs_layer + wc;
+    const int64_t ol = (int64_t)(p.ob_period ? b % p.ob_period : b) * p.bs_layer + wc;
     const double *tl = p.tlevel + (int64_t)b * V;
     const double *pl = p.plevel + (int64_t)b * V;
     const double u = p.variant ? p.ubar1[b] : p.ubar1[ac];
     const double inv_u = 1.0 / u;
-    const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + wcc] : 0.0;
+    const double r = p.surf ? p.surf[(int64_t)(p.ob_period ? b % p.ob_period : b) * p.bs_wave + wcc] : 0.0;
     double *sB = smem;
     double *tiles = smem + (size_t)V * 32;
     const int tile = NW * TNQ * 32;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
     double result;
     {
         // top boundary: fake isothermal overburden, fluxes.py:1797-1800; row 0 :155-158
-        const double tau_top = __ldg(p.dtau + (int64_t)b * p.bs_layer + wcc) * pl[0] / (pl[1] - pl[0]);
+        const double tau_top = __ldg(p.dtau + (int64_t)(p.ob_period ? b % p.ob_period : b) * p.bs_layer + wcc) * pl[0] / (pl[1] - pl[0]);
         const double b_top = (1.0 - exp(-tau_top / kMu1)) * B0 * PB_PI;
         const double b_ = gam_n + 1.0, c_ = gam_n - 1.0, d_ = b_top - cmu_n;
         const double xi = pbm::krcp(b_ - c_ * AS);
@@ -323,10 +324,10 @@ __global__ void __launch_bounds__(128, PB_THERM_WAVE_MINB) therm_toa_wave_kernel
     if (w >= p.W) return;
     const int L = p.L, V = p.L + 1;
     const int64_t ld = p.ld;
-    const int64_t ol = (int64_t)b * p.bs_layer + w;
+    const int64_t ol = (int64_t)(p.ob_period ? b % p.ob_period : b) * p.bs_layer + w;
     const double *tl = p.tlevel + (int64_t)b * V;
     const double *pl = p.plevel + (int64_t)b * V;
-    const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + w] : 0.0;
+    const double r = p.surf ? p.surf[(int64_t)(p.ob_period ? b % p.ob_period : b) * p.bs_wave + w] : 0.0;
     double u[G], inv_u[G], Pp[G], Rp[G];
 #pragma unroll
     for (int a = 0; a < G; ++a) {
@@ -485,12 +486,12 @@ __global__ void __launch_bounds__(256) therm_levels_kernel(ThermParams p)
     if (w >= p.W || a >= p.G) return;
     const int L = p.L, V = p.L + 1;
     const int64_t ld = p.ld;
-    const int64_t ol = (int64_t)b * p.bs_layer + w;
+    const int64_t ol = (int64_t)(p.ob_period ? b % p.ob_period : b) * p.bs_layer + w;
     const int64_t oo = (((int64_t)b * p.G + a) * V) * p.W + w;
     const double *tl = p.tlevel + (int64_t)b * V;
     const double *pl = p.plevel + (int64_t)b * V;
     const double u = p.ubar1[a];
-    const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + w] : 0.0;
+    const double r = p.surf ? p.surf[(int64_t)(p.ob_period ? b % p.ob_period : b) * p.bs_wave + w] : 0.0;
     Planck planck;
     planck.init(p.calc_type, p.wno[w], p.dwno ? p.dwno[w] : 0.0);
 
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(128) therm_layer_records_kernel(ThermParams p,
     const double *tl = p.tlevel + (int64_t)b * V;
     Planck planck;
     planck.init(p.calc_type, p.wno[w], p.dwno ? p.dwno[w] : 0.0);
-    const int64_t il = (int64_t)b * p.bs_layer + (int64_t)l * p.ld + w;
+    const int64_t il = (int64_t)(p.ob_period ? b % p.ob_period : b) * p.bs_layer + (int64_t)l * p.ld + w;
     const double dt = p.dtau[il];
     TLayer t;
     thermal_layer(dt, p.w0[il], p.cosb[il], planck(tl[l]), planck(tl[l + 1]), t);
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(256) therm_levels_rec_kernel(ThermParams p, co
     const double *tl = p.tlevel + (int64_t)b * V;
     const double *pl = p.plevel + (int64_t)b * V;
     const double u = p.ubar1[a];
-    const double r = p.surf ? p.surf[(int64_t)b * p.bs_wave + w] : 0.0;
+    const double r = p.surf ? p.surf[(int64_t)(p.ob_period ? b % p.ob_period : b) * p.bs_wave + w] : 0.0;
     const double *R = rec + ((int64_t)b * L * LR_N) * W + w;           // + (l * LR_N + field) * W
     const double *X = xrec + ((((int64_t)b * p.G + a) * L) * 2) * W + w;  // + (l * 2 + {0,1}) * W
     Planck planck;
@@ -831,6 +832,8 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
         return pb_fail(ctx, PB_ERR_ARG, "thermal: level fluxes need all four arrays");
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool host = memspace == PB_HOST;
+    if (a->opacity_period > 0 && (memspace != PB_DEVICE || a->variant || a->opacity_period > B))
+        return pb_fail(ctx, PB_ERR_ARG, "thermal: opacity_period needs PB_DEVICE arrays, variant 0 and period <= nbatch");
     const size_t nW = (size_t)W * sizeof(double);
     const bool fuse = a->thermal && !want_lvl && G <= 8;
     const bool need_ftop = a->flux_at_top || (a->thermal && !fuse);
@@ -859,6 +862,7 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
     PB_TRY(pb_stage_in(ctx, a->surf_reflect, memspace, a->variant ? 1 : B, W, W, &p.surf, &ldo));
     p.ld = host ? W : a->ld;
     p.bs_layer = (int64_t)L * p.ld; p.bs_wave = W;
+    p.ob_period = a->opacity_period > 0 ? a->opacity_period : 0;
     PB_TRY(pb_upload_small(ctx, a->tlevel, (size_t)B * V, &p.tlevel));
     PB_TRY(pb_upload_small(ctx, a->plevel, (size_t)B * V, &p.plevel));
     PB_TRY(pb_upload_small(ctx, a->ubar1, a->variant ? B : G, &p.ubar1));

@@ -94,3 +94,89 @@ def test_gpu_net_fluxes_only():
             assert np.array_equal(net[i], full[i]), k
         else:
             assert net[i] is None
+
+
+def test_bound_call_is_callable_from_numba_nopython():
+    """CPU: pb_climate_run_bound takes two integers, so numba's ctypes support can call it from jitted code (the
+    reference's solver loop is numba-nopython, climate.py:804).  Without a context it answers PB_ERR_ARG."""
+    import numba
+    from picaso_b200 import _lib
+    run = _lib.load_library().pb_climate_run_bound
+
+    @numba.njit
+    def call(addr, handle):
+        return run(addr, handle)
+
+    assert call(0, 0) == 2      # PB_ERR_ARG: no such binding - but the call itself went through nopython code
+
+
+def _perturbed_profiles(t_level):
+    """the Jacobian loop of t_start (climate.py:1108-1180): one level temperature perturbed per profile"""
+    V = t_level.size
+    tl = np.tile(t_level, (V + 1, 1))
+    for j in range(V):
+        tl[j + 1, j] += 0.01 * t_level[j]
+    return tl
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["clim_k4", "clim_k8_disk5"])
+def test_gpu_jacobian_batch(name):
+    """get_fluxes_jacobian: all perturbed temperature profiles in one call == one thermal get_fluxes per profile"""
+    import picaso_b200 as pb
+    case = C.climate_cases()[name]
+    d = C.build_climate(case)
+    args = list(C.climate_args(d, case))
+    atm = args[0]
+    tls = _perturbed_profiles(np.asarray(atm.t_level, dtype=np.float64))
+    lay, net = pb.get_fluxes_jacobian(*args[:6], tls)
+    assert lay.shape == net.shape == tls.shape
+    for p in (0, 1, tls.shape[0] // 2, tls.shape[0] - 1):
+        a2 = list(args)
+        a2[0] = atm._replace(t_level=tls[p])
+        a2[7], a2[8] = False, True
+        one = pb.get_fluxes(*a2, full_arrays=False)
+        # same kernels, same per-column arithmetic (the batch size may select the fused or the record-based level kernel:
+        # identical expressions, so allow rounding-level slack only)
+        assert np.allclose(lay[p], one[4], rtol=1e-12, atol=1e-12 * np.max(np.abs(one[4]))), (name, p)
+        assert np.allclose(net[p], one[5], rtol=1e-12, atol=1e-12 * np.max(np.abs(one[5]))), (name, p)
+    # and against the oracle with the net-flux criterion
+    a2 = list(args)
+    a2[0] = atm._replace(t_level=tls[3])
+    a2[7], a2[8] = False, True
+    ref = oclim.get_fluxes(*a2, nthreads=4)
+    scale = np.max(np.abs(ref[5]))
+    assert np.all(np.abs(net[3] - ref[5]) <= 1e-6 * np.abs(ref[5]) + 1e-6 * scale)
+
+
+@pytest.mark.gpu
+def test_gpu_bound_call_from_numba():
+    """a bound thermal get_fluxes driven from a numba-jitted loop that rewrites the temperatures in place"""
+    import numba
+    import picaso_b200 as pb
+    case = C.climate_cases()["clim_k4"]
+    d = C.build_climate(case)
+    args = list(C.climate_args(d, case))
+    atm = args[0]
+    bf = pb.BoundFluxes(*args[:7], reflected=False, thermal=True)
+    run, addr, h = bf.run, bf.ctx_address, bf.handle
+
+    @numba.njit
+    def sweep(t_level, net_ir, out):
+        for j in range(out.shape[0]):
+            keep = t_level[j]
+            t_level[j] = keep * 1.01
+            rc = run(addr, h)
+            if rc != 0:
+                return rc
+            out[j, :] = net_ir
+            t_level[j] = keep
+        return 0
+
+    V = bf.t_level.size
+    out = np.zeros((3, V))
+    assert sweep(bf.t_level, bf.flux_net_ir, out) == 0
+    tls = _perturbed_profiles(np.asarray(atm.t_level, dtype=np.float64))
+    _, net = pb.get_fluxes_jacobian(*args[:6], tls)
+    assert np.allclose(out, net[1:4], rtol=1e-12, atol=1e-12 * np.max(np.abs(net)))
+    bf.close()
