@@ -561,6 +561,38 @@ def main():
     ms_per_step = ms / args.steps
     value = world * W * args.steps / (ms * 1e-3)
 
+    if os.environ.get("PB_BENCH_SWEEP") and gather_mode == "p2p":
+        # diagnostic (stderr, not part of the bench line): where the coupled step's extra time goes - every delivery mode
+        # of pb_peer_gather and no exchange at all, over short and long timed regions (fixed vs per-step cost)
+        sweep = []
+        for mode, pushv in (("none", None), ("lazy", 2), ("push", 1), ("fused", 0)):
+            for k in (20, 200):
+                if pushv is not None:
+                    pag.push = pushv
+                barrier()
+                if world > 1:
+                    pag.barrier()
+                ctx.timer_start()
+                th0 = time.perf_counter()
+                for i in range(k):
+                    a_ = cargs[i % NSETS][0]
+                    a_.gather = pag.next() if pushv is not None else None
+                    ctx.check(fn(ctx.h, ctypes.byref(a_), PB_DEVICE))
+                host_us = (time.perf_counter() - th0) / k * 1e6
+                if pushv is not None:
+                    pag.wait()
+                t_ms = ctx.timer_stop()
+                if world > 1:
+                    t = torch.tensor([t_ms, host_us], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    t_ms, host_us = float(t[0]), float(t[1])
+                sweep.append({"mode": mode, "steps": k, "us_per_step": round(1e3 * t_ms / k, 2),
+                              "host_enqueue_us_per_step": round(host_us, 2)})
+        pag.push = 2 if push == "lazy" else int(bool(push))
+        barrier()
+        if rank == 0:
+            sys.stderr.write("PB_BENCH_SWEEP " + json.dumps({"n_gpus": world, "sweep": sweep}) + "\n")
+
     # ---- end to end: public API, pinned host inputs, H2D + kernel + D2H per step ----
     ke = args.e2e_steps or min(args.steps, 40)
     pinned_sets = []

@@ -394,7 +394,16 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
         keep.append(jf)
     elif raman == 1:
         pol = pollack_factor(opa)
-        a.raman_pollack = addr(pol)
+        if device_outputs:
+            # raman_pollack follows memspace (include/picaso_b200.h): the [nwno] factor goes to HBM once per connection
+            dpol = getattr(opa, "_pollack_dev", None)
+            if dpol is None:
+                dpol = opa._buffer("raman_pollack", (W,))
+                ctx.check(ctx.lib.pb_memcpy_h2d(ctx.h, dpol.ptr, pol.ctypes.data, pol.nbytes))
+                opa._pollack_dev = dpol
+            a.raman_pollack = dpol.ptr
+        else:
+            a.raman_pollack = addr(pol)
         keep.append(pol)
     cloud = atm.layer.get("cloud") if isinstance(atm.layer, dict) else atm.layer["cloud"]
     memspace = PB_DEVICE if device_outputs else PB_HOST

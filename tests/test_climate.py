@@ -13,7 +13,30 @@ import pytest
 import cases as C
 import oracle
 from oracle import climate as oclim
-from util import assert_level_close, assert_level_close_yardstick, golden
+from util import assert_level_close, assert_level_close_yardstick, golden, log_yardstick
+
+NET_SLACK = 64.0
+
+
+def check_net(a, b, x, what):
+    """[nlevel] net-flux vector `a` against the fp64 reference `b` and its binary128 evaluation `x`.
+    (i) yardstick: 1e-6 |x| + 1e-9 max|x| + NET_SLACK x the fp64 reference's own largest error;
+    (ii) plain rtol 1e-6 against the fp64 reference at every level where the reference itself is well conditioned
+    (within 1e-8 of its binary128 evaluation): there an independent fp64 implementation has no excuse."""
+    scale = np.max(np.abs(x)) if x.size else 0.0
+    ref_err = np.max(np.abs(b - x)) if x.size else 0.0
+    err = np.abs(a - x)
+    plain = 1e-6 * np.abs(x) + 1e-9 * scale
+    bad = err > plain + NET_SLACK * ref_err
+    excess = err - plain
+    need = float(np.max(excess) / ref_err) if (x.size and ref_err > 0 and np.max(excess) > 0) else 0.0
+    log_yardstick(what, need, int((excess > 0).sum()), int(a.size), NET_SLACK)
+    assert not bad.any(), "%s: %d entries off, max abs err %.3e (scale %.3e, fp64 reference err %.3e)" % (
+        what, int(bad.sum()), float(np.max(err)), scale, ref_err)
+    well = np.abs(b - x) <= 1e-8 * np.abs(x)
+    off = well & (np.abs(a - b) > 1e-6 * np.abs(b))
+    assert not off.any(), "%s: %d well-conditioned levels differ from the fp64 reference by more than rtol 1e-6" % (
+        what, int(off.sum()))
 
 
 def check(got, ref, what, exact=None):
@@ -25,11 +48,7 @@ def check(got, ref, what, exact=None):
         if exact is not None:
             x = np.asarray(exact[i])
             if k.startswith("flux_net"):
-                scale = np.max(np.abs(x)) if x.size else 0.0
-                ref_err = np.max(np.abs(b - x)) if x.size else 0.0
-                bad = np.abs(a - x) > 1e-6 * np.abs(x) + 1e-9 * scale + 64.0 * ref_err
-                assert not bad.any(), "%s %s: %d entries off, max abs err %.3e (scale %.3e, fp64 reference err %.3e)" % (
-                    what, k, int(bad.sum()), float(np.max(np.abs(a - x))), scale, ref_err)
+                check_net(a, b, x, what + " " + k)
             else:
                 assert_level_close_yardstick(a, b, x, what=what + " " + k)
             continue
@@ -145,8 +164,9 @@ def test_gpu_jacobian_batch(name):
     a2[0] = atm._replace(t_level=tls[3])
     a2[7], a2[8] = False, True
     ref = oclim.get_fluxes(*a2, nthreads=4)
-    scale = np.max(np.abs(ref[5]))
-    assert np.all(np.abs(net[3] - ref[5]) <= 1e-6 * np.abs(ref[5]) + 1e-6 * scale)
+    exact = oclim.get_fluxes(*a2, nthreads=8, quad=True)
+    check_net(net[3], np.asarray(ref[5]), np.asarray(exact[5]), name + " jacobian profile 3 flux_net_ir")
+    check_net(lay[3], np.asarray(ref[4]), np.asarray(exact[4]), name + " jacobian profile 3 flux_net_ir_layer")
 
 
 @pytest.mark.gpu
