@@ -79,7 +79,8 @@ void orc_get_reflected_SH(
     const double *F0PI, int w_single_form, int w_multi_form, int psingle_form,
     int w_single_rayleigh, int w_multi_rayleigh, int psingle_rayleigh,
     double frac_a, double frac_b, double frac_c, double constant_back, double constant_forward,
-    int stream, const double *b_top, int single_form, double *xint_at_top, int nthreads);
+    int stream, const double *b_top, int single_form, double *xint_at_top,
+    double *flux /* flx = 1: [numg*numt][stream*nlevel][nwno]; NULL: flx = 0 */, int nthreads);
 
 /* follows fluxes.py:2979-3186 (get_thermal_SH, flx = 0).  Arguments the reference accepts
  * but never reads (tau, dtau_og, tau_og, w0_og, w0_no_raman) are not part of this signature. */

@@ -112,7 +112,9 @@ void ORC_NAME(orc_get_reflected_SH)(
     int w_single_form, int w_multi_form, int psingle_form, int w_single_rayleigh,
     int w_multi_rayleigh, int psingle_rayleigh,
     f64 frac_a, f64 frac_b, f64 frac_c, f64 constant_back, f64 constant_forward,
-    int stream, const f64 *b_top, int single_form, f64 *xint_at_top, int nthreads)
+    int stream, const f64 *b_top, int single_form, f64 *xint_at_top,
+    f64 *flux /* flx = 1: [G][S * nlevel][W] layer fluxes F.X + G (fluxes.py:2889-2890, :3311-3331, :3551-3598); NULL: flx = 0 */,
+    int nthreads)
 {
     const int L = nlevel - 1, W = nwno, G = numg * numt, S = stream;
     const int n = S * L, k = 3 * S / 2 - 1, ldab = 3 * k + 1;
@@ -238,6 +240,16 @@ void ORC_NAME(orc_get_reflected_SH)(
                     flux_bot_row[1] = Q1[nn] / em[nn];
                     G_bot = zpu[nn];
                     band_solve(n, k, ab, ldab, ipiv, B);
+                    if (flux) {
+                        /* calculate_flux(F, G, X), F and G of fluxes.py:3311-3331 (dot products in index order) */
+                        f64 *fo = flux + (size_t)ai * 2 * nlevel * W + w;
+                        fo[0] = (f64)((Q1[0] * B[0] + Q2[0] * B[1]) + zmd[0]);
+                        fo[(size_t)W] = (f64)((Q2[0] * B[0] + Q1[0] * B[1]) + zpd[0]);
+                        for (int kk = 0; kk < L; ++kk) {
+                            fo[(size_t)(2 * kk + 2) * W] = (f64)(((Q1[kk] * em[kk]) * B[2 * kk] + (Q2[kk] / em[kk]) * B[2 * kk + 1]) + zmu[kk]);
+                            fo[(size_t)(2 * kk + 3) * W] = (f64)(((Q2[kk] * em[kk]) * B[2 * kk] + (Q1[kk] / em[kk]) * B[2 * kk + 1]) + zpu[kk]);
+                        }
+                    }
                 } else {
                     /* setup_4_stream_fluxes, fluxes.py:3387-3607.  per-layer scratch in Am:
                      * 8 p/q values, 2 exps, 8 z values */
@@ -357,6 +369,21 @@ void ORC_NAME(orc_get_reflected_SH)(
                     flux_bot_row[2] = F22(nn); flux_bot_row[3] = F23(nn);
                     G_bot = zz[2 * L + nn];
                     band_solve(n, k, ab, ldab, ipiv, B);
+                    if (flux) {
+                        /* calculate_flux(F, G, X), F and G of fluxes.py:3551-3598 */
+                        f64 *fo = flux + (size_t)ai * 4 * nlevel * W + w;
+                        fo[0] = (f64)((((P1MN(0) * B[0] + P1PL(0) * B[1]) + P2MN(0) * B[2]) + P2PL(0) * B[3]) + zz[4 * L + 0]);
+                        fo[(size_t)W] = (f64)((((Q1MN(0) * B[0] + Q1PL(0) * B[1]) + Q2MN(0) * B[2]) + Q2PL(0) * B[3]) + zz[5 * L + 0]);
+                        fo[(size_t)2 * W] = (f64)((((P1PL(0) * B[0] + P1MN(0) * B[1]) + P2PL(0) * B[2]) + P2MN(0) * B[3]) + zz[6 * L + 0]);
+                        fo[(size_t)3 * W] = (f64)((((Q1PL(0) * B[0] + Q1MN(0) * B[1]) + Q2PL(0) * B[2]) + Q2MN(0) * B[3]) + zz[7 * L + 0]);
+                        for (int kk = 0; kk < L; ++kk) {
+                            const real *x = B + 4 * kk;
+                            fo[(size_t)(4 * kk + 4) * W] = (f64)((((F00(kk) * x[0] + F01(kk) * x[1]) + F02(kk) * x[2]) + F03(kk) * x[3]) + zz[0 * L + kk]);
+                            fo[(size_t)(4 * kk + 5) * W] = (f64)((((F10(kk) * x[0] + F11(kk) * x[1]) + F12(kk) * x[2]) + F13(kk) * x[3]) + zz[1 * L + kk]);
+                            fo[(size_t)(4 * kk + 6) * W] = (f64)((((F20(kk) * x[0] + F21(kk) * x[1]) + F22(kk) * x[2]) + F23(kk) * x[3]) + zz[2 * L + kk]);
+                            fo[(size_t)(4 * kk + 7) * W] = (f64)((((F30(kk) * x[0] + F31(kk) * x[1]) + F32(kk) * x[2]) + F33(kk) * x[3]) + zz[3 * L + kk]);
+                        }
+                    }
                 }
                 /* B now holds X.  flux at the bottom, fluxes.py:2891 */
                 real flux_bot = G_bot;

@@ -26,6 +26,8 @@ struct pb_ctx {
     bool push_pending[8] = {};               // pb_peer_gather push mode: ev_chunk[slot] has been recorded
     uint64_t launches = 0;
     char err[512] = {0};
+    // kernels whose dynamic shared-memory limit this context has already raised (pb_ensure_smem)
+    struct SmemAttr { const void *fn; int bytes; } smem_attr[24] = {};
     // grow-only device arena used to stage PB_HOST calls and small geometry vectors
     char *arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
@@ -47,7 +49,15 @@ struct pb_ctx {
         size_t cap = 0;
         cudaEvent_t ev = nullptr;
         bool pending = false;
+        // Host mirror of the first `shadow_valid` bytes of `dev` (what earlier flushes of this slot copied there, on
+        // `shadow_stream`).  A flush whose bytes equal the mirror issues NO copy: a solver called in a loop with the same
+        // geometry (ubar0/ubar1/gweight/tweight) stops paying an in-stream H2D copy + event per call once the ring
+        // has turned (pb_upload_flush).
+        char *shadow = nullptr;
+        size_t shadow_valid = 0;
+        cudaStream_t shadow_stream = nullptr;
     };
+    static constexpr size_t kShadowMax = 16 * 1024;  // larger blobs (batched level vectors) are not mirrored
     static constexpr int kPinSlots = 8;
     PinSlot pin[kPinSlots];
     int pin_cur = 0;
@@ -68,6 +78,28 @@ int pb_fail(pb_ctx *ctx, int code, const char *fmt, ...);
             return pb_fail((ctx), PB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, \
                            cudaGetErrorString(e__));                                        \
     } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (context, kernel, size): it is a driver call
+// that does not belong on the per-launch path of a solver called in a loop
+template <typename K>
+inline cudaError_t pb_ensure_smem(pb_ctx *ctx, K kern, size_t bytes)
+{
+    const void *fn = (const void *)kern;
+    for (auto &e : ctx->smem_attr) {
+        if (e.fn == fn) {
+            if (e.bytes >= (int)bytes) return cudaSuccess;
+            cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (rc == cudaSuccess) e.bytes = (int)bytes;
+            return rc;
+        }
+        if (!e.fn) {
+            cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (rc == cudaSuccess) { e.fn = fn; e.bytes = (int)bytes; }
+            return rc;
+        }
+    }
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);  // table full
+}
 
 #define PB_CHECK_LAUNCH(ctx)                       \
     do {                                           \

@@ -788,7 +788,7 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
         const int nwa = G < 8 ? G : 8;
         const size_t tsmem = ((size_t)pbm::kExpTabDoubles + (size_t)2 * TS_N * 32) * sizeof(double);
         dim3 tgrid((W + 31) / 32, (G + nwa - 1) / nwa, B);
-        PB_CUDA(ctx, cudaFuncSetAttribute(sh4_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        PB_CUDA(ctx, pb_ensure_smem(ctx, sh4_tile_kernel, tsmem));
         sh4_tile_kernel<<<tgrid, (nwa + 1) * 32, tsmem, ctx->stream>>>(p);
     } else if (a->stream == 2) sh_reflected_kernel<2><<<grid, block, smem, ctx->stream>>>(p);
     else sh_reflected_kernel<4><<<grid, block, smem, ctx->stream>>>(p);

@@ -1107,7 +1107,7 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             for (int i = 0; i < (a->variant ? B : G); ++i) same = same && (fabs(a->ubar0[i]) == fabs(a->ubar1[i]));
             dim3 ggrid((wc + wt - 1) / wt, (G + ay - 1) / ay, B);
             auto go = [&](auto kern) -> int {
-                PB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PB_CUDA(ctx, pb_ensure_smem(ctx, kern, smem));
                 kern<<<ggrid, nw * 32, smem, ctx->stream>>>(q);
                 return PB_OK;
             };

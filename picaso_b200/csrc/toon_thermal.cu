@@ -957,7 +957,7 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
             const size_t smem = ((size_t)V * 32 + (size_t)2 * ay * TNQ * 32) * sizeof(double);
             if (smem > 200 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "thermal: nlevel=%d exceeds the shared-memory Planck tile", V);
             if (smem > 48 * 1024)
-                PB_CUDA(ctx, cudaFuncSetAttribute(therm_toa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PB_CUDA(ctx, pb_ensure_smem(ctx, therm_toa_kernel<false>, smem));
             therm_toa_kernel<false><<<grid, block, smem, ctx->stream>>>(p);
         } else {
             p.wt = wt; p.ay = ay;
@@ -965,7 +965,7 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
             const size_t smem = ((size_t)V * 32 + (size_t)2 * nwarp * TNQ * 32) * sizeof(double);
             if (smem > 200 * 1024) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "thermal: nlevel=%d exceeds the shared-memory Planck tile", V);
             if (smem > 48 * 1024)
-                PB_CUDA(ctx, cudaFuncSetAttribute(therm_toa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PB_CUDA(ctx, pb_ensure_smem(ctx, therm_toa_kernel<true>, smem));
             dim3 ggrid((W + wt - 1) / wt, (G + ay - 1) / ay, B);
             therm_toa_kernel<true><<<ggrid, nthreads, smem, ctx->stream>>>(p);
         }

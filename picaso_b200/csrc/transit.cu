@@ -144,7 +144,7 @@ extern "C" int pb_transit_1d(pb_ctx *ctx, const pb_transit_args *a, int memspace
     transit_path_kernel<<<gp, 128, 0, ctx->stream>>>(V, Vp, d_z, d_dz, d_p, d_t, a->k_b, d_MT, d_zdz);
     PB_CHECK_LAUNCH(ctx);
     if (smem > 48 * 1024)
-        PB_CUDA(ctx, cudaFuncSetAttribute(transit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PB_CUDA(ctx, pb_ensure_smem(ctx, transit_kernel, smem));
     dim3 grid((W + kThreads - 1) / kThreads, B);
     transit_kernel<<<grid, kThreads, smem, ctx->stream>>>(V, Vp, W, ld, (int64_t)L * ld, d_dtau, d_scale, d_MT, d_zdz,
                                                           d_zmin, a->rstar, d_F);

@@ -368,6 +368,8 @@ def main():
         bench_sh(ctx, 60, 10000, 5, max(5, a.reps // 5), stream=4)
         bench_sh(ctx, 60, 196000, 5, 5, stream=4)
         bench_sh(ctx, 60, 196000, 5, 5, stream=4, forms=(1, 1, 1, 1, 1, 1))
+    if "shcfg3" in only:   # the one launch an ncu capture of cfg3 wants
+        bench_sh(ctx, 60, 196000, 5, 1, stream=4, forms=(1, 1, 1, 1, 1, 1))
     if "opacity" in only:
         bench_opacity(ctx, 80, 50000, 12, a.reps, outputs=("DTAU_OG",), tag=" (cfg4: transit needs DTAU only)")
         bench_opacity(ctx, 80, 50000, 12, a.reps, tag=" (cfg4, all 13 outputs)")

@@ -144,7 +144,16 @@ def build_sh(case):
     return d
 
 
-def sh_args(d, case):
+def sh_flux_cases():
+    """get_reflected_SH(flx=1) (fluxes.py:2889-2890): the cases whose layer fluxes F.X + G are pinned
+    (tests/golden/sh_flux.npz, make_golden_sh_flux.py)"""
+    c = sh_cases()
+    names = [f"sh{s}_{n}" for s in (2, 4) for n in ("othg_sf0", "tthg_sf0", "mix2_sf1", "cfg3_othg", "cfg3_tthg",
+                                                     "no_deltaM", "one_layer")]
+    return {n: c[n] for n in names}
+
+
+def sh_args(d, case, flx=0):
     """positional argument list of get_reflected_SH (fluxes.py:2675-2679); f_deltaM is copied
     because the reference modifies it in place."""
     f = case["forms"]
@@ -152,7 +161,7 @@ def sh_args(d, case):
             d["ftau_cld"], d["ftau_ray"], d["f_deltaM"].copy(), d["dtau_og"], d["tau_og"], d["w0_og"],
             d["cosb_og"], d["surf_reflect"], d["ubar0"], d["ubar1"], d["cos_theta"], d["F0PI"],
             f[0], f[1], f[2], f[3], f[4], f[5], d["frac_a"], d["frac_b"], d["frac_c"],
-            d["constant_back"], d["constant_forward"], case["stream"], 0.0, 0, case["single_form"])
+            d["constant_back"], d["constant_forward"], case["stream"], 0.0, flx, case["single_form"])
 
 
 def optics_cases():

@@ -6,7 +6,8 @@ the largest |net flux| of the column (deep levels cancel to ~0).  [nlevel, nwno]
 level-flux criterion of tests/util.py (rtol 1e-6 + 1e-9 of the column maximum).  The reference's level-flux
 formulas are ill-conditioned in optically thick layers: where the fp64 reference
 itself is further than that from the binary128 evaluation of its own formulas, an independent fp64
-implementation is held to 64 x the reference's own error instead (the yardstick criterion)."""
+implementation is held to 32 x (level arrays) / 4 x (net fluxes) the reference's own error instead (the
+yardstick criterion; the factors follow from the measured need, profiles/r2_yardstick.jsonl)."""
 import numpy as np
 import pytest
 
@@ -15,7 +16,7 @@ import oracle
 from oracle import climate as oclim
 from util import assert_level_close, assert_level_close_yardstick, golden, log_yardstick
 
-NET_SLACK = 64.0
+NET_SLACK = 4.0    # measured need <= 0.95 (profiles/r2_yardstick.jsonl); 64 in round 1
 
 
 def check_net(a, b, x, what):
