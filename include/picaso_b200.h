@@ -161,11 +161,12 @@ typedef struct pb_sh_args {
     int w_single_rayleigh, w_multi_rayleigh, psingle_rayleigh; /* 0 off, 1 on */
     double frac_a, frac_b, frac_c, constant_back, constant_forward;
     int stream;      /* 2 or 4 */
-    int flx;         /* must be 0 */
+    int flx;         /* 0 | 1: also return the layer fluxes (calculate_fluxes, justdoit.py:4638; fluxes.py:2889-2890) */
     int single_form; /* 0 explicit, 1 legendre */
     double *xint_at_top;  /* [numg*numt][nwno] or NULL */
     double *albedo;       /* [nwno] or NULL */
     double *f_deltaM_out; /* [nlayer][nwno] or NULL */
+    double *flux;         /* flx = 1: [nbatch][numg*numt][stream*nlevel][nwno] = F.X + G; follows memspace */
 } pb_sh_args;
 
 int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *args, int memspace);

@@ -52,7 +52,7 @@ class ShArgs(ctypes.Structure):
                               "w_multi_rayleigh", "psingle_rayleigh")] +
         [(n, c_dbl) for n in ("frac_a", "frac_b", "frac_c", "constant_back", "constant_forward")] +
         [("stream", c_int), ("flx", c_int), ("single_form", c_int)] +
-        [(n, c_vp) for n in ("xint_at_top", "albedo", "f_deltaM_out")])
+        [(n, c_vp) for n in ("xint_at_top", "albedo", "f_deltaM_out", "flux")])
 
 
 class ThermalShArgs(ctypes.Structure):

@@ -39,9 +39,16 @@ struct ShParams {
     int wsf, wmf, psf, wsr, wmr, psr, single_form;
     double *xint, *albedo, *fdm_out;
     int fuse_albedo;
+    // flx = 1 (layer fluxes, fluxes.py:2889-2890): wavelengths [w_begin, w_end) of this launch, pivot-row scratch
+    // piv [L-1][kPivN][ncols] (column = ((b G + a) wcap + w - w_begin)), output flux [B][G][S V][W]
+    int w_begin, w_end, wcap;
+    double *piv, *flux;
 };
 
 constexpr int kWaves = 32;
+// pivot rows kept per eliminated layer for the back-substitution of the flx = 1 path: row k of the S pivot rows keeps
+// its entries k .. 2S (upper triangle over [X_{l+1} | X_l | rhs])
+template <int S> struct PivRows { static constexpr int N = S * (2 * S + 1) - S * (S - 1) / 2; };
 
 __device__ __forceinline__ double clip35(double x) { return fmin(fmax(x, -35.0), 35.0); }
 
@@ -287,16 +294,25 @@ __device__ __forceinline__ void sh_layer(const ShParams &p, int64_t il, int64_t 
     o.xa = pbm::kexp(-dt * inv_u1);
 }
 
-template <int S>
+// FLX: also return the layer fluxes calculate_flux(F, G, X) (fluxes.py:2889-2890, F and G of :3311-3331 / :3551-3598).
+// They need the whole solution X, which the TOA-only sweep never forms: the S pivot rows of every eliminated layer go
+// to a scratch array in HBM (wavelength fastest, so the stores coalesce), the closed top system gives X_0, and a
+// second, top-down pass substitutes X_{l+1} from X_l and the stored rows (the substitution LAPACK's dgbtrs does with
+// U) and evaluates level 0 = T_0 X_0 + Zd_0, level l+1 = Fb_l X_l + Zu_l.  Not a hot path (calculate_fluxes is 'off'
+// by default, justdoit.py:4638): the layer quantities are simply recomputed in the second pass.
+template <int S, bool FLX = false>
 __global__ void __launch_bounds__(128) sh_reflected_kernel(ShParams p)
 {
     constexpr int H = S / 2, NR = H + S, NC = 2 * S + 1;
     extern __shared__ double s_int[];
     const int lane = threadIdx.x;
-    const int w = blockIdx.x * kWaves + lane;
+    const int w = (FLX ? p.w_begin : 0) + blockIdx.x * kWaves + lane;
     const int a = blockIdx.y * blockDim.y + threadIdx.y;
     const int b = blockIdx.z;
-    const bool active = (w < p.W) && (a < p.G);
+    const bool active = (w < (FLX ? p.w_end : p.W)) && (a < p.G);
+    // FLX: this thread's column of the pivot-row scratch
+    const int64_t pcols = FLX ? (int64_t)gridDim.z * p.G * p.wcap : 0;
+    double *pcol = FLX ? p.piv + ((int64_t)b * p.G + a) * p.wcap + (w - p.w_begin) : nullptr;
     double result = 0.0;
     if (active) {
         const int L = p.L;
@@ -370,6 +386,15 @@ __global__ void __launch_bounds__(128) sh_reflected_kernel(ShParams p)
                 for (int c = 0; c < S; ++c) { F[c] = J[c]; F[S + c] = 0.0; }
                 F[2 * S] = J[S];
                 eliminate<S, NR, NC>(R, F);
+                if (FLX) {
+                    // pivot row k: sum_{c >= k} R[k][c] x_c = R[k][2S] over x = [X_{l+1} | X_l]
+                    double *o = pcol + (int64_t)l * PivRows<S>::N * pcols;
+                    int e = 0;
+#pragma unroll
+                    for (int k = 0; k < S; ++k)
+#pragma unroll
+                        for (int c = k; c < NC; ++c, ++e) o[(int64_t)e * pcols] = R[k][c];
+                }
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
 #pragma unroll
@@ -407,6 +432,66 @@ __global__ void __launch_bounds__(128) sh_reflected_kernel(ShParams p)
             for (int c = 0; c <= S; ++c) F[c] = J[c];
             eliminate<S, S, S + 1>(R, F);
             result = F[S];
+            if (FLX) {
+                // X_0 from the triangular top system, then the top-down substitution pass
+                double X[S];
+#pragma unroll
+                for (int k = S - 1; k >= 0; --k) {
+                    double sacc = R[k][S];
+#pragma unroll
+                    for (int c = k + 1; c < S; ++c) sacc = fma(-R[k][c], X[c], sacc);
+                    X[k] = sacc / R[k][k];
+                }
+                const int V = L + 1;
+                double *fo = p.flux + ((int64_t)b * p.G + a) * S * V * p.W + w;
+                for (int l = 0; l < L; ++l) {
+                    Layer<S> y;
+                    double et;
+                    // exp(-tau_{l+1}/u0) exactly as the sweep above saw it (division at the surface, 1/u0 elsewhere)
+                    const double tb = __ldg(p.tau + ov + (int64_t)(l + 1) * ld);
+                    const double ebl = (l == L - 1) ? pbm::kexp(-tb / u0) : pbm::kexp(-tb * (1.0 / u0));
+                    sh_layer<S>(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, u0, u1, f0, Pu0, Pu1, mus, a, et, ebl, y,
+                                nullptr);
+                    if (l == 0) {
+#pragma unroll
+                        for (int i = 0; i < S; ++i) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int c = 0; c < S; ++c) acc = fma(y.T[i][c], X[c], acc);
+                            fo[(int64_t)i * p.W] = acc + y.Zd[i];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < S; ++i) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int c = 0; c < S; ++c) acc = fma(y.T[i][c] * y.cs[c], X[c], acc);
+                        fo[(int64_t)(S * (l + 1) + i) * p.W] = acc + y.Zu[i];
+                    }
+                    if (l < L - 1) {
+                        // X_{l+1} from the pivot rows of the window [X_{l+1} | X_l]
+                        const double *o = pcol + (int64_t)l * PivRows<S>::N * pcols;
+                        double Rk[S][NC];
+                        int e = 0;
+#pragma unroll
+                        for (int k = 0; k < S; ++k)
+#pragma unroll
+                            for (int c = k; c < NC; ++c, ++e) Rk[k][c] = o[(int64_t)e * pcols];
+                        double Xn[S];
+#pragma unroll
+                        for (int k = S - 1; k >= 0; --k) {
+                            double sacc = Rk[k][2 * S];
+#pragma unroll
+                            for (int c = 0; c < S; ++c) sacc = fma(-Rk[k][S + c], X[c], sacc);
+#pragma unroll
+                            for (int c = k + 1; c < S; ++c) sacc = fma(-Rk[k][c], Xn[c], sacc);
+                            Xn[k] = sacc / Rk[k][k];
+                        }
+#pragma unroll
+                        for (int c = 0; c < S; ++c) X[c] = Xn[c];
+                    }
+                }
+            }
         }
         if (p.xint) p.xint[((int64_t)b * p.G + a) * p.W + w] = result;
     }
@@ -706,7 +791,9 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
     const int B = a->nbatch > 0 ? a->nbatch : 1;
     if (L < 1 || W < 0 || G < 1) return pb_fail(ctx, PB_ERR_ARG, "reflected_sh: bad sizes L=%d W=%d G=%d", L, W, G);
     if (a->stream != 2 && a->stream != 4) return pb_fail(ctx, PB_ERR_ARG, "reflected_sh: stream must be 2 or 4");
-    if (a->flx != 0) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "reflected_sh: flx=1 (layer fluxes) is not implemented");
+    if (a->flx != 0 && a->flx != 1) return pb_fail(ctx, PB_ERR_ARG, "reflected_sh: flx must be 0 or 1");
+    const bool flx = a->flx == 1;
+    if (flx && !a->flux) return pb_fail(ctx, PB_ERR_ARG, "reflected_sh: flx=1 needs the flux array [nbatch][numg*numt][stream*nlevel][nwno]");
     if (W == 0) return PB_OK;
     if (a->ld < W) return pb_fail(ctx, PB_ERR_ARG, "reflected_sh: ld < nwno");
     if (!a->dtau || !a->tau || !a->w0 || !a->ftau_cld || !a->ftau_ray || !a->f_deltaM || !a->dtau_og ||
@@ -725,7 +812,7 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
     const char *tile_e = getenv("PB_SH_TILE");
     const int tile_env = tile_e ? atoi(tile_e) : 1;
     const bool tile = tile_env != 0 && a->stream == 4 && a->w_single_form == 1 && a->w_multi_form == 1 &&
-                      a->single_form == 0 && !a->f_deltaM_out;
+                      a->single_form == 0 && !a->f_deltaM_out && !flx;
     const bool fuse = a->albedo && G <= (tile ? 8 : 4);
     const bool need_xint = a->xint_at_top || (a->albedo && !fuse);
     size_t need = 16 * 256 + 4 * pb_align((size_t)G * 8);
@@ -734,6 +821,22 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
         need += pb_align((size_t)B * G * nW) + pb_align(B * nW) + pb_align((size_t)B * L * nW);
     } else {
         need += pb_align((size_t)B * G * nW);
+    }
+    // flx = 1: pivot-row scratch for a chunk of `wcap` wavelengths (<= ~1 GB; multiple of the 32-wavelength tile)
+    const int S = a->stream;
+    const size_t piv_per_wave = (size_t)(L - 1) * (S == 2 ? PivRows<2>::N : PivRows<4>::N) * B * G * sizeof(double);
+    int wcap = (W + kWaves - 1) / kWaves * kWaves;
+    if (flx) {
+        if (piv_per_wave > 0) {
+            const size_t fit = ((size_t)1 << 30) / piv_per_wave / kWaves * kWaves;
+            if (fit < (size_t)wcap) wcap = fit < (size_t)kWaves ? kWaves : (int)fit;
+        }
+        if (const char *e = getenv("PB_SH_FLX_WCAP")) {   // tests: force several chunks on a small case
+            const int v = atoi(e) / kWaves * kWaves;
+            if (v >= kWaves && v < wcap) wcap = v;
+        }
+        need += pb_align(piv_per_wave * wcap + 256);
+        if (host) need += pb_align((size_t)B * G * S * V * nW);
     }
     pb_arena_reset(ctx);
     PB_TRY(pb_arena_reserve(ctx, need));
@@ -779,12 +882,29 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
         d_fdm = a->f_deltaM_out;
     }
     p.xint = d_xint; p.albedo = d_alb; p.fdm_out = d_fdm; p.fuse_albedo = fuse ? 1 : 0;
+    double *d_flux = nullptr;
+    if (flx) {
+        if (host) PB_TRY(pb_arena_alloc(ctx, (size_t)B * G * S * V * nW, (void **)&d_flux));
+        else d_flux = a->flux;
+        PB_TRY(pb_arena_alloc(ctx, piv_per_wave * wcap + 256, (void **)&p.piv));
+        p.flux = d_flux; p.wcap = wcap;
+    }
     PB_TRY(pb_upload_flush(ctx));
     const int ay = G < 4 ? G : 4;
     dim3 block(kWaves, ay, 1);
     dim3 grid((W + kWaves - 1) / kWaves, (G + ay - 1) / ay, B);
     const size_t smem = fuse ? (size_t)ay * kWaves * sizeof(double) : 0;
-    if (tile) {
+    if (flx) {
+        // one launch per wavelength chunk; launches of a stream run in order, so they can share the scratch
+        for (int wb = 0; wb < W; wb += wcap) {
+            p.w_begin = wb;
+            p.w_end = wb + wcap < W ? wb + wcap : W;
+            dim3 cgrid((p.w_end - p.w_begin + kWaves - 1) / kWaves, (G + ay - 1) / ay, B);
+            if (S == 2) sh_reflected_kernel<2, true><<<cgrid, block, smem, ctx->stream>>>(p);
+            else sh_reflected_kernel<4, true><<<cgrid, block, smem, ctx->stream>>>(p);
+            PB_CHECK_LAUNCH(ctx);
+        }
+    } else if (tile) {
         const int nwa = G < 8 ? G : 8;
         const size_t tsmem = ((size_t)pbm::kExpTabDoubles + (size_t)2 * TS_N * 32) * sizeof(double);
         dim3 tgrid((W + 31) / 32, (G + nwa - 1) / nwa, B);
@@ -792,7 +912,7 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
         sh4_tile_kernel<<<tgrid, (nwa + 1) * 32, tsmem, ctx->stream>>>(p);
     } else if (a->stream == 2) sh_reflected_kernel<2><<<grid, block, smem, ctx->stream>>>(p);
     else sh_reflected_kernel<4><<<grid, block, smem, ctx->stream>>>(p);
-    PB_CHECK_LAUNCH(ctx);
+    if (!flx) PB_CHECK_LAUNCH(ctx);
     if (a->albedo && !fuse) {
         dim3 g2((W + 127) / 128, B);
         sh_compress_kernel<<<g2, 128, 0, ctx->stream>>>(W, G, a->numt, a->cos_theta, d_xint, p.gweight, p.tweight,
@@ -803,6 +923,7 @@ extern "C" int pb_reflected_sh(pb_ctx *ctx, const pb_sh_args *a, int memspace)
         if (a->xint_at_top) PB_CUDA(ctx, cudaMemcpyAsync(a->xint_at_top, d_xint, (size_t)B * G * nW, cudaMemcpyDeviceToHost, ctx->stream));
         if (a->albedo) PB_CUDA(ctx, cudaMemcpyAsync(a->albedo, d_alb, B * nW, cudaMemcpyDeviceToHost, ctx->stream));
         if (a->f_deltaM_out) PB_CUDA(ctx, cudaMemcpyAsync(a->f_deltaM_out, d_fdm, (size_t)B * L * nW, cudaMemcpyDeviceToHost, ctx->stream));
+        if (flx) PB_CUDA(ctx, cudaMemcpyAsync(a->flux, d_flux, (size_t)B * G * S * V * nW, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return PB_OK;

@@ -207,13 +207,14 @@ def get_reflected_SH(nlevel, nwno, numg, numt, dtau, tau, w0, cosb, ftau_cld, ft
     """CUDA replacement of fluxes.get_reflected_SH (picaso/fluxes.py:2675-2976), stream 2 or 4.
 
     Returns ``(xint_at_top[numg,numt,nwno], flux)`` where ``flux`` is the reference's
-    all-zero ``[numg,numt,stream*nlevel,nwno]`` array (flx=0; a read-only zero view).
+    ``[numg,numt,stream*nlevel,nwno]`` array: all zero for flx=0 (a read-only zero view), the layer fluxes
+    ``calculate_flux(F, G, X)`` for flx=1 (fluxes.py:2889-2890; ``calculate_fluxes='on'``, justdoit.py:4638).
     ``inplace_f_deltaM=True`` reproduces the reference's side effect on a writeable float64
     ``f_deltaM`` argument (it is scaled once per angle when a TTHG form is active,
     fluxes.py:2823-2824).  ``cosb`` is accepted and ignored, as in the reference.
     """
-    if flx != 0:
-        raise NotImplementedError("get_reflected_SH(flx=1): layer fluxes are not implemented")
+    if flx not in (0, 1):
+        raise ValueError("get_reflected_SH: flx must be 0 or 1")
     ctx = ctx or _lib.default_context()
     nlayer = nlevel - 1
     same = (dtau_og is dtau, w0_og is w0, tau_og is tau)
@@ -249,13 +250,16 @@ def get_reflected_SH(nlevel, nwno, numg, numt, dtau, tau, w0, cosb, ftau_cld, ft
     a.w_single_rayleigh, a.w_multi_rayleigh, a.psingle_rayleigh = int(w_single_rayleigh), int(w_multi_rayleigh), int(psingle_rayleigh)
     a.frac_a, a.frac_b, a.frac_c = float(frac_a), float(frac_b), float(frac_c)
     a.constant_back, a.constant_forward = float(constant_back), float(constant_forward)
-    a.stream, a.flx, a.single_form = int(stream), 0, int(single_form)
+    a.stream, a.flx, a.single_form = int(stream), int(flx), int(single_form)
     a.xint_at_top, a.albedo, a.f_deltaM_out = addr(xint), addr(alb), addr(fd_out)
+    flux = np.zeros((numg, numt, stream * nlevel, nwno)) if flx else None
+    a.flux = addr(flux)
     if nwno > 0:
         ctx.check(ctx.lib.pb_reflected_sh(ctx.h, ctypes.byref(a), PB_HOST))
         if drift:
             f_deltaM[...] = fd_out
-    flux = np.broadcast_to(_ZERO, (numg, numt, stream * nlevel, nwno))
+    if flux is None:
+        flux = np.broadcast_to(_ZERO, (numg, numt, stream * nlevel, nwno))
     if return_albedo:
         return xint, flux, alb
     return xint, flux

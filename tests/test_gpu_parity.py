@@ -114,6 +114,39 @@ def test_reflected_sh_vs_golden_and_oracle(name):
     assert_close(xint, ox, RTOL, name + " xint vs oracle")
 
 
+@pytest.mark.parametrize("name", sorted(C.sh_flux_cases()))
+def test_reflected_sh_layer_fluxes(name):
+    """get_reflected_SH(flx=1) (calculate_fluxes='on', fluxes.py:2889-2890): flux = F.X + G at every level against
+    the unmodified reference (tests/golden/sh_flux.npz) and the oracle.  The kernel substitutes X from the pivot
+    rows of its windowed elimination where the reference calls LAPACK; level fluxes are judged by the level-flux
+    criterion (rtol 1e-6 + 1e-9 of the column maximum; yardstick slack only where the fp64 reference itself is
+    off its binary128 evaluation).  xint_at_top of the same call must not change."""
+    g = golden("sh_flux")
+    case = C.sh_flux_cases()[name]
+    d = C.build_sh(case)
+    xint, flux, alb = pb.get_reflected_SH(*C.sh_args(d, case, flx=1), gweight=d["gweight"], tweight=d["tweight"],
+                                          return_albedo=True)
+    assert flux.shape == g[name + "/flux"].shape
+    assert_close(xint, g[name + "/xint"], RTOL, name + " xint (flx=1) vs reference")
+    x0, _, alb0 = pb.get_reflected_SH(*C.sh_args(d, case), gweight=d["gweight"], tweight=d["tweight"], return_albedo=True)
+    assert_close(xint, x0, 1e-12, name + " xint flx=1 vs flx=0")
+    assert_close(alb, alb0, 1e-12, name + " albedo flx=1 vs flx=0")
+    _, oflux = oracle.get_reflected_SH(*C.sh_args(d, case, flx=1))
+    _, exact = oracle.get_reflected_SH(*C.sh_args(d, case, flx=1), quad=True)
+    assert_level_close_yardstick(flux, g[name + "/flux"], exact, what=name + " flux vs reference")
+    assert_level_close_yardstick(flux, oflux, exact, what=name + " flux vs oracle")
+
+
+def test_reflected_sh_layer_fluxes_chunked(monkeypatch):
+    """the pivot-row scratch is sized per wavelength chunk: several chunks give the same bits as one"""
+    case = C.sh_flux_cases()["sh4_cfg3_tthg"]
+    d = C.build_sh(case)
+    x1, f1 = pb.get_reflected_SH(*C.sh_args(d, case, flx=1))
+    monkeypatch.setenv("PB_SH_FLX_WCAP", "32")
+    x2, f2 = pb.get_reflected_SH(*C.sh_args(d, case, flx=1))
+    assert np.array_equal(x1, x2) and np.array_equal(f1, f2)
+
+
 @pytest.mark.parametrize("name", sorted(C.transit_cases()))
 def test_transit_vs_golden_and_oracle(name):
     g = golden("transit")

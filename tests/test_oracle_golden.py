@@ -50,6 +50,23 @@ def test_reflected_sh(name):
     assert_close(a[10], g[name + "/f_deltaM_after"], 1e-14, name + " in-place f_deltaM drift")
 
 
+@pytest.mark.parametrize("name", sorted(C.sh_flux_cases()))
+def test_reflected_sh_flux(name):
+    """get_reflected_SH(flx=1): layer fluxes F.X + G (fluxes.py:2889-2890) against the unmodified reference
+    (tests/golden/sh_flux.npz).  The fluxes of deep levels are as ill-conditioned as the Toon level fluxes - the
+    reference's own fp64 output is up to 4e-3 (mixed criterion) away from the binary128 evaluation of its formulas -
+    so they are held to the yardstick criterion of tests/util.py; xint_at_top of the same call stays at rtol 1e-9."""
+    from util import assert_level_close_yardstick
+    g = golden("sh_flux")
+    case = C.sh_flux_cases()[name]
+    d = C.build_sh(case)
+    xint, flux = oracle.get_reflected_SH(*C.sh_args(d, case, flx=1))
+    _, exact = oracle.get_reflected_SH(*C.sh_args(d, case, flx=1), quad=True)
+    assert flux.shape == g[name + "/flux"].shape
+    assert_close(xint, g[name + "/xint"], 1e-9, name + " xint (flx=1)")
+    assert_level_close_yardstick(flux, g[name + "/flux"], exact, what=name + " oracle flux vs reference")
+
+
 @pytest.mark.parametrize("name", sorted(C.transit_cases()))
 def test_transit(name):
     g = golden("transit")
