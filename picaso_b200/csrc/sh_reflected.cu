@@ -294,6 +294,20 @@ __device__ __forceinline__ void sh_layer(const ShParams &p, int64_t il, int64_t 
     o.xa = pbm::kexp(-dt * inv_u1);
 }
 
+// One out-of-line instance of sh_layer for the flx = 1 kernel, which evaluates every layer twice (elimination sweep,
+// substitution pass).  Inlined twice, the two copies get different FMA contractions from the compiler; in
+// near-resonant columns (1/u0^2 ~ a0 a1: the particular solution is ~1e7 x the flux it leaves after cancelling against
+// the homogeneous part) a last-bit difference in Del = 1/u0^2 - a0 a1 moves Z by 1e-12 relative, and fluxes formed
+// with one copy's Z from an X solved against the other's came out 1e-9 off (measured: 240 x the level-flux tolerance).
+// Sharing the code makes the second evaluation bit-identical to the first.
+template <int S>
+__device__ __noinline__ void sh_layer_shared(const ShParams &p, int64_t il, int64_t iv, double u0, double u1, double f0,
+                                             const double (&Pu0)[4], const double (&Pu1)[4], double mus, int angle_index,
+                                             double &et, double eb, Layer<S> &o, double *fdm_out)
+{
+    sh_layer<S>(p, il, iv, u0, u1, f0, Pu0, Pu1, mus, angle_index, et, eb, o, fdm_out);
+}
+
 // FLX: also return the layer fluxes calculate_flux(F, G, X) (fluxes.py:2889-2890, F and G of :3311-3331 / :3551-3598).
 // They need the whole solution X, which the TOA-only sweep never forms: the S pivot rows of every eliminated layer go
 // to a scratch array in HBM (wavelength fastest, so the stores coalesce), the closed top system gives X_0, and a
@@ -352,8 +366,12 @@ __global__ void __launch_bounds__(128) sh_reflected_kernel(ShParams p)
 #endif
             Layer<S> y;
             double et;
-            sh_layer<S>(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, u0, u1, f0, Pu0, Pu1, mus, a, et, eb, y,
-                        fdm_out ? fdm_out + ((int64_t)b * L + l) * p.W + w : nullptr);
+            if (FLX)
+                sh_layer_shared<S>(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, u0, u1, f0, Pu0, Pu1, mus, a, et, eb, y,
+                                   fdm_out ? fdm_out + ((int64_t)b * L + l) * p.W + w : nullptr);
+            else
+                sh_layer<S>(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, u0, u1, f0, Pu0, Pu1, mus, a, et, eb, y,
+                            fdm_out ? fdm_out + ((int64_t)b * L + l) * p.W + w : nullptr);
             if (l == L - 1) {
                 // surface rows (fluxes.py:3286-3289 | :3483-3494) and I_L = flux_bot/pi (:2891, :2967)
 #pragma unroll
@@ -450,8 +468,8 @@ __global__ void __launch_bounds__(128) sh_reflected_kernel(ShParams p)
                     // exp(-tau_{l+1}/u0) exactly as the sweep above saw it (division at the surface, 1/u0 elsewhere)
                     const double tb = __ldg(p.tau + ov + (int64_t)(l + 1) * ld);
                     const double ebl = (l == L - 1) ? pbm::kexp(-tb / u0) : pbm::kexp(-tb * (1.0 / u0));
-                    sh_layer<S>(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, u0, u1, f0, Pu0, Pu1, mus, a, et, ebl, y,
-                                nullptr);
+                    sh_layer_shared<S>(p, ol + (int64_t)l * ld, ov + (int64_t)l * ld, u0, u1, f0, Pu0, Pu1, mus, a, et, ebl,
+                                       y, nullptr);
                     if (l == 0) {
 #pragma unroll
                         for (int i = 0; i < S; ++i) {

@@ -70,7 +70,12 @@ def assert_level_close_yardstick(a, ref64, exact, rtol=1e-6, col_atol=1e-9, slac
     with np.errstate(divide="ignore", invalid="ignore"):
         need = np.where(excess > 0, excess / ref_noise, 0.0)
     log_yardstick(what, float(np.max(need)) if need.size else 0.0, int((excess > 0).sum()), int(a.size), slack)
-    assert not bad.any(), f"{what}: {int(bad.sum())} level-flux entries outside tolerance"
+    if bad.any():
+        i = np.unravel_index(np.argmax(err / tol), err.shape)
+        raise AssertionError(f"{what}: {int(bad.sum())} level-flux entries outside tolerance; worst at {tuple(int(x) for x in i)}: "
+                             f"|err| {err[i]:.3e} = {float(err[i] / tol[i]):.2f} x tolerance, |exact| {abs(exact[i]):.3e}, "
+                             f"column max {float(np.max(np.abs(exact[i[:-2] + (slice(None), i[-1])]))):.3e}, fp64 reference "
+                             f"error there {abs(ref64[i] - exact[i]):.3e}")
 
 
 def log_yardstick(what, slack_needed, n_beyond_plain, n, slack):
