@@ -27,16 +27,28 @@ _PATCHED = ("get_reflected_1d", "get_reflected_3d", "get_reflected_SH", "get_the
             "compress_thermal", "get_fluxes", "mean_regrid")
 
 
+class Patched(dict):
+    """{name: original} of the names `patch` rebound; `.missing` lists the names the module does not bind
+    (picaso.justdoit binds neither `get_fluxes` nor - in 4.0.1 - anything of the climate solver's jitted loop:
+    that path is reached through picaso_b200.get_fluxes / BoundFluxes)"""
+    missing = ()
+
+
 def patch(module):
     """Rebind the hot-path names of a loaded `picaso.justdoit` module (justdoit.py:2,9) to
-    the CUDA implementations.  Returns a dict of the replaced originals for `unpatch`."""
+    the CUDA implementations.  Returns the replaced originals (a dict, for `unpatch`); its `.missing`
+    attribute names what the module does not bind, so a caller can see what was NOT replaced."""
     import sys
     me = sys.modules[__name__]
-    old = {}
+    old = Patched()
+    missing = []
     for name in _PATCHED:
         if hasattr(module, name):
             old[name] = getattr(module, name)
             setattr(module, name, getattr(me, name))
+        else:
+            missing.append(name)
+    old.missing = tuple(missing)
     return old
 
 

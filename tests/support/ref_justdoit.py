@@ -75,6 +75,25 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         pass
 
 
+class _Const:
+    """astropy.constants entry as atmsetup.get_constants uses it (atmsetup.py:53-56): .value (SI) and .to(cgs unit).value"""
+    def __init__(self, si, cgs):
+        self.value, self._cgs = si, cgs
+
+    def to(self, *a, **k):
+        return _Const(self._cgs, self._cgs)
+
+
+def _install_constants():
+    """CODATA 2018 (astropy's default set) for the four constants ATMSETUP reads; only needed when astropy is a stub"""
+    m = sys.modules.get("astropy.constants")
+    if isinstance(m, _StubModule):
+        m.k_B = _Const(1.380649e-23, 1.380649e-16)
+        m.G = _Const(6.6743e-11, 6.6743e-08)
+        m.u = _Const(1.66053906660e-27, 1.66053906660e-24)
+        m.R = _Const(8.31446261815324, 8.31446261815324e7)
+
+
 def available():
     return os.path.isfile(os.path.join(REF_ROOT, "picaso", "justdoit.py"))
 
@@ -83,7 +102,8 @@ def load():
     """-> the reference's justdoit module object (its sibling modules are the real reference files)"""
     if "refpicaso.justdoit" in sys.modules:
         return sys.modules["refpicaso.justdoit"]
-    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+    # own numba cache: oracle/ref_loader.py caches the same source files under other module names
+    os.environ["NUMBA_CACHE_DIR"] = os.environ.get("PB_JUSTDOIT_NUMBA_CACHE", "/tmp/numba_cache_justdoit")
     os.environ.setdefault("picaso_refdata", os.path.join(REF_ROOT, "reference"))
     cdbs = os.environ.setdefault("PYSYN_CDBS", "/tmp/picaso_b200_cdbs")
     os.makedirs(cdbs, exist_ok=True)
@@ -93,4 +113,6 @@ def load():
         pkg = types.ModuleType("refpicaso")
         pkg.__path__ = [os.path.join(REF_ROOT, "picaso")]
         sys.modules["refpicaso"] = pkg
+    importlib.import_module("astropy.constants")
+    _install_constants()
     return importlib.import_module("refpicaso.justdoit")
