@@ -394,8 +394,8 @@ def main():
     # kernel; p2p_fused: stores + fence + flags in the solver's epilogue
     if world > 1 and "PB_BENCH_GATHER" not in os.environ:
         gather_mode = "p2p_lazy"
-    push = {"p2p": True, "p2p_fused": False, "p2p_lazy": "lazy"}.get(gather_mode, True)
-    if gather_mode in ("p2p_fused", "p2p_lazy"):
+    push = {"p2p": True, "p2p_fused": False, "p2p_lazy": "lazy", "p2p_deferred": "deferred"}.get(gather_mode, True)
+    if gather_mode in ("p2p_fused", "p2p_lazy", "p2p_deferred"):
         gather_mode = "p2p"
     NBUF = int(os.environ.get("PB_BENCH_NBUF", "3"))  # rotating gathered buffers: ranks may run NBUF - 2 steps apart
     if gather_mode == "nccl":
@@ -565,7 +565,7 @@ def main():
         # diagnostic (stderr, not part of the bench line): where the coupled step's extra time goes - every delivery mode
         # of pb_peer_gather and no exchange at all, over short and long timed regions (fixed vs per-step cost)
         sweep = []
-        for mode, pushv in (("none", None), ("lazy", 2), ("push", 1), ("fused", 0)):
+        for mode, pushv in (("none", None), ("deferred", 3), ("lazy", 2), ("push", 1), ("fused", 0), ("deferred", 3)):
             for k in (20, 200):
                 if pushv is not None:
                     pag.push = pushv
@@ -588,7 +588,7 @@ def main():
                     t_ms, host_us = float(t[0]), float(t[1])
                 sweep.append({"mode": mode, "steps": k, "us_per_step": round(1e3 * t_ms / k, 2),
                               "host_enqueue_us_per_step": round(host_us, 2)})
-        pag.push = 2 if push == "lazy" else int(bool(push))
+        pag.push = 2 if push == "lazy" else 3 if push == "deferred" else int(bool(push))
         barrier()
         if rank == 0:
             sys.stderr.write("PB_BENCH_SWEEP " + json.dumps({"n_gpus": world, "sweep": sweep}) + "\n")
@@ -665,8 +665,10 @@ def main():
                                          "side-stream copy kernel pushes it to every peer and publishes release flags while the "
                                          "next step computes" if push is True else ("P2P stores in the solver kernel's epilogue, the flags "
                                          "of step s published by the first CTA of launch s + 1 (no fence on any launch's critical path)"
-                                         if push == "lazy" else "P2P stores + release flags in the solver kernel's "
-                                         "epilogue")) + "; device-side start barrier; %d rotating buffers; checked bit-for-bit against ncclAllGather before "
+                                         if push == "lazy" else ("the solver CTAs fill the local row only; one extra (courier) CTA of the launch "
+                                         "of step s + 1 pushes the slab of step s to every peer over NVLink and publishes its flags "
+                                         "while the solver CTAs compute" if push == "deferred" else "P2P stores + release flags in the "
+                                         "solver kernel's epilogue"))) + "; device-side start barrier; %d rotating buffers; checked bit-for-bit against ncclAllGather before "
                                          "timing; the timed region ends after pb_gather_wait saw the last step of every rank" % NBUF,
                                   "nccl": "ncclAllGather of the per-rank albedo [W] every step, double-buffered on a second "
                                           "stream (PB_BENCH_GATHER=nccl)"}[gather_mode],

@@ -103,8 +103,15 @@ typedef struct pb_peer_gather {
      *   event that keeps a later launch from overwriting a row whose push is still in flight.
      * push = 2 ("lazy"): as push = 0, but the epilogue only stores; the flags of step s are published by the first
      *   CTA of the launch of step s + 1 (a finished grid's stores are performed system-wide), the last step's by
-     *   pb_peer_signal.  No fence, counter or NVLink round trip on any launch's critical path. */
+     *   pb_peer_signal.  No fence, counter or NVLink round trip on any launch's critical path.
+     * push = 3 ("deferred"): the solver CTAs write the slab into row `rank` of the LOCAL gathered buffer only.  The
+     *   launch of step s + 1 carries one extra CTA (the 3 x 148 resident slots of a single-wave launch leave room
+     *   for it) that pushes the slab of step s (buffers `albedo_prev`) to the peers, fences and publishes the
+     *   flags while the solver CTAs compute: no peer store, fence or flag poll sits in any solver CTA, and the
+     *   grid does not wait for an NVLink round trip at its tail.  pb_peer_flush delivers the last step.
+     *   refl_toa_kernel5 only. */
     int push, slot;
+    double *const *albedo_prev;             /* push = 3: host array [nranks], the buffers of step - 1 (NULL for step 1) */
 } pb_peer_gather;
 
 typedef struct pb_reflected_args {
@@ -144,8 +151,8 @@ int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *args, int memspac
 /* ---- reflected light, spherical harmonics (P1 "SH2" / P3 "SH4") ---------------------- */
 /* replaces get_reflected_SH, picaso/fluxes.py:2675-2976 (setup_2_stream_fluxes :3189,
  * setup_4_stream_fluxes :3336, solve_4_stream_banded :3610 = scipy/LAPACK dgbsv, legP :3639)
- * and, when `albedo` is given, compress_disco.  flx must be 0 (the reference's flx=1 branch
- * is only used for diagnostics).  The reference scales its f_deltaM argument in place, once
+ * and, when `albedo` is given, compress_disco.  flx = 1 (calculate_fluxes, off by default) also returns the
+ * layer fluxes F.X + G in `flux`.  The reference scales its f_deltaM argument in place, once
  * per angle, when a TTHG form is active; results reproduce that, the
  * input array is NOT modified, and the final scaled array is written to `f_deltaM_out` if
  * that is non-NULL. */
@@ -414,6 +421,9 @@ int pb_gather_wait(pb_ctx *ctx, const unsigned long long *flags, int nranks, uns
 /* stream-ordered: after everything queued before it, store `value` into word `offset + rank` of every rank's flag
  * array (flags: host array [nranks] of device pointers as mapped here; release at system scope).  Publishes the last
  * step of a push = 2 ("lazy") gather, and - with pb_gather_wait on flags + offset - makes a device-side barrier. */
+/* push = 3 ("deferred"): deliver the slab of step `g->step` (row `rank` of the local buffer g->albedo[rank]) to every
+ * peer and publish its flags, stream-ordered - what the next solver launch would have done for it. */
+int pb_peer_flush(pb_ctx *ctx, const struct pb_peer_gather *g, int nwno);
 int pb_peer_signal(pb_ctx *ctx, unsigned long long *const *flags, int nranks, int rank, int offset,
                    unsigned long long value);
 

@@ -38,7 +38,7 @@ class ReflectedArgs(ctypes.Structure):
 class PeerGather(ctypes.Structure):
     _fields_ = [("nranks", c_int), ("rank", c_int), ("albedo", c_vp), ("flags", c_vp),
                 ("step", ctypes.c_uint64), ("wait_step", ctypes.c_uint64), ("done_counter", c_vp),
-                ("push", c_int), ("slot", c_int)]
+                ("push", c_int), ("slot", c_int), ("albedo_prev", c_vp)]
 
 
 class ShArgs(ctypes.Structure):
@@ -149,6 +149,7 @@ SYMBOLS = {
     "pb_climate_run_bound": (c_int, [ctypes.c_ulonglong, c_int]),
     "pb_climate_unbind": (c_int, [c_vp, c_int]),
     "pb_peer_signal": (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.c_ulonglong]),
+    "pb_peer_flush": (c_int, [c_vp, c_vp, c_int]),
     "pb_selftest_exp_tab": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "pb_optab_create": (c_int, [c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
     "pb_optab_destroy": (c_int, [c_vp, c_vp]),

@@ -47,6 +47,8 @@ struct ReflParams {
     int ch;        // refl_toa_kernel5: layers per chunk (= producing warps)
     int g_n, g_rank;
     int g_lazy;    // push = 2: flags of step g_step - 1 are published by the first CTA of this launch, none at its end
+    int g_defer;   // push = 3: solver CTAs store locally; CTA gridDim.x - 1 pushes step g_step - 1 (g_prev) and publishes it
+    double *g_prev[8];
     double *g_alb[8];
     unsigned long long *g_flag[8];
     unsigned long long g_step, g_wait;
@@ -106,6 +108,41 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PushParams p)
     if (threadIdx.x == 0) {
         __threadfence_system();
         st_release_sys(p.flag[r] + p.rank, p.step);
+    }
+}
+
+// push = 3: the spare CTA of the launch of step s + 1 delivers the slab of step s.  Same three phases as
+// peer_push_kernel - rotation guard, copy of row `rank` to every peer, fence + release flags - by one CTA.
+__device__ __noinline__ void peer_deferred_push(const ReflParams &p)
+{
+    const unsigned long long prev = p.g_step - 1;
+    if (prev == 0 || !p.g_prev[p.g_rank]) return;
+    const unsigned long long guard = p.g_wait > 0 ? p.g_wait - 1 : 0;   // wait_step of the previous step
+    if (guard && threadIdx.x == 0) {
+        const unsigned long long *mine = p.g_flag[p.g_rank];
+        const long long t0 = clock64();
+        for (int rk = 0; rk < p.g_n; ++rk)
+            while (ld_acquire_sys(mine + rk) < guard)
+                if (clock64() - t0 > kSpinLimit) { atomicExch(p.g_done + 1, 1u); break; }
+    }
+    __syncthreads();
+    const double *row = p.g_prev[p.g_rank] + (int64_t)p.g_rank * p.W;
+    for (int r = 0; r < p.g_n; ++r) {
+        if (r == p.g_rank) continue;
+        double *out = p.g_prev[r] + (int64_t)p.g_rank * p.W;
+        if (((reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+            const double2 *src = reinterpret_cast<const double2 *>(row);
+            double2 *dst = reinterpret_cast<double2 *>(out);
+            for (int i = threadIdx.x; i < p.W / 2; i += blockDim.x) dst[i] = src[i];
+            if ((p.W & 1) && threadIdx.x == 0) out[p.W - 1] = row[p.W - 1];
+        } else {
+            for (int i = threadIdx.x; i < p.W; i += blockDim.x) out[i] = row[i];
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < p.g_n) {
+        __threadfence_system();
+        st_release_sys(p.g_flag[threadIdx.x] + p.g_rank, prev);
     }
 }
 
@@ -929,6 +966,23 @@ __global__ void compress_disco_kernel(int W, int G, int nt, double cos_theta, co
 
 } // namespace
 
+extern "C" int pb_peer_flush(pb_ctx *ctx, const pb_peer_gather *gt, int nwno)
+{
+    if (!ctx || !gt) return PB_ERR_ARG;
+    if (gt->nranks < 1 || gt->nranks > 8 || gt->rank < 0 || gt->rank >= gt->nranks || !gt->albedo || !gt->flags ||
+        !gt->done_counter || nwno < 1)
+        return pb_fail(ctx, PB_ERR_ARG, "peer_flush: bad arguments");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PushParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.n = gt->nranks; pp.rank = gt->rank; pp.W = nwno;
+    for (int r = 0; r < gt->nranks; ++r) { pp.alb[r] = gt->albedo[r]; pp.flag[r] = gt->flags[r]; }
+    pp.step = gt->step; pp.wait = gt->wait_step; pp.done = gt->done_counter;
+    peer_push_kernel<<<gt->nranks, 256, 0, ctx->stream>>>(pp);
+    PB_CHECK_LAUNCH(ctx);
+    return PB_OK;
+}
+
 extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int memspace)
 {
     if (!ctx || !a) return PB_ERR_ARG;
@@ -958,10 +1012,12 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
         const pb_peer_gather *gt = a->gather;
         if (memspace != PB_DEVICE || !a->albedo || B != 1 || G > 8 || !want_toa || a->variant != 0 || gt->nranks < 1 ||
             gt->nranks > 8 || gt->rank < 0 || gt->rank >= gt->nranks || !gt->albedo || !gt->flags || !gt->done_counter ||
-            gt->slot < 0 || gt->slot > 7 || gt->push < 0 || gt->push > 2)
+            gt->slot < 0 || gt->slot > 7 || gt->push < 0 || gt->push > 3)
             return pb_fail(ctx, PB_ERR_ARG, "reflected: peer gather needs PB_DEVICE, a fused albedo (numg*numt <= 8), nbatch 1, 1 <= nranks <= 8");
         static const int kv = []() { const char *e = getenv("PB_REFL_KERNEL"); return e ? atoi(e) : 5; }();
         if (kv < 4) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "reflected: peer gather is implemented in refl_toa_kernel4/5 only");
+        if (gt->push == 3 && kv != 5) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "reflected: push = 3 (deferred) is implemented in refl_toa_kernel5 only");
+        if (gt->push == 3 && gt->step > 1 && !gt->albedo_prev) return pb_fail(ctx, PB_ERR_ARG, "reflected: push = 3 needs albedo_prev from step 2 on");
     }
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
 
@@ -1074,6 +1130,9 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             for (int r = 0; r < gt->nranks; ++r) { q.g_alb[r] = gt->albedo[r]; q.g_flag[r] = gt->flags[r]; }
             q.g_step = gt->step; q.g_wait = gt->wait_step; q.g_done = gt->done_counter;
             q.g_lazy = gt->push == 2;
+            q.g_defer = gt->push == 3;
+            if (q.g_defer && gt->albedo_prev && gt->step > 1)
+                for (int r = 0; r < gt->nranks; ++r) q.g_prev[r] = gt->albedo_prev[r];
         }
         dim3 grid((wc + kWavesPerCta - 1) / kWavesPerCta, (G + ay - 1) / ay, B);
         // PB_REFL_KERNEL=2|3 select the previous generations (bottom-up sweeps) for A/B runs
@@ -1105,7 +1164,8 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             const size_t smem = ((size_t)pbm::kExpTabDoubles + (size_t)q.ch * (3 * NP5 + 2 * NC5) * 32) * sizeof(double) + 16;
             bool same = true;
             for (int i = 0; i < (a->variant ? B : G); ++i) same = same && (fabs(a->ubar0[i]) == fabs(a->ubar1[i]));
-            dim3 ggrid((wc + wt - 1) / wt, (G + ay - 1) / ay, B);
+            // push = 3: one more CTA at the head of the x axis pushes the previous step's slab (peer_deferred_push)
+            dim3 ggrid((wc + wt - 1) / wt + (q.g_defer ? 1 : 0), (G + ay - 1) / ay, B);
             auto go = [&](auto kern) -> int {
                 PB_CUDA(ctx, pb_ensure_smem(ctx, kern, smem));
                 kern<<<ggrid, nw * 32, smem, ctx->stream>>>(q);

@@ -102,6 +102,12 @@ template <int MP /*multi_phase*/, bool SAME>
 __device__ __forceinline__ void refl5_body(const ReflParams &p)
 {
     extern __shared__ double smem[];
+    // push = 3: CTA 0 of the x axis (dispatched first) is the previous step's courier, the tiles start at 1
+    if (p.g_defer && blockIdx.x == 0) {
+        if (blockIdx.y == 0 && blockIdx.z == 0) peer_deferred_push(p);
+        return;
+    }
+    const int bx = (int)blockIdx.x - p.g_defer;
     // layout: exp table [64][16] | P tiles [3][CH][NP5][32] | C tiles [2][CH][NC5][32] | flag
     const int tid = threadIdx.x;
     const int lane = tid & 31, wy = tid >> 5;
@@ -112,9 +118,9 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
     const bool is_chain = wy == NWC;
     const bool is_cons = tid < WT * AY;
     const int cw = is_cons ? tid % WT : 0, ca = is_cons ? tid / WT : 0;  // consumer identity
-    const int w = blockIdx.x * WT + cw;
+    const int w = bx * WT + cw;
     const int wc = w < p.W ? w : p.W - 1;
-    const int wp = blockIdx.x * WT + (lane < WT ? lane : WT - 1);        // producer / chain column
+    const int wp = bx * WT + (lane < WT ? lane : WT - 1);        // producer / chain column
     const int wpc = wp < p.W ? wp : p.W - 1;
     const int a = blockIdx.y * AY + ca;
     const int ac = a < p.G ? a : p.G - 1;
@@ -326,7 +332,7 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
     // Pipeline, one barrier per chunk: in iteration c the consumers integrate chunk c (P[c % 3], C[c & 1]), the chain warp
     // eliminates chunk c + 1 (P[(c+1) % 3] -> C[(c+1) & 1]) and every producing warp writes its layer of chunk c + 2
     // (P[(c+2) % 3]) from registers loaded one iteration earlier, then loads its layer of chunk c + 3.
-    if (p.g_n > 0 && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    if (p.g_n > 0 && !p.g_defer && tid == 0 && bx == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
         if (p.g_lazy && p.g_step > 1) {
             // lazy flags: the previous launch's peer stores are performed (its grid has retired): publish its step
             __threadfence_system();
@@ -401,7 +407,7 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
     const bool active = is_cons && (w < p.W) && (a < p.G);
     if (active && p.xint) p.xint[((int64_t)b * p.G + a) * p.W + w] = result;
     if (p.fuse_albedo) {
-        if (p.g_n > 0 && tid == 0) {
+        if (p.g_n > 0 && !p.g_defer && tid == 0) {
             // hold the peer stores until CTA 0 has seen every rank publish wait_step (go word = this launch's step)
             const long long t0 = clock64();
             while (*(volatile unsigned *)(p.g_done + 4) != (unsigned)p.g_step)
@@ -422,9 +428,10 @@ __device__ __forceinline__ void refl5_body(const ReflParams &p)
             const double alb = sym * 0.5 * acc / g.f0 * (p.cos_theta + 1.0);
             p.albedo[(int64_t)b * p.W + w] = alb;
             // fused all-gather: this rank's slab goes to row g_rank of every rank's buffer (NVLink P2P stores)
-            for (int rk = 0; rk < p.g_n; ++rk) p.g_alb[rk][(int64_t)p.g_rank * p.W + w] = alb;
+            if (p.g_defer) p.g_alb[p.g_rank][(int64_t)p.g_rank * p.W + w] = alb;   // local row only; pushed by the next launch
+            else for (int rk = 0; rk < p.g_n; ++rk) p.g_alb[rk][(int64_t)p.g_rank * p.W + w] = alb;
         }
-        if (p.g_n > 0 && !p.g_lazy) {
+        if (p.g_n > 0 && !p.g_lazy && !p.g_defer) {
             // last CTA to finish publishes the step on every rank (ordering argument: toon_reflected_toa4.cuh)
             __syncthreads();
             if (tid == 0) {

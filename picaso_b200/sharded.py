@@ -170,7 +170,10 @@ class PeerAllGather:
     push=False: the solver kernel's epilogue stores to the peers itself and publishes the flags before it retires;
     push="lazy": the epilogue only stores - the flags of step s are published by the FIRST CTA of launch s + 1
     (stores of a finished grid are performed system-wide, so no fence / NVLink round trip sits on any launch's
-    critical path); `wait()` publishes the last step.  `barrier()` is a device-side barrier over the same peer
+    critical path); `wait()` publishes the last step.
+    push="deferred": the solver CTAs only fill the local row; the launch of step s + 1 carries one extra CTA that
+    pushes the slab of step s to the peers and publishes it while the solver CTAs compute (no peer store in any
+    solver CTA, nothing at the grid's tail); `wait()` delivers the last step (pb_peer_flush).  `barrier()` is a device-side barrier over the same peer
     mappings (stream-ordered): ranks leave it within a microsecond of each other whatever the host skew."""
 
     def __init__(self, ctx, rank, world, nwno, nbuf=3, push=True, exchange=None, _peers=None):
@@ -181,8 +184,8 @@ class PeerAllGather:
         if not 3 <= int(nbuf) <= 8:
             raise ValueError("PeerAllGather: nbuf must be 3..8 (ranks may run nbuf - 2 steps apart; pb_peer_gather has 8 slots)")
         self.ctx, self.rank, self.world, self.nwno, self.nbuf = ctx, rank, world, nwno, int(nbuf)
-        self.push = 2 if push == "lazy" else int(bool(push))
-        self.step, self.epoch = 0, 0
+        self.push = 2 if push == "lazy" else 3 if push == "deferred" else int(bool(push))
+        self.step, self.epoch, self._flushed = 0, 0, 0
         gbytes = self.nbuf * world * nwno * 8
         self.d_gath, self.d_flags, self.d_done = ctx.dev_alloc(gbytes), ctx.dev_alloc(256), ctx.dev_alloc(256)
         for ptr, nb in ((self.d_gath, gbytes), (self.d_flags, 256), (self.d_done, 256)):
@@ -248,12 +251,18 @@ class PeerAllGather:
         s = self._structs[self.step % self.nbuf]
         s.step, s.wait_step = self.step, max(0, self.step - (self.nbuf - 1))
         s.push, s.slot = self.push, self.step % self.nbuf
+        s.albedo_prev = ctypes.addressof(self._alb_ptrs[(self.step - 1) % self.nbuf]) if self.step > 1 else None
         return ctypes.addressof(s)
 
     def wait(self):
         if self.step > 0:
             if self.push == 2:  # lazy flags: nobody has published the last step yet
                 self.ctx.check(self.ctx.lib.pb_peer_signal(self.ctx.h, ctypes_addr(self._flag_ptrs), self.world, self.rank, 0, self.step))
+            elif self.push == 3:  # deferred: the last step's slab has no next launch to carry it
+                last = self._structs[self.step % self.nbuf]
+                if self._flushed != self.step:
+                    self.ctx.check(self.ctx.lib.pb_peer_flush(self.ctx.h, ctypes_addr(last), self.nwno))
+                    self._flushed = self.step
             self.ctx.check(self.ctx.lib.pb_gather_wait(self.ctx.h, self.d_flags, self.world, self.step, self.d_done + 8))
 
     BARRIER_OFFSET = 16   # flag words 16 .. 16 + world of the 256-byte flag block count barrier epochs

@@ -1,7 +1,7 @@
 """The all-gather over peer memory (pb_peer_gather, sharded.PeerAllGather) with the ranks simulated inside
 one process on one GPU (one Context = one stream per rank; plain device pointers instead of IPC mappings).
-All delivery modes: in the solver kernel's epilogue (flags published at its end, or lazily by the next launch), and
-pushed by the side-stream copy kernel.  The
+All delivery modes: in the solver kernel's epilogue (flags published at its end, or lazily by the next launch),
+pushed by the side-stream copy kernel, and deferred to a courier CTA of the next launch.  The
 multi-process / multi-GPU path (CUDA IPC over NVLink) is exercised by bench.py, which checks the gathered
 buffers bit-for-bit against ncclAllGather before timing."""
 import ctypes
@@ -39,7 +39,7 @@ def _args(ctx, d, keep):
     return a
 
 
-@pytest.mark.parametrize("push", [False, True, "lazy"])
+@pytest.mark.parametrize("push", [False, True, "lazy", "deferred"])
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_peer_all_gather_in_process(world, push):
     W, nsteps = 333, 7
