@@ -390,10 +390,12 @@ def main():
     gather_mode = os.environ.get("PB_BENCH_GATHER", "p2p" if world > 1 else "none")
     if world == 1 and gather_mode == "nccl":
         gather_mode = "none"
-    # p2p_lazy (default): stores in the solver's epilogue, flags published by the next launch; p2p: side-stream push
-    # kernel; p2p_fused: stores + fence + flags in the solver's epilogue
+    # p2p_deferred (default): a courier CTA of the next launch pushes the slab and publishes it (measured at N = 2,
+    # us per step over 200 steps: no exchange 61.9, deferred 62.5, lazy 65.0, push 67.0, fused 69.8 - profiles/);
+    # p2p_lazy: stores in the solver's epilogue, flags published by the next launch; p2p: side-stream push kernel;
+    # p2p_fused: stores + fence + flags in the solver's epilogue
     if world > 1 and "PB_BENCH_GATHER" not in os.environ:
-        gather_mode = "p2p_lazy"
+        gather_mode = "p2p_deferred"
     push = {"p2p": True, "p2p_fused": False, "p2p_lazy": "lazy", "p2p_deferred": "deferred"}.get(gather_mode, True)
     if gather_mode in ("p2p_fused", "p2p_lazy", "p2p_deferred"):
         gather_mode = "p2p"
