@@ -552,11 +552,18 @@ def main():
     ms = ctx.timer_stop()
     sampler.active = False
     launches = ctx.launch_count() - l0
+    courier_us = None
     if gather_mode == "p2p":
         if pag.timed_out():
             raise SystemExit("rank %d: peer all-gather timed out waiting for a flag" % rank)
+        if push == "deferred":
+            courier_us = pag.courier_us()
     barrier()
     if world > 1:
+        if courier_us is not None:
+            t = torch.tensor([courier_us], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            courier_us = round(float(t.item()), 2)
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
@@ -675,7 +682,8 @@ def main():
                                   "nccl": "ncclAllGather of the per-rank albedo [W] every step, double-buffered on a second "
                                           "stream (PB_BENCH_GATHER=nccl)"}[gather_mode],
                    "parity_albedo_max_rel_err": parity,
-                   "kernel_us_per_rank_without_exchange": uncoupled},
+                   "kernel_us_per_rank_without_exchange": uncoupled,
+                   "courier_cta_us_max_over_ranks": courier_us},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": ke, "ms_per_step": 1e3 * e2e_dt / ke,

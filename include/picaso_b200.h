@@ -94,7 +94,8 @@ typedef struct pb_peer_gather {
     unsigned long long *const *flags;       /* host array [nranks]: rank r's flag array, as mapped here */
     unsigned long long step, wait_step;
     unsigned int *done_counter;             /* device, this rank, 8 words, zero-initialised: CTA counter | timeout flag |
-                                             * (pb_gather_wait's timeout flag) | - | go word of the current launch */
+                                             * (pb_gather_wait's timeout flag) | - | go word of the current launch |
+                                             * duration of the last push = 3 courier in ns (diagnostic) */
     /* push = 0: the stores and the flag publication happen in the solver kernel's epilogue (one launch; costs
      *   4-10 us at the kernel tail: system-scope fence + NVLink round trip before the grid can retire).
      * push = 1: the solver kernel writes its slab into row `rank` of the LOCAL gathered buffer only; a small

@@ -279,6 +279,12 @@ class PeerAllGather:
         step = self.step if step is None else step
         return self.ctx.from_device(self.d_gath + (step % self.nbuf) * self.world * self.nwno * 8, (self.world, self.nwno))
 
+    def courier_us(self):
+        """push="deferred": how long the last courier CTA took (guard wait + copies + fence), microseconds"""
+        import struct
+        w = struct.unpack("<8I", self.ctx.from_device(self.d_done, (4,)).tobytes())
+        return w[5] / 1e3
+
     def timed_out(self):
         import struct
         w = struct.unpack("<4I", self.ctx.from_device(self.d_done, (2,)).tobytes())
