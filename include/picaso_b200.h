@@ -95,7 +95,7 @@ typedef struct pb_peer_gather {
     unsigned long long step, wait_step;
     unsigned int *done_counter;             /* device, this rank, 8 words, zero-initialised: CTA counter | timeout flag |
                                              * (pb_gather_wait's timeout flag) | - | go word of the current launch |
-                                             * duration of the last push = 3 courier in ns (diagnostic) */
+                                             * duration of the last push = 3 courier in ns (diagnostic) | courier counter */
     /* push = 0: the stores and the flag publication happen in the solver kernel's epilogue (one launch; costs
      *   4-10 us at the kernel tail: system-scope fence + NVLink round trip before the grid can retire).
      * push = 1: the solver kernel writes its slab into row `rank` of the LOCAL gathered buffer only; a small
@@ -106,9 +106,9 @@ typedef struct pb_peer_gather {
      *   CTA of the launch of step s + 1 (a finished grid's stores are performed system-wide), the last step's by
      *   pb_peer_signal.  No fence, counter or NVLink round trip on any launch's critical path.
      * push = 3 ("deferred"): the solver CTAs write the slab into row `rank` of the LOCAL gathered buffer only.  The
-     *   launch of step s + 1 carries one extra CTA (the 3 x 148 resident slots of a single-wave launch leave room
-     *   for it) that pushes the slab of step s (buffers `albedo_prev`) to the peers, fences and publishes the
-     *   flags while the solver CTAs compute: no peer store, fence or flag poll sits in any solver CTA, and the
+     *   launch of step s + 1 carries four extra CTAs (the tile width of a single-wave launch is chosen so that the
+     *   3 x 148 resident slots leave room for them) that push the slab of step s (buffers `albedo_prev`) to the
+     *   peers, fence, and - the last one to finish - publish the flags while the solver CTAs compute: no peer store, fence or flag poll sits in any solver CTA, and the
      *   grid does not wait for an NVLink round trip at its tail.  pb_peer_flush delivers the last step.
      *   refl_toa_kernel5 only. */
     int push, slot;

@@ -47,7 +47,8 @@ struct ReflParams {
     int ch;        // refl_toa_kernel5: layers per chunk (= producing warps)
     int g_n, g_rank;
     int g_lazy;    // push = 2: flags of step g_step - 1 are published by the first CTA of this launch, none at its end
-    int g_defer;   // push = 3: solver CTAs store locally; CTA gridDim.x - 1 pushes step g_step - 1 (g_prev) and publishes it
+    int g_defer;   // push = 3: solver CTAs store locally; the first g_nc CTAs push step g_step - 1 (g_prev) and publish it
+    int g_nc;      // push = 3: courier CTAs at the head of the x axis (0 otherwise)
     double *g_prev[8];
     double *g_alb[8];
     unsigned long long *g_flag[8];
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PushParams p)
 
 // push = 3: the spare CTA of the launch of step s + 1 delivers the slab of step s.  Same three phases as
 // peer_push_kernel - rotation guard, copy of row `rank` to every peer, fence + release flags - by one CTA.
-__device__ __noinline__ void peer_deferred_push(const ReflParams &p)
+__device__ __noinline__ void peer_deferred_push(const ReflParams &p, int c /* courier index, < p.g_nc */)
 {
     const unsigned long long prev = p.g_step - 1;
     if (prev == 0 || !p.g_prev[p.g_rank]) return;
@@ -152,12 +153,14 @@ __device__ __noinline__ void peer_deferred_push(const ReflParams &p)
         constexpr int kU = 8;
         const double2 *src = reinterpret_cast<const double2 *>(row);
         const int n2 = p.W / 2, nt = (int)blockDim.x;
-        for (int base = 0; base < n2; base += nt * kU) {
+        const int seg = (n2 + p.g_nc - 1) / p.g_nc;                 // this courier's share of the slab
+        const int lo = c * seg, hi = lo + seg < n2 ? lo + seg : n2;
+        for (int base = lo; base < hi; base += nt * kU) {
             double2 v[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
                 const int i = base + u * nt + (int)threadIdx.x;
-                if (i < n2) v[u] = src[i];
+                if (i < hi) v[u] = src[i];
             }
             for (int r = 0; r < p.g_n; ++r) {
                 if (r == p.g_rank) continue;
@@ -165,30 +168,35 @@ __device__ __noinline__ void peer_deferred_push(const ReflParams &p)
 #pragma unroll
                 for (int u = 0; u < kU; ++u) {
                     const int i = base + u * nt + (int)threadIdx.x;
-                    if (i < n2) dst[i] = v[u];
+                    if (i < hi) dst[i] = v[u];
                 }
             }
         }
-        if ((p.W & 1) && threadIdx.x == 0)
+        if ((p.W & 1) && c == 0 && threadIdx.x == 0)
             for (int r = 0; r < p.g_n; ++r)
                 if (r != p.g_rank) p.g_prev[r][(int64_t)p.g_rank * p.W + p.W - 1] = row[p.W - 1];
     } else {
-        for (int i = threadIdx.x; i < p.W; i += blockDim.x) {
+        for (int i = c * (int)blockDim.x + (int)threadIdx.x; i < p.W; i += p.g_nc * (int)blockDim.x) {
             const double v = row[i];
             for (int r = 0; r < p.g_n; ++r)
                 if (r != p.g_rank) p.g_prev[r][(int64_t)p.g_rank * p.W + i] = v;
         }
     }
     __syncthreads();
-    if ((int)threadIdx.x < p.g_n) {
-        __threadfence_system();
-        st_release_sys(p.g_flag[threadIdx.x] + p.g_rank, prev);
-    }
     if (threadIdx.x == 0) {
-        // diagnostic: how long this courier took (guard wait + copies + fence), ns, word 5 of the counter block
-        unsigned long long t_end;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-        p.g_done[5] = (unsigned)(t_end - t_begin);
+        // this courier's peer stores are performed system-wide; the LAST courier to get here publishes the step
+        // (same fence / counter / release chain as the fused mode's last-CTA publication below)
+        __threadfence_system();
+        const unsigned arrived = atomicAdd(p.g_done + 6, 1u);
+        if (arrived == (unsigned)p.g_nc - 1) {
+            atomicExch(p.g_done + 6, 0u);
+            __threadfence_system();
+            for (int r = 0; r < p.g_n; ++r) st_release_sys(p.g_flag[r] + p.g_rank, prev);
+            // diagnostic: how long the last courier took (guard wait + copies + fences), ns, word 5 of the counter block
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            p.g_done[5] = (unsigned)(t_end - t_begin);
+        }
     }
 }
 
@@ -1177,6 +1185,9 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             q.g_step = gt->step; q.g_wait = gt->wait_step; q.g_done = gt->done_counter;
             q.g_lazy = gt->push == 2;
             q.g_defer = gt->push == 3;
+            // four courier CTAs share the slab: one alone needs ~20 us for 3 peers (measured at N = 4) - hidden under a
+            // 57 us sweep, but with little margin at 7 peers
+            q.g_nc = q.g_defer ? 4 : 0;
             if (q.g_defer && gt->albedo_prev && gt->step > 1)
                 for (int r = 0; r < gt->nranks; ++r) q.g_prev[r] = gt->albedo_prev[r];
         }
@@ -1199,7 +1210,8 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
                 const int std_ctas = (wc + cap - 1) / cap;
                 const int per_sm = (std_ctas + nsm - 1) / nsm;
                 if (B == 1 && per_sm <= 3 && (double)per_sm * nsm > 1.05 * std_ctas) {
-                    const int cand = (wc + nsm * per_sm - 1) / (nsm * per_sm);
+                    const int slots = nsm * per_sm - q.g_nc;   // the couriers of a deferred gather need resident slots too
+                    const int cand = (wc + slots - 1) / slots;
                     if (cand >= 12 && cand < cap) wt = cand;
                 }
             }
@@ -1210,8 +1222,8 @@ extern "C" int pb_reflected_toon_1d(pb_ctx *ctx, const pb_reflected_args *a, int
             const size_t smem = ((size_t)pbm::kExpTabDoubles + (size_t)q.ch * (3 * NP5 + 2 * NC5) * 32) * sizeof(double) + 16;
             bool same = true;
             for (int i = 0; i < (a->variant ? B : G); ++i) same = same && (fabs(a->ubar0[i]) == fabs(a->ubar1[i]));
-            // push = 3: one more CTA at the head of the x axis pushes the previous step's slab (peer_deferred_push)
-            dim3 ggrid((wc + wt - 1) / wt + (q.g_defer ? 1 : 0), (G + ay - 1) / ay, B);
+            // push = 3: g_nc more CTAs at the head of the x axis push the previous step's slab (peer_deferred_push)
+            dim3 ggrid((wc + wt - 1) / wt + q.g_nc, (G + ay - 1) / ay, B);
             auto go = [&](auto kern) -> int {
                 PB_CUDA(ctx, pb_ensure_smem(ctx, kern, smem));
                 kern<<<ggrid, nw * 32, smem, ctx->stream>>>(q);

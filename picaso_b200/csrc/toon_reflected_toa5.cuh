@@ -102,12 +102,12 @@ template <int MP /*multi_phase*/, bool SAME>
 __device__ __forceinline__ void refl5_body(const ReflParams &p)
 {
     extern __shared__ double smem[];
-    // push = 3: CTA 0 of the x axis (dispatched first) is the previous step's courier, the tiles start at 1
-    if (p.g_defer && blockIdx.x == 0) {
-        if (blockIdx.y == 0 && blockIdx.z == 0) peer_deferred_push(p);
+    // push = 3: the first g_nc CTAs of the x axis (dispatched first) are the previous step's couriers, the tiles follow
+    if ((int)blockIdx.x < p.g_nc) {
+        if (blockIdx.y == 0 && blockIdx.z == 0) peer_deferred_push(p, (int)blockIdx.x);
         return;
     }
-    const int bx = (int)blockIdx.x - p.g_defer;
+    const int bx = (int)blockIdx.x - p.g_nc;
     // layout: exp table [64][16] | P tiles [3][CH][NP5][32] | C tiles [2][CH][NC5][32] | flag
     const int tid = threadIdx.x;
     const int lane = tid & 31, wy = tid >> 5;

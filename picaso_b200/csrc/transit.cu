@@ -22,6 +22,9 @@ constexpr int kThreads = 128;
 #ifndef PB_TRANSIT_UNROLL
 #define PB_TRANSIT_UNROLL 4
 #endif
+#ifndef PB_TRANSIT_PF
+#define PB_TRANSIT_PF 0
+#endif
 constexpr int kBlk = PB_TRANSIT_BLK;  // tangent levels per pass (accumulators per thread)
 constexpr int kUnroll = PB_TRANSIT_UNROLL;
 
@@ -74,6 +77,33 @@ __global__ void __launch_bounds__(kThreads) transit_kernel(int V, int Vp, int W,
 #pragma unroll
         for (int u = 0; u < kBlk; ++u) t[u] = 0.0;
         const int kend = (i0 + kBlk - 1 < L) ? i0 + kBlk - 1 : L;  // rows k < i <= i0 + kBlk - 1
+#if PB_TRANSIT_PF
+        // software pipeline: the raw sigma values of the NEXT kUnroll layers are requested before the current kUnroll
+        // layers are folded in, and nothing touches them until the next trip (the in-order issue of a warp stalls at
+        // the first instruction that needs a load, so the scale multiply waits until the value is consumed)
+        double nxt[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) nxt[u] = u < kend ? __ldg(col + (int64_t)u * ld) : 0.0;
+        for (int k = 0; k < kend; k += kUnroll) {
+            double cur[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) cur[u] = nxt[u];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int kn = k + kUnroll + u;
+                nxt[u] = kn < kend ? __ldg(col + (int64_t)kn * ld) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (k + u < kend) {
+                    const double s = cur[u] * s_sc[k + u];
+                    const double *m = s_mt + (k + u) * Vp + i0;
+#pragma unroll
+                    for (int v = 0; v < kBlk; ++v) t[v] = fma(s, m[v], t[v]);
+                }
+            }
+        }
+#else
         // four sigma loads in flight per trip: the loop is otherwise one load -> kBlk dependent-free DFMAs
 #pragma unroll kUnroll
         for (int k = 0; k < kend; ++k) {
@@ -82,6 +112,7 @@ __global__ void __launch_bounds__(kThreads) transit_kernel(int V, int Vp, int W,
 #pragma unroll
             for (int u = 0; u < kBlk; ++u) t[u] = fma(s, m[u], t[u]);
         }
+#endif
 #pragma unroll
         for (int u = 0; u < kBlk; ++u) acc += (1.0 - exp(-t[u])) * s_zdz[i0 + u];  // padded levels carry zdz = 0
     }

@@ -1,4 +1,5 @@
 #!/bin/bash
+# A/B of transit kernel variants built by scripts/ab_build.py: scripts/ab_transit.sh base b48u4 pf32u4 ...
 for t in "$@"; do
   lib=picaso_b200/_build/libpb_$t.so
   [ "$t" = base ] && lib=picaso_b200/_build/libpicaso_b200.so
