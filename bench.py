@@ -232,7 +232,18 @@ def spectrum_gpu_factory(pb, ctx, db, ray, ducks):
                              query_method="linear", ctx=ctx)
     gweight, tweight, cos_theta, tail = _spectrum_geometry()
 
+    ubar0, ubar1 = tail[1], tail[2]
+
     def one(i):
+        a = ducks[i % NPROF]
+        opa.get_opacities(a)
+        # one C call: opacity kernel -> flux kernel (fused disk integration) -> one D2H copy (pb_spectrum_reflected)
+        return pb.reflected_spectrum(a, opa, ubar0, ubar1, cos_theta, gweight, tweight, single_phase=KW["single_phase"],
+                                     multi_phase=KW["multi_phase"], toon_coefficients=KW["toon_coefficients"],
+                                     stream=2, delta_eddington=True, raman=2)
+
+    def chain(i):
+        """the same spectrum through the three public calls (compute_opacity -> get_reflected_1d + fused albedo)"""
         a = ducks[i % NPROF]
         opa.get_opacities(a)
         dev = pb.compute_opacity(a, opa, ngauss=1, stream=2, delta_eddington=True, test_mode=None, raman=2,
@@ -243,6 +254,7 @@ def spectrum_gpu_factory(pb, ctx, db, ray, ducks):
                                         sl(fcld), sl(fray), sl(DTAU_OG), sl(TAU_OG), sl(W0_OG), sl(COSB_OG), *tail,
                                         gweight=gweight, tweight=tweight, return_albedo=True, ctx=ctx)
         return alb
+    one.chain = chain
     return opa, one
 
 
@@ -728,6 +740,8 @@ def main():
         sp_par = float(np.max(np.abs(got - want) / np.abs(want)))
         if not sp_par < 1e-6:
             raise SystemExit("spectrum-level parity gate failed: %.3e" % sp_par)
+        if not np.array_equal(got, one.chain(0)):
+            raise SystemExit("pb_spectrum_reflected differs from the compute_opacity -> get_reflected_1d chain")
         for i in range(3):
             one(i)
         ns = max(ke, 40)
@@ -740,8 +754,15 @@ def main():
               "gpu_launches_per_step": (ctx.launch_count() - l0) / ns,
               "h2d_bytes_per_step": int(L * (NMOL_SPEC + len(db["continuum"]) + len(ray) + 12) * 8),
               "d2h_bytes_per_step": int((NG + 1) * W * 8), "parity_albedo_max_rel_err": sp_par,
-              "api": "DeviceOpacities.get_opacities(linear) + compute_opacity(device_outputs=True, %d molecules, clear, "
-                     "no Raman) + get_reflected_1d(DeviceArray..., return_albedo=True); tables resident in HBM" % NMOL_SPEC}
+              "api": "DeviceOpacities.get_opacities(linear) + picaso_b200.reflected_spectrum (pb_spectrum_reflected: "
+                     "compute_opacity, %d molecules, clear, no Raman -> get_reflected_1d -> compress_disco in one C call, "
+                     "one D2H copy); tables resident in HBM" % NMOL_SPEC}
+        for i in range(3):
+            one.chain(i)
+        t0 = time.perf_counter()
+        for i in range(ns):
+            one.chain(i)
+        sp["three_call_chain_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / ns
         if not args.no_cpu_baseline:
             cv, cn, cel = time_spectrum_cpu(db, ray, atms, os.cpu_count() or 1)
             sp["cpu_port_value"] = cv

@@ -323,6 +323,26 @@ typedef struct pb_opacity_args {
 
 int pb_compute_opacity(pb_ctx *ctx, pb_optab *tab, const pb_opacity_args *args, int memspace);
 
+/* One call per spectrum: what picaso() does between `get_opacities(atm)` and `returns['albedo']` for a reflected-light
+ * Toon run (justdoit.py:243-310, :530) - compute_opacity, get_reflected_1d, compress_disco - with nothing of size
+ * O(nlayer x nwno) crossing the C boundary: the opacity kernel writes its 11 arrays into a context-owned workspace
+ * in HBM, the flux kernel (fused disk integration) reads them there, and ONE device-to-host copy returns the albedo
+ * (and the TOA intensities if wanted).  `opacity` is filled as for pb_compute_opacity with PB_DEVICE (its output
+ * pointers are ignored; ngauss must be 0 or 1); the remaining fields are those of pb_reflected_args. */
+typedef struct pb_spectrum_args {
+    pb_opacity_args opacity;
+    int nwno, numg, numt;
+    const double *ubar0, *ubar1, *gweight, *tweight;  /* host: [numg*numt], [numg*numt], [numg], [numt] */
+    double cos_theta;
+    const double *surf_reflect, *F0PI, *b_top;        /* DEVICE [nwno] vectors or NULL (= 0, 1, 0) */
+    int single_phase, multi_phase, toon_coefficients;
+    double frac_a, frac_b, frac_c, constant_back, constant_forward;
+    double *albedo;       /* host [nwno] */
+    double *xint_at_top;  /* host [numg*numt][nwno] or NULL */
+} pb_spectrum_args;
+
+int pb_spectrum_reflected(pb_ctx *ctx, pb_optab *tab, const pb_spectrum_args *args);
+
 /* ---- resort-rebin mixing of per-gas correlated-k tables ----------------------------------
  * Replaces deq_chem.mix_all_gases_gasesfly / do_mixing_mono_gasesfly / mix_2_gases
  * (deq_chem.py:334-386, :388-432, :538-597) and the interpolation + exp * N_A of

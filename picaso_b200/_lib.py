@@ -78,6 +78,15 @@ class OpacityArgs(ctypes.Structure):
          ("TAUCLD", c_vp)])
 
 
+class SpectrumArgs(ctypes.Structure):
+    _fields_ = ([("opacity", OpacityArgs), ("nwno", c_int), ("numg", c_int), ("numt", c_int)] +
+                [(n, c_vp) for n in ("ubar0", "ubar1", "gweight", "tweight")] + [("cos_theta", c_dbl)] +
+                [(n, c_vp) for n in ("surf_reflect", "F0PI", "b_top")] +
+                [(n, c_int) for n in ("single_phase", "multi_phase", "toon_coefficients")] +
+                [(n, c_dbl) for n in ("frac_a", "frac_b", "frac_c", "constant_back", "constant_forward")] +
+                [("albedo", c_vp), ("xint_at_top", c_vp)])
+
+
 class CkMixArgs(ctypes.Structure):
     _fields_ = ([(n, c_int) for n in ("nlayer", "nwno", "ngauss", "ngas", "np", "nt")] +
                 [(n, c_vp) for n in ("kappas", "mixes", "indices", "t_interp", "p_interp", "gauss_pts", "gauss_wts",
@@ -150,6 +159,7 @@ SYMBOLS = {
     "pb_climate_unbind": (c_int, [c_vp, c_int]),
     "pb_peer_signal": (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.c_ulonglong]),
     "pb_peer_flush": (c_int, [c_vp, c_vp, c_int]),
+    "pb_spectrum_reflected": (c_int, [c_vp, c_vp, c_vp]),
     "pb_selftest_exp_tab": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "pb_optab_create": (c_int, [c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
     "pb_optab_destroy": (c_int, [c_vp, c_vp]),

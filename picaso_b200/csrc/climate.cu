@@ -501,6 +501,52 @@ extern "C" int pb_climate_get_fluxes(pb_ctx *ctx, const pb_climate_args *a, int 
     return rc_thermal;
 }
 
+// ---- one call per reflected spectrum: opacity -> flux -> disk integration (include/picaso_b200.h) ----------
+extern "C" int pb_spectrum_reflected(pb_ctx *ctx, pb_optab *tab, const pb_spectrum_args *a)
+{
+    if (!ctx || !tab || !a) return PB_ERR_ARG;
+    const int L = a->opacity.nlayer, W = a->nwno, G = a->numg * a->numt, V = L + 1;
+    if (L < 1 || W < 1 || G < 1) return pb_fail(ctx, PB_ERR_ARG, "spectrum: bad sizes L=%d W=%d G=%d", L, W, G);
+    if (a->opacity.ngauss > 1) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "spectrum: correlated-k tables (ngauss > 1) go through pb_compute_opacity + one flux call per gauss point");
+    if (!a->albedo || !a->ubar0 || !a->ubar1 || !a->gweight || !a->tweight)
+        return pb_fail(ctx, PB_ERR_ARG, "spectrum: albedo, ubar0, ubar1, gweight, tweight are required");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nLW = pb_align((size_t)L * W * sizeof(double)), nVW = pb_align((size_t)V * W * sizeof(double));
+    const size_t nW = (size_t)W * sizeof(double);
+    PB_TRY(aux_reserve(ctx, 9 * nLW + 2 * nVW + pb_align(nW) + pb_align((size_t)G * nW) + 256));
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> double * {
+        double *ptr = (double *)(ctx->aux + off);
+        off += pb_align(bytes);
+        return ptr;
+    };
+    pb_opacity_args o = a->opacity;
+    o.DTAU = take(nLW); o.TAU = take(nVW); o.W0 = take(nLW); o.COSB = take(nLW); o.ftau_cld = take(nLW);
+    o.ftau_ray = take(nLW); o.GCOS2 = take(nLW); o.DTAU_OG = take(nLW); o.TAU_OG = take(nVW); o.W0_OG = take(nLW);
+    o.COSB_OG = take(nLW);
+    o.W0_no_raman = nullptr; o.f_deltaM = nullptr; o.TAUGAS = o.TAURAY = o.TAUCLD = nullptr;
+    double *d_alb = take(nW), *d_xint = a->xint_at_top ? take((size_t)G * nW) : nullptr;
+    PB_TRY(pb_compute_opacity(ctx, tab, &o, PB_DEVICE));
+    pb_reflected_args r;
+    memset(&r, 0, sizeof(r));
+    r.nlayer = L; r.nwno = W; r.numg = a->numg; r.numt = a->numt; r.nbatch = 1; r.ld = W;
+    r.dtau = o.DTAU; r.tau = o.TAU; r.w0 = o.W0; r.cosb = o.COSB; r.gcos2 = o.GCOS2; r.ftau_cld = o.ftau_cld;
+    r.ftau_ray = o.ftau_ray; r.dtau_og = o.DTAU_OG; r.tau_og = o.TAU_OG; r.w0_og = o.W0_OG; r.cosb_og = o.COSB_OG;
+    r.surf_reflect = a->surf_reflect; r.F0PI = a->F0PI; r.b_top = a->b_top;
+    r.ubar0 = a->ubar0; r.ubar1 = a->ubar1; r.gweight = a->gweight; r.tweight = a->tweight;
+    r.cos_theta = a->cos_theta;
+    r.single_phase = a->single_phase; r.multi_phase = a->multi_phase; r.toon_coefficients = a->toon_coefficients;
+    r.frac_a = a->frac_a; r.frac_b = a->frac_b; r.frac_c = a->frac_c;
+    r.constant_back = a->constant_back; r.constant_forward = a->constant_forward;
+    r.get_toa_intensity = 1; r.get_lvl_flux = 0;
+    r.albedo = d_alb; r.xint_at_top = d_xint;
+    PB_TRY(pb_reflected_toon_1d(ctx, &r, PB_DEVICE));
+    PB_CUDA(ctx, cudaMemcpyAsync(a->albedo, d_alb, nW, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_xint) PB_CUDA(ctx, cudaMemcpyAsync(a->xint_at_top, d_xint, (size_t)G * nW, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
 // ---- bound calls (numba nopython -> ctypes) -------------------------------------------------------------
 namespace {
 struct BoundCall { pb_ctx *ctx; pb_climate_args args; int memspace; bool live; };

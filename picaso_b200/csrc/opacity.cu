@@ -148,6 +148,9 @@ struct Vec<2> {
     __device__ __forceinline__ void store(double *p) const { *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]); }
 };
 
+#ifndef PB_OPA_PF
+#define PB_OPA_PF 1
+#endif
 template <int VEC>
 __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
 {
@@ -244,12 +247,30 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
     // molecular (optics.py:243-250)
     if (p.query == 1) {
         const double w1 = s_w[0], w2 = s_w[1], w3 = s_w[2], w4 = s_w[3];
+#if PB_OPA_PF
+        // software pipeline over the molecules: the four table rows of molecule m + 1 are requested before molecule m's
+        // exponentials are evaluated (ncu r1: long_scoreboard 8.0 of the stall cycles per issue - each trip of the plain
+        // loop waited for its own four gathers)
+        Vec<VEC> n1, n2, n3, n4;
+        if (p.nmol > 0) {
+            n1.load(s_ptr[0] + w); n2.load(s_ptr[1] + w); n3.load(s_ptr[2] + w); n4.load(s_ptr[3] + w);
+        }
+        for (int m = 0; m < p.nmol; ++m) {
+            const Vec<VEC> a1 = n1, a2 = n2, a3 = n3, a4 = n4;
+            if (m + 1 < p.nmol) {
+                n1.load(s_ptr[4 * m + 4] + w);
+                n2.load(s_ptr[4 * m + 5] + w);
+                n3.load(s_ptr[4 * m + 6] + w);
+                n4.load(s_ptr[4 * m + 7] + w);
+            }
+#else
         for (int m = 0; m < p.nmol; ++m) {
             Vec<VEC> a1, a2, a3, a4;
             a1.load(s_ptr[4 * m] + w);
             a2.load(s_ptr[4 * m + 1] + w);
             a3.load(s_ptr[4 * m + 2] + w);
             a4.load(s_ptr[4 * m + 3] + w);
+#endif
             const double sc = s_ms[m];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
@@ -260,6 +281,7 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
             }
         }
     } else {
+#pragma unroll 4
         for (int m = 0; m < p.nmol; ++m) {
             Vec<VEC> k;
             k.load(s_ptr[m] + w);

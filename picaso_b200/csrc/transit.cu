@@ -7,23 +7,27 @@
 // fluxes.py:2624-2644, :2656; zero for k >= i) plus z*dz.  The main kernel assigns one
 // wavelength per thread and evaluates the lower-triangular contraction
 //     tau_i = sum_{k<i} sigma_k MT[k][i],   sigma_k = DTAU_k / colden_k * mmw_k * amu
-// eight tangent levels at a time in registers: per k one coalesced sigma load (L1-resident
-// after the first pass over the tile) and one 64-byte shared-memory broadcast of
-// MT[k][i0..i0+7] feed eight DFMAs.  The reference is compiled with fastmath, so the
-// summation order is free.
+// 32 tangent levels at a time in registers: per k one coalesced sigma load and shared-memory broadcasts of
+// MT[k][i0..i0+31] feed 32 DFMAs; the sigma loads of the next four layers are in flight while the current four
+// are folded in (software pipeline: ncu showed the v1 loop waiting on its own loads, long_scoreboard 4.0 of
+// 6.2 stall cycles per issue at 12 warps per SM).  The reference is compiled with fastmath, so the summation
+// order is free.
 #include "pb_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 128;
+// A/B on B200, 80 x 50 000 (profiles/r2_ab_transit.log): (levels per pass, loads per trip) without the software pipeline
+// (16,4) 80.2 us, (32,4) 80.1, (48,4) 71.8, (96,4) 114.8 (255 registers: two residency waves); with it (PB_TRANSIT_PF)
+// (16,4) 61.8, (32,4) 57.8, (32,8) 57.6, (48,4) 59.8
 #ifndef PB_TRANSIT_BLK
-#define PB_TRANSIT_BLK 16
+#define PB_TRANSIT_BLK 32
 #endif
 #ifndef PB_TRANSIT_UNROLL
 #define PB_TRANSIT_UNROLL 4
 #endif
 #ifndef PB_TRANSIT_PF
-#define PB_TRANSIT_PF 0
+#define PB_TRANSIT_PF 1
 #endif
 constexpr int kBlk = PB_TRANSIT_BLK;  // tangent levels per pass (accumulators per thread)
 constexpr int kUnroll = PB_TRANSIT_UNROLL;

@@ -336,49 +336,17 @@ def pollack_factor(opa):
     return opa._pollack
 
 
-def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddington=True, test_mode=False,
-                    raman=0, plot_opacity=False, full_output=False, return_mode=False, fthin_cld=None,
-                    do_holes=False, *, device_outputs=False, outputs=None):
-    """CUDA replacement of optics.compute_opacity (optics.py:26-431) for a ``DeviceOpacities``
-    connection: returns the reference's 13-tuple (DTAU, TAU, W0, COSB, ftau_cld, ftau_ray, GCOS2,
-    DTAU_OG, TAU_OG, W0_OG, COSB_OG, W0_no_raman, f_deltaM), each [nlayer|nlevel, nwno, 1] like the
-    reference's ngauss axis.  ``device_outputs=True`` returns ``DeviceArray`` handles instead
-    (2-D, sliceable with [:, :, 0]) that live in buffers pooled on the connection - they are
-    overwritten by the next compute_opacity call on the same ``DeviceOpacities``; ``outputs``
-    restricts the computed set to the given names (others are returned as None).
-
-    ``raman=1`` ('pollack', the reference's config default): the per-wavelength factor is the reference's
-    np.interp(1e4 / wno, w, f) of ``$picaso_refdata/opacities/raman_fortran.txt`` (optics.py:584-660), read once
-    per connection, or of ``opacityclass.raman_pollack_table = (w, f)`` if that is set.
-    ``full_output=True`` sets ``atmosphere.taugas / tauray / taucld`` ([nlayer, nwno, 1] numpy arrays) like the
-    reference (optics.py:322-325).
-    Not supported on this path: test_mode strings, plot_opacity, return_mode (host-side diagnostics).
-    ``test_mode`` None/False both mean "normal run": the reference's own default False would enter its test
-    branch (optics.py:372), real callers pass None."""
-    from .optics_ck import DeviceCKs, compute_opacity_ck
-    if not isinstance(opacityclass, (DeviceOpacities, DeviceCKs)):
-        raise TypeError("picaso_b200.compute_opacity needs a DeviceOpacities or DeviceCKs connection")
-    if isinstance(opacityclass, DeviceOpacities) and ngauss != 1:
-        raise ValueError("monochromatic DeviceOpacities have ngauss = 1")
-    if isinstance(opacityclass, DeviceCKs) and ngauss != opacityclass.ngauss:
-        raise ValueError("ngauss must equal the number of gauss points of the DeviceCKs table")
-    if test_mode not in (None, False):
-        raise NotImplementedError("compute_opacity test modes are not implemented on the GPU path")
-    if plot_opacity or return_mode:
-        raise NotImplementedError("plot_opacity / return_mode are host-side diagnostics")
-    opa, atm = opacityclass, atmosphere
-    if isinstance(opa, DeviceCKs):
-        import copy
-        atm_ck = copy.copy(atm)
-        atm_ck.molecules = []   # pre-mixed tables already contain every molecule (optics.py:257-262)
-        return compute_opacity_ck(atm_ck, opa, stream, delta_eddington, raman, fthin_cld, do_holes,
-                                  device_outputs, outputs)
+def _fill_opacity_args(atm, opa, stream, delta_eddington, raman, fthin_cld, do_holes, device_outputs, into=None):
+    """Everything pb_compute_opacity reads except the output pointers: table rows / weights of the atmosphere (from
+    opacityclass.get_opacities), per-layer multipliers, Raman inputs, clouds.  Returns (args, memspace, keep): `keep`
+    holds the host arrays whose addresses were taken and must outlive the call; `into` fills an existing struct (the
+    `opacity` member of a SpectrumArgs)."""
     ctx = opa.ctx
     if opa._plan is None or opa._plan["nlayer"] != atm.c.nlayer:
         raise RuntimeError("call opacityclass.get_opacities(atmosphere) first (justdoit.py:236)")
     L, W = atm.c.nlayer, opa.nwno
     mol, cont, ray = _layer_scalars(atm, opa)
-    a = OpacityArgs()
+    a = OpacityArgs() if into is None else into
     a.nlayer = L
     a.query = 1 if opa.query_method == "linear" else 0
     idx, wts, cia = opa._plan["idx"], opa._plan["wts"], opa._plan["cia"]
@@ -425,6 +393,49 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
     a.fthin_cld = float(fthin_cld) if fthin_cld is not None else 0.0
     a.do_holes = int(bool(do_holes))
     a.stream, a.delta_eddington = int(stream), int(bool(delta_eddington))
+    return a, memspace, keep
+
+
+def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddington=True, test_mode=False,
+                    raman=0, plot_opacity=False, full_output=False, return_mode=False, fthin_cld=None,
+                    do_holes=False, *, device_outputs=False, outputs=None):
+    """CUDA replacement of optics.compute_opacity (optics.py:26-431) for a ``DeviceOpacities``
+    connection: returns the reference's 13-tuple (DTAU, TAU, W0, COSB, ftau_cld, ftau_ray, GCOS2,
+    DTAU_OG, TAU_OG, W0_OG, COSB_OG, W0_no_raman, f_deltaM), each [nlayer|nlevel, nwno, 1] like the
+    reference's ngauss axis.  ``device_outputs=True`` returns ``DeviceArray`` handles instead
+    (2-D, sliceable with [:, :, 0]) that live in buffers pooled on the connection - they are
+    overwritten by the next compute_opacity call on the same ``DeviceOpacities``; ``outputs``
+    restricts the computed set to the given names (others are returned as None).
+
+    ``raman=1`` ('pollack', the reference's config default): the per-wavelength factor is the reference's
+    np.interp(1e4 / wno, w, f) of ``$picaso_refdata/opacities/raman_fortran.txt`` (optics.py:584-660), read once
+    per connection, or of ``opacityclass.raman_pollack_table = (w, f)`` if that is set.
+    ``full_output=True`` sets ``atmosphere.taugas / tauray / taucld`` ([nlayer, nwno, 1] numpy arrays) like the
+    reference (optics.py:322-325).
+    Not supported on this path: test_mode strings, plot_opacity, return_mode (host-side diagnostics).
+    ``test_mode`` None/False both mean "normal run": the reference's own default False would enter its test
+    branch (optics.py:372), real callers pass None."""
+    from .optics_ck import DeviceCKs, compute_opacity_ck
+    if not isinstance(opacityclass, (DeviceOpacities, DeviceCKs)):
+        raise TypeError("picaso_b200.compute_opacity needs a DeviceOpacities or DeviceCKs connection")
+    if isinstance(opacityclass, DeviceOpacities) and ngauss != 1:
+        raise ValueError("monochromatic DeviceOpacities have ngauss = 1")
+    if isinstance(opacityclass, DeviceCKs) and ngauss != opacityclass.ngauss:
+        raise ValueError("ngauss must equal the number of gauss points of the DeviceCKs table")
+    if test_mode not in (None, False):
+        raise NotImplementedError("compute_opacity test modes are not implemented on the GPU path")
+    if plot_opacity or return_mode:
+        raise NotImplementedError("plot_opacity / return_mode are host-side diagnostics")
+    opa, atm = opacityclass, atmosphere
+    if isinstance(opa, DeviceCKs):
+        import copy
+        atm_ck = copy.copy(atm)
+        atm_ck.molecules = []   # pre-mixed tables already contain every molecule (optics.py:257-262)
+        return compute_opacity_ck(atm_ck, opa, stream, delta_eddington, raman, fthin_cld, do_holes,
+                                  device_outputs, outputs)
+    a, memspace, keep = _fill_opacity_args(atm, opa, stream, delta_eddington, raman, fthin_cld, do_holes, device_outputs)
+    ctx = opa.ctx
+    L, W = atm.c.nlayer, opa.nwno
     want = set(OUTPUT_NAMES if outputs is None else outputs)
     res = {}
     for n in OUTPUT_NAMES:
@@ -456,3 +467,59 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
     if device_outputs:
         return tuple(res[n] for n in OUTPUT_NAMES)
     return tuple(None if res[n] is None else res[n][:, :, np.newaxis] for n in OUTPUT_NAMES)
+
+
+def reflected_spectrum(atmosphere, opacityclass, ubar0, ubar1, cos_theta, gweight, tweight, *, F0PI=None, surf_reflect=None,
+                       b_top=None, single_phase=3, multi_phase=0, frac_a=1.0, frac_b=-1.0, frac_c=2.0, constant_back=-0.5,
+                       constant_forward=1.0, toon_coefficients=0, stream=2, delta_eddington=True, raman=2, fthin_cld=None,
+                       do_holes=False, return_xint=False):
+    """One call per reflected-light spectrum (pb_spectrum_reflected): what picaso() does between
+    ``opacityclass.get_opacities(atm)`` and ``returns['albedo']`` for a Toon run - compute_opacity, get_reflected_1d,
+    compress_disco (justdoit.py:243-310, :530) - with the 11 opacity arrays living only in HBM.  Call
+    ``opacityclass.get_opacities(atmosphere)`` first, exactly as picaso() does.  ``F0PI`` / ``surf_reflect`` / ``b_top``:
+    None (= 1 / 0 / 0), a scalar, or a [nwno] vector (uploaded once per distinct array object and cached on the
+    connection).  Defaults are the reference's config.json (TTHG_ray, N=2, quadrature, delta-Eddington, no Raman).
+    Returns albedo[nwno] (and xint_at_top[ng, nt, nwno] with ``return_xint=True``)."""
+    from ._lib import SpectrumArgs
+    opa, atm = opacityclass, atmosphere
+    if not isinstance(opa, DeviceOpacities):
+        raise TypeError("reflected_spectrum needs a DeviceOpacities connection")
+    sa = SpectrumArgs()
+    _, _, keep = _fill_opacity_args(atm, opa, stream, delta_eddington, raman, fthin_cld, do_holes, True, into=sa.opacity)
+    ctx, W = opa.ctx, opa.nwno
+    u0 = np.ascontiguousarray(ubar0, dtype=np.float64)
+    u1 = np.ascontiguousarray(ubar1, dtype=np.float64)
+    ng, nt = u0.shape if u0.ndim == 2 else (u0.size, 1)
+    u0, u1 = u0.reshape(-1), u1.reshape(-1)
+    gw = np.ascontiguousarray(gweight, dtype=np.float64)
+    tw = np.ascontiguousarray(tweight, dtype=np.float64)
+    sa.nwno, sa.numg, sa.numt = W, ng, nt
+    sa.ubar0, sa.ubar1, sa.gweight, sa.tweight = addr(u0), addr(u1), addr(gw), addr(tw)
+    sa.cos_theta = float(cos_theta)
+
+    def wave_vector(name, value, default):
+        """device pointer of a per-wavelength vector, or None when it equals the kernel's default"""
+        if value is None or (np.isscalar(value) and value == default):
+            return None
+        cache = opa.__dict__.setdefault("_wave_vectors", {})
+        hit = cache.get(name)
+        if hit is not None and hit[0] is value:
+            return hit[1].ptr
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.float64), (W,)))
+        d = opa._buffer("spectrum_" + name, (W,))
+        ctx.check(ctx.lib.pb_memcpy_h2d(ctx.h, d.ptr, v.ctypes.data, v.nbytes))
+        ctx.sync()
+        cache[name] = (value, d)
+        return d.ptr
+
+    sa.surf_reflect = wave_vector("surf_reflect", surf_reflect, 0.0)
+    sa.F0PI = wave_vector("F0PI", F0PI, 1.0)
+    sa.b_top = wave_vector("b_top", b_top, 0.0)
+    sa.single_phase, sa.multi_phase, sa.toon_coefficients = int(single_phase), int(multi_phase), int(toon_coefficients)
+    sa.frac_a, sa.frac_b, sa.frac_c = float(frac_a), float(frac_b), float(frac_c)
+    sa.constant_back, sa.constant_forward = float(constant_back), float(constant_forward)
+    alb = np.empty(W)
+    xint = np.empty((ng, nt, W)) if return_xint else None
+    sa.albedo, sa.xint_at_top = addr(alb), addr(xint)
+    ctx.check(ctx.lib.pb_spectrum_reflected(ctx.h, opa._tab, ctypes.byref(sa)))
+    return (alb, xint) if return_xint else alb

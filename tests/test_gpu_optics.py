@@ -75,6 +75,35 @@ def test_device_resident_chain_matches_oracle():
     opa.close()
 
 
+@pytest.mark.parametrize("name", ["opt_linear_raman", "opt_nearest_noraman", "opt_linear_clear_nodedd"])
+def test_reflected_spectrum_one_call(name):
+    """pb_spectrum_reflected (opacity -> flux -> disk integration behind one C call) returns the bits of the
+    compute_opacity(device_outputs=True) -> get_reflected_1d(return_albedo=True) chain, for scalar / vector / default
+    surface reflectivity and stellar flux"""
+    case, g, db, atm, ins = load_case(name)
+    opa = device_opacities(pb, case, db, ins)
+    a = duck_atmosphere(db, atm)
+    L, W = atm["nlayer"], db["nwno"]
+    gangle, gweight, tangle, tweight, ubar0, ubar1, cos_theta = synth.geometry_1d(5, 0.0)
+    rng = np.random.default_rng(5)
+    for F0PI, surf in ((None, None), (1.0 + rng.random(W), 0.3), (None, 0.5 * rng.random(W))):
+        opa.get_opacities(a)
+        dev = pb.compute_opacity(a, opa, stream=case["stream"], delta_eddington=case["dedd"], test_mode=None,
+                                 raman=case["raman"], device_outputs=True)
+        sl = [d[:, :, 0] for d in dev[:11]]
+        DTAU, TAU, W0, COSB, fcld, fray, GCOS2, DTAU_OG, TAU_OG, W0_OG, COSB_OG = sl
+        x0, _, alb0 = pb.get_reflected_1d(L + 1, db["wno"], W, 5, 1, DTAU, TAU, W0, COSB, GCOS2, fcld, fray, DTAU_OG, TAU_OG,
+                                          W0_OG, COSB_OG, 0 if surf is None else surf, ubar0, ubar1, cos_theta,
+                                          np.ones(W) if F0PI is None else F0PI, 3, 0, 1.0, -1.0, 2.0, -0.5, 1.0,
+                                          gweight=gweight, tweight=tweight, return_albedo=True)
+        opa.get_opacities(a)
+        alb, xint = pb.reflected_spectrum(a, opa, ubar0, ubar1, cos_theta, gweight, tweight, F0PI=F0PI, surf_reflect=surf,
+                                          stream=case["stream"], delta_eddington=case["dedd"], raman=case["raman"],
+                                          return_xint=True)
+        assert np.array_equal(alb, alb0) and np.array_equal(xint, x0)
+    opa.close()
+
+
 def test_pollack_raman_and_full_output(tmp_path, monkeypatch):
     """raman=1 ('pollack', the reference's config default) and full_output=True through the public mirror: the table
     comes from $picaso_refdata/opacities/raman_fortran.txt like the reference's (optics.py:652); golden vectors from
