@@ -10,7 +10,8 @@ One step = one such spectrum per GPU (get_reflected_1d + compress_disco): a sing
 launch on device-resident inputs.  Steps rotate over NSETS distinct input sets whose total
 size exceeds the 126 MB L2, so every step streams its inputs from HBM.
 Multi-GPU: weak scaling - each rank owns its own 10 000-wavelength slab (wavelengths are
-independent); the per-rank albedo vectors are all-gathered (NCCL) inside the timed step.
+independent); the per-rank albedo vectors are all-gathered inside the timed step over NVLink peer
+memory (pb_peer_gather; PB_BENCH_GATHER selects the delivery mode or NCCL).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -707,8 +708,10 @@ def main():
                      "fp64_pipe_pct_ncu": fp64_pct, "fp64_peak_tflops_measured": fp64_peak,
                      "fp64_roof_note": "second roof: DFMA loop measured in this run (pb_microbench); the kernel issues ~14 M fp64 "
                                        "warp-instructions per launch = 24 us at that rate, against 8.2 us of HBM time",
-                     "note": "not HBM-bound: ~45 fp64 flop/B; 435 CTAs of 5 warps = 15 warps per SM, dependent fp64 "
-                             "chains (ncu stall_wait); DRAM traffic = algorithmic bytes; see DESIGN.md 4.1 and profiles/"},
+                     "note": "not HBM-bound: ~45 fp64 flop/B; 435 CTAs of 5 warps = 15 warps per SM (the problem has only "
+                             "10.6 consumer warps per SM), dependent fp64 chains (ncu stall_wait 2.4 of 7.3 cycles per issue); "
+                             "DRAM traffic = algorithmic bytes; see DESIGN.md 4.1, profiles/r2_refl_toa_v5.summary.json and "
+                             "profiles/r2_refl_toa_v5_sass.txt"},
         "clocks": sampler.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
