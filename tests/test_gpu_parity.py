@@ -157,6 +157,28 @@ def test_transit_vs_golden_and_oracle(name):
     assert_close(F, oracle.get_transit_1d(*C.transit_args(d)), RTOL, name + " vs oracle")
 
 
+def test_upload_mirror_tracks_changing_geometry():
+    """The small host vectors of a call (geometry, weights) are not copied again when the pinned slot's device block
+    already holds the same bytes (pb_upload_flush).  Alternating geometries through more calls than the ring has slots
+    must give, call for call, the results of a context that always copies."""
+    d = synth.reflected_inputs(L=7, W=45, seed=77)
+    kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
+    geos = [synth.geometry_1d(5, 0.0), synth.geometry_1d(6, 0.7), synth.geometry_1d(5, 0.3)]
+    ctx = pb.Context(0)
+    want = []
+    for gangle, gweight, tangle, tweight, ubar0, ubar1, cos_theta in geos:
+        dd = dict(d, ubar0=ubar0, ubar1=ubar1, cos_theta=cos_theta, numg=ubar0.shape[0], numt=ubar0.shape[1])
+        want.append(pb.get_reflected_1d(*C.reflected_args(dd, kw), gweight=gweight, tweight=tweight, return_albedo=True))
+    for i in range(40):     # ring of 8 slots: every slot sees every geometry, in changing order
+        k = (i * 7 + i // 3) % 3
+        gangle, gweight, tangle, tweight, ubar0, ubar1, cos_theta = geos[k]
+        dd = dict(d, ubar0=ubar0, ubar1=ubar1, cos_theta=cos_theta, numg=ubar0.shape[0], numt=ubar0.shape[1])
+        x, _, alb = pb.get_reflected_1d(*C.reflected_args(dd, kw), gweight=gweight, tweight=tweight, return_albedo=True,
+                                        ctx=ctx)
+        assert np.array_equal(x, want[k][0]) and np.array_equal(alb, want[k][2]), (i, k)
+    ctx.close()
+
+
 def test_empty_wave_axis():
     d = synth.reflected_inputs(L=5, W=0, seed=1)
     kw = dict(single_phase=3, multi_phase=0, toon_coefficients=0, get_lvl_flux=0)
