@@ -29,12 +29,17 @@ struct ThermParams {
     double *fm, *fp, *fmm, *fpm;
     int fuse;
     int variant;  // 1: get_thermal_3d per-facet semantics (fluxes.py:2148-2352)
-    int wt, ay;   // therm_toa_kernel<GEN = true>: wavelengths / angles per CTA
+    int wt, ay;   // therm_toa_kernel<GEN = true>, therm_toa_chain_kernel: wavelengths / angles per CTA
+    int ch;       // therm_toa_chain_kernel: layers per chunk (= producing warps)
     int ob_period; // > 0: batch entry b reads opacity / surf block b % ob_period (pb_thermal_args.opacity_period)
 };
 
 constexpr int kWavesPerCta = 32;
 constexpr double kMu1 = 0.5;  // fluxes.py:1748
+#ifndef PB_THERM_CHAIN
+#define PB_THERM_CHAIN 0
+#endif
+constexpr bool kThermChainDefault = PB_THERM_CHAIN != 0;  // therm_toa_chain_kernel for angle-parallel launches
 
 struct Planck {
     double c1w, c2w;      // calc_type 0: B = c1w / (exp(c2w / T) - 1)
@@ -290,6 +295,227 @@ __global__ void __launch_bounds__(256) therm_toa_kernel(ThermParams p)
         if (ca < AY) s_f[ca * kWavesPerCta + cw] = result;
         __syncthreads();
         if (ca == 0 && w < p.W) {
+            double acc = 0.0;
+            for (int aa = 0; aa < p.G; ++aa) {
+                const int ig = aa / p.nt, it = aa - ig * p.nt;
+                acc = acc + s_f[aa * kWavesPerCta + cw] * p.gweight[ig] * p.tweight[it];
+            }
+            const double sym = (p.nt == 1) ? 1.0 : 1 / (2 * PB_PI);
+            p.thermal[(int64_t)b * p.W + w] = acc * sym;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// TOA flux with the elimination taken out of the angle threads (round 2; the recipe of refl_toa_kernel5).
+//
+// In get_thermal_1d the tridiagonal system - matrix AND right-hand side - is the same for every viewing angle
+// (fluxes.py:1812-1831); therm_toa_kernel repeats its bottom-up elimination (two reciprocals and ~30 fp64
+// instructions per layer) in all G angle threads of a wavelength.  Here one extra warp per CTA, the CHAIN WARP
+// (lane = wavelength), walks the elimination once, one chunk ahead of the consumers, and publishes four numbers per
+// layer (AS, DS of the odd and of the even interface row); an angle thread keeps the angle-dependent Table-3 terms
+// and the two affine updates of its functional  flux_at_top = Rp + Pp X[2l].  The chain warp also closes the system
+// (top boundary row -> X[0]).  Pipeline per chunk of CH layers, one barrier: consumers integrate chunk c
+// (P[c % 3], C[c & 1]), the chain warp eliminates chunk c + 1 (P[(c+1) % 3] -> C[(c+1) & 1]), the producing warps
+// write chunk c + 2 (P[(c+2) % 3]) from inputs loaded one iteration earlier.  Same expressions as therm_toa_kernel.
+// ---------------------------------------------------------------------------------------
+enum { TC_ASE = 0, TC_DSE, TC_AS, TC_DS, TNC };
+
+__global__ void __maxnreg__(112) therm_toa_chain_kernel(ThermParams p)
+{
+    extern __shared__ double smem[];  // Planck [V][32] | P tiles [3][CH][TNQ][32] | C tiles [2][CH][TNC][32] | X0 [32]
+    const int tid = (int)threadIdx.x;
+    const int lane = tid & 31, wy = tid >> 5;
+    const int NW = (int)(blockDim.x >> 5), NWC = NW - 1;  // the last warp is the chain warp
+    const int CH = p.ch, WT = p.wt, AY = p.ay;
+    const bool is_chain = wy == NWC;
+    const bool is_cons = tid < WT * AY;
+    const int cw = is_cons ? tid % WT : 0, ca = is_cons ? tid / WT : 0;  // consumer identity
+    const int w = blockIdx.x * WT + cw;
+    const int wp = blockIdx.x * WT + (lane < WT ? lane : WT - 1);        // producer / chain column
+    const int wc = wp < p.W ? wp : p.W - 1;
+    const int wcc = w < p.W ? w : p.W - 1;
+    const int a = blockIdx.y * AY + ca;
+    const int ac = a < p.G ? a : p.G - 1;
+    const int b = blockIdx.z;
+    const int L = p.L, V = p.L + 1;
+    const int64_t ld = p.ld;
+    const int ob = p.ob_period ? b % p.ob_period : b;
+    const int64_t ol = (int64_t)ob * p.bs_layer + wc;
+    const double *tl = p.tlevel + (int64_t)b * V;
+    const double *pl = p.plevel + (int64_t)b * V;
+    const double u = p.ubar1[ac];
+    const double inv_u = 1.0 / u;
+    double *sB = smem;
+    double *ptile = smem + (size_t)V * 32;
+    const int psz = CH * TNQ * 32, csz = CH * TNC * 32;
+    double *ctile = ptile + 3 * psz;
+    double *sX0 = ctile + 2 * csz;
+    const int nchunks = (L + CH - 1) / CH;
+    {
+        Planck planck;
+        planck.init(p.calc_type, p.wno[wc], p.dwno ? p.dwno[wc] : 0.0);
+        for (int v = wy; v < V; v += NW) sB[v * 32 + lane] = planck(tl[v]);
+    }
+    __syncthreads();
+
+    // producers: warp wy < CH owns layer L - 1 - (c CH + wy) of chunk c
+    auto load_in = [&](int c, double &dt, double &om, double &cb) -> bool {
+        const int l = L - 1 - (c * CH + wy);
+        if (wy >= CH || c >= nchunks || l < 0) return false;
+        const int64_t il = ol + (int64_t)l * ld;
+        dt = __ldg(p.dtau + il);
+        om = __ldg(p.w0 + il);
+        cb = __ldg(p.cosb + il);
+        return true;
+    };
+    auto produce = [&](int c, double dt, double om, double cb) {
+        const int l = L - 1 - (c * CH + wy);
+        therm_produce(dt, om, cb, sB[l * 32 + lane], sB[(l + 1) * 32 + lane], ptile + (c % 3) * psz + wy * TNQ * 32 + lane);
+    };
+
+    // chain-warp state (fluxes.py:289-323 bottom-up: X[n] = DS - AS X[n-1])
+    double cAS = 0.0, cDS = 0.0, c_gam = 0.0, c_cpu = 0.0, c_cmu = 0.0;
+    auto chain = [&](int c) {
+        const double *pt = ptile + (c % 3) * psz + lane;
+        double *ct = ctile + (c & 1) * csz + lane;
+        const int lbase = L - 1 - c * CH;
+        const int nk = lbase + 1 < CH ? lbase + 1 : CH;
+        for (int k = 0; k < nk; ++k) {
+            const int l = lbase - k;
+            const double *q = pt + k * TNQ * 32;
+            double *o = ct + k * TNC * 32;
+            const double gam = q[T_GAM * 32], EP = q[T_EP * 32], EM = q[T_EM * 32];
+            const double cpu = q[T_CPU * 32], cmu = q[T_CMU * 32], cpd = q[T_CPD * 32], cmd = q[T_CMD * 32];
+            const double e1 = EP + gam * EM, e2 = EP - gam * EM;
+            const double e3 = gam * EP + EM, e4 = gam * EP - EM;
+            if (l == L - 1) {
+                // surface boundary, fluxes.py:1802-1806, last row :178-181
+                const double b1 = q[T_B1 * 32];
+                const double BL = sB[L * 32 + lane];
+                const double r = p.surf ? p.surf[(int64_t)ob * p.bs_wave + wc] : 0.0;
+                const double b_surface = p.hard_surface ? (1.0 - r) * BL * PB_PI : (BL + b1 * kMu1) * PB_PI;
+                const double a_ = e1 - r * e3, b_ = e2 - r * e4;
+                const double d_ = b_surface - cpd + r * cmd;
+                const double ib = pbm::krcp(b_);
+                cAS = a_ * ib;
+                cDS = d_ * ib;
+                o[TC_ASE * 32] = 0.0;
+                o[TC_DSE * 32] = 0.0;
+            } else {
+                const double gm1 = c_gam - 1.0;
+                const double e13 = (e1 + e3) * gm1;
+                double a_ = 2.0 * (1.0 - gam * gam);
+                double b_ = (e1 - e3) * (c_gam + 1.0);
+                double d_ = e3 * (c_cpu - cpd) + e1 * (cmd - c_cmu);
+                double xi = pbm::krcp(b_ - e13 * cAS);
+                const double ASe = a_ * xi, DSe = (d_ - e13 * cDS) * xi;
+                o[TC_ASE * 32] = ASe;
+                o[TC_DSE * 32] = DSe;
+                b_ = (e2 + e4) * gm1;
+                const double c_ = 2.0 * (1.0 - c_gam * c_gam);
+                d_ = gm1 * (c_cpu - cpd) - gm1 * (cmd - c_cmu);
+                xi = pbm::krcp(b_ - c_ * ASe);
+                cAS = e13 * xi;
+                cDS = (d_ - c_ * DSe) * xi;
+            }
+            o[TC_AS * 32] = cAS;
+            o[TC_DS * 32] = cDS;
+            c_gam = gam;
+            c_cpu = cpu;
+            c_cmu = cmu;
+        }
+    };
+
+    // consumer state: flux_at_top = Rp + Pp X[2l] over the first not-yet-eliminated unknown
+    double Pp = 0.0, Rp = 0.0;
+    const double r_c = p.surf ? p.surf[(int64_t)ob * p.bs_wave + wcc] : 0.0;
+    const double BLc = sB[L * 32 + cw];
+    auto consume = [&](int c) {
+        const double *pt = ptile + (c % 3) * psz + cw;
+        const double *ct = ctile + (c & 1) * csz + cw;
+        const int lbase = L - 1 - c * CH;
+        const int nk = lbase + 1 < CH ? lbase + 1 : CH;
+        for (int k = 0; k < nk; ++k) {
+            const int l = lbase - k;
+            const double *q = pt + k * TNQ * 32;
+            const double *o = ct + k * TNC * 32;
+            const double lam = q[T_LAM * 32], gam = q[T_GAM * 32], EP = q[T_EP * 32], EM = q[T_EM * 32];
+            const double dt = q[T_DT * 32], al1 = q[T_AL1 * 32], al2 = q[T_AL2 * 32];
+            // Table 3 of Toon89 (fluxes.py:1842-1849): G = (1/mu1 - lam) Y+, H = gam (lam + 1/mu1) Y-
+            const double lu = lam * u;
+            const double inv_l = pbm::krcp(lu * lu - 1.0);
+            const double kG = (1 / kMu1 - lam) * ((lu + 1.0) * inv_l);
+            const double kH = gam * (lam + 1 / kMu1) * ((lu - 1.0) * inv_l);
+            double x, cG, cH, K;
+            if (l > 0) {
+                // flux_plus recurrence, fluxes.py:1897-1901
+                x = pbm::kexp(-dt * inv_u);
+                cG = kG * (EP * x - 1.0);
+                cH = kH * (1.0 - EM * x);
+                K = al1 * (1. - x) + al2 * (u - (dt + u) * x);
+            } else {
+                // flux_plus_mdpt[0], fluxes.py:1903-1910
+                x = pbm::kexp(-0.5 * dt * inv_u);
+                const double EPh = pbm::kexp(0.5 * q[T_E * 32]), EMh = pbm::krcp(EPh);
+                cG = kG * (EP * x - EPh);
+                cH = -kH * (EM * x - EMh);
+                K = al1 * (1. - x) + al2 * (u + 0.5 * dt - (dt + u) * x);
+            }
+            double alpha, beta;
+            if (l == L - 1) {
+                // fluxes.py:1869-1873
+                const double b1 = q[T_B1 * 32];
+                alpha = p.hard_surface ? (1.0 - r_c) * BLc * 2 * PB_PI : (BLc + b1 * u) * 2 * PB_PI;
+                beta = 0.0;
+            } else {
+                alpha = Rp + Pp * o[TC_DSE * 32];
+                beta = -Pp * o[TC_ASE * 32];
+            }
+            // F+_l = x (alpha + beta X[2l+1]) + cG (X0 + X1) + cH (X0 - X1) + K
+            const double P = cG + cH;
+            const double Q = x * beta + (cG - cH);
+            const double R = x * alpha + K;
+            Pp = P - Q * o[TC_AS * 32];
+            Rp = R + Q * o[TC_DS * 32];
+        }
+    };
+
+    double ndt = 0.0, nom = 0.0, ncb = 0.0;
+    if (load_in(0, ndt, nom, ncb)) produce(0, ndt, nom, ncb);
+    bool have = load_in(1, ndt, nom, ncb);
+    __syncthreads();
+    if (is_chain) chain(0);
+    if (have) produce(1, ndt, nom, ncb);
+    have = load_in(2, ndt, nom, ncb);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        if (is_chain) {
+            if (c + 1 < nchunks) chain(c + 1);
+        } else if (is_cons) {
+            consume(c);
+        }
+        if (have) produce(c + 2, ndt, nom, ncb);
+        have = load_in(c + 3, ndt, nom, ncb);
+        __syncthreads();
+    }
+    if (is_chain) {
+        // top boundary: fake isothermal overburden, fluxes.py:1797-1800; row 0 :155-158
+        const double tau_top = __ldg(p.dtau + (int64_t)ob * p.bs_layer + wc) * pl[0] / (pl[1] - pl[0]);
+        const double b_top = (1.0 - exp(-tau_top / kMu1)) * sB[lane] * PB_PI;
+        const double b_ = c_gam + 1.0, c_ = c_gam - 1.0, d_ = b_top - c_cmu;
+        const double xi = pbm::krcp(b_ - c_ * cAS);
+        sX0[lane] = (d_ - c_ * cDS) * xi;
+    }
+    __syncthreads();
+    const double result = Rp + Pp * sX0[cw];
+    const bool active = is_cons && (w < p.W) && (a < p.G);
+    if (active && p.ftop) p.ftop[((int64_t)b * p.G + a) * p.W + w] = result;
+    if (p.fuse) {
+        double *s_f = ptile;
+        if (is_cons) s_f[ca * kWavesPerCta + cw] = result;
+        __syncthreads();
+        if (is_cons && ca == 0 && w < p.W) {
             double acc = 0.0;
             for (int aa = 0; aa < p.G; ++aa) {
                 const int ig = aa / p.nt, it = aa - ig * p.nt;
@@ -895,6 +1121,16 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
     bool use_wave_kernel = !want_lvl && a->variant == 0 && G <= 8 && (!a->thermal || fuse) && (long)W * B >= wave_min;
     if (force && force[0] == 'a') use_wave_kernel = false;
     if (force && force[0] == 'w' && !want_lvl && a->variant == 0 && G <= 8 && (!a->thermal || fuse)) use_wave_kernel = true;
+    // angle-parallel launches: the chain-warp kernel shares the elimination between the angles of a wavelength
+    // (PB_THERM_KERNEL=chain opts in, =angle keeps therm_toa_kernel); it needs all angles of a wavelength in one CTA
+    // and its tiles (3 CTAs per SM) in shared memory
+    const size_t chain_smem = ((size_t)V * 32 + (size_t)4 * (3 * TNQ + 2 * TNC) * 32 + 32) * sizeof(double);
+    bool use_chain_kernel = kThermChainDefault && !want_lvl && !use_wave_kernel && a->variant == 0 && G >= 2 && G <= 8 && chain_smem <= 75 * 1024;
+    if (force && force[0] == 'c' && !want_lvl && a->variant == 0 && G >= 2 && G <= 8 && chain_smem <= 200 * 1024) {
+        use_chain_kernel = true;
+        use_wave_kernel = false;
+    }
+    if (force && force[0] == 'a') use_chain_kernel = false;
     if (want_lvl) {
         p.fm = d_lv[0]; p.fp = d_lv[1]; p.fmm = d_lv[2]; p.fpm = d_lv[3];
         // Short wavelength axes (the climate solver) are serial-latency bound: precompute the layer records with
@@ -936,6 +1172,30 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
         case 7: launch_therm_wave<7>(p, B, ctx->stream); break;
         default: launch_therm_wave<8>(p, B, ctx->stream); break;
         }
+        PB_CHECK_LAUNCH(ctx);
+    } else if (use_chain_kernel) {
+        p.fuse = fuse ? 1 : 0;
+        const int nsm = ctx->sm_count > 0 ? ctx->sm_count : 148;
+        const char *wte = getenv("PB_THERM_WT");
+        int wt = wte ? atoi(wte) : 0;
+        const int cap = 160 / ay < 32 ? 160 / ay : 32;   // at most five consumer warps
+        if (wt <= 0 || wt > cap) {
+            wt = cap;
+            // narrowed, when the whole launch is a single residency wave (3 CTAs per SM), to an even CTA count per SM
+            const int std_ctas = (W + cap - 1) / cap;
+            const int per_sm = (std_ctas + nsm - 1) / nsm;
+            if (B == 1 && per_sm <= 3 && (double)per_sm * nsm > 1.05 * std_ctas) {
+                const int cand = (W + nsm * per_sm - 1) / (nsm * per_sm);
+                if (cand >= 12 && cand < cap) wt = cand;
+            }
+        }
+        p.wt = wt; p.ay = ay;
+        const int nw = (wt * ay + 31) / 32 + 1;
+        p.ch = nw < 4 ? nw : 4;
+        const size_t smem = ((size_t)V * 32 + (size_t)p.ch * (3 * TNQ + 2 * TNC) * 32 + 32) * sizeof(double);
+        if (smem > 48 * 1024) PB_CUDA(ctx, pb_ensure_smem(ctx, therm_toa_chain_kernel, smem));
+        dim3 cgrid((W + wt - 1) / wt, 1, B);
+        therm_toa_chain_kernel<<<cgrid, nw * 32, smem, ctx->stream>>>(p);
         PB_CHECK_LAUNCH(ctx);
     } else {
         p.fuse = fuse ? 1 : 0;

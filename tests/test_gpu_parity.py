@@ -99,6 +99,24 @@ def test_thermal_vs_golden_and_oracle(name):
                        what="compress_thermal 4-D")
 
 
+@pytest.mark.parametrize("kernel", ["chain", "angle", "wave"])
+@pytest.mark.parametrize("name", sorted(C.thermal_cases()))
+def test_thermal_toa_kernels(name, kernel, monkeypatch):
+    """every TOA kernel of get_thermal_1d (PB_THERM_KERNEL): the chain-warp kernel (elimination once per wavelength on an
+    extra warp), the angle-parallel kernel and the one-thread-per-wavelength kernel against the reference"""
+    g = golden("thermal")
+    d = C.build_thermal(C.thermal_cases()[name])
+    monkeypatch.setenv("PB_THERM_KERNEL", kernel)
+    ftop, none, th = pb.get_thermal_1d(*C.thermal_args(d), level_fluxes=False, gweight=d["gweight"], tweight=d["tweight"],
+                                       return_thermal=True)
+    assert none is None
+    assert_close(ftop, g[name + "/ftop"], RTOL, "%s ftop (%s kernel) vs reference" % (name, kernel))
+    assert_close(th, g[name + "/thermal"], RTOL, "%s fused thermal (%s kernel) vs reference" % (name, kernel))
+    monkeypatch.setenv("PB_THERM_WT", "17")    # narrow tiles: partial warps, several chunks per warp
+    f2, _ = pb.get_thermal_1d(*C.thermal_args(d), level_fluxes=False)
+    assert_close(f2, g[name + "/ftop"], RTOL, "%s ftop (%s kernel, 17-wide tiles) vs reference" % (name, kernel))
+
+
 @pytest.mark.parametrize("name", sorted(C.sh_cases()))
 def test_reflected_sh_vs_golden_and_oracle(name):
     g = golden("sh")
