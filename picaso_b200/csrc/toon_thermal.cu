@@ -37,8 +37,15 @@ struct ThermParams {
 constexpr int kWavesPerCta = 32;
 constexpr double kMu1 = 0.5;  // fluxes.py:1748
 #ifndef PB_THERM_CHAIN
-#define PB_THERM_CHAIN 0
+#define PB_THERM_CHAIN 1
 #endif
+// PB_THERM_CHAIN_TAB 1: the consumers' exp(-dtau/u) through the 64-entry table of pb_math.cuh (9 fp64 instructions, 8 KB of
+// shared memory: chunks of 3 layers instead of 4 keep three CTAs per SM)
+#ifndef PB_THERM_CHAIN_TAB
+#define PB_THERM_CHAIN_TAB 0
+#endif
+constexpr int kThermChainCh = PB_THERM_CHAIN_TAB ? 3 : 4;
+constexpr int kThermChainTab = PB_THERM_CHAIN_TAB ? pbm::kExpTabDoubles : 0;
 constexpr bool kThermChainDefault = PB_THERM_CHAIN != 0;  // therm_toa_chain_kernel for angle-parallel launches
 
 struct Planck {
@@ -346,12 +353,19 @@ __global__ void __maxnreg__(112) therm_toa_chain_kernel(ThermParams p)
     const double *pl = p.plevel + (int64_t)b * V;
     const double u = p.ubar1[ac];
     const double inv_u = 1.0 / u;
-    double *sB = smem;
-    double *ptile = smem + (size_t)V * 32;
+    double *sB = smem + kThermChainTab;
+    double *ptile = sB + (size_t)V * 32;
     const int psz = CH * TNQ * 32, csz = CH * TNC * 32;
     double *ctile = ptile + 3 * psz;
     double *sX0 = ctile + 2 * csz;
     const int nchunks = (L + CH - 1) / CH;
+#if PB_THERM_CHAIN_TAB
+    pbm::exp_tab_fill(smem, tid, (int)blockDim.x);
+    const double *tab = smem + (lane & 15);
+#define PB_TC_EXP(x) pbm::exp_tab((x), tab)
+#else
+#define PB_TC_EXP(x) pbm::kexp(x)
+#endif
     {
         Planck planck;
         planck.init(p.calc_type, p.wno[wc], p.dwno ? p.dwno[wc] : 0.0);
@@ -450,14 +464,14 @@ __global__ void __maxnreg__(112) therm_toa_chain_kernel(ThermParams p)
             double x, cG, cH, K;
             if (l > 0) {
                 // flux_plus recurrence, fluxes.py:1897-1901
-                x = pbm::kexp(-dt * inv_u);
+                x = PB_TC_EXP(-dt * inv_u);
                 cG = kG * (EP * x - 1.0);
                 cH = kH * (1.0 - EM * x);
                 K = al1 * (1. - x) + al2 * (u - (dt + u) * x);
             } else {
                 // flux_plus_mdpt[0], fluxes.py:1903-1910
-                x = pbm::kexp(-0.5 * dt * inv_u);
-                const double EPh = pbm::kexp(0.5 * q[T_E * 32]), EMh = pbm::krcp(EPh);
+                x = PB_TC_EXP(-0.5 * dt * inv_u);
+                const double EPh = PB_TC_EXP(0.5 * q[T_E * 32]), EMh = pbm::krcp(EPh);
                 cG = kG * (EP * x - EPh);
                 cH = -kH * (EM * x - EMh);
                 K = al1 * (1. - x) + al2 * (u + 0.5 * dt - (dt + u) * x);
@@ -1124,7 +1138,7 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
     // angle-parallel launches: the chain-warp kernel shares the elimination between the angles of a wavelength
     // (PB_THERM_KERNEL=chain opts in, =angle keeps therm_toa_kernel); it needs all angles of a wavelength in one CTA
     // and its tiles (3 CTAs per SM) in shared memory
-    const size_t chain_smem = ((size_t)V * 32 + (size_t)4 * (3 * TNQ + 2 * TNC) * 32 + 32) * sizeof(double);
+    const size_t chain_smem = ((size_t)kThermChainTab + (size_t)V * 32 + (size_t)kThermChainCh * (3 * TNQ + 2 * TNC) * 32 + 32) * sizeof(double);
     bool use_chain_kernel = kThermChainDefault && !want_lvl && !use_wave_kernel && a->variant == 0 && G >= 2 && G <= 8 && chain_smem <= 75 * 1024;
     if (force && force[0] == 'c' && !want_lvl && a->variant == 0 && G >= 2 && G <= 8 && chain_smem <= 200 * 1024) {
         use_chain_kernel = true;
@@ -1191,8 +1205,8 @@ extern "C" int pb_thermal_toon_1d(pb_ctx *ctx, const pb_thermal_args *a, int mem
         }
         p.wt = wt; p.ay = ay;
         const int nw = (wt * ay + 31) / 32 + 1;
-        p.ch = nw < 4 ? nw : 4;
-        const size_t smem = ((size_t)V * 32 + (size_t)p.ch * (3 * TNQ + 2 * TNC) * 32 + 32) * sizeof(double);
+        p.ch = nw < kThermChainCh ? nw : kThermChainCh;
+        const size_t smem = ((size_t)kThermChainTab + (size_t)V * 32 + (size_t)p.ch * (3 * TNQ + 2 * TNC) * 32 + 32) * sizeof(double);
         if (smem > 48 * 1024) PB_CUDA(ctx, pb_ensure_smem(ctx, therm_toa_chain_kernel, smem));
         dim3 cgrid((W + wt - 1) / wt, 1, B);
         therm_toa_chain_kernel<<<cgrid, nw * 32, smem, ctx->stream>>>(p);
