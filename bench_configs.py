@@ -76,7 +76,7 @@ class Cfg2:
     metric = "wave-points/sec (90-layer x 10k-wave thermal Toon spectrum)"
     workload = "thermal_toon_1d L=90 W=10000 G=5 calc_type=0 hard_surface=0 (BASELINE config 2)"
     scaling = "weak"
-    kernel = "therm_toa_kernel"
+    kernel = "therm_toa_chain_kernel"
     dtype = "f64"
 
     def __init__(self, pb, ctx, rank, world, torch=None, dist=None):
@@ -162,7 +162,8 @@ class Cfg2:
                 "single_thread_value": self.W / one, "host_cpus": os.cpu_count()}
 
     def note(self):
-        return "fp64-pipe / latency bound (see DESIGN.md 4.3): the tridiagonal is angle-independent, Planck per level once per CTA"
+        return ("issue / fp64-latency bound (DESIGN.md 4.3, profiles/r2_therm_chain_cfg2.summary.json): the angle-independent "
+                "tridiagonal elimination runs once per wavelength on a chain warp, Planck per level once per CTA")
 
 
 # ---------------------------------------------------------------------------------------------------------
