@@ -44,6 +44,10 @@ constexpr double kMu1 = 0.5;  // fluxes.py:1748
 #ifndef PB_THERM_CHAIN_TAB
 #define PB_THERM_CHAIN_TAB 0
 #endif
+#ifndef PB_THERM_CHAIN_UNROLL
+#define PB_THERM_CHAIN_UNROLL 1
+#endif
+constexpr int kThermChainUnroll = PB_THERM_CHAIN_UNROLL;
 constexpr int kThermChainCh = PB_THERM_CHAIN_TAB ? 3 : 4;
 constexpr int kThermChainTab = PB_THERM_CHAIN_TAB ? pbm::kExpTabDoubles : 0;
 constexpr bool kThermChainDefault = PB_THERM_CHAIN != 0;  // therm_toa_chain_kernel for angle-parallel launches
@@ -450,6 +454,7 @@ __global__ void __maxnreg__(112) therm_toa_chain_kernel(ThermParams p)
         const double *ct = ctile + (c & 1) * csz + cw;
         const int lbase = L - 1 - c * CH;
         const int nk = lbase + 1 < CH ? lbase + 1 : CH;
+#pragma unroll kThermChainUnroll
         for (int k = 0; k < nk; ++k) {
             const int l = lbase - k;
             const double *q = pt + k * TNQ * 32;
