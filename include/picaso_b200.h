@@ -319,6 +319,11 @@ typedef struct pb_opacity_args {
     /* full_output (optics.py:322-325, atmosphere.taugas / tauray / taucld): the three per-layer optical depths the
      * totals are built from, [nlayer][nwno(*ngauss)]; NULL = not wanted */
     double *TAUGAS, *TAURAY, *TAUCLD;
+    /* test modes of compute_opacity (optics.py:372-399, the Dlugach & Yanovitskij checks): 0 = off (test_mode None),
+     * 1 = 'rayleigh' (DTAU = TAURAY, GCOS2 = 0.5, ftau_ray = 1, ftau_cld = 0), 2 = any other string (DTAU = cloud opd,
+     * GCOS2 = 0, ftau_ray = 0, ftau_cld = 1); in both W0 = W0_no_raman = cloud w0 (values <= 0 -> 1e-10), COSB = cloud g0,
+     * DTAU <= 0 -> 1e-10.  Needs the cloud arrays. */
+    int test_mode;
 } pb_opacity_args;
 
 int pb_compute_opacity(pb_ctx *ctx, pb_optab *tab, const pb_opacity_args *args, int memspace);

@@ -119,8 +119,9 @@ def raman_pollack(wno, table_w, table_f, nlayer):
 
 
 def compute_opacity(atm, molecular_opa, continuum_opa, rayleigh_opa, raman_factor, stream=2,
-                    delta_eddington=True, fthin_cld=None, do_holes=False, full=None):
-    """optics.py:147-431 for ngauss = 1 and test_mode = None.
+                    delta_eddington=True, fthin_cld=None, do_holes=False, full=None, test_mode=None):
+    """optics.py:147-431 for ngauss = 1; test_mode None, 'rayleigh' or any other string (optics.py:372-399; like the
+    reference, a test mode replaces non-positive cloud single-scattering albedos by 1e-10 IN atm["cloud_w0"]).
 
     atm: dict from picaso_b200.synth.atmosphere_profile; molecular_opa {mol: [L, W]} (already x N_A),
     continuum_opa {pair: [L, W]}, rayleigh_opa {mol: [W]}, raman_factor [L, W] BEFORE the 0.99999
@@ -182,6 +183,27 @@ def compute_opacity(atm, molecular_opa, continuum_opa, rayleigh_opa, raman_facto
         W0_no_raman = (TAURAY * 0.99999 + TAUCLD * w0c) / (TAUGAS + TAURAY + TAUCLD)
         TAU = np.zeros((L + 1, W))
         TAU[1:] = np.cumsum(DTAU, axis=0)
+        if test_mode is not None:
+            # optics.py:372-399 (check against Dlugach & Yanovitskij): Rayleigh-only or cloud-only optical depths with
+            # the cloud's single-scattering albedo and asymmetry everywhere
+            if test_mode == 'rayleigh':
+                DTAU = TAURAY
+                GCOS2 = np.zeros(DTAU.shape) + 0.5
+                ftau_ray = np.zeros(DTAU.shape) + 1.0
+                ftau_cld = np.zeros(DTAU.shape)
+            else:
+                DTAU = np.zeros(DTAU.shape)
+                DTAU[:, :] = atm["cloud_opd"]
+                GCOS2 = np.zeros(DTAU.shape)
+                ftau_ray = np.zeros(DTAU.shape)
+                ftau_cld = np.zeros(DTAU.shape) + 1.
+            atm["cloud_w0"][atm["cloud_w0"] <= 0] = 1e-10
+            DTAU[DTAU <= 0] = 1e-10
+            COSB = np.zeros(DTAU.shape) + atm["cloud_g0"]
+            W0 = np.zeros(DTAU.shape) + atm["cloud_w0"]
+            W0_no_raman = W0
+            TAU = np.zeros((L + 1, W))
+            TAU[1:] = np.cumsum(DTAU, axis=0)
         if delta_eddington:
             f = COSB ** stream
             w0_d = W0 * (1. - f) / (1.0 - W0 * f)

@@ -75,7 +75,7 @@ class OpacityArgs(ctypes.Structure):
                              "W0_OG", "COSB_OG", "W0_no_raman", "f_deltaM")] +
         [("ngauss", c_int), ("ck_index", c_vp), ("ck_weights", c_vp), ("ck_scale", c_vp), ("cont_mode", c_int),
          ("cont_index_hi", c_vp), ("cont_t", c_vp), ("ck_direct", c_vp), ("TAUGAS", c_vp), ("TAURAY", c_vp),
-         ("TAUCLD", c_vp)])
+         ("TAUCLD", c_vp), ("test_mode", c_int)])
 
 
 class SpectrumArgs(ctypes.Structure):

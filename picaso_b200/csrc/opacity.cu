@@ -81,6 +81,7 @@ struct OpaParams {
     int do_holes, stream, dedd;
     double *o[13];
     double *x[3];              // full_output: TAUGAS, TAURAY, TAUCLD
+    int test_mode;             // 0 off, 1 'rayleigh', 2 other (optics.py:372-399)
     int64_t bs_out;
 };
 
@@ -325,9 +326,9 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
         for (int v = 0; v < VEC; ++v) rf[v] = fmin(pl.v[v], 0.99999);
     }
     // cloud (optics.py:309-315)
-    Vec<VEC> opd, cw0, cg0;
+    Vec<VEC> opd, cw0, cg0, opd_raw;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) opd.v[v] = cw0.v[v] = cg0.v[v] = 0.0;
+    for (int v = 0; v < VEC; ++v) opd.v[v] = cw0.v[v] = cg0.v[v] = opd_raw.v[v] = 0.0;
     if (p.cld_opd) {
         const int64_t ic = (int64_t)l * p.ld + w;
         if (VEC == 1 || (p.ld & 1) == 0) {
@@ -336,6 +337,7 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { opd.v[v] = __ldg(p.cld_opd + ic + v); cw0.v[v] = __ldg(p.cld_w0 + ic + v); cg0.v[v] = __ldg(p.cld_g0 + ic + v); }
         }
+        opd_raw = opd;   // atm.layer['cloud']['opd'] itself: the test modes ignore fthin_cld (optics.py:386)
         if (p.do_holes) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) opd.v[v] = p.fthin * opd.v[v];
@@ -346,17 +348,28 @@ __global__ void __launch_bounds__(128) opacity_layer_kernel(OpaParams p)
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         const double taucld = opd.v[v], w0c = cw0.v[v], g0 = cg0.v[v];
-        const double dtau = taugas[v] + tauray[v] + taucld;
+        double dtau = taugas[v] + tauray[v] + taucld;
         const double sc = w0c * taucld;
-        const double w0 = (tauray[v] * rf[v] + taucld * w0c) / dtau;
+        double w0 = (tauray[v] * rf[v] + taucld * w0c) / dtau;
         const double fray = tauray[v] / (tauray[v] + sc);
         o4.v[v] = sc / (sc + tauray[v]);
         o5.v[v] = fray;
         o6.v[v] = 0.5 * fray;
+        o11.v[v] = (tauray[v] * 0.99999 + taucld * w0c) / dtau;
+        if (p.test_mode) {
+            // optics.py:372-399: Rayleigh-only / cloud-only optical depth, the cloud's w0 and g0 everywhere
+            const bool ray = p.test_mode == 1;
+            dtau = ray ? tauray[v] : opd_raw.v[v];
+            if (dtau <= 0) dtau = 1e-10;
+            o4.v[v] = ray ? 0.0 : 1.0;
+            o5.v[v] = ray ? 1.0 : 0.0;
+            o6.v[v] = ray ? 0.5 : 0.0;
+            w0 = w0c <= 0 ? 1e-10 : w0c;
+            o11.v[v] = w0;
+        }
         o7.v[v] = dtau;
         o9.v[v] = w0;
         o10.v[v] = g0;
-        o11.v[v] = (tauray[v] * 0.99999 + taucld * w0c) / dtau;
         if (p.dedd) {
             double f = 1.0;
             for (int s = 0; s < p.stream; ++s) f *= g0;
@@ -598,6 +611,9 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
     if (a->query == 1 && t->nmol && !a->weights) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: bilinear query needs weights");
     if (a->raman == 0 && (!t->shifts || !a->jfrac)) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: raman=0 needs pb_optab_set_raman and jfrac");
     if (a->raman == 1 && !a->raman_pollack) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: raman=1 needs raman_pollack[nwno]");
+    if (a->test_mode < 0 || a->test_mode > 2) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: test_mode must be 0, 1 or 2");
+    if (a->test_mode && (!a->cloud_opd || !a->cloud_w0 || !a->cloud_g0))
+        return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: test modes read the cloud arrays (optics.py:386-395)");
     const bool cloud = a->cloud_opd != nullptr;
     if (cloud && (!a->cloud_w0 || !a->cloud_g0)) return pb_fail(ctx, PB_ERR_ARG, "compute_opacity: cloud needs opd, w0 and g0");
     for (int m = 0; m < t->nmol; ++m) {
@@ -698,6 +714,7 @@ extern "C" int pb_compute_opacity(pb_ctx *ctx, pb_optab *t, const pb_opacity_arg
         p.ld = host ? W : ldc;
     }
     p.fthin = a->fthin_cld; p.do_holes = a->do_holes; p.stream = a->stream; p.dedd = a->delta_eddington;
+    p.test_mode = a->test_mode;
     for (int k = 0; k < 13; ++k) {
         p.o[k] = nullptr;
         if (!outs[k]) continue;

@@ -336,7 +336,8 @@ def pollack_factor(opa):
     return opa._pollack
 
 
-def _fill_opacity_args(atm, opa, stream, delta_eddington, raman, fthin_cld, do_holes, device_outputs, into=None):
+def _fill_opacity_args(atm, opa, stream, delta_eddington, raman, fthin_cld, do_holes, device_outputs, into=None,
+                       test_mode=None):
     """Everything pb_compute_opacity reads except the output pointers: table rows / weights of the atmosphere (from
     opacityclass.get_opacities), per-layer multipliers, Raman inputs, clouds.  Returns (args, memspace, keep): `keep`
     holds the host arrays whose addresses were taken and must outlive the call; `into` fills an existing struct (the
@@ -376,7 +377,19 @@ def _fill_opacity_args(atm, opa, stream, delta_eddington, raman, fthin_cld, do_h
     cloud = atm.layer.get("cloud") if isinstance(atm.layer, dict) else atm.layer["cloud"]
     memspace = PB_DEVICE if device_outputs else PB_HOST
     tmp_dev = []
-    if cloud is not None and np.any(np.asarray(cloud["opd"]) != 0):
+    a.test_mode = 0
+    if test_mode not in (None, False):
+        # optics.py:372-399: 'rayleigh', or anything else = cloud-only.  The reference replaces non-positive cloud
+        # single-scattering albedos by 1e-10 in the atmosphere's own array (:393); so does this mirror.
+        a.test_mode = 1 if test_mode == "rayleigh" else 2
+        if cloud is None:
+            raise TypeError("compute_opacity test modes read atmosphere.layer['cloud'] (optics.py:386-395)")
+        w0c = cloud["w0"]
+        if isinstance(w0c, np.ndarray) and w0c.flags.writeable:
+            w0c[w0c <= 0] = 1e-10
+        else:
+            cloud = dict(cloud, w0=np.where(np.asarray(w0c, dtype=np.float64) <= 0, 1e-10, w0c))
+    if cloud is not None and (a.test_mode or np.any(np.asarray(cloud["opd"]) != 0)):
         cl = [np.asarray(cloud[k], dtype=np.float64) for k in ("opd", "w0", "g0")]
         cl = [c if (c.shape == (L, W) and c.flags.c_contiguous) else
               np.ascontiguousarray(np.broadcast_to(c, (L, W))) for c in cl]
@@ -412,9 +425,11 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
     per connection, or of ``opacityclass.raman_pollack_table = (w, f)`` if that is set.
     ``full_output=True`` sets ``atmosphere.taugas / tauray / taucld`` ([nlayer, nwno, 1] numpy arrays) like the
     reference (optics.py:322-325).
-    Not supported on this path: test_mode strings, plot_opacity, return_mode (host-side diagnostics).
+    ``test_mode='rayleigh'`` / any other string: the reference's test modes (optics.py:372-399) inside the same kernel;
+    like the reference they replace non-positive ``layer['cloud']['w0']`` entries by 1e-10 in the caller's array.
     ``test_mode`` None/False both mean "normal run": the reference's own default False would enter its test
-    branch (optics.py:372), real callers pass None."""
+    branch (optics.py:372), real callers pass None.
+    Not supported on this path: plot_opacity, return_mode (host-side plotting)."""
     from .optics_ck import DeviceCKs, compute_opacity_ck
     if not isinstance(opacityclass, (DeviceOpacities, DeviceCKs)):
         raise TypeError("picaso_b200.compute_opacity needs a DeviceOpacities or DeviceCKs connection")
@@ -422,18 +437,19 @@ def compute_opacity(atmosphere, opacityclass, ngauss=1, stream=2, delta_eddingto
         raise ValueError("monochromatic DeviceOpacities have ngauss = 1")
     if isinstance(opacityclass, DeviceCKs) and ngauss != opacityclass.ngauss:
         raise ValueError("ngauss must equal the number of gauss points of the DeviceCKs table")
-    if test_mode not in (None, False):
-        raise NotImplementedError("compute_opacity test modes are not implemented on the GPU path")
     if plot_opacity or return_mode:
         raise NotImplementedError("plot_opacity / return_mode are host-side diagnostics")
     opa, atm = opacityclass, atmosphere
     if isinstance(opa, DeviceCKs):
+        if test_mode not in (None, False):
+            raise NotImplementedError("compute_opacity test modes are implemented for monochromatic opacities (ngauss = 1)")
         import copy
         atm_ck = copy.copy(atm)
         atm_ck.molecules = []   # pre-mixed tables already contain every molecule (optics.py:257-262)
         return compute_opacity_ck(atm_ck, opa, stream, delta_eddington, raman, fthin_cld, do_holes,
                                   device_outputs, outputs)
-    a, memspace, keep = _fill_opacity_args(atm, opa, stream, delta_eddington, raman, fthin_cld, do_holes, device_outputs)
+    a, memspace, keep = _fill_opacity_args(atm, opa, stream, delta_eddington, raman, fthin_cld, do_holes, device_outputs,
+                                           test_mode=test_mode)
     ctx = opa.ctx
     L, W = atm.c.nlayer, opa.nwno
     want = set(OUTPUT_NAMES if outputs is None else outputs)

@@ -104,6 +104,28 @@ def test_reflected_spectrum_one_call(name):
     opa.close()
 
 
+@pytest.mark.parametrize("dev", [False, True])
+@pytest.mark.parametrize("mode", ["rayleigh", "constant_tau"])
+@pytest.mark.parametrize("name", ["opt_linear_raman", "opt_nearest_noraman"])
+def test_compute_opacity_test_modes(name, mode, dev):
+    """compute_opacity(test_mode='rayleigh' | other) (optics.py:372-399) inside the opacity kernel, against the unmodified
+    reference (tests/golden/testmode.npz); the caller's cloud w0 array gets the reference's <= 0 -> 1e-10 replacement"""
+    from util import golden
+    g = golden("testmode")
+    case, _, db, atm, ins = load_case(name)
+    atm["cloud_w0"][::3, ::5] = 0.0
+    opa = device_opacities(pb, dict(case, raman=2), db, ins)
+    a = duck_atmosphere(db, atm)
+    opa.get_opacities(a)
+    res = pb.compute_opacity(a, opa, ngauss=1, stream=case["stream"], delta_eddington=case["dedd"], test_mode=mode,
+                             raman=2, device_outputs=dev)
+    for n, arr in zip(OUT_NAMES, res):
+        got = arr.numpy() if dev else arr[:, :, 0]
+        assert_close(got, g[f"{name}/{mode}/{n}"], 1e-12, "%s test_mode=%s %s" % (name, mode, n))
+    assert np.array_equal(a.layer["cloud"]["w0"], g[f"{name}/{mode}/cloud_w0_after"])
+    opa.close()
+
+
 def test_pollack_raman_and_full_output(tmp_path, monkeypatch):
     """raman=1 ('pollack', the reference's config default) and full_output=True through the public mirror: the table
     comes from $picaso_refdata/opacities/raman_fortran.txt like the reference's (optics.py:652); golden vectors from

@@ -76,3 +76,27 @@ def test_pollack_raman_and_full_output():
         assert_close(arr, g["out/" + n], 1e-11, "pollack " + n)
     for n in ("taugas", "tauray", "taucld"):
         assert_close(full[n], g["full/" + n], 1e-11, "full_output " + n)
+
+
+@pytest.mark.parametrize("mode", ["rayleigh", "constant_tau"])
+@pytest.mark.parametrize("name", ["opt_linear_raman", "opt_nearest_noraman"])
+def test_compute_opacity_test_modes(name, mode):
+    """compute_opacity(test_mode=...) (optics.py:372-399): oracle against the unmodified reference
+    (tests/golden/make_golden_testmode.py), including the in-place w0 <= 0 -> 1e-10 replacement"""
+    from util import golden
+    g = golden("testmode")
+    case, _, db, atm, ins = load_case(name)
+    atm["cloud_w0"][::3, ::5] = 0.0
+    pbar = atm["player"] / atm["pconv"]
+    if case["query"] == "linear":
+        ti, pi, ill, ihl, ilh, ihh = oo.find_needed_pts(db["temps"], db["pressures"], db["nc_p"], atm["tlayer"], pbar)
+        mol = {m: oo.interp_molecular(db["tables"][m], ti, pi, ill, ihl, ilh, ihh) for m in db["molecules"]}
+    else:
+        mol = {m: oo.nearest_molecular(db["tables"][m], oo.nearest_pt(db["pt_pairs"], atm["tlayer"], pbar)) for m in db["molecules"]}
+    ic = oo.nearest_cia_temp(db["cia_temps"], atm["tlayer"])
+    cont = {k: db["continuum"][k][ic] for k in db["continuum"]}
+    res = oo.compute_opacity(atm, mol, cont, ins["rayleigh"], None, stream=case["stream"], delta_eddington=case["dedd"],
+                             test_mode=mode)
+    for n, arr in zip(OUT_NAMES, res):
+        assert_close(arr, g[f"{name}/{mode}/{n}"], 1e-12, "%s test_mode=%s %s" % (name, mode, n))
+    assert np.array_equal(atm["cloud_w0"], g[f"{name}/{mode}/cloud_w0_after"])
