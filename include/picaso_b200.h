@@ -348,6 +348,35 @@ typedef struct pb_spectrum_args {
 
 int pb_spectrum_reflected(pb_ctx *ctx, pb_optab *tab, const pb_spectrum_args *args);
 
+/* The same for thermal emission (justdoit.py:243, :337-342, :567: compute_opacity -> get_thermal_1d on DTAU_OG,
+ * W0_no_raman, COSB_OG -> compress_thermal) and for transmission (:243, :388-396: compute_opacity -> get_transit_1d
+ * on DTAU_OG).  `opacity` as for pb_spectrum_reflected; the remaining fields are those of pb_thermal_args /
+ * pb_transit_args with nbatch = 1. */
+typedef struct pb_spectrum_thermal_args {
+    pb_opacity_args opacity;
+    int nwno, numg, numt;
+    const double *tlevel, *plevel;            /* host [nlevel] */
+    const double *ubar1, *gweight, *tweight;  /* host */
+    const double *wno;                        /* DEVICE [nwno] */
+    const double *surf_reflect;               /* DEVICE [nwno] or NULL (= 0) */
+    int hard_surface;
+    double *thermal;      /* host [nwno] */
+    double *flux_at_top;  /* host [numg*numt][nwno] or NULL */
+} pb_spectrum_thermal_args;
+
+int pb_spectrum_thermal(pb_ctx *ctx, pb_optab *tab, const pb_spectrum_thermal_args *args);
+
+typedef struct pb_spectrum_transit_args {
+    pb_opacity_args opacity;
+    int nwno;
+    const double *z, *dz, *player, *tlayer;   /* host [nlevel] (level pressures / temperatures, justdoit.py:394-395) */
+    const double *mmw, *colden;               /* host [nlayer] */
+    double rstar, k_b, amu;
+    double *F;            /* host [nwno]: (rp/rs)^2 */
+} pb_spectrum_transit_args;
+
+int pb_spectrum_transit(pb_ctx *ctx, pb_optab *tab, const pb_spectrum_transit_args *args);
+
 /* ---- resort-rebin mixing of per-gas correlated-k tables ----------------------------------
  * Replaces deq_chem.mix_all_gases_gasesfly / do_mixing_mono_gasesfly / mix_2_gases
  * (deq_chem.py:334-386, :388-432, :538-597) and the interpolation + exp * N_A of

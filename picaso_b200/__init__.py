@@ -12,7 +12,8 @@ from ._lib import PicasoB200Error, Context, default_context, load_library  # noq
 from .fluxes import get_reflected_1d, get_reflected_SH, get_thermal_1d, get_transit_1d  # noqa: F401
 from .fluxes_sh_thermal import get_thermal_SH  # noqa: F401
 from .fluxes_3d import get_reflected_3d, get_thermal_3d  # noqa: F401
-from .optics import DeviceArray, DeviceOpacities, compute_opacity, reflected_spectrum  # noqa: F401
+from .optics import (DeviceArray, DeviceOpacities, compute_opacity, reflected_spectrum, thermal_spectrum,  # noqa: F401
+                     transit_spectrum)
 from .optics_ck import DeviceCKs, DeviceGasCKs  # noqa: F401
 from .opacity_db import opannection, read_opacity_db  # noqa: F401
 from .climate import get_fluxes, get_fluxes_jacobian, BoundFluxes  # noqa: F401

@@ -87,6 +87,18 @@ class SpectrumArgs(ctypes.Structure):
                 [("albedo", c_vp), ("xint_at_top", c_vp)])
 
 
+class SpectrumThermalArgs(ctypes.Structure):
+    _fields_ = ([("opacity", OpacityArgs), ("nwno", c_int), ("numg", c_int), ("numt", c_int)] +
+                [(n, c_vp) for n in ("tlevel", "plevel", "ubar1", "gweight", "tweight", "wno", "surf_reflect")] +
+                [("hard_surface", c_int), ("thermal", c_vp), ("flux_at_top", c_vp)])
+
+
+class SpectrumTransitArgs(ctypes.Structure):
+    _fields_ = ([("opacity", OpacityArgs), ("nwno", c_int)] +
+                [(n, c_vp) for n in ("z", "dz", "player", "tlayer", "mmw", "colden")] +
+                [(n, c_dbl) for n in ("rstar", "k_b", "amu")] + [("F", c_vp)])
+
+
 class CkMixArgs(ctypes.Structure):
     _fields_ = ([(n, c_int) for n in ("nlayer", "nwno", "ngauss", "ngas", "np", "nt")] +
                 [(n, c_vp) for n in ("kappas", "mixes", "indices", "t_interp", "p_interp", "gauss_pts", "gauss_wts",
@@ -160,6 +172,8 @@ SYMBOLS = {
     "pb_peer_signal": (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.c_ulonglong]),
     "pb_peer_flush": (c_int, [c_vp, c_vp, c_int]),
     "pb_spectrum_reflected": (c_int, [c_vp, c_vp, c_vp]),
+    "pb_spectrum_thermal": (c_int, [c_vp, c_vp, c_vp]),
+    "pb_spectrum_transit": (c_int, [c_vp, c_vp, c_vp]),
     "pb_selftest_exp_tab": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "pb_optab_create": (c_int, [c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
     "pb_optab_destroy": (c_int, [c_vp, c_vp]),

@@ -547,6 +547,75 @@ extern "C" int pb_spectrum_reflected(pb_ctx *ctx, pb_optab *tab, const pb_spectr
     return PB_OK;
 }
 
+extern "C" int pb_spectrum_thermal(pb_ctx *ctx, pb_optab *tab, const pb_spectrum_thermal_args *a)
+{
+    if (!ctx || !tab || !a) return PB_ERR_ARG;
+    const int L = a->opacity.nlayer, W = a->nwno, G = a->numg * a->numt;
+    if (L < 1 || W < 1 || G < 1) return pb_fail(ctx, PB_ERR_ARG, "spectrum_thermal: bad sizes L=%d W=%d G=%d", L, W, G);
+    if (a->opacity.ngauss > 1) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "spectrum_thermal: correlated-k tables (ngauss > 1) go through pb_compute_opacity + one flux call per gauss point");
+    if (!a->thermal || !a->tlevel || !a->plevel || !a->ubar1 || !a->gweight || !a->tweight || !a->wno)
+        return pb_fail(ctx, PB_ERR_ARG, "spectrum_thermal: thermal, tlevel, plevel, ubar1, gweight, tweight, wno are required");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nLW = pb_align((size_t)L * W * sizeof(double)), nW = (size_t)W * sizeof(double);
+    PB_TRY(aux_reserve(ctx, 3 * nLW + pb_align(nW) + pb_align((size_t)G * nW) + 256));
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> double * {
+        double *ptr = (double *)(ctx->aux + off);
+        off += pb_align(bytes);
+        return ptr;
+    };
+    pb_opacity_args o = a->opacity;
+    o.DTAU = o.TAU = o.W0 = o.COSB = o.ftau_cld = o.ftau_ray = o.GCOS2 = o.TAU_OG = o.W0_OG = o.f_deltaM = nullptr;
+    o.TAUGAS = o.TAURAY = o.TAUCLD = nullptr;
+    o.DTAU_OG = take(nLW); o.W0_no_raman = take(nLW); o.COSB_OG = take(nLW);
+    double *d_th = take(nW), *d_ft = a->flux_at_top ? take((size_t)G * nW) : nullptr;
+    PB_TRY(pb_compute_opacity(ctx, tab, &o, PB_DEVICE));
+    pb_thermal_args t;
+    memset(&t, 0, sizeof(t));
+    t.nlayer = L; t.nwno = W; t.numg = a->numg; t.numt = a->numt; t.nbatch = 1; t.ld = W;
+    t.dtau = o.DTAU_OG; t.w0 = o.W0_no_raman; t.cosb = o.COSB_OG;   // justdoit.py:337-342
+    t.wno = a->wno; t.dwno = nullptr; t.surf_reflect = a->surf_reflect;
+    t.tlevel = a->tlevel; t.plevel = a->plevel;
+    t.ubar1 = a->ubar1; t.gweight = a->gweight; t.tweight = a->tweight;
+    t.hard_surface = a->hard_surface; t.calc_type = 0;
+    t.thermal = d_th; t.flux_at_top = d_ft;
+    PB_TRY(pb_thermal_toon_1d(ctx, &t, PB_DEVICE));
+    PB_CUDA(ctx, cudaMemcpyAsync(a->thermal, d_th, nW, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_ft) PB_CUDA(ctx, cudaMemcpyAsync(a->flux_at_top, d_ft, (size_t)G * nW, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+extern "C" int pb_spectrum_transit(pb_ctx *ctx, pb_optab *tab, const pb_spectrum_transit_args *a)
+{
+    if (!ctx || !tab || !a) return PB_ERR_ARG;
+    const int L = a->opacity.nlayer, W = a->nwno;
+    if (L < 1 || W < 1) return pb_fail(ctx, PB_ERR_ARG, "spectrum_transit: bad sizes L=%d W=%d", L, W);
+    if (a->opacity.ngauss > 1) return pb_fail(ctx, PB_ERR_UNSUPPORTED, "spectrum_transit: correlated-k tables (ngauss > 1) go through pb_compute_opacity + one call per gauss point");
+    if (!a->F || !a->z || !a->dz || !a->player || !a->tlayer || !a->mmw || !a->colden)
+        return pb_fail(ctx, PB_ERR_ARG, "spectrum_transit: F, z, dz, player, tlayer, mmw, colden are required");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nLW = pb_align((size_t)L * W * sizeof(double)), nW = (size_t)W * sizeof(double);
+    PB_TRY(aux_reserve(ctx, nLW + pb_align(nW) + 256));
+    pb_opacity_args o = a->opacity;
+    o.DTAU = o.TAU = o.W0 = o.COSB = o.ftau_cld = o.ftau_ray = o.GCOS2 = o.TAU_OG = o.W0_OG = o.COSB_OG = nullptr;
+    o.W0_no_raman = o.f_deltaM = o.TAUGAS = o.TAURAY = o.TAUCLD = nullptr;
+    o.DTAU_OG = (double *)ctx->aux;
+    double *d_F = (double *)(ctx->aux + nLW);
+    PB_TRY(pb_compute_opacity(ctx, tab, &o, PB_DEVICE));
+    pb_transit_args t;
+    memset(&t, 0, sizeof(t));
+    t.nlevel = L + 1; t.nwno = W; t.nbatch = 1; t.ld = W;
+    t.DTAU = o.DTAU_OG;                                              // justdoit.py:392-396
+    t.z = a->z; t.dz = a->dz; t.player = a->player; t.tlayer = a->tlayer; t.mmw = a->mmw; t.colden = a->colden;
+    t.rstar = a->rstar; t.k_b = a->k_b; t.amu = a->amu;
+    t.F = d_F;
+    PB_TRY(pb_transit_1d(ctx, &t, PB_DEVICE));
+    PB_CUDA(ctx, cudaMemcpyAsync(a->F, d_F, nW, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
 // ---- bound calls (numba nopython -> ctypes) -------------------------------------------------------------
 namespace {
 struct BoundCall { pb_ctx *ctx; pb_climate_args args; int memspace; bool live; };

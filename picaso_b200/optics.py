@@ -539,3 +539,74 @@ def reflected_spectrum(atmosphere, opacityclass, ubar0, ubar1, cos_theta, gweigh
     sa.albedo, sa.xint_at_top = addr(alb), addr(xint)
     ctx.check(ctx.lib.pb_spectrum_reflected(ctx.h, opa._tab, ctypes.byref(sa)))
     return (alb, xint) if return_xint else alb
+
+
+def _wno_on_device(opa):
+    """the connection's wavenumber grid in HBM (uploaded once): pb_thermal_toon_1d reads it with PB_DEVICE"""
+    d = getattr(opa, "_wno_dev", None)
+    if d is None:
+        d = DeviceArray.from_numpy(opa.ctx, opa.wno)
+        opa._wno_dev = d
+    return d.ptr
+
+
+def thermal_spectrum(atmosphere, opacityclass, ubar1, gweight, tweight, *, surf_reflect=None, hard_surface=0, stream=2,
+                     delta_eddington=True, raman=2, fthin_cld=None, do_holes=False, return_flux=False):
+    """One call per thermal-emission spectrum (pb_spectrum_thermal): compute_opacity -> get_thermal_1d on DTAU_OG,
+    W0_no_raman, COSB_OG -> compress_thermal, as picaso() chains them (justdoit.py:243, :337-342, :567); temperatures and
+    pressures are ``atmosphere.level``'s.  Call ``opacityclass.get_opacities(atmosphere)`` first.  Returns thermal[nwno]
+    (and flux_at_top[ng, nt, nwno] with ``return_flux=True``)."""
+    from ._lib import SpectrumThermalArgs
+    opa, atm = opacityclass, atmosphere
+    if not isinstance(opa, DeviceOpacities):
+        raise TypeError("thermal_spectrum needs a DeviceOpacities connection")
+    sa = SpectrumThermalArgs()
+    _, _, keep = _fill_opacity_args(atm, opa, stream, delta_eddington, raman, fthin_cld, do_holes, True, into=sa.opacity)
+    ctx, W = opa.ctx, opa.nwno
+    u1 = np.ascontiguousarray(ubar1, dtype=np.float64)
+    ng, nt = u1.shape if u1.ndim == 2 else (u1.size, 1)
+    u1 = u1.reshape(-1)
+    gw = np.ascontiguousarray(gweight, dtype=np.float64)
+    tw = np.ascontiguousarray(tweight, dtype=np.float64)
+    tl = np.ascontiguousarray(atm.level["temperature"], dtype=np.float64)
+    pl = np.ascontiguousarray(atm.level["pressure"], dtype=np.float64)
+    sa.nwno, sa.numg, sa.numt = W, ng, nt
+    sa.tlevel, sa.plevel, sa.ubar1, sa.gweight, sa.tweight = addr(tl), addr(pl), addr(u1), addr(gw), addr(tw)
+    sa.wno = _wno_on_device(opa)
+    sa.surf_reflect = None
+    if surf_reflect is not None and not (np.isscalar(surf_reflect) and surf_reflect == 0):
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(surf_reflect, dtype=np.float64), (W,)))
+        d = opa._buffer("spectrum_thermal_surf", (W,))
+        ctx.check(ctx.lib.pb_memcpy_h2d(ctx.h, d.ptr, v.ctypes.data, v.nbytes))
+        ctx.sync()
+        sa.surf_reflect = d.ptr
+    sa.hard_surface = int(hard_surface)
+    th = np.empty(W)
+    ft = np.empty((ng, nt, W)) if return_flux else None
+    sa.thermal, sa.flux_at_top = addr(th), addr(ft)
+    ctx.check(ctx.lib.pb_spectrum_thermal(ctx.h, opa._tab, ctypes.byref(sa)))
+    return (th, ft) if return_flux else th
+
+
+def transit_spectrum(atmosphere, opacityclass, rstar, *, z=None, dz=None, stream=2, delta_eddington=True, raman=2,
+                     fthin_cld=None, do_holes=False):
+    """One call per transmission spectrum (pb_spectrum_transit): compute_opacity -> get_transit_1d on DTAU_OG
+    (justdoit.py:243, :388-396).  z / dz default to ``atmosphere.level['z']`` / ``['dz']``; like picaso() the LEVEL
+    pressures and temperatures are what get_transit_1d receives.  Returns (rp/rs)^2 [nwno]."""
+    from ._lib import SpectrumTransitArgs
+    opa, atm = opacityclass, atmosphere
+    if not isinstance(opa, DeviceOpacities):
+        raise TypeError("transit_spectrum needs a DeviceOpacities connection")
+    sa = SpectrumTransitArgs()
+    _, _, keep = _fill_opacity_args(atm, opa, stream, delta_eddington, raman, fthin_cld, do_holes, True, into=sa.opacity)
+    ctx, W = opa.ctx, opa.nwno
+    vec = [np.ascontiguousarray(x, dtype=np.float64) for x in (
+        atm.level["z"] if z is None else z, atm.level["dz"] if dz is None else dz, atm.level["pressure"],
+        atm.level["temperature"], atm.layer["mmw"], atm.layer["colden"])]
+    sa.nwno = W
+    sa.z, sa.dz, sa.player, sa.tlayer, sa.mmw, sa.colden = [addr(v) for v in vec]
+    sa.rstar, sa.k_b, sa.amu = float(rstar), float(atm.c.k_b), float(atm.c.amu)
+    F = np.empty(W)
+    sa.F = addr(F)
+    ctx.check(ctx.lib.pb_spectrum_transit(ctx.h, opa._tab, ctypes.byref(sa)))
+    return F

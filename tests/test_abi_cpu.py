@@ -51,7 +51,8 @@ def test_ctypes_structs_match_the_compiled_header(tmp_path):
     pairs = {"pb_reflected_args": _lib.ReflectedArgs, "pb_thermal_args": _lib.ThermalArgs,
              "pb_transit_args": _lib.TransitArgs, "pb_sh_args": _lib.ShArgs, "pb_thermal_sh_args": _lib.ThermalShArgs,
              "pb_opacity_args": _lib.OpacityArgs, "pb_ck_mix_args": _lib.CkMixArgs, "pb_climate_args": _lib.ClimateArgs,
-             "pb_peer_gather": _lib.PeerGather, "pb_spectrum_args": _lib.SpectrumArgs}
+             "pb_peer_gather": _lib.PeerGather, "pb_spectrum_args": _lib.SpectrumArgs,
+             "pb_spectrum_thermal_args": _lib.SpectrumThermalArgs, "pb_spectrum_transit_args": _lib.SpectrumTransitArgs}
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "picaso_b200.h"\nint main(void){\n' +
                    "".join('printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in pairs) + "return 0;}\n")

@@ -104,6 +104,38 @@ def test_reflected_spectrum_one_call(name):
     opa.close()
 
 
+@pytest.mark.parametrize("name", ["opt_linear_raman", "opt_nearest_noraman", "opt_linear_clear_nodedd"])
+def test_thermal_and_transit_spectrum_one_call(name):
+    """pb_spectrum_thermal / pb_spectrum_transit return the bits of compute_opacity(device_outputs=True) ->
+    get_thermal_1d(return_thermal=True) / get_transit_1d on the arrays picaso() passes (justdoit.py:337-342, :388-396)"""
+    case, g, db, atm, ins = load_case(name)
+    opa = device_opacities(pb, case, db, ins)
+    a = duck_atmosphere(db, atm)
+    L, W = atm["nlayer"], db["nwno"]
+    gangle, gweight, tangle, tweight, ubar0, ubar1, cos_theta = synth.geometry_1d(5, 0.0)
+    z = np.linspace(8.0e9, 7.0e9, L + 1)
+    dz = np.full(L + 1, (z[0] - z[1]))
+    a.level["z"], a.level["dz"] = z, dz
+    rng = np.random.default_rng(9)
+    for surf, hard in ((None, 0), (0.3 * rng.random(W), 1)):
+        opa.get_opacities(a)
+        dev = pb.compute_opacity(a, opa, stream=case["stream"], delta_eddington=case["dedd"], test_mode=None,
+                                 raman=case["raman"], device_outputs=True)
+        DTAU_OG, COSB_OG, W0_no_raman = dev[7][:, :, 0], dev[10][:, :, 0], dev[11][:, :, 0]
+        ft0, _, th0 = pb.get_thermal_1d(L + 1, db["wno"], W, 5, 1, atm["tlevel"], DTAU_OG, W0_no_raman, COSB_OG,
+                                        atm["plevel"], ubar1, 0 if surf is None else surf, hard, db["wno"] * 0, 0,
+                                        level_fluxes=False, gweight=gweight, tweight=tweight, return_thermal=True)
+        F0 = pb.get_transit_1d(z, dz, L + 1, W, 6.957e10, atm["mmw"], atm["k_b"], atm["amu"], atm["plevel"], atm["tlevel"],
+                               atm["colden"], DTAU_OG)
+        opa.get_opacities(a)
+        th, ft = pb.thermal_spectrum(a, opa, ubar1, gweight, tweight, surf_reflect=surf, hard_surface=hard,
+                                     stream=case["stream"], delta_eddington=case["dedd"], raman=case["raman"], return_flux=True)
+        assert np.array_equal(th, th0) and np.array_equal(ft, ft0)
+        F = pb.transit_spectrum(a, opa, 6.957e10, stream=case["stream"], delta_eddington=case["dedd"], raman=case["raman"])
+        assert np.array_equal(F, F0)
+    opa.close()
+
+
 @pytest.mark.parametrize("dev", [False, True])
 @pytest.mark.parametrize("mode", ["rayleigh", "constant_tau"])
 @pytest.mark.parametrize("name", ["opt_linear_raman", "opt_nearest_noraman"])
