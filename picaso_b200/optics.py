@@ -29,10 +29,17 @@ OUTPUT_NAMES = ("DTAU", "TAU", "W0", "COSB", "ftau_cld", "ftau_ray", "GCOS2", "D
 _LEVEL = {"TAU", "TAU_OG"}
 
 
-def find_needed_pts_grid(t_inv_grid, p_log_grid, nc_p, tlayer, player):
+def grid_is_monotonic(t_inv_grid, p_log_grid):
+    """(1/T grid strictly descending, log10 P grid strictly ascending): what every table of the reference looks like"""
+    return (bool(t_inv_grid.size > 1 and np.all(t_inv_grid[1:] < t_inv_grid[:-1])),
+            bool(p_log_grid.size > 1 and np.all(p_log_grid[1:] > p_log_grid[:-1])))
+
+
+def find_needed_pts_grid(t_inv_grid, p_log_grid, nc_p, tlayer, player, monotonic=None):
     """RetrieveOpacities.find_needed_pts (picaso/optics.py:2048-2123) for all layers at once: the bilinear
     neighbours in (1/T, log10 P) of every layer on a (T-major, P-minor, possibly ragged) table grid.
-    Returns t_interp[:, None], p_interp[:, None] and the four 0-based row indices (ll, hl, lh, hh)."""
+    Returns t_interp[:, None], p_interp[:, None] and the four 0-based row indices (ll, hl, lh, hh).
+    `monotonic` = grid_is_monotonic(...) if the caller has it cached."""
     t_inv = 1 / np.asarray(tlayer, dtype=np.float64)
     p_log = np.log10(np.asarray(player, dtype=np.float64))
     nT = t_inv_grid.size
@@ -42,11 +49,20 @@ def find_needed_pts_grid(t_inv_grid, p_log_grid, nc_p, tlayer, player):
         n = mask.shape[1]
         return np.where(mask.any(axis=1), n - 1 - np.argmax(mask[:, ::-1], axis=1), 0)
 
-    # last grid temperature strictly below T, last grid pressure <= P
-    t_low = last_true(t_inv_grid[None, :] > t_inv[:, None])
+    # last grid temperature strictly below T (1/T grid entry > 1/T), last grid pressure <= P.  On monotonic grids (every
+    # table of the reference: temperatures ascending = 1/T descending, pressures ascending) a binary search counts the
+    # entries that satisfy the comparison - the same comparisons, hence the same indices, as the masks
+    t_mono, p_mono = grid_is_monotonic(t_inv_grid, p_log_grid) if monotonic is None else monotonic
+    if t_mono:
+        t_low = np.maximum(np.searchsorted(-t_inv_grid, -t_inv, side="left") - 1, 0)
+    else:
+        t_low = last_true(t_inv_grid[None, :] > t_inv[:, None])
     t_low = np.where(t_low == nT - 1, nT - 2, t_low)
     t_hi = t_low + 1
-    p_low = last_true(p_log_grid[None, :] <= p_log[:, None])
+    if p_mono:
+        p_low = np.maximum(np.searchsorted(p_log_grid, p_log, side="right") - 1, 0)
+    else:
+        p_low = last_true(p_log_grid[None, :] <= p_log[:, None])
     p_low = np.minimum(p_low, nc_p[t_hi] - 3)
     p_hi = p_low + 1
     off = np.concatenate([[0], np.cumsum(nc_p)])
@@ -226,7 +242,10 @@ class DeviceOpacities:
     def find_needed_pts(self, tlayer, player):
         """bilinear neighbours in (1/T, log10 P); same return convention as the reference:
         t_interp[:,None], p_interp[:,None], and the four 0-based row indices."""
-        return find_needed_pts_grid(self.t_inv_grid, self.p_log_grid, self.nc_p, tlayer, player)
+        mono = self.__dict__.get("_grid_mono")
+        if mono is None:
+            mono = self._grid_mono = grid_is_monotonic(self.t_inv_grid, self.p_log_grid)
+        return find_needed_pts_grid(self.t_inv_grid, self.p_log_grid, self.nc_p, tlayer, player, monotonic=mono)
 
     def get_opacities(self, atmosphere, exclude_mol=1):
         """Record the table rows / weights for this atmosphere; nothing is fetched or copied.
@@ -234,22 +253,24 @@ class DeviceOpacities:
         tlayer = np.asarray(atmosphere.layer["temperature"], dtype=np.float64)
         pbar = np.asarray(atmosphere.layer["pressure"], dtype=np.float64) / atmosphere.c.pconv
         L = tlayer.size
-        idx = np.zeros((L, 4), dtype=np.int32)
-        wts = np.zeros((L, 4))
         if self.query_method == "linear":
             t, p, ill, ihl, ilh, ihh = self.find_needed_pts(tlayer, pbar)
             t, p = t[:, 0], p[:, 0]
-            idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3] = ill, ihl, ihh, ilh
-            wts[:, 0], wts[:, 1], wts[:, 2], wts[:, 3] = (1 - t) * (1 - p), t * (1 - p), t * p, (1 - t) * p
-            atmosphere.layer["pt_opa_index"] = 1 + np.unique(np.concatenate([ill, ihl, ilh, ihh]))
+            idx = np.stack([ill, ihl, ihh, ilh], axis=1).astype(np.int32)
+            t1, p1 = 1 - t, 1 - p
+            wts = np.stack([t1 * p1, t * p1, t * p, t1 * p], axis=1)
+            atmosphere.layer["pt_opa_index"] = 1 + np.unique(idx).astype(np.int64)
         else:
+            idx = np.zeros((L, 4), dtype=np.int32)
+            wts = np.zeros((L, 4))
             rows = np.argmin(np.hypot(self._lnP[None, :] - np.log(pbar)[:, None], self._T[None, :] - tlayer[:, None]), axis=1)
             idx[:, 0] = rows
             atmosphere.layer["pt_opa_index"] = [int(self._ptid[r]) for r in rows]
         cia = np.abs(self._cia_unique[None, :] - tlayer[:, None]).argmin(axis=1).astype(np.int32)
-        fac = {}
-        for m in atmosphere.molecules:
-            fac[m] = 1 if (np.isscalar(exclude_mol) and exclude_mol == 1) else exclude_mol[m]
+        if np.isscalar(exclude_mol) and exclude_mol == 1:
+            fac = dict.fromkeys(atmosphere.molecules, 1)
+        else:
+            fac = {m: exclude_mol[m] for m in atmosphere.molecules}
         self._plan = dict(idx=idx, wts=wts, cia=cia, fac=fac, nlayer=L)
         # the reference exposes dicts of [nlayer, nwno] arrays here; on this path they never exist
         self.molecular_opa = None
@@ -271,7 +292,10 @@ class DeviceOpacities:
 
 
 def _layer_scalars(atm, opa):
-    """per-layer multipliers exactly as compute_opacity parenthesises them (optics.py:147-271)."""
+    """per-layer multipliers exactly as compute_opacity parenthesises them (optics.py:147-271).  The species of a
+    group (molecules, Rayleigh scatterers, CIA pairs) are stacked so that each group costs one numpy expression -
+    elementwise the same operations in the same order as the per-species statements of the reference
+    (tests/test_host_plan_cpu.py holds the result to the statement-per-species version bit for bit)."""
     L = atm.c.nlayer
     tlevel = np.asarray(atm.level["temperature"], dtype=np.float64)
     plevel = np.asarray(atm.level["pressure"], dtype=np.float64) / atm.c.pconv
@@ -282,36 +306,44 @@ def _layer_scalars(atm, opa):
     player = np.asarray(atm.layer["pressure"], dtype=np.float64)
     mix = atm.layer["mixingratios"]
     x = lambda s: np.asarray(mix[s].values if hasattr(mix[s], "values") else mix[s], dtype=np.float64)
-    ACOEF = (tlayer / (tlevel[:-1] * tlevel[1:])) * (
-        tlevel[1:] * plevel[1:] - tlevel[:-1] * plevel[:-1]) / (plevel[1:] - plevel[:-1])
-    BCOEF = (tlayer / (tlevel[:-1] * tlevel[1:])) * (tlevel[:-1] - tlevel[1:]) / (plevel[1:] - plevel[:-1])
+    t0, t1, p0, p1 = tlevel[:-1], tlevel[1:], plevel[:-1], plevel[1:]
+    dp = p1 - p0
+    tt = tlayer / (t0 * t1)
+    ACOEF = tt * (t1 * p1 - t0 * p0) / dp
+    BCOEF = tt * (t0 - t1) / dp
     COEF1 = atm.c.rgas * 273.15 ** 2 * .5E5 * (
-        ACOEF * (plevel[1:] ** 2 - plevel[:-1] ** 2) + BCOEF * (2. / 3.) * (plevel[1:] ** 3 - plevel[:-1] ** 3)) / (
+        ACOEF * (p1 ** 2 - p0 ** 2) + BCOEF * (2. / 3.) * (p1 ** 3 - p0 ** 3)) / (
         1.01325 ** 2 * gravity * tlayer * mmw)
     cont = np.zeros((len(opa._cont_index), L))
-    used = set()
+    cia_rows, cia_a, cia_b = [], [], []
     for m in atm.continuum_molecules:
         key = m[0] + m[1]
         if key not in opa._cont_index:
             raise KeyError(f"continuum pair {key} is not in the uploaded tables")
-        used.add(key)
         if m[0] == "H-" and m[1] == "bf":
-            s = (x("H-") * colden / (mmw * atm.c.amu))
+            cont[opa._cont_index[key]] = (x("H-") * colden / (mmw * atm.c.amu))
         elif m[0] == "H-" and m[1] == "ff":
-            s = (player * x("H") * np.asarray(atm.layer["electrons"]) * colden / (tlayer * mmw * atm.c.amu * atm.c.k_b))
+            cont[opa._cont_index[key]] = (player * x("H") * np.asarray(atm.layer["electrons"]) * colden /
+                                          (tlayer * mmw * atm.c.amu * atm.c.k_b))
         elif m[0] == "H2-" and m[1] == "":
-            s = (player * x("H2") * np.asarray(atm.layer["electrons"]) * colden / (mmw * atm.c.amu))
+            cont[opa._cont_index[key]] = (player * x("H2") * np.asarray(atm.layer["electrons"]) * colden / (mmw * atm.c.amu))
         else:
-            s = (COEF1 * x(m[0]) * x(m[1]))
-        cont[opa._cont_index[key]] = s
+            cia_rows.append(opa._cont_index[key])
+            cia_a.append(x(m[0]))
+            cia_b.append(x(m[1]))
+    if cia_rows:
+        cont[cia_rows] = (COEF1 * np.array(cia_a) * np.array(cia_b))
     mol = np.zeros((len(opa._mol_index), L))
-    for m in atm.molecules:
-        if m not in opa._mol_index:
-            raise KeyError(f"molecule {m} is not in the uploaded tables")
-        mol[opa._mol_index[m]] = opa._plan["fac"][m] * (colden * x(m) / mmw)
+    if len(atm.molecules):
+        for m in atm.molecules:
+            if m not in opa._mol_index:
+                raise KeyError(f"molecule {m} is not in the uploaded tables")
+        fac = np.array([opa._plan["fac"][m] for m in atm.molecules])[:, None]
+        mol[[opa._mol_index[m] for m in atm.molecules]] = fac * (colden * np.array([x(m) for m in atm.molecules]) / mmw)
     ray = np.zeros((len(opa._ray_index), L))
-    for m in atm.rayleigh_molecules:
-        ray[opa._ray_index[m]] = (colden * x(m) / mmw)
+    if len(atm.rayleigh_molecules):
+        ray[[opa._ray_index[m] for m in atm.rayleigh_molecules]] = (
+            colden * np.array([x(m) for m in atm.rayleigh_molecules]) / mmw)
     return mol, cont, ray
 
 
