@@ -326,6 +326,19 @@ typedef struct pb_opacity_args {
     int test_mode;
 } pb_opacity_args;
 
+/* Host-side planning of a bilinear opacity query, no device involved: replaces the per-layer loop of
+ * RetrieveOpacities.find_needed_pts + the index / weight bookkeeping of get_opacities (optics.py:2048-2123, :2265,
+ * :2269-2298).  t_inv = 1/T_layer and p_log = log10(P_layer [bar]) are formed by the caller; the grid is described as
+ * get_available_data does (optics.py:2019-2025): 1/T of the unique temperatures, log10 of the unique pressures, nc_p
+ * pressures per temperature, row_offset = [0, cumsum(nc_p)].  t_mono / p_mono: the 1/T grid is strictly descending /
+ * the pressure grid strictly ascending (binary search; otherwise the reference's "last True" scan).  Outputs are the
+ * pt_index / weights / cont_index arrays of pb_opacity_args and the sorted unique 1-based rows (layer['pt_opa_index']). */
+int pb_host_plan_bilinear(int nlayer, const double *t_inv, const double *p_log, const double *tlayer,
+                          int nT, const double *t_inv_grid, int nPg, const double *p_log_grid,
+                          const int64_t *nc_p, const int64_t *row_offset, int t_mono, int p_mono,
+                          int ncia, const double *cia_unique, int32_t *idx, double *wts, int32_t *cia,
+                          int64_t *rows_used, int *nrows_used);
+
 int pb_compute_opacity(pb_ctx *ctx, pb_optab *tab, const pb_opacity_args *args, int memspace);
 
 /* One call per spectrum: what picaso() does between `get_opacities(atm)` and `returns['albedo']` for a reflected-light

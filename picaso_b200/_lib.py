@@ -171,6 +171,8 @@ SYMBOLS = {
     "pb_climate_unbind": (c_int, [c_vp, c_int]),
     "pb_peer_signal": (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.c_ulonglong]),
     "pb_peer_flush": (c_int, [c_vp, c_vp, c_int]),
+    "pb_host_plan_bilinear": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp,
+                                      c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pb_spectrum_reflected": (c_int, [c_vp, c_vp, c_vp]),
     "pb_spectrum_thermal": (c_int, [c_vp, c_vp, c_vp]),
     "pb_spectrum_transit": (c_int, [c_vp, c_vp, c_vp]),

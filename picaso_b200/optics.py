@@ -253,20 +253,43 @@ class DeviceOpacities:
         tlayer = np.asarray(atmosphere.layer["temperature"], dtype=np.float64)
         pbar = np.asarray(atmosphere.layer["pressure"], dtype=np.float64) / atmosphere.c.pconv
         L = tlayer.size
+        cia = None
         if self.query_method == "linear":
-            t, p, ill, ihl, ilh, ihh = self.find_needed_pts(tlayer, pbar)
-            t, p = t[:, 0], p[:, 0]
-            idx = np.stack([ill, ihl, ihh, ilh], axis=1).astype(np.int32)
-            t1, p1 = 1 - t, 1 - p
-            wts = np.stack([t1 * p1, t * p1, t * p, t1 * p], axis=1)
-            atmosphere.layer["pt_opa_index"] = 1 + np.unique(idx).astype(np.int64)
+            # one host-side C call (csrc/host_plan.cu) instead of ~40 small numpy calls: same comparisons and IEEE
+            # operations as find_needed_pts_grid, bit-identical plan (tests/test_host_plan_cpu.py)
+            g = self.__dict__.get("_plan_grid")
+            if g is None or g["L"] != L:
+                tg = np.ascontiguousarray(self.t_inv_grid, dtype=np.float64)
+                pg = np.ascontiguousarray(self.p_log_grid, dtype=np.float64)
+                ncp = np.ascontiguousarray(self.nc_p, dtype=np.int64)
+                off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(ncp)]), dtype=np.int64)
+                cu = np.ascontiguousarray(self._cia_unique, dtype=np.float64)
+                t_mono, p_mono = grid_is_monotonic(tg, pg)
+                # output buffers of the plan are owned by the connection and reused by the next get_opacities call (the
+                # plan always describes the LAST atmosphere); their addresses are looked up once (ndarray.ctypes is slow)
+                out = (np.empty((L, 4), dtype=np.int32), np.empty((L, 4)), np.empty(L, dtype=np.int32),
+                       np.empty(4 * L, dtype=np.int64), ctypes.c_int(0))
+                g = self._plan_grid = dict(
+                    L=L, keep=(tg, pg, ncp, off, cu), out=out, fn=_lib.load_library().pb_host_plan_bilinear,
+                    static=(tg.size, tg.ctypes.data, pg.size, pg.ctypes.data, ncp.ctypes.data, off.ctypes.data, int(t_mono),
+                            int(p_mono), cu.size, cu.ctypes.data, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data,
+                            out[3].ctypes.data, ctypes.addressof(out[4])))
+            tl = np.ascontiguousarray(tlayer)
+            t_inv = 1 / tl
+            p_log = np.log10(pbar)
+            idx, wts, cia, rows, nrows = g["out"]
+            rc = g["fn"](L, t_inv.ctypes.data, p_log.ctypes.data, tl.ctypes.data, *g["static"])
+            if rc != 0:
+                raise _lib.PicasoB200Error("pb_host_plan_bilinear: bad table grid (needs >= 2 temperatures and pressures)")
+            atmosphere.layer["pt_opa_index"] = rows[:nrows.value].copy()
         else:
             idx = np.zeros((L, 4), dtype=np.int32)
             wts = np.zeros((L, 4))
             rows = np.argmin(np.hypot(self._lnP[None, :] - np.log(pbar)[:, None], self._T[None, :] - tlayer[:, None]), axis=1)
             idx[:, 0] = rows
             atmosphere.layer["pt_opa_index"] = [int(self._ptid[r]) for r in rows]
-        cia = np.abs(self._cia_unique[None, :] - tlayer[:, None]).argmin(axis=1).astype(np.int32)
+        if cia is None:
+            cia = np.abs(self._cia_unique[None, :] - tlayer[:, None]).argmin(axis=1).astype(np.int32)
         if np.isscalar(exclude_mol) and exclude_mol == 1:
             fac = dict.fromkeys(atmosphere.molecules, 1)
         else:
@@ -305,7 +328,10 @@ def _layer_scalars(atm, opa):
     colden = np.asarray(atm.layer["colden"], dtype=np.float64)
     player = np.asarray(atm.layer["pressure"], dtype=np.float64)
     mix = atm.layer["mixingratios"]
-    x = lambda s: np.asarray(mix[s].values if hasattr(mix[s], "values") else mix[s], dtype=np.float64)
+    if isinstance(mix, dict):
+        x = mix.__getitem__                      # numpy vectors (np.array below converts anything else)
+    else:
+        x = lambda s: mix[s].values              # pandas DataFrame, as ATMSETUP builds it
     t0, t1, p0, p1 = tlevel[:-1], tlevel[1:], plevel[:-1], plevel[1:]
     dp = p1 - p0
     tt = tlayer / (t0 * t1)
@@ -321,29 +347,31 @@ def _layer_scalars(atm, opa):
         if key not in opa._cont_index:
             raise KeyError(f"continuum pair {key} is not in the uploaded tables")
         if m[0] == "H-" and m[1] == "bf":
-            cont[opa._cont_index[key]] = (x("H-") * colden / (mmw * atm.c.amu))
+            cont[opa._cont_index[key]] = (np.asarray(x("H-"), dtype=np.float64) * colden / (mmw * atm.c.amu))
         elif m[0] == "H-" and m[1] == "ff":
-            cont[opa._cont_index[key]] = (player * x("H") * np.asarray(atm.layer["electrons"]) * colden /
-                                          (tlayer * mmw * atm.c.amu * atm.c.k_b))
+            cont[opa._cont_index[key]] = (player * np.asarray(x("H"), dtype=np.float64) * np.asarray(atm.layer["electrons"]) *
+                                          colden / (tlayer * mmw * atm.c.amu * atm.c.k_b))
         elif m[0] == "H2-" and m[1] == "":
-            cont[opa._cont_index[key]] = (player * x("H2") * np.asarray(atm.layer["electrons"]) * colden / (mmw * atm.c.amu))
+            cont[opa._cont_index[key]] = (player * np.asarray(x("H2"), dtype=np.float64) * np.asarray(atm.layer["electrons"]) *
+                                          colden / (mmw * atm.c.amu))
         else:
             cia_rows.append(opa._cont_index[key])
             cia_a.append(x(m[0]))
             cia_b.append(x(m[1]))
     if cia_rows:
-        cont[cia_rows] = (COEF1 * np.array(cia_a) * np.array(cia_b))
+        cont[cia_rows] = (COEF1 * np.array(cia_a, dtype=np.float64) * np.array(cia_b, dtype=np.float64))
     mol = np.zeros((len(opa._mol_index), L))
     if len(atm.molecules):
-        for m in atm.molecules:
-            if m not in opa._mol_index:
-                raise KeyError(f"molecule {m} is not in the uploaded tables")
+        try:
+            rows = [opa._mol_index[m] for m in atm.molecules]
+        except KeyError as e:
+            raise KeyError(f"molecule {e.args[0]} is not in the uploaded tables") from None
         fac = np.array([opa._plan["fac"][m] for m in atm.molecules])[:, None]
-        mol[[opa._mol_index[m] for m in atm.molecules]] = fac * (colden * np.array([x(m) for m in atm.molecules]) / mmw)
+        mol[rows] = fac * (colden * np.array([x(m) for m in atm.molecules], dtype=np.float64) / mmw)
     ray = np.zeros((len(opa._ray_index), L))
     if len(atm.rayleigh_molecules):
         ray[[opa._ray_index[m] for m in atm.rayleigh_molecules]] = (
-            colden * np.array([x(m) for m in atm.rayleigh_molecules]) / mmw)
+            colden * np.array([x(m) for m in atm.rayleigh_molecules], dtype=np.float64) / mmw)
     return mol, cont, ray
 
 

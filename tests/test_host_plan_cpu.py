@@ -103,3 +103,50 @@ def test_plan_and_layer_scalars_bit_for_bit(seed, frame):
     want = ref._layer_scalars(a, opa)
     for g_, w_ in zip(got, want):
         assert np.array_equal(g_, w_)
+
+
+def c_plan(t_inv_grid, p_log_grid, nc_p, tlayer, pbar, cia_unique):
+    """pb_host_plan_bilinear called directly (what DeviceOpacities.get_opacities does for query_method='linear')"""
+    import ctypes
+    from picaso_b200 import _lib
+    fn = _lib.load_library().pb_host_plan_bilinear
+    L = tlayer.size
+    tg, pg = np.ascontiguousarray(t_inv_grid), np.ascontiguousarray(p_log_grid)
+    ncp = np.ascontiguousarray(nc_p, dtype=np.int64)
+    off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(ncp)]), dtype=np.int64)
+    t_mono, p_mono = optics.grid_is_monotonic(tg, pg)
+    tl = np.ascontiguousarray(tlayer)
+    t_inv, p_log = 1 / tl, np.log10(pbar)
+    idx, wts = np.empty((L, 4), dtype=np.int32), np.empty((L, 4))
+    cia, rows, n = np.empty(L, dtype=np.int32), np.empty(4 * L, dtype=np.int64), ctypes.c_int(0)
+    cu = np.ascontiguousarray(cia_unique)
+    rc = fn(L, t_inv.ctypes.data, p_log.ctypes.data, tl.ctypes.data, tg.size, tg.ctypes.data, pg.size, pg.ctypes.data,
+            ncp.ctypes.data, off.ctypes.data, int(t_mono), int(p_mono), cu.size, cu.ctypes.data, idx.ctypes.data,
+            wts.ctypes.data, cia.ctypes.data, rows.ctypes.data, ctypes.addressof(n))
+    assert rc == 0
+    return idx, wts, cia, rows[:n.value], (t_mono, p_mono)
+
+
+@pytest.mark.parametrize("seed,ragged,shuffle", [(1, True, False), (2, False, False), (3, True, False), (4, False, True)])
+def test_c_planner_bit_for_bit(seed, ragged, shuffle):
+    """the C planner (csrc/host_plan.cu) against the mask-based numpy version: random profiles, profiles far outside the
+    grid, layers exactly on grid points, ragged pressure columns, and a non-monotonic temperature axis (scan path)"""
+    rng = np.random.default_rng(seed)
+    db = synth.opacity_database(W=8, nmol=1, seed=seed, nT=13, nP=9, ragged=ragged)
+    temps, press, nc_p = db["temps"], db["pressures"], db["nc_p"]
+    if shuffle:
+        perm = rng.permutation(temps.size)
+        temps, nc_p = temps[perm], nc_p[perm]
+    n_extra = temps.size + press.size
+    tlayer = np.concatenate([rng.uniform(30.0, 6000.0, size=120), temps, rng.uniform(200, 2000, size=press.size)])
+    pbar = np.concatenate([10.0 ** rng.uniform(-8.0, 4.5, size=120), 10.0 ** rng.uniform(-6, 2, size=temps.size), press])
+    cia_unique = np.unique(rng.uniform(50, 3000, size=17))
+    idx, wts, cia, rows, mono = c_plan(1 / temps, np.log10(press), nc_p, tlayer, pbar, cia_unique)
+    assert mono == (not shuffle, True)
+    t, p, ill, ihl, ilh, ihh = ref.find_needed_pts_grid(1 / temps, np.log10(press), nc_p, tlayer, pbar)
+    t, p = t[:, 0], p[:, 0]
+    assert np.array_equal(idx, np.stack([ill, ihl, ihh, ilh], axis=1))
+    assert np.array_equal(wts, np.stack([(1 - t) * (1 - p), t * (1 - p), t * p, (1 - t) * p], axis=1), equal_nan=True)
+    assert np.array_equal(cia, np.abs(cia_unique[None, :] - tlayer[:, None]).argmin(axis=1))
+    assert np.array_equal(rows, 1 + np.unique(np.concatenate([ill, ihl, ilh, ihh])))
+    assert n_extra > 0
