@@ -315,6 +315,18 @@ def bench_climate(ctx, L, W, K, ng, reps):
     ms_cpu1 = wall(lambda: oclim.get_fluxes(*args, nthreads=1), 1)
     # algorithmic bytes: 12 opacity arrays read once + the 4 level arrays written and read back by the reductions
     alg = (12 * L + 2) * W * K * 8 + 2 * 4 * (1 + ng) * (L + 1) * W * K * 8
+    # the Jacobian of t_start in one call: nlevel + 1 temperature profiles over one set of opacities (thermal half)
+    V = L + 1
+    t0_ = np.asarray(d["Atmosphere"].t_level, dtype=np.float64)
+    tls = np.tile(t0_, (V + 1, 1))
+    for j in range(V):
+        tls[j + 1, j] += 0.01 * t0_[j]
+    ms_jac = wall(lambda: pb.get_fluxes_jacobian(*dd[:6], tls, ctx=ctx), max(2, reps // 4))
+    ms_one_ir = wall(lambda: pb.get_fluxes(*dd[:7], False, True, ctx=ctx, full_arrays=False), reps)
+    print(json.dumps({"config": "climate.get_fluxes_jacobian L=%d W=%d ngauss=%d ng=%d: %d temperature profiles, thermal half" % (
+                          L, W, K, ng, V + 1),
+                      "ms_per_call": ms_jac, "ms_per_profile": ms_jac / (V + 1),
+                      "ms_one_profile_per_call_thermal_only": ms_one_ir}), flush=True)
     print(json.dumps({"config": "climate.get_fluxes L=%d W=%d ngauss=%d ng=%d (reflected + thermal)" % (L, W, K, ng),
                       "ms_per_call_host_arrays": ms_host, "ms_per_call_device_opacities": ms_dev,
                       "ms_per_call_device_opacities_net_fluxes_only": ms_net,
