@@ -247,6 +247,16 @@ class DeviceOpacities:
             mono = self._grid_mono = grid_is_monotonic(self.t_inv_grid, self.p_log_grid)
         return find_needed_pts_grid(self.t_inv_grid, self.p_log_grid, self.nc_p, tlayer, player, monotonic=mono)
 
+    def _plan_numpy(self, tlayer, pbar):
+        """the bilinear plan in numpy statements (find_needed_pts_grid + the bookkeeping of optics.py:2265-2298)"""
+        t, p, ill, ihl, ilh, ihh = self.find_needed_pts(tlayer, pbar)
+        t, p = t[:, 0], p[:, 0]
+        idx = np.stack([ill, ihl, ihh, ilh], axis=1).astype(np.int32)
+        t1, p1 = 1 - t, 1 - p
+        wts = np.stack([t1 * p1, t * p1, t * p, t1 * p], axis=1)
+        cia = np.abs(self._cia_unique[None, :] - tlayer[:, None]).argmin(axis=1).astype(np.int32)
+        return idx, wts, cia, 1 + np.unique(idx).astype(np.int64)
+
     def get_opacities(self, atmosphere, exclude_mol=1):
         """Record the table rows / weights for this atmosphere; nothing is fetched or copied.
         Sets atmosphere.layer['pt_opa_index'] like the reference (optics.py:2265, :2333)."""
@@ -274,14 +284,29 @@ class DeviceOpacities:
                     static=(tg.size, tg.ctypes.data, pg.size, pg.ctypes.data, ncp.ctypes.data, off.ctypes.data, int(t_mono),
                             int(p_mono), cu.size, cu.ctypes.data, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data,
                             out[3].ctypes.data, ctypes.addressof(out[4])))
-            tl = np.ascontiguousarray(tlayer)
-            t_inv = 1 / tl
-            p_log = np.log10(pbar)
-            idx, wts, cia, rows, nrows = g["out"]
-            rc = g["fn"](L, t_inv.ctypes.data, p_log.ctypes.data, tl.ctypes.data, *g["static"])
-            if rc != 0:
-                raise _lib.PicasoB200Error("pb_host_plan_bilinear: bad table grid (needs >= 2 temperatures and pressures)")
-            atmosphere.layer["pt_opa_index"] = rows[:nrows.value].copy()
+                g["checked"] = False
+            if g["fn"] is not None:
+                tl = np.ascontiguousarray(tlayer)
+                t_inv = 1 / tl
+                p_log = np.log10(pbar)
+                idx, wts, cia, rows, nrows = g["out"]
+                rc = g["fn"](L, t_inv.ctypes.data, p_log.ctypes.data, tl.ctypes.data, *g["static"])
+                if rc != 0:
+                    raise _lib.PicasoB200Error("pb_host_plan_bilinear: bad table grid (needs >= 2 temperatures and pressures)")
+                used = rows[:nrows.value].copy()
+                if not g["checked"]:
+                    # once per connection: the C planner against the numpy statements it replaces, on this very profile
+                    g["checked"] = True
+                    i2, w2, c2, u2 = self._plan_numpy(tlayer, pbar)
+                    if not (np.array_equal(idx, i2) and np.array_equal(wts, w2, equal_nan=True) and np.array_equal(cia, c2)
+                            and np.array_equal(used, u2)):
+                        import warnings
+                        warnings.warn("picaso_b200: pb_host_plan_bilinear disagrees with the numpy planner on this table grid; "
+                                      "using the numpy planner for this connection")
+                        g["fn"] = None
+            if g["fn"] is None:
+                idx, wts, cia, used = self._plan_numpy(tlayer, pbar)
+            atmosphere.layer["pt_opa_index"] = used
         else:
             idx = np.zeros((L, 4), dtype=np.int32)
             wts = np.zeros((L, 4))
