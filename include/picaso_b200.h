@@ -87,7 +87,12 @@ uint64_t pb_launch_count(const pb_ctx *ctx);
  * in flags[r][rank] on every rank r (fence.sys + release store).  A consumer waits with pb_gather_wait
  * (stream-ordered) until all of its flags reached `step`.  `wait_step` makes the kernel itself hold its
  * peer stores until all local flags reached that value: with 3 rotating buffers and wait_step = step - 2
- * a rank never overwrites a row a peer may still be reading, and ranks may run one step apart. */
+ * a rank never overwrites a row a peer may still be reading, and ranks may run one step apart.
+ * Reader contract (all modes): the slab of step t is complete on this rank once pb_gather_wait(t) has passed; a rank
+ * must enqueue its reads of step t (stream-ordered after that wait) BEFORE it launches step t + nbuf - 1.  That launch
+ * is what publishes this rank's progress past step t + nbuf - 2 (immediately in the fused / push modes, one launch
+ * later in the lazy / deferred ones), and a peer overwrites the slot of step t (with step t + nbuf) only after it has
+ * seen every rank publish wait_step = t + 1. */
 typedef struct pb_peer_gather {
     int nranks, rank;                       /* nranks <= 8 */
     double *const *albedo;                  /* host array [nranks]: rank r's gathered buffer, as mapped here */
