@@ -88,11 +88,11 @@ uint64_t pb_launch_count(const pb_ctx *ctx);
  * (stream-ordered) until all of its flags reached `step`.  `wait_step` makes the kernel itself hold its
  * peer stores until all local flags reached that value: with 3 rotating buffers and wait_step = step - 2
  * a rank never overwrites a row a peer may still be reading, and ranks may run one step apart.
- * Reader contract (all modes): the slab of step t is complete on this rank once pb_gather_wait(t) has passed; a rank
- * must enqueue its reads of step t (stream-ordered after that wait) BEFORE it launches step t + nbuf - 1.  That launch
- * is what publishes this rank's progress past step t + nbuf - 2 (immediately in the fused / push modes, one launch
- * later in the lazy / deferred ones), and a peer overwrites the slot of step t (with step t + nbuf) only after it has
- * seen every rank publish wait_step = t + 1. */
+ * Reader contract: the slab of step t is complete on this rank once pb_gather_wait(t) has passed.  A peer overwrites
+ * the slot of step t (with step t + nbuf) only after it has seen every rank publish wait_step = t + nbuf - (nbuf - 1)
+ * = t + 1, so a rank must enqueue its reads of step t (stream-ordered after that wait) BEFORE the launch that publishes
+ * its step t + 1: the launch of step t + 1 itself in the fused / push modes, the launch of step t + 2 in the lazy /
+ * deferred modes (there the flags of a step are published by the following launch). */
 typedef struct pb_peer_gather {
     int nranks, rank;                       /* nranks <= 8 */
     double *const *albedo;                  /* host array [nranks]: rank r's gathered buffer, as mapped here */
