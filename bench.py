@@ -736,42 +736,47 @@ def main():
                                "all_threads_value": W * n / el, "all_threads_cores": nthreads, "host_cpus": os.cpu_count()}
     if rank == 0 and world == 1:
         # ---- spectrum-level end to end: profile in, albedo out, opacity tables resident in HBM ----
-        db, ray, atms, ducks = _spectrum_setup()
-        opa, one = spectrum_gpu_factory(pb, ctx, db, ray, ducks)
-        got = one(0)
-        want = spectrum_cpu(db, ray, atms[0], os.cpu_count() or 1)
-        sp_par = float(np.max(np.abs(got - want) / np.abs(want)))
-        if not sp_par < 1e-6:
-            raise SystemExit("spectrum-level parity gate failed: %.3e" % sp_par)
-        if not np.array_equal(got, one.chain(0)):
-            raise SystemExit("pb_spectrum_reflected differs from the compute_opacity -> get_reflected_1d chain")
-        for i in range(3):
-            one(i)
-        ns = max(ke, 40)
-        l0 = ctx.launch_count()
-        t0 = time.perf_counter()
-        for i in range(ns):
-            one(i)
-        sdt = time.perf_counter() - t0
-        sp = {"value": W * ns / sdt, "unit": UNIT, "steps": ns, "ms_per_step": 1e3 * sdt / ns,
-              "gpu_launches_per_step": (ctx.launch_count() - l0) / ns,
-              "h2d_bytes_per_step": int(L * (NMOL_SPEC + len(db["continuum"]) + len(ray) + 12) * 8),
-              "d2h_bytes_per_step": int((NG + 1) * W * 8), "parity_albedo_max_rel_err": sp_par,
-              "api": "DeviceOpacities.get_opacities(linear) + picaso_b200.reflected_spectrum (pb_spectrum_reflected: "
-                     "compute_opacity, %d molecules, clear, no Raman -> get_reflected_1d -> compress_disco in one C call, "
-                     "one D2H copy); tables resident in HBM" % NMOL_SPEC}
-        for i in range(3):
-            one.chain(i)
-        t0 = time.perf_counter()
-        for i in range(ns):
-            one.chain(i)
-        sp["three_call_chain_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / ns
-        if not args.no_cpu_baseline:
-            cv, cn, cel = time_spectrum_cpu(db, ray, atms, os.cpu_count() or 1)
-            sp["cpu_port_value"] = cv
-            sp["cpu_port_sample"] = "%d spectra in %.1f s on %d threads" % (cn, cel, os.cpu_count() or 1)
-        out["e2e_spectrum"] = sp
-        opa.close()
+        # (an extra key: a failure here is reported IN the line instead of taking the headline numbers down with it)
+        try:
+            db, ray, atms, ducks = _spectrum_setup()
+            opa, one = spectrum_gpu_factory(pb, ctx, db, ray, ducks)
+            got = one(0)
+            want = spectrum_cpu(db, ray, atms[0], os.cpu_count() or 1)
+            sp_par = float(np.max(np.abs(got - want) / np.abs(want)))
+            if not sp_par < 1e-6:
+                raise SystemExit("spectrum-level parity gate failed: %.3e" % sp_par)
+            if not np.array_equal(got, one.chain(0)):
+                raise SystemExit("pb_spectrum_reflected differs from the compute_opacity -> get_reflected_1d chain")
+            for i in range(3):
+                one(i)
+            ns = max(ke, 40)
+            l0 = ctx.launch_count()
+            t0 = time.perf_counter()
+            for i in range(ns):
+                one(i)
+            sdt = time.perf_counter() - t0
+            sp = {"value": W * ns / sdt, "unit": UNIT, "steps": ns, "ms_per_step": 1e3 * sdt / ns,
+                  "gpu_launches_per_step": (ctx.launch_count() - l0) / ns,
+                  "h2d_bytes_per_step": int(L * (NMOL_SPEC + len(db["continuum"]) + len(ray) + 12) * 8),
+                  "d2h_bytes_per_step": int((NG + 1) * W * 8), "parity_albedo_max_rel_err": sp_par,
+                  "api": "DeviceOpacities.get_opacities(linear) + picaso_b200.reflected_spectrum (pb_spectrum_reflected: "
+                         "compute_opacity, %d molecules, clear, no Raman -> get_reflected_1d -> compress_disco in one C call, "
+                         "one D2H copy); tables resident in HBM" % NMOL_SPEC}
+            for i in range(3):
+                one.chain(i)
+            t0 = time.perf_counter()
+            for i in range(ns):
+                one.chain(i)
+            sp["three_call_chain_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / ns
+            if not args.no_cpu_baseline:
+                cv, cn, cel = time_spectrum_cpu(db, ray, atms, os.cpu_count() or 1)
+                sp["cpu_port_value"] = cv
+                sp["cpu_port_sample"] = "%d spectra in %.1f s on %d threads" % (cn, cel, os.cpu_count() or 1)
+            out["e2e_spectrum"] = sp
+            opa.close()
+        except (Exception, SystemExit) as exc:
+            sys.stderr.write("e2e_spectrum failed: %r\n" % (exc,))
+            out["e2e_spectrum"] = {"error": str(exc)}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
